@@ -1,0 +1,225 @@
+/* l2s.h -- C ABI of libl2s.so: the B200 (sm_100a) kernels behind lang2seg's
+ * language-conditioned segmentation hot path.
+ *
+ * Conventions:
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - all tensors are dense row-major ("NCHW" where a shape is given), fp32 unless noted;
+ *   - the caller owns every buffer (outputs, saved state, workspace); the library never
+ *     allocates, frees or retains pointers across calls;
+ *   - calls are asynchronous on `stream` (a cudaStream_t), re-entrant across streams and
+ *     devices, CUDA-graph capturable (no host sync, no malloc);
+ *   - return value: 0 on success, negative L2S_ERR_* otherwise; the message is available
+ *     from l2s_last_error_string() (per host thread).  The library never calls exit() and
+ *     never throws across this boundary.
+ *
+ * Each entry point cites the reference interface it replaces; paths are relative to the
+ * lang2seg reference tree, MFR = pyutils/mask-faster-rcnn/lib.
+ */
+#ifndef L2S_H_
+#define L2S_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* l2s_stream_t; /* cudaStream_t */
+
+#define L2S_OK 0
+#define L2S_ERR_SHAPE (-1)       /* bad / unsupported size */
+#define L2S_ERR_ALIGN (-2)       /* pointer not aligned as required */
+#define L2S_ERR_WORKSPACE (-3)   /* workspace missing or too small */
+#define L2S_ERR_CUDA (-4)        /* CUDA runtime / launch error */
+#define L2S_ERR_ARG (-5)         /* null pointer / invalid flag */
+
+#define L2S_NUM_FILTERS 7
+
+/* flags */
+#define L2S_GATE_SIGMOID 0  /* Y = X * sigmoid(r)  network_cycle_response.py:570            */
+#define L2S_GATE_LINEAR 1   /* Y = X * r           network_7f.py:534, network_cycle_res5_2.py:562 */
+#define L2S_CROP_MAX_POOL 1 /* 2S x 2S samples then 2x2 max (network_cycle_response.py:140-144) */
+#define L2S_CROP_ALIGN 2    /* _crop_pool_layer_align (network_cycle_response.py:151-182)  */
+
+int l2s_version(void);
+const char* l2s_last_error_string(void);
+/* number of kernels this library launched since load (process wide) */
+uint64_t l2s_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------
+ * (1) Spatial dynamic filter response + fusion + gate.
+ * Replaces MFR/nets/network_cycle_response.py:534-570 (7 masked 1x1 F.conv2d, cat, fuse conv,
+ * sigmoid, gate) and, through resp_target, the response loss at :415-422.
+ *
+ *   X        (I,C,H,W)   backbone C4 map of each image
+ *   filt     (E,7,C)     f_k = tanh(dynamic_fc_k(hidden))   (:510-529)
+ *   fuse     (E,7)       w   = tanh(response_fc(hidden))    (:531-532)
+ *   expr2img (E) int32   image of each expression, NON-DECREASING (expressions grouped by image)
+ *   response (E,H,W)     pre-sigmoid fused response  (_predictions['response'], :568)
+ *   rk_saved (E,7,H,W) or NULL: the masked per-filter responses r_k, kept for the backward
+ *   Y        (E,C,H,W)   gated features (:570)
+ *   resp_target (E,H,W) or NULL ; resp_loss (E) or NULL: per-expression mean BCE-with-logits.
+ * ------------------------------------------------------------------------------------- */
+int l2s_dynfilter_fwd(const float* X, const float* filt, const float* fuse, const int32_t* expr2img,
+                      float* response, float* rk_saved, float* Y, const float* resp_target,
+                      float* resp_loss, int I, int E, int C, int H, int W, int flags,
+                      l2s_stream_t stream);
+
+/* Backward of the above.
+ *   rk_saved: what the forward kept, or NULL (then r_k is recomputed into the workspace) ;
+ *   dY (E,C,H,W) ; dresponse (E,H,W) or NULL (explicit upstream gradient on the response) ;
+ *   resp_target (E,H,W) + resp_gscale (E) or NULL: adds resp_gscale[e]*(sigmoid(r)-t)/(H*W),
+ *   the gradient of the response loss, without materialising it.
+ *   dX (I,C,H,W) is OVERWRITTEN with the sum over the image's expressions ;
+ *   dfilt (E,7,C), dfuse (E,7) are overwritten.
+ *   workspace: l2s_dynfilter_bwd_workspace_bytes(). */
+size_t l2s_dynfilter_bwd_workspace_bytes(int I, int E, int C, int H, int W);
+int l2s_dynfilter_bwd(const float* X, const float* filt, const float* fuse, const int32_t* expr2img,
+                      const float* response, const float* rk_saved, const float* dY,
+                      const float* dresponse, const float* resp_target, const float* resp_gscale,
+                      float* dX, float* dfilt,
+                      float* dfuse, int I, int E, int C, int H, int W, int flags, void* workspace,
+                      size_t workspace_bytes, l2s_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * (2a) Crop-and-resize ROI pooling.  Replaces Network._crop_pool_layer / _crop_pool_layer_align
+ * (MFR/nets/network_cycle_response.py:107-182: affine_grid + grid_sample [+ max_pool2d]).
+ *
+ *   bottom (B,C,H,W) ; rois (N,5) [batch,x1,y1,x2,y2] in image pixels, batch in [0,B)
+ *   (the reference always has batch 0; here it selects the expression's map) ;
+ *   out (N,C,pool,pool) ; argmax (N,C,pool,pool) uint8 winner of each 2x2 block, only with
+ *   L2S_CROP_MAX_POOL (may be NULL when no backward is needed) ;
+ *   im_h, im_w: image size, used only with L2S_CROP_ALIGN.
+ *   workspace: l2s_roi_crop_workspace_bytes(B,N).
+ * ------------------------------------------------------------------------------------- */
+size_t l2s_roi_crop_workspace_bytes(int B, int N);
+int l2s_roi_crop_fwd(const float* bottom, const float* rois, float* out, uint8_t* argmax, int B, int C,
+                     int H, int W, int N, int pool, int flags, float im_h, float im_w, void* workspace,
+                     size_t workspace_bytes, l2s_stream_t stream);
+/* dbottom (B,C,H,W) is OVERWRITTEN with the scatter-add over all ROIs (deterministic order). */
+int l2s_roi_crop_bwd(const float* dout, const float* rois, const uint8_t* argmax, float* dbottom, int B,
+                     int C, int H, int W, int N, int pool, int flags, float im_h, float im_w,
+                     void* workspace, size_t workspace_bytes, l2s_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * (2b) Caffe RoI max-pool.  Replaces
+ *   int roi_pooling_forward_cuda(int pooled_height, int pooled_width, float spatial_scale,
+ *        THCudaTensor* features, THCudaTensor* rois, THCudaTensor* output, THCudaIntTensor* argmax)
+ *   int roi_pooling_backward_cuda(... top_grad, rois, bottom_grad, argmax)
+ * (MFR/layer_utils/roi_pooling/src/roi_pooling_cuda.h:1-4, kernels in
+ *  src/cuda/roi_pooling_kernel.cu:15-75,104-179).  Unlike the reference, any batch size B is
+ * accepted; argmax is the flat (c*H+h)*W+w index inside the ROI's image, -1 for empty bins.
+ * ------------------------------------------------------------------------------------- */
+int l2s_roi_maxpool_fwd(int pooled_height, int pooled_width, float spatial_scale, const float* features,
+                        const float* rois, float* output, int32_t* argmax, int B, int C, int H, int W,
+                        int N, l2s_stream_t stream);
+int l2s_roi_maxpool_bwd(int pooled_height, int pooled_width, float spatial_scale, const float* top_grad,
+                        const float* rois, float* bottom_grad, const int32_t* argmax, int B, int C,
+                        int H, int W, int N, l2s_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * GEMM building block of the mask head: fp32-accurate products on the bf16 tensor pipe.
+ * Each fp32 operand is split into bf16 (hi, lo) planes; D = Ahi*Bhi + Ahi*Blo + Alo*Bhi is
+ * accumulated in fp32 in TMEM by tcgen05.mma (relative error ~2^-16, inside the 1e-4 budget).
+ *
+ * l2s_split_bf16: src fp32 (rows, cols) with row stride ld_src -> hi, lo bf16 (rows, ld_dst),
+ *                 zero-filling columns [cols, ld_dst).
+ * l2s_gemm_bf16x3: D (M,N) fp32, ldd = N.
+ *     a_layout/b_layout 0: operand stored K-major  (A: [M][K], B: [N][K])
+ *                       1: operand stored MN-major (A: [K][M], B: [K][N])
+ *     epilogue  0: D = acc ; 1: D += acc ; 2: D = relu(acc + bias[col/bias_div])
+ *     split_k >= 1 (with split_k > 1 the epilogue accumulates atomically; D must be zeroed
+ *     or hold the value to accumulate into).
+ *     Requirements: M % 128 == 0, N % 64 == 0, K % 32 == 0, 16-byte aligned pointers.
+ * ------------------------------------------------------------------------------------- */
+int l2s_split_bf16(const float* src, uint16_t* hi, uint16_t* lo, int64_t rows, int64_t cols, int64_t ld_src,
+                   int64_t ld_dst, l2s_stream_t stream);
+int l2s_gemm_bf16x3(const uint16_t* a_hi, const uint16_t* a_lo, const uint16_t* b_hi, const uint16_t* b_lo,
+                    float* D, const float* bias, int bias_div, int M, int N, int K, int a_layout,
+                    int b_layout, int epilogue, int split_k, l2s_stream_t stream);
+/* exact fp32 FFMA GEMM for small / ragged shapes: D[m,n] (+)= sum_k A[m*sam + k*sak] * B[n*sbn + k*sbk] */
+int l2s_gemm_f32(const float* A, const float* B, float* D, int M, int N, int K, int64_t sam, int64_t sak,
+                 int64_t sbn, int64_t sbk, int64_t ldd, int accumulate, l2s_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Mask head.  Replaces Network._mask_prediction (MFR/nets/network_cycle_response.py:292-307:
+ * ConvTranspose2d(Cin,Cmid,2,2) -> ReLU -> Conv2d(Cmid,ncls,1) -> sigmoid) and the mask loss
+ * (:404-413: gather class channel, BCE-with-logits, mean).
+ *
+ *   x (n,Cin,7,7) ; up_w (Cin,Cmid,2,2) ; up_b (Cmid) ; pred_w (ncls,Cmid) ; pred_b (ncls)
+ *   score, prob (n,ncls,14,14)
+ *   saved: caller-owned buffer of l2s_mask_head_saved_bytes() kept until the backward call.
+ *   backward: dscore (n,ncls,14,14) -> dx, d_up_w, d_up_b, d_pred_w, d_pred_b (overwritten).
+ *   Requirements: Cin % 64 == 0, Cmid % 16 == 0 (reference: 2048, 256, 81).
+ * ------------------------------------------------------------------------------------- */
+size_t l2s_mask_head_saved_bytes(int n, int Cin, int Cmid, int ncls);
+size_t l2s_mask_head_workspace_bytes(int n, int Cin, int Cmid, int ncls);
+int l2s_mask_head_fwd(const float* x, const float* up_w, const float* up_b, const float* pred_w,
+                      const float* pred_b, float* score, float* prob, void* saved, int n, int Cin,
+                      int Cmid, int ncls, void* workspace, size_t workspace_bytes, l2s_stream_t stream);
+int l2s_mask_head_bwd(const float* dscore, const float* up_w, const float* pred_w, const void* saved,
+                      float* dx, float* d_up_w, float* d_up_b, float* d_pred_w, float* d_pred_b, int n,
+                      int Cin, int Cmid, int ncls, void* workspace, size_t workspace_bytes,
+                      l2s_stream_t stream);
+/* loss = mean_{i,y,x} BCEWithLogits(score[i,label_i,y,x], target[i,y,x]) ; labels int64 (n).
+ * bwd writes dscore (n,ncls,hw) = gscale * dloss/dscore (zero outside the label channel). */
+int l2s_mask_bce_fwd(const float* score, const int64_t* labels, const float* target, float* loss, int n,
+                     int ncls, int hw, l2s_stream_t stream);
+int l2s_mask_bce_bwd(const float* score, const int64_t* labels, const float* target, const float* gscale,
+                     float* dscore, int n, int ncls, int hw, l2s_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * (3) att2in2 attention step.  Replaces Attention.forward
+ * (lib/caption_models/AttModel.py:406-423) after the h2att Linear:
+ *   e_a = alpha_w . tanh(p_att[b,a,:] + att_h[b,:]) + alpha_b ; weight = softmax_a(e) ;
+ *   att_res[b,:] = sum_a weight[b,a] * att_feats[b,a,:]
+ *
+ *   att_h (B,Dh) ; att_feats (B,A,D) ; p_att (B,A,Dh) ; alpha_w (Dh) ; alpha_b (1)
+ *   weight (B,A) and att_res (B,D) are outputs.  D, Dh multiples of 4 and <= 1024.
+ *   backward: datt_res (B,D) ->
+ *     datt_h (B,Dh) overwritten ; de (B,A) overwritten (gradient on the scores) ;
+ *     dp_att (B,A,Dh) ACCUMULATED (+=) when non-NULL ; datt_feats (B,A,D) ACCUMULATED when
+ *     non-NULL ; dalpha_w (Dh) ACCUMULATED atomically when non-NULL.
+ * ------------------------------------------------------------------------------------- */
+int l2s_att_step_fwd(const float* att_h, const float* att_feats, const float* p_att, const float* alpha_w,
+                     const float* alpha_b, float* weight, float* att_res, int B, int A, int D, int Dh,
+                     l2s_stream_t stream);
+int l2s_att_step_bwd(const float* datt_res, const float* att_h, const float* att_feats, const float* p_att,
+                     const float* alpha_w, const float* weight, float* datt_h, float* de, float* dp_att,
+                     float* datt_feats, float* dalpha_w, int B, int A, int D, int Dh, l2s_stream_t stream);
+
+/* att2in2 gate epilogue.  Replaces Att2in2Core.forward lines AttModel.py:450-464 after the three
+ * Linears: sums (B,5D) = i2h(xt)+h2h(h) ; a2c_out (B,2D) = a2c(att_res) ; c_prev (B,D)
+ *   i,f,o = sigmoid(sums[:, 0:3D]) ; g = max-halves(sums[:,3D:5D] + a2c_out)
+ *   c = f*c_prev + i*g ; h = o*tanh(c)
+ * backward: dh, dc (B,D) -> dsums (B,5D), da2c (B,2D), dc_prev (B,D). */
+int l2s_att2in2_gates_fwd(const float* sums, const float* a2c_out, const float* c_prev, float* h, float* c,
+                          int B, int D, l2s_stream_t stream);
+int l2s_att2in2_gates_bwd(const float* sums, const float* a2c_out, const float* c_prev, const float* c,
+                          const float* dh, const float* dc, float* dsums, float* da2c, float* dc_prev,
+                          int B, int D, l2s_stream_t stream);
+
+/* log-softmax + masked NLL (AttModel.py:98 + lib/misc/utils.py:43-53) on logits (R,V):
+ *   logp = log_softmax(logits) (written when non-NULL) ; nll[r] = -logp[r,target[r]]*mask[r]
+ * backward: dlogits[r,:] = gscale*mask[r]*(softmax - onehot(target)). */
+int l2s_logsoftmax_nll_fwd(const float* logits, const int64_t* target, const float* mask, float* logp,
+                           float* nll, int R, int V, l2s_stream_t stream);
+int l2s_logsoftmax_nll_bwd(const float* logits, const int64_t* target, const float* mask, const float* gscale,
+                           float* dlogits, int R, int V, l2s_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Caption feature prep ("next" row f1).  Replaces network_cycle_response.py:428-432:
+ *   fc[b,c] = mean_{hw} feats[b,c,:,:] ; att[b,i,j,c] = adaptive_avg_pool2d(feats,[S,S]) in NHWC,
+ * written into column block [col_off, col_off+C) of fc (B,ldc) and att (B,S,S,ldc) so that the
+ * before/after concat (:437-438) needs no extra pass.  Backward accumulates into dfeats (=).
+ * ------------------------------------------------------------------------------------- */
+int l2s_caption_feats_fwd(const float* feats, float* fc, float* att, int B, int C, int H, int W, int S,
+                          int ldc, int col_off, l2s_stream_t stream);
+int l2s_caption_feats_bwd(const float* dfc, const float* datt, float* dfeats, int B, int C, int H, int W,
+                          int S, int ldc, int col_off, l2s_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* L2S_H_ */

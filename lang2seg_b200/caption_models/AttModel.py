@@ -1,0 +1,143 @@
+"""att2in2 caption model on the sm_100a kernels -- drop-in for lib/caption_models/AttModel.py.
+
+Classes, constructor options, parameter names and call signatures follow the reference
+(AttModel :27-110, Attention :397-423, Att2in2Core :426-466, Att2in2Model :479-484) so that
+`caption_model.core.attention.h2att.weight` etc. load from its checkpoints.  What changes is where
+the arithmetic runs:
+
+  Attention.forward    h2att Linear (cuBLAS) + ONE fused kernel: score, softmax, weighted sum
+  Att2in2Core.forward  i2h/h2h/a2c Linears (cuBLAS) + one gate kernel (sigmoid/maxout/tanh/cell)
+  AttModel.forward     same T-step loop with the reference's early break; `forward_loss` fuses
+                       logit -> log-softmax -> masked NLL (LanguageModelCriterion) per step
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import functional as L2F
+
+
+class Attention(nn.Module):
+    def __init__(self, opt):
+        super().__init__()
+        self.rnn_size = opt["rnn_size"]
+        self.att_hid_size = opt["att_hid_size"]
+        self.h2att = nn.Linear(self.rnn_size, self.att_hid_size)
+        self.alpha_net = nn.Linear(self.att_hid_size, 1)
+
+    def forward(self, h, att_feats, p_att_feats):
+        B = att_feats.size(0)
+        att_size = att_feats.numel() // B // self.rnn_size
+        att_h = self.h2att(h)
+        res, _ = L2F.attention_step(att_h, att_feats.reshape(B, att_size, self.rnn_size),
+                                    p_att_feats.reshape(B, att_size, self.att_hid_size),
+                                    self.alpha_net.weight, self.alpha_net.bias)
+        return res
+
+
+class Att2in2Core(nn.Module):
+    def __init__(self, opt):
+        super().__init__()
+        self.input_encoding_size = opt["input_encoding_size"]
+        self.rnn_size = opt["rnn_size"]
+        self.drop_prob_lm = opt["drop_prob_lm"]
+        self.fc_feat_size = opt["fc_feat_size"]
+        self.att_feat_size = opt["att_feat_size"]
+        self.att_hid_size = opt["att_hid_size"]
+        self.a2c = nn.Linear(self.rnn_size, 2 * self.rnn_size)
+        self.i2h = nn.Linear(self.input_encoding_size, 5 * self.rnn_size)
+        self.h2h = nn.Linear(self.rnn_size, 5 * self.rnn_size)
+        self.dropout = nn.Dropout(self.drop_prob_lm)
+        self.attention = Attention(opt)
+
+    def forward(self, xt, fc_feats, att_feats, p_att_feats, state):
+        h_prev, c_prev = state[0][-1], state[1][-1]
+        att_res = self.attention(h_prev, att_feats, p_att_feats)
+        sums = self.i2h(xt) + self.h2h(h_prev)
+        next_h, next_c = L2F.att2in2_gates(sums, self.a2c(att_res), c_prev)
+        output = self.dropout(next_h)
+        return output, (next_h.unsqueeze(0), next_c.unsqueeze(0))
+
+
+class AttModel(nn.Module):
+    def __init__(self, opt):
+        super().__init__()
+        self.vocab_size = opt["vocab_size"]
+        self.input_encoding_size = opt["input_encoding_size"]
+        self.rnn_size = opt["rnn_size"]
+        self.num_layers = opt["num_layers"]
+        self.drop_prob_lm = opt["drop_prob_lm"]
+        self.seq_length = opt["seq_length"]
+        self.fc_feat_size = opt["fc_feat_size"]
+        self.att_feat_size = opt["att_feat_size"]
+        self.att_hid_size = opt["att_hid_size"]
+        self.ss_prob = 0.0
+        self.embed = nn.Sequential(nn.Embedding(self.vocab_size + 1, self.input_encoding_size), nn.ReLU(),
+                                   nn.Dropout(self.drop_prob_lm))
+        self.fc_embed = nn.Sequential(nn.Linear(self.fc_feat_size, self.rnn_size), nn.ReLU(),
+                                      nn.Dropout(self.drop_prob_lm))
+        self.att_embed = nn.Sequential(nn.Linear(self.att_feat_size, self.rnn_size), nn.ReLU(),
+                                       nn.Dropout(self.drop_prob_lm))
+        self.logit = nn.Linear(self.rnn_size, self.vocab_size + 1)
+        self.ctx2att = nn.Linear(self.rnn_size, self.att_hid_size)
+
+    def init_hidden(self, bsz):
+        w = next(self.parameters())
+        return (w.new_zeros(self.num_layers, bsz, self.rnn_size), w.new_zeros(self.num_layers, bsz, self.rnn_size))
+
+    @staticmethod
+    def decode_steps(seq):
+        """T of the reference loop: stop at the first column i >= 1 that is all zero (AttModel.py:92-93)."""
+        cols = (seq[:, 1:-1] != 0).any(0) if seq.size(1) > 2 else seq.new_zeros(0, dtype=torch.bool)
+        nz = torch.nonzero(~cols)
+        k = int(nz[0]) if nz.numel() else cols.numel()
+        return min(seq.size(1) - 1, 1 + k)
+
+    def _prepare(self, fc_feats, att_feats):
+        fc_feats = self.fc_embed(fc_feats)
+        att = self.att_embed(att_feats.reshape(-1, self.att_feat_size))
+        att = att.view(*(att_feats.size()[:-1] + (self.rnn_size,)))
+        p_att = self.ctx2att(att.view(-1, self.rnn_size)).view(*(att.size()[:-1] + (self.att_hid_size,)))
+        return fc_feats, att, p_att
+
+    def forward(self, fc_feats, att_feats, seq):
+        """fc_feats (B,F) ; att_feats (B,14,14,F) ; seq (B,L+2) -> log-probs (B,T,V+1)."""
+        B = fc_feats.size(0)
+        state = self.init_hidden(B)
+        fc_feats, att, p_att = self._prepare(fc_feats, att_feats)
+        outputs = []
+        for i in range(self.decode_steps(seq)):
+            xt = self.embed(seq[:, i])
+            output, state = self.core(xt, fc_feats, att, p_att, state)
+            outputs.append(L2F.log_softmax(self.logit(output)) if not torch.is_grad_enabled()
+                           else F.log_softmax(self.logit(output), dim=1))
+        return torch.stack(outputs, 1)
+
+    def forward_loss(self, fc_feats, att_feats, seq, masks):
+        """crit(model(fc, att, seq), seq[:,1:], masks[:,1:]) of network_cycle_response.py:443 without
+        materialising the (B,T,V+1) log-probs: per step logit -> fused log-softmax + masked NLL."""
+        B = fc_feats.size(0)
+        state = self.init_hidden(B)
+        fc_feats, att, p_att = self._prepare(fc_feats, att_feats)
+        T = self.decode_steps(seq)
+        masks = masks.to(att.dtype)
+        total = att.new_zeros(())
+        for i in range(T):
+            xt = self.embed(seq[:, i])
+            output, state = self.core(xt, fc_feats, att, p_att, state)
+            nll, _ = L2F.logsoftmax_nll(self.logit(output), seq[:, i + 1], masks[:, i + 1])
+            total = total + nll
+        return total / masks[:, 1:T + 1].sum()
+
+    def get_logprobs_state(self, it, tmp_fc_feats, tmp_att_feats, tmp_p_att_feats, state):
+        xt = self.embed(it)
+        output, state = self.core(xt, tmp_fc_feats, tmp_att_feats, tmp_p_att_feats, state)
+        return L2F.log_softmax(self.logit(output)), state
+
+
+class Att2in2Model(AttModel):
+    def __init__(self, opt):
+        super().__init__(opt)
+        self.core = Att2in2Core(opt)
+        delattr(self, "fc_embed")
+        self.fc_embed = lambda x: x

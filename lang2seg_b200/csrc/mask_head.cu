@@ -1,0 +1,628 @@
+// Mask head (deconv 2x + ReLU + 1x1 conv + sigmoid, and its loss) on the tcgen05 tensor pipe.
+//
+// Semantics: Network._mask_prediction and the mask loss of the lang2seg reference
+// (pyutils/mask-faster-rcnn/lib/nets/network_cycle_response.py:292-307, :404-413); SURVEY A.3.
+//
+//   U[(n,y,x),(dy,dx,o)]   = relu( sum_c F[n,c,y,x] * Wd[c,o,dy,dx] + bd[o] )    GEMM1  M=49n K=Cin N=4Cmid
+//   S[(n,y,x,dy,dx),cls]   = sum_o U[..,o] * Wp[cls,o] + bp[cls]                 GEMM2  M=196n K=Cmid N=ncls
+// backward: dU = dS Wp (masked by U>0), dF = dU Wd^T, dWd = F^T dU, dWp = dS^T U -- the two weight
+// gradients read the activation planes in place through MN-major UMMA descriptors.
+// All GEMMs run as bf16x3 split products with fp32 TMEM accumulation (gemm_tc.cuh); operands are
+// produced directly as (hi, lo) bf16 planes by the repack kernels / GEMM epilogues below, so no
+// fp32 intermediate (U, dU) ever touches HBM.
+#include <cuda.h>
+
+#include <algorithm>
+#include <mutex>
+
+#include "gemm_tc.cuh"
+
+namespace l2s {
+namespace tc {
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+int make_operand_map(CUtensorMap* out, const void* ptr, int64_t rows, int64_t K, int64_t ld, bool mn_major,
+                     int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  L2S_REQUIRE(fn, L2S_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  L2S_REQUIRE(aligned16(ptr) && (ld * 2) % 16 == 0, L2S_ERR_ALIGN,
+              "gemm operand: pointer and row stride (%lld elements) must be 16-byte aligned", (long long)ld);
+  cuuint64_t dims[2], strides[1];
+  cuuint32_t box[2], estr[2] = {1, 1};
+  CUtensorMapSwizzle swz;
+  if (!mn_major) {
+    dims[0] = (cuuint64_t)K; dims[1] = (cuuint64_t)rows;
+    box[0] = BK; box[1] = (cuuint32_t)box_rows;
+    swz = CU_TENSOR_MAP_SWIZZLE_64B;
+  } else {
+    dims[0] = (cuuint64_t)rows; dims[1] = (cuuint64_t)K;
+    box[0] = 64; box[1] = BK;
+    swz = CU_TENSOR_MAP_SWIZZLE_128B;
+  }
+  strides[0] = (cuuint64_t)ld * 2;
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  L2S_REQUIRE(r == CUDA_SUCCESS, L2S_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d (rows=%lld K=%lld ld=%lld mn=%d)",
+              (int)r, (long long)rows, (long long)K, (long long)ld, (int)mn_major);
+  return L2S_OK;
+}
+
+}  // namespace tc
+
+namespace {
+
+// ---- bf16 split helpers --------------------------------------------------------------------
+__device__ __forceinline__ void split2(float v, uint16_t* hi, uint16_t* lo) {
+  const __nv_bfloat16 h = __float2bfloat16_rn(v);
+  const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+  *hi = __bfloat16_as_ushort(h);
+  *lo = __bfloat16_as_ushort(l);
+}
+
+// pack 32 floats of one accumulator row into hi / lo bf16 and store 64 contiguous bytes each
+__device__ __forceinline__ void store_split32(uint16_t* hi, uint16_t* lo, const float (&v)[32]) {
+  uint32_t ph[16], pl[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    uint16_t h0, l0, h1, l1;
+    split2(v[2 * j], &h0, &l0);
+    split2(v[2 * j + 1], &h1, &l1);
+    ph[j] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+    pl[j] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    reinterpret_cast<uint4*>(hi)[j] = make_uint4(ph[4 * j], ph[4 * j + 1], ph[4 * j + 2], ph[4 * j + 3]);
+    reinterpret_cast<uint4*>(lo)[j] = make_uint4(pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
+  }
+}
+
+__global__ void split_kernel(const float* __restrict__ src, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
+                             int64_t rows, int64_t cols, int64_t ld_src, int64_t ld_dst) {
+  const int64_t total = rows * ld_dst;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / ld_dst, c = i - r * ld_dst;
+    const float v = c < cols ? __ldg(src + r * ld_src + c) : 0.f;
+    split2(v, hi + i, lo + i);
+  }
+}
+
+// ---- generic epilogue ------------------------------------------------------------------------
+struct EpiGeneric {
+  float* D;
+  int64_t ldd;
+  const float* bias;
+  int bias_div;
+  int mode;   // 0 store, 1 accumulate (+=), 2 relu(acc+bias), 3 atomic accumulate
+  __device__ __forceinline__ void operator()(int row, int col0, const float (&v)[32], int M, int N, int) const {
+    if (row >= M) return;
+    float* d = D + (size_t)row * ldd + col0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (col0 + j < N) {
+        float x = v[j];
+        if (mode == 2) x = fmaxf(x + (bias ? __ldg(bias + (col0 + j) / bias_div) : 0.f), 0.f);
+        if (mode == 1) d[j] += x;
+        else if (mode == 3) atomicAdd(d + j, x);
+        else d[j] = x;
+      }
+    }
+  }
+};
+
+// ---- mask head epilogues ----------------------------------------------------------------------
+// GEMM1: U = relu(acc + bd[o]) -> bf16 planes [M][4*Cmid], column = q*Cmid + o
+struct EpiUp {
+  uint16_t *hi, *lo;
+  const float* bias;
+  int Cmid, ld;
+  __device__ __forceinline__ void operator()(int row, int col0, const float (&v)[32], int M, int N, int) const {
+    if (row >= M) return;
+    float u[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int col = col0 + j;
+      u[j] = col < N ? fmaxf(v[j] + __ldg(bias + col % Cmid), 0.f) : 0.f;
+    }
+    if (col0 + 32 <= N) {
+      store_split32(hi + (size_t)row * ld + col0, lo + (size_t)row * ld + col0, u);
+    } else {
+      for (int j = 0; j < 32 && col0 + j < N; ++j) split2(u[j], hi + (size_t)row * ld + col0 + j, lo + (size_t)row * ld + col0 + j);
+    }
+  }
+};
+
+// GEMM2: rows (m, q) -> NCHW score / prob (n, ncls, 14, 14)
+struct EpiScore {
+  float *score, *prob;
+  const float* bias;
+  int ncls;
+  __device__ __forceinline__ void operator()(int row, int col0, const float (&v)[32], int M, int N, int) const {
+    if (row >= M) return;
+    const int m = row >> 2, q = row & 3;
+    const int n = m / 49, yx = m - n * 49;
+    const int y = yx / 7, x = yx - y * 7;
+    const int pos = (2 * y + (q >> 1)) * 14 + 2 * x + (q & 1);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int cls = col0 + j;
+      if (cls < ncls) {
+        const float s = v[j] + __ldg(bias + cls);
+        const size_t o = ((size_t)n * ncls + cls) * 196 + pos;
+        score[o] = s;
+        if (prob) prob[o] = sigmoidf_acc(s);
+      }
+    }
+  }
+};
+
+// dU = acc * [U > 0] -> bf16 planes [4M][Cmid] (same memory order as U) ; column sums -> d_up_b
+struct EpiDU {
+  uint16_t *hi, *lo;
+  const uint16_t* u_hi;
+  float* d_up_b;
+  int Cmid;
+  __device__ __forceinline__ void operator()(int row, int col0, const float (&v)[32], int M, int N, int) const {
+    float d[32];
+    const bool ok = row < M;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int col = col0 + j;
+      float x = 0.f;
+      if (ok && col < N) {
+        const __nv_bfloat16 u = __ushort_as_bfloat16(u_hi[(size_t)row * Cmid + col]);
+        x = (__bfloat162float(u) > 0.f) ? v[j] : 0.f;
+      }
+      d[j] = x;
+    }
+    if (ok) {
+      if (col0 + 32 <= N) store_split32(hi + (size_t)row * Cmid + col0, lo + (size_t)row * Cmid + col0, d);
+      else
+        for (int j = 0; j < 32 && col0 + j < N; ++j)
+          split2(d[j], hi + (size_t)row * Cmid + col0 + j, lo + (size_t)row * Cmid + col0 + j);
+    }
+    // bias gradient: sum over the 32 rows of this warp, one atomic per column
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const float s = warp_sum(d[j]);
+      if (lane == j && col0 + j < N) atomicAdd(d_up_b + col0 + j, s);
+    }
+  }
+};
+
+// dF[m][c] -> dx NCHW (n, Cin, 7, 7): lanes are consecutive m, so each column store is coalesced
+struct EpiDx {
+  float* dx;
+  int Cin;
+  __device__ __forceinline__ void operator()(int row, int col0, const float (&v)[32], int M, int N, int) const {
+    if (row >= M) return;
+    const int n = row / 49, yx = row - n * 49;
+    float* d = dx + ((size_t)n * Cin + col0) * 49 + yx;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (col0 + j < N) d[(size_t)j * 49] = v[j];
+  }
+};
+
+// dWd[c][(q,o)] -> d_up_w (Cin, Cmid, 2, 2) ; atomic because of split-K
+struct EpiDWd {
+  float* dw;
+  int Cmid;
+  __device__ __forceinline__ void operator()(int row, int col0, const float (&v)[32], int M, int N, int) const {
+    if (row >= M) return;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      const int col = col0 + j;
+      if (col < N) {
+        const int q = col / Cmid, o = col - q * Cmid;
+        atomicAdd(dw + ((size_t)row * Cmid + o) * 4 + q, v[j]);
+      }
+    }
+  }
+};
+
+// dWp[cls][o] ; rows >= ncls are padding
+struct EpiDWp {
+  float* dw;
+  int ncls, Cmid;
+  __device__ __forceinline__ void operator()(int row, int col0, const float (&v)[32], int M, int N, int) const {
+    if (row >= ncls) return;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (col0 + j < N) atomicAdd(dw + (size_t)row * Cmid + col0 + j, v[j]);
+  }
+};
+
+// ---- repack kernels ----------------------------------------------------------------------------
+// x (n,Cin,49) fp32 -> A planes [n*49][Cin] bf16.  CTA = (64-channel chunk, n)
+__global__ void __launch_bounds__(256)
+repack_x_kernel(const float* __restrict__ x, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int Cin) {
+  __shared__ float s[64 * 49];
+  const int n = blockIdx.y, c0 = blockIdx.x * 64, t = threadIdx.x;
+  const int nc = min(64, Cin - c0);
+  const float* src = x + ((size_t)n * Cin + c0) * 49;
+  for (int i = t; i < nc * 49; i += 256) s[i] = __ldg(src + i);
+  __syncthreads();
+  for (int i = t; i < 49 * 64; i += 256) {
+    const int yx = i >> 6, c = i & 63;
+    if (c < nc) {
+      const size_t o = ((size_t)n * 49 + yx) * Cin + c0 + c;
+      split2(s[c * 49 + yx], hi + o, lo + o);
+    }
+  }
+}
+
+// up_w (Cin,Cmid,2,2) -> B1 [4Cmid][Cin] (row = q*Cmid+o, K-major over c)  and  B3 [Cin][4Cmid] (col = q*Cmid+o)
+__global__ void repack_upw_kernel(const float* __restrict__ w, uint16_t* __restrict__ b1h, uint16_t* __restrict__ b1l,
+                                  uint16_t* __restrict__ b3h, uint16_t* __restrict__ b3l, int Cin, int Cmid) {
+  const int64_t total = (int64_t)Cin * Cmid * 4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int q = (int)(i & 3);
+    const int o = (int)((i >> 2) % Cmid);
+    const int c = (int)((i >> 2) / Cmid);
+    uint16_t h, l;
+    split2(__ldg(w + i), &h, &l);
+    const int col = q * Cmid + o;
+    if (b1h) { b1h[(size_t)col * Cin + c] = h; b1l[(size_t)col * Cin + c] = l; }
+    if (b3h) { b3h[(size_t)c * 4 * Cmid + col] = h; b3l[(size_t)c * 4 * Cmid + col] = l; }
+  }
+}
+
+// pred_w (ncls,Cmid) -> B2 [ncls][Cmid] (as is)  and  B4 [Cmid][KP] = transpose, zero padded
+__global__ void repack_predw_kernel(const float* __restrict__ w, uint16_t* __restrict__ b2h, uint16_t* __restrict__ b2l,
+                                    uint16_t* __restrict__ b4h, uint16_t* __restrict__ b4l, int ncls, int Cmid, int KP) {
+  const int total = Cmid * KP;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int o = i / KP, cls = i - o * KP;
+    uint16_t h = 0, l = 0;
+    if (cls < ncls) split2(__ldg(w + (size_t)cls * Cmid + o), &h, &l);
+    if (b4h) { b4h[i] = h; b4l[i] = l; }
+    if (b2h && cls < ncls) { b2h[(size_t)cls * Cmid + o] = h; b2l[(size_t)cls * Cmid + o] = l; }
+  }
+}
+
+// dscore (n,ncls,196) -> dS planes [n*196 rows (yx,q)][KP] ; plane sums -> d_pred_b
+__global__ void __launch_bounds__(256)
+repack_dscore_kernel(const float* __restrict__ ds, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
+                     float* __restrict__ d_pred_b, int ncls, int KP) {
+  extern __shared__ float s[];   // [ncls][197]
+  const int n = blockIdx.x, t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  const float* src = ds + (size_t)n * ncls * 196;
+  for (int i = t; i < ncls * 196; i += 256) {
+    const int cls = i / 196, pos = i - cls * 196;
+    s[cls * 197 + pos] = __ldg(src + i);
+  }
+  __syncthreads();
+  if (d_pred_b)
+    for (int cls = wid; cls < ncls; cls += 8) {
+      float a = 0.f;
+      for (int p = lane; p < 196; p += 32) a += s[cls * 197 + p];
+      a = warp_sum(a);
+      if (lane == 0) atomicAdd(d_pred_b + cls, a);
+    }
+  for (int i = t; i < 196 * KP; i += 256) {
+    const int r = i / KP, cls = i - r * KP;
+    const int yx = r >> 2, q = r & 3;
+    const int y = yx / 7, x = yx - y * 7;
+    const int pos = (2 * y + (q >> 1)) * 14 + 2 * x + (q & 1);
+    uint16_t h = 0, l = 0;
+    if (cls < ncls) split2(s[cls * 197 + pos], &h, &l);
+    const size_t o = ((size_t)n * 196 + r) * KP + cls;
+    hi[o] = h;
+    lo[o] = l;
+  }
+}
+
+// ---- exact fp32 GEMM (FFMA) for small / ragged shapes -------------------------------------------
+__global__ void __launch_bounds__(256)
+gemm_f32_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D, int M, int N, int K,
+                int64_t sam, int64_t sak, int64_t sbn, int64_t sbk, int64_t ldd, int accumulate) {
+  __shared__ float As[16][65], Bs[16][65];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+      const int r = i >> 4, k = i & 15;
+      As[k][r] = (m0 + r < M && k0 + k < K) ? __ldg(A + (int64_t)(m0 + r) * sam + (int64_t)(k0 + k) * sak) : 0.f;
+      Bs[k][r] = (n0 + r < N && k0 + k < K) ? __ldg(B + (int64_t)(n0 + r) * sbn + (int64_t)(k0 + k) * sbk) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = As[k][ty * 4 + i]; b[i] = Bs[k][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int m = m0 + ty * 4 + i, n = n0 + tx * 4 + j;
+      if (m < M && n < N) {
+        float* d = D + (int64_t)m * ldd + n;
+        *d = accumulate ? *d + acc[i][j] : acc[i][j];
+      }
+    }
+}
+
+// ---- mask BCE ----------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+mask_bce_fwd_kernel(const float* __restrict__ score, const int64_t* __restrict__ labels,
+                    const float* __restrict__ target, float* __restrict__ loss, int n, int ncls, int hw) {
+  const int i = blockIdx.x, t = threadIdx.x;
+  const int64_t lab = labels[i];
+  float a = 0.f;
+  if (lab >= 0 && lab < ncls) {
+    const float* s = score + ((size_t)i * ncls + lab) * hw;
+    for (int p = t; p < hw; p += 256) {
+      const float x = __ldg(s + p), tg = __ldg(target + (size_t)i * hw + p);
+      a += fmaxf(x, 0.f) - x * tg + log1pf(expf(-fabsf(x)));
+    }
+  }
+  a = warp_sum(a);
+  __shared__ float sr[8];
+  if ((t & 31) == 0) sr[t >> 5] = a;
+  __syncthreads();
+  if (t == 0) {
+    float tot = 0.f;
+    for (int w = 0; w < 8; ++w) tot += sr[w];
+    atomicAdd(loss, tot / ((float)n * (float)hw));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+mask_bce_bwd_kernel(const float* __restrict__ score, const int64_t* __restrict__ labels,
+                    const float* __restrict__ target, const float* __restrict__ gscale, float* __restrict__ dscore,
+                    int n, int ncls, int hw) {
+  const int i = blockIdx.x, t = threadIdx.x;
+  const int64_t lab = labels[i];
+  const float gs = __ldg(gscale) / ((float)n * (float)hw);
+  for (int idx = t; idx < ncls * hw; idx += 256) {
+    const int cls = idx / hw, p = idx - cls * hw;
+    float g = 0.f;
+    if (cls == lab) {
+      const float x = __ldg(score + ((size_t)i * ncls + cls) * hw + p);
+      g = gs * (sigmoidf_acc(x) - __ldg(target + (size_t)i * hw + p));
+    }
+    dscore[((size_t)i * ncls) * hw + idx] = g;
+  }
+}
+
+inline size_t al(size_t x) { return (x + 255) & ~(size_t)255; }
+inline int kpad(int ncls) { return (ncls + 31) / 32 * 32; }
+
+struct Saved {   // layout of the caller-owned `saved` buffer
+  uint16_t *a_hi, *a_lo, *u_hi, *u_lo;
+  size_t bytes;
+};
+Saved saved_layout(void* base, int n, int Cin, int Cmid) {
+  Saved s;
+  uint8_t* p = reinterpret_cast<uint8_t*>(base);
+  const size_t M = (size_t)n * 49;
+  const size_t a = al(M * Cin * 2), u = al(M * 4 * Cmid * 2);
+  s.a_hi = reinterpret_cast<uint16_t*>(p);
+  s.a_lo = reinterpret_cast<uint16_t*>(p + a);
+  s.u_hi = reinterpret_cast<uint16_t*>(p + 2 * a);
+  s.u_lo = reinterpret_cast<uint16_t*>(p + 2 * a + u);
+  s.bytes = 2 * a + 2 * u;
+  return s;
+}
+
+int check_head(int n, int Cin, int Cmid, int ncls) {
+  L2S_REQUIRE(n >= 0 && Cin > 0 && Cmid > 0 && ncls > 0, L2S_ERR_SHAPE, "mask_head: bad shape");
+  L2S_REQUIRE(Cin % 8 == 0 && Cmid % 8 == 0, L2S_ERR_SHAPE,
+              "mask_head: Cin and Cmid must be multiples of 8 (TMA row alignment); got %d, %d", Cin, Cmid);
+  return L2S_OK;
+}
+
+int split_for(int tiles) {
+  const int sms = sm_count();
+  return tiles >= sms ? 1 : (2 * sms + tiles - 1) / tiles;
+}
+
+}  // namespace
+}  // namespace l2s
+
+using namespace l2s;
+
+extern "C" int l2s_split_bf16(const float* src, uint16_t* hi, uint16_t* lo, int64_t rows, int64_t cols, int64_t ld_src,
+                              int64_t ld_dst, l2s_stream_t stream) {
+  L2S_REQUIRE(src && hi && lo, L2S_ERR_ARG, "split_bf16: null pointer");
+  L2S_REQUIRE(rows >= 0 && cols >= 0 && ld_dst >= cols && ld_src >= cols, L2S_ERR_SHAPE, "split_bf16: bad shape");
+  if (rows * ld_dst == 0) return L2S_OK;
+  const int blocks = (int)std::min<int64_t>((rows * ld_dst + 255) / 256, (int64_t)sm_count() * 16);
+  split_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, hi, lo, rows, cols, ld_src, ld_dst);
+  L2S_LAUNCH_OK("split_kernel");
+  count_launch();
+  return L2S_OK;
+}
+
+extern "C" int l2s_gemm_bf16x3(const uint16_t* a_hi, const uint16_t* a_lo, const uint16_t* b_hi, const uint16_t* b_lo,
+                               float* D, const float* bias, int bias_div, int M, int N, int K, int a_layout,
+                               int b_layout, int epilogue, int split_k, l2s_stream_t stream) {
+  L2S_REQUIRE(a_hi && a_lo && b_hi && b_lo && D, L2S_ERR_ARG, "gemm_bf16x3: null pointer");
+  L2S_REQUIRE(M > 0 && N > 0 && K > 0, L2S_ERR_SHAPE, "gemm_bf16x3: bad shape");
+  L2S_REQUIRE(epilogue >= 0 && epilogue <= 2, L2S_ERR_ARG, "gemm_bf16x3: unknown epilogue %d", epilogue);
+  cudaStream_t st = (cudaStream_t)stream;
+
+  EpiGeneric epi{D, N, bias, bias_div > 0 ? bias_div : 1, epilogue};
+  if (split_k > 1) {
+    L2S_REQUIRE(epilogue != 2, L2S_ERR_ARG, "gemm_bf16x3: split-K cannot be combined with the bias/ReLU epilogue");
+    if (epilogue == 0) L2S_CUDA_OK(cudaMemsetAsync(D, 0, sizeof(float) * (size_t)M * N, st));
+    epi.mode = 3;
+  }
+  const int64_t lda = a_layout ? M : K, ldb = b_layout ? N : K;
+  if (!a_layout && !b_layout) return tc::launch_gemm<256, false, false>(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, split_k, epi, st);
+  if (a_layout && b_layout) return tc::launch_gemm<256, true, true>(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, split_k, epi, st);
+  if (a_layout) return tc::launch_gemm<256, true, false>(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, split_k, epi, st);
+  return tc::launch_gemm<256, false, true>(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, split_k, epi, st);
+}
+
+extern "C" int l2s_gemm_f32(const float* A, const float* B, float* D, int M, int N, int K, int64_t sam, int64_t sak,
+                            int64_t sbn, int64_t sbk, int64_t ldd, int accumulate, l2s_stream_t stream) {
+  L2S_REQUIRE(A && B && D, L2S_ERR_ARG, "gemm_f32: null pointer");
+  L2S_REQUIRE(M > 0 && N > 0 && K > 0, L2S_ERR_SHAPE, "gemm_f32: bad shape");
+  gemm_f32_kernel<<<dim3((N + 63) / 64, (M + 63) / 64), 256, 0, (cudaStream_t)stream>>>(A, B, D, M, N, K, sam, sak, sbn,
+                                                                                          sbk, ldd, accumulate);
+  L2S_LAUNCH_OK("gemm_f32_kernel");
+  count_launch();
+  return L2S_OK;
+}
+
+extern "C" size_t l2s_mask_head_saved_bytes(int n, int Cin, int Cmid, int ncls) {
+  (void)ncls;
+  return saved_layout(nullptr, n > 0 ? n : 0, Cin, Cmid).bytes + 256;
+}
+
+extern "C" size_t l2s_mask_head_workspace_bytes(int n, int Cin, int Cmid, int ncls) {
+  const size_t M = (size_t)(n > 0 ? n : 0) * 49;
+  const int KP = kpad(ncls);
+  const size_t wts = 4 * al((size_t)4 * Cmid * Cin * 2) + 2 * al((size_t)ncls * Cmid * 2) + 2 * al((size_t)Cmid * KP * 2);
+  const size_t acts = 2 * al(M * 4 * KP * 2) + 2 * al(M * 4 * Cmid * 2);
+  return wts + acts + 1024;
+}
+
+namespace {
+struct Work {
+  uint16_t *b1h, *b1l, *b3h, *b3l, *b2h, *b2l, *b4h, *b4l, *dsh, *dsl, *duh, *dul;
+};
+Work work_layout(void* base, int n, int Cin, int Cmid, int ncls) {
+  uint8_t* p = reinterpret_cast<uint8_t*>(base);
+  const size_t M = (size_t)n * 49;
+  const int KP = kpad(ncls);
+  Work w;
+  auto take = [&](size_t bytes) { uint16_t* r = reinterpret_cast<uint16_t*>(p); p += al(bytes); return r; };
+  w.b1h = take((size_t)4 * Cmid * Cin * 2); w.b1l = take((size_t)4 * Cmid * Cin * 2);
+  w.b3h = take((size_t)4 * Cmid * Cin * 2); w.b3l = take((size_t)4 * Cmid * Cin * 2);
+  w.b2h = take((size_t)ncls * Cmid * 2); w.b2l = take((size_t)ncls * Cmid * 2);
+  w.b4h = take((size_t)Cmid * KP * 2); w.b4l = take((size_t)Cmid * KP * 2);
+  w.dsh = take(M * 4 * KP * 2); w.dsl = take(M * 4 * KP * 2);
+  w.duh = take(M * 4 * Cmid * 2); w.dul = take(M * 4 * Cmid * 2);
+  return w;
+}
+}  // namespace
+
+extern "C" int l2s_mask_head_fwd(const float* x, const float* up_w, const float* up_b, const float* pred_w,
+                                 const float* pred_b, float* score, float* prob, void* saved, int n, int Cin, int Cmid,
+                                 int ncls, void* workspace, size_t workspace_bytes, l2s_stream_t stream) {
+  int rc = check_head(n, Cin, Cmid, ncls);
+  if (rc) return rc;
+  if (n == 0) return L2S_OK;
+  L2S_REQUIRE(x && up_w && up_b && pred_w && pred_b && score && saved, L2S_ERR_ARG, "mask_head_fwd: null pointer");
+  L2S_REQUIRE(workspace && workspace_bytes >= l2s_mask_head_workspace_bytes(n, Cin, Cmid, ncls), L2S_ERR_WORKSPACE,
+              "mask_head_fwd: workspace too small");
+  L2S_REQUIRE(aligned16(saved) && aligned16(workspace), L2S_ERR_ALIGN, "mask_head_fwd: saved / workspace must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int M = n * 49;
+  const Saved sv = saved_layout(saved, n, Cin, Cmid);
+  const Work w = work_layout(workspace, n, Cin, Cmid, ncls);
+  repack_x_kernel<<<dim3((Cin + 63) / 64, n), 256, 0, st>>>(x, sv.a_hi, sv.a_lo, Cin);
+  L2S_LAUNCH_OK("repack_x_kernel");
+  repack_upw_kernel<<<std::min(1024, (Cin * Cmid * 4 + 255) / 256), 256, 0, st>>>(up_w, w.b1h, w.b1l, nullptr, nullptr, Cin, Cmid);
+  L2S_LAUNCH_OK("repack_upw_kernel");
+  repack_predw_kernel<<<std::min(256, (Cmid * kpad(ncls) + 255) / 256), 256, 0, st>>>(pred_w, w.b2h, w.b2l, nullptr, nullptr,
+                                                                                     ncls, Cmid, kpad(ncls));
+  L2S_LAUNCH_OK("repack_predw_kernel");
+  count_launch(3);
+  // GEMM1: [M x Cin] * [4Cmid x Cin]^T -> U planes
+  EpiUp e1{sv.u_hi, sv.u_lo, up_b, Cmid, 4 * Cmid};
+  rc = tc::launch_gemm<256, false, false>(sv.a_hi, sv.a_lo, Cin, w.b1h, w.b1l, Cin, M, 4 * Cmid, Cin, 1, e1, st);
+  if (rc) return rc;
+  // GEMM2: [4M x Cmid] * [ncls x Cmid]^T -> score / prob
+  EpiScore e2{score, prob, pred_b, ncls};
+  return tc::launch_gemm<128, false, false>(sv.u_hi, sv.u_lo, Cmid, w.b2h, w.b2l, Cmid, 4 * M, ncls, Cmid, 1, e2, st);
+}
+
+extern "C" int l2s_mask_head_bwd(const float* dscore, const float* up_w, const float* pred_w, const void* saved,
+                                 float* dx, float* d_up_w, float* d_up_b, float* d_pred_w, float* d_pred_b, int n,
+                                 int Cin, int Cmid, int ncls, void* workspace, size_t workspace_bytes,
+                                 l2s_stream_t stream) {
+  int rc = check_head(n, Cin, Cmid, ncls);
+  if (rc) return rc;
+  L2S_REQUIRE(up_w && pred_w && d_up_w && d_up_b && d_pred_w && d_pred_b, L2S_ERR_ARG, "mask_head_bwd: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  L2S_CUDA_OK(cudaMemsetAsync(d_up_w, 0, sizeof(float) * (size_t)Cin * Cmid * 4, st));
+  L2S_CUDA_OK(cudaMemsetAsync(d_up_b, 0, sizeof(float) * Cmid, st));
+  L2S_CUDA_OK(cudaMemsetAsync(d_pred_w, 0, sizeof(float) * (size_t)ncls * Cmid, st));
+  L2S_CUDA_OK(cudaMemsetAsync(d_pred_b, 0, sizeof(float) * ncls, st));
+  if (n == 0) return L2S_OK;
+  L2S_REQUIRE(dscore && saved && dx, L2S_ERR_ARG, "mask_head_bwd: null pointer");
+  L2S_REQUIRE(workspace && workspace_bytes >= l2s_mask_head_workspace_bytes(n, Cin, Cmid, ncls), L2S_ERR_WORKSPACE,
+              "mask_head_bwd: workspace too small");
+  const int M = n * 49, KP = kpad(ncls);
+  const Saved sv = saved_layout(const_cast<void*>(saved), n, Cin, Cmid);
+  const Work w = work_layout(workspace, n, Cin, Cmid, ncls);
+  const size_t smem = (size_t)ncls * 197 * 4;
+  L2S_REQUIRE(smem <= (size_t)max_smem_optin(), L2S_ERR_SHAPE, "mask_head_bwd: ncls=%d too large", ncls);
+  L2S_CUDA_OK(cudaFuncSetAttribute(repack_dscore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  repack_dscore_kernel<<<n, 256, smem, st>>>(dscore, w.dsh, w.dsl, d_pred_b, ncls, KP);
+  L2S_LAUNCH_OK("repack_dscore_kernel");
+  repack_upw_kernel<<<std::min(1024, (Cin * Cmid * 4 + 255) / 256), 256, 0, st>>>(up_w, nullptr, nullptr, w.b3h, w.b3l, Cin, Cmid);
+  L2S_LAUNCH_OK("repack_upw_kernel");
+  repack_predw_kernel<<<std::min(256, (Cmid * KP + 255) / 256), 256, 0, st>>>(pred_w, nullptr, nullptr, w.b4h, w.b4l, ncls, Cmid, KP);
+  L2S_LAUNCH_OK("repack_predw_kernel");
+  count_launch(3);
+  // dU[4M x Cmid] = dS[4M x KP] * Wp^T[Cmid x KP]^T, masked by U > 0
+  EpiDU e3{w.duh, w.dul, sv.u_hi, d_up_b, Cmid};
+  rc = tc::launch_gemm<256, false, false>(w.dsh, w.dsl, KP, w.b4h, w.b4l, KP, 4 * M, Cmid, KP, 1, e3, st);
+  if (rc) return rc;
+  // dWp[KP x Cmid] = dS^T * U   (both MN-major, K = 4M)
+  EpiDWp e4{d_pred_w, ncls, Cmid};
+  rc = tc::launch_gemm<256, true, true>(w.dsh, w.dsl, KP, sv.u_hi, sv.u_lo, Cmid, KP, Cmid, 4 * M,
+                                        split_for(((Cmid + 255) / 256)), e4, st);
+  if (rc) return rc;
+  // dF[M x Cin] = dU[M x 4Cmid] * Wd[Cin x 4Cmid]^T -> dx NCHW
+  EpiDx e5{dx, Cin};
+  rc = tc::launch_gemm<256, false, false>(w.duh, w.dul, 4 * Cmid, w.b3h, w.b3l, 4 * Cmid, M, Cin, 4 * Cmid, 1, e5, st);
+  if (rc) return rc;
+  // dWd[Cin x 4Cmid] = F^T * dU   (both MN-major, K = M)
+  EpiDWd e6{d_up_w, Cmid};
+  const int tiles = ((Cin + 127) / 128) * ((4 * Cmid + 255) / 256);
+  return tc::launch_gemm<256, true, true>(sv.a_hi, sv.a_lo, Cin, w.duh, w.dul, 4 * Cmid, Cin, 4 * Cmid, M,
+                                          split_for(tiles), e6, st);
+}
+
+extern "C" int l2s_mask_bce_fwd(const float* score, const int64_t* labels, const float* target, float* loss, int n,
+                                int ncls, int hw, l2s_stream_t stream) {
+  L2S_REQUIRE(score && labels && target && loss, L2S_ERR_ARG, "mask_bce_fwd: null pointer");
+  L2S_REQUIRE(n >= 0 && ncls > 0 && hw > 0, L2S_ERR_SHAPE, "mask_bce_fwd: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  L2S_CUDA_OK(cudaMemsetAsync(loss, 0, sizeof(float), st));
+  if (n == 0) return L2S_OK;
+  mask_bce_fwd_kernel<<<n, 256, 0, st>>>(score, labels, target, loss, n, ncls, hw);
+  L2S_LAUNCH_OK("mask_bce_fwd_kernel");
+  count_launch();
+  return L2S_OK;
+}
+
+extern "C" int l2s_mask_bce_bwd(const float* score, const int64_t* labels, const float* target, const float* gscale,
+                                float* dscore, int n, int ncls, int hw, l2s_stream_t stream) {
+  L2S_REQUIRE(score && labels && target && gscale && dscore, L2S_ERR_ARG, "mask_bce_bwd: null pointer");
+  L2S_REQUIRE(n >= 0 && ncls > 0 && hw > 0, L2S_ERR_SHAPE, "mask_bce_bwd: bad shape");
+  if (n == 0) return L2S_OK;
+  mask_bce_bwd_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(score, labels, target, gscale, dscore, n, ncls, hw);
+  L2S_LAUNCH_OK("mask_bce_bwd_kernel");
+  count_launch();
+  return L2S_OK;
+}

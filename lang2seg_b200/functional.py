@@ -1,0 +1,405 @@
+"""torch.autograd bindings of the libl2s.so kernels.
+
+Every function here runs on CUDA tensors through the C ABI of include/l2s.h on the current
+torch stream.  There is no CPU path and no PyTorch fallback: a missing library or a CPU tensor
+raises.  Shapes are the reference's logical NCHW shapes.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import call, f32c, ptr, stream
+
+NUM_FILTERS = 7
+GATE_SIGMOID, GATE_LINEAR = 0, 1
+CROP_MAX_POOL, CROP_ALIGN = 1, 2
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+# ------------------------------------------------------------------------------------------------
+# (1) dynamic filter response layer
+# ------------------------------------------------------------------------------------------------
+class _DynamicFilter(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, X, filt, fuse, expr2img, gate, resp_target):
+        X, filt, fuse = f32c(X), f32c(filt), f32c(fuse)
+        I, C, H, W = X.shape
+        E = filt.shape[0]
+        assert filt.shape == (E, NUM_FILTERS, C) and fuse.shape == (E, NUM_FILTERS)
+        e2i = expr2img.to(device=X.device, dtype=torch.int32).contiguous()
+        response = torch.empty(E, 1, H, W, device=X.device, dtype=torch.float32)
+        rk = torch.empty(E, NUM_FILTERS, H, W, device=X.device, dtype=torch.float32)
+        Y = torch.empty(E, C, H, W, device=X.device, dtype=torch.float32)
+        tgt = f32c(resp_target) if resp_target is not None else None
+        loss = torch.empty(E, device=X.device, dtype=torch.float32) if tgt is not None else None
+        call("l2s_dynfilter_fwd", ptr(X), ptr(filt), ptr(fuse), ptr(e2i), ptr(response), ptr(rk), ptr(Y),
+             ptr(tgt), ptr(loss), I, E, C, H, W, gate, stream())
+        ctx.save_for_backward(X, filt, fuse, e2i, response, rk, tgt)
+        ctx.gate = gate
+        if loss is None:
+            loss = X.new_zeros(E)
+        return response, Y, loss
+
+    @staticmethod
+    def backward(ctx, dresp, dY, dloss):
+        X, filt, fuse, e2i, response, rk, tgt = ctx.saved_tensors
+        I, C, H, W = X.shape
+        E = filt.shape[0]
+        dY = f32c(dY) if dY is not None else torch.zeros(E, C, H, W, device=X.device)
+        dresp = f32c(dresp) if dresp is not None else None
+        gscale = f32c(dloss) if (dloss is not None and tgt is not None) else None
+        dX = torch.empty_like(X)
+        dfilt = torch.empty_like(filt)
+        dfuse = torch.empty_like(fuse)
+        nbytes = _lib.size("l2s_dynfilter_bwd_workspace_bytes", I, E, C, H, W)
+        ws = _ws(nbytes, X.device)
+        call("l2s_dynfilter_bwd", ptr(X), ptr(filt), ptr(fuse), ptr(e2i), ptr(response), ptr(rk), ptr(dY),
+             ptr(dresp), ptr(tgt if gscale is not None else None), ptr(gscale), ptr(dX), ptr(dfilt), ptr(dfuse),
+             I, E, C, H, W, ctx.gate, ptr(ws), nbytes, stream())
+        return dX, dfilt, dfuse, None, None, None
+
+
+def dynamic_filter(X, filt, fuse, expr2img=None, gate="sigmoid", resp_target=None):
+    """Spatial dynamic filtering + fusion + gate (network_cycle_response.py:534-570).
+
+    X (I,C,H,W) ; filt (E,7,C) ; fuse (E,7) ; expr2img (E,) non-decreasing image index per expression.
+    Returns (response (E,1,H,W) pre-sigmoid, Y (E,C,H,W), resp_loss (E,)) where resp_loss is the
+    per-expression response BCE (:415-422) against resp_target (E,H,W) (zeros when no target).
+    """
+    E = filt.shape[0]
+    if expr2img is None:
+        assert X.shape[0] == E, "expr2img is required when #images != #expressions"
+        expr2img = torch.arange(E, device=X.device, dtype=torch.int32)
+    g = GATE_SIGMOID if gate == "sigmoid" else GATE_LINEAR
+    return _DynamicFilter.apply(X, filt, fuse, expr2img, g, resp_target)
+
+
+# ------------------------------------------------------------------------------------------------
+# (2a) crop-and-resize ROI pooling
+# ------------------------------------------------------------------------------------------------
+class _RoICrop(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, bottom, rois, flags, im_h, im_w, pool):
+        bottom = f32c(bottom)
+        rois = f32c(rois.detach())
+        B, C, H, W = bottom.shape
+        N = rois.shape[0]
+        assert rois.dim() == 2 and rois.shape[1] == 5, "rois must be (N,5) [batch,x1,y1,x2,y2]"
+        out = torch.empty(N, C, pool, pool, device=bottom.device, dtype=torch.float32)
+        arg = torch.empty(N, C, pool, pool, device=bottom.device, dtype=torch.uint8) if flags & CROP_MAX_POOL else None
+        nbytes = _lib.size("l2s_roi_crop_workspace_bytes", B, N)
+        ws = _ws(nbytes, bottom.device)
+        call("l2s_roi_crop_fwd", ptr(bottom), ptr(rois), ptr(out), ptr(arg), B, C, H, W, N, pool, flags,
+             float(im_h), float(im_w), ptr(ws), nbytes, stream())
+        ctx.save_for_backward(rois, arg)
+        ctx.meta = (B, C, H, W, N, pool, flags, float(im_h), float(im_w))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        rois, arg = ctx.saved_tensors
+        B, C, H, W, N, pool, flags, im_h, im_w = ctx.meta
+        dout = f32c(dout)
+        dbottom = torch.empty(B, C, H, W, device=dout.device, dtype=torch.float32)
+        nbytes = _lib.size("l2s_roi_crop_workspace_bytes", B, N)
+        ws = _ws(nbytes, dout.device)
+        call("l2s_roi_crop_bwd", ptr(dout), ptr(rois), ptr(arg), ptr(dbottom), B, C, H, W, N, pool, flags,
+             im_h, im_w, ptr(ws), nbytes, stream())
+        return dbottom, None, None, None, None, None
+
+
+def roi_crop(bottom, rois, max_pool=False, align_im_hw=None, pool=7):
+    """Network._crop_pool_layer / _crop_pool_layer_align (network_cycle_response.py:107-182)."""
+    flags = (CROP_MAX_POOL if max_pool else 0) | (CROP_ALIGN if align_im_hw is not None else 0)
+    im_h, im_w = align_im_hw if align_im_hw is not None else (0.0, 0.0)
+    return _RoICrop.apply(bottom, rois, flags, im_h, im_w, pool)
+
+
+# ------------------------------------------------------------------------------------------------
+# (2b) RoI max-pool
+# ------------------------------------------------------------------------------------------------
+class _RoIMaxPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, features, rois, ph, pw, scale):
+        features = f32c(features)
+        rois = f32c(rois.detach())
+        B, C, H, W = features.shape
+        N = rois.shape[0]
+        if rois.dim() != 2 or rois.shape[1] != 5:
+            raise _lib.L2SError("roi_pooling: rois must be (N,5)")     # reference returns 0 (roi_pooling_cuda.c:20-23)
+        out = torch.empty(N, C, ph, pw, device=features.device, dtype=torch.float32)
+        arg = torch.empty(N, C, ph, pw, device=features.device, dtype=torch.int32)
+        call("l2s_roi_maxpool_fwd", ph, pw, float(scale), ptr(features), ptr(rois), ptr(out), ptr(arg), B, C, H, W, N,
+             stream())
+        ctx.save_for_backward(rois, arg)
+        ctx.meta = (B, C, H, W, N, ph, pw, float(scale))
+        ctx.mark_non_differentiable(arg)
+        return out, arg
+
+    @staticmethod
+    def backward(ctx, dout, _darg):
+        rois, arg = ctx.saved_tensors
+        B, C, H, W, N, ph, pw, scale = ctx.meta
+        dout = f32c(dout)
+        g = torch.empty(B, C, H, W, device=dout.device, dtype=torch.float32)
+        call("l2s_roi_maxpool_bwd", ph, pw, scale, ptr(dout), ptr(rois), ptr(g), ptr(arg), B, C, H, W, N, stream())
+        return g, None, None, None, None
+
+
+def roi_max_pool(features, rois, pooled_height=7, pooled_width=7, spatial_scale=1.0 / 16, return_argmax=False):
+    """RoIPoolFunction (layer_utils/roi_pooling/roi_pool.py:6-50)."""
+    out, arg = _RoIMaxPool.apply(features, rois, int(pooled_height), int(pooled_width), float(spatial_scale))
+    return (out, arg) if return_argmax else out
+
+
+# ------------------------------------------------------------------------------------------------
+# mask head
+# ------------------------------------------------------------------------------------------------
+class _MaskHead(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, up_w, up_b, pred_w, pred_b):
+        x, up_w, up_b, pred_w, pred_b = (f32c(t) for t in (x, up_w, up_b, pred_w, pred_b))
+        n, Cin = x.shape[0], x.shape[1]
+        assert x.shape[2:] == (7, 7), "mask head expects (n,Cin,7,7) res5 features"
+        Cmid, ncls = up_w.shape[1], pred_w.shape[0]
+        assert up_w.shape == (Cin, Cmid, 2, 2) and pred_w.shape[:2] == (ncls, Cmid)
+        score = torch.empty(n, ncls, 14, 14, device=x.device, dtype=torch.float32)
+        prob = torch.empty_like(score)
+        saved = _ws(_lib.size("l2s_mask_head_saved_bytes", n, Cin, Cmid, ncls), x.device)
+        nbytes = _lib.size("l2s_mask_head_workspace_bytes", n, Cin, Cmid, ncls)
+        ws = _ws(nbytes, x.device)
+        call("l2s_mask_head_fwd", ptr(x), ptr(up_w), ptr(up_b), ptr(pred_w), ptr(pred_b), ptr(score), ptr(prob),
+             ptr(saved), n, Cin, Cmid, ncls, ptr(ws), nbytes, stream())
+        ctx.save_for_backward(up_w, pred_w, saved, prob)
+        ctx.meta = (n, Cin, Cmid, ncls)
+        return score, prob
+
+    @staticmethod
+    def backward(ctx, dscore, dprob):
+        up_w, pred_w, saved, prob = ctx.saved_tensors
+        n, Cin, Cmid, ncls = ctx.meta
+        if dscore is None:
+            dscore = torch.zeros_like(prob)
+        dscore = f32c(dscore)
+        if dprob is not None:
+            dscore = dscore + dprob * prob * (1 - prob)
+        dx = torch.empty(n, Cin, 7, 7, device=dscore.device, dtype=torch.float32)
+        d_up_w = torch.empty_like(up_w)
+        d_up_b = torch.empty(Cmid, device=dscore.device, dtype=torch.float32)
+        d_pred_w = torch.empty(ncls, Cmid, device=dscore.device, dtype=torch.float32)
+        d_pred_b = torch.empty(ncls, device=dscore.device, dtype=torch.float32)
+        nbytes = _lib.size("l2s_mask_head_workspace_bytes", n, Cin, Cmid, ncls)
+        ws = _ws(nbytes, dscore.device)
+        call("l2s_mask_head_bwd", ptr(dscore), ptr(up_w), ptr(pred_w), ptr(saved), ptr(dx), ptr(d_up_w), ptr(d_up_b),
+             ptr(d_pred_w), ptr(d_pred_b), n, Cin, Cmid, ncls, ptr(ws), nbytes, stream())
+        return dx, d_up_w, d_up_b, d_pred_w.view_as(pred_w), d_pred_b
+
+
+def mask_head(x, up_w, up_b, pred_w, pred_b):
+    """Network._mask_prediction (network_cycle_response.py:292-307) -> (mask_score, mask_prob)."""
+    return _MaskHead.apply(x, up_w, up_b, pred_w, pred_b)
+
+
+class _MaskBCE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, score, labels, target):
+        score, target = f32c(score), f32c(target)
+        labels = labels.to(torch.int64).contiguous()
+        n, ncls = score.shape[:2]
+        hw = score.shape[2] * score.shape[3]
+        loss = torch.empty(1, device=score.device, dtype=torch.float32)
+        call("l2s_mask_bce_fwd", ptr(score), ptr(labels), ptr(target), ptr(loss), n, ncls, hw, stream())
+        ctx.save_for_backward(score, labels, target)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        score, labels, target = ctx.saved_tensors
+        n, ncls = score.shape[:2]
+        hw = score.shape[2] * score.shape[3]
+        dscore = torch.empty_like(score)
+        gs = f32c(g).reshape(1)
+        call("l2s_mask_bce_bwd", ptr(score), ptr(labels), ptr(target), ptr(gs), ptr(dscore), n, ncls, hw, stream())
+        return dscore, None, None
+
+
+def mask_bce_loss(mask_score, labels, mask_targets):
+    """Mask loss of network_cycle_response.py:404-413."""
+    return _MaskBCE.apply(mask_score, labels, mask_targets)
+
+
+# ------------------------------------------------------------------------------------------------
+# (3) attention step and the att2in2 epilogues
+# ------------------------------------------------------------------------------------------------
+class _AttStep(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, att_h, att_feats, p_att, alpha_w, alpha_b):
+        att_h, att_feats, p_att = f32c(att_h), f32c(att_feats), f32c(p_att)
+        ctx.w_shape, ctx.b_shape = alpha_w.shape, alpha_b.shape
+        alpha_w, alpha_b = f32c(alpha_w).view(-1), f32c(alpha_b).view(-1)
+        B, A, D = att_feats.shape
+        Dh = p_att.shape[2]
+        weight = torch.empty(B, A, device=att_h.device, dtype=torch.float32)
+        res = torch.empty(B, D, device=att_h.device, dtype=torch.float32)
+        call("l2s_att_step_fwd", ptr(att_h), ptr(att_feats), ptr(p_att), ptr(alpha_w), ptr(alpha_b), ptr(weight),
+             ptr(res), B, A, D, Dh, stream())
+        ctx.save_for_backward(att_h, att_feats, p_att, alpha_w, weight)
+        return res, weight
+
+    @staticmethod
+    def backward(ctx, dres, _dweight):
+        att_h, att_feats, p_att, alpha_w, weight = ctx.saved_tensors
+        B, A, D = att_feats.shape
+        Dh = p_att.shape[2]
+        dres = f32c(dres)
+        datt_h = torch.empty_like(att_h)
+        de = torch.empty_like(weight)
+        dp_att = torch.zeros_like(p_att)
+        datt = torch.zeros_like(att_feats)
+        dalpha = torch.zeros_like(alpha_w)
+        call("l2s_att_step_bwd", ptr(dres), ptr(att_h), ptr(att_feats), ptr(p_att), ptr(alpha_w), ptr(weight),
+             ptr(datt_h), ptr(de), ptr(dp_att), ptr(datt), ptr(dalpha), B, A, D, Dh, stream())
+        return datt_h, datt, dp_att, dalpha.view(ctx.w_shape), de.sum().reshape(ctx.b_shape)
+
+
+def attention_step(att_h, att_feats, p_att, alpha_w, alpha_b):
+    """Attention.forward after h2att (AttModel.py:411-421) -> (att_res (B,D), weight (B,A))."""
+    return _AttStep.apply(att_h, att_feats, p_att, alpha_w, alpha_b)
+
+
+class _Gates(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, sums, a2c_out, c_prev):
+        sums, a2c_out, c_prev = f32c(sums), f32c(a2c_out), f32c(c_prev)
+        B, D = c_prev.shape
+        h = torch.empty_like(c_prev)
+        c = torch.empty_like(c_prev)
+        call("l2s_att2in2_gates_fwd", ptr(sums), ptr(a2c_out), ptr(c_prev), ptr(h), ptr(c), B, D, stream())
+        ctx.save_for_backward(sums, a2c_out, c_prev, c)
+        return h, c
+
+    @staticmethod
+    def backward(ctx, dh, dc):
+        sums, a2c_out, c_prev, c = ctx.saved_tensors
+        B, D = c_prev.shape
+        dh = f32c(dh) if dh is not None else torch.zeros_like(c)
+        dc = f32c(dc) if dc is not None else None
+        dsums = torch.empty_like(sums)
+        da2c = torch.empty_like(a2c_out)
+        dcp = torch.empty_like(c_prev)
+        call("l2s_att2in2_gates_bwd", ptr(sums), ptr(a2c_out), ptr(c_prev), ptr(c), ptr(dh), ptr(dc), ptr(dsums),
+             ptr(da2c), ptr(dcp), B, D, stream())
+        return dsums, da2c, dcp
+
+
+def att2in2_gates(sums, a2c_out, c_prev):
+    """Att2in2Core gate epilogue (AttModel.py:450-462) -> (next_h, next_c)."""
+    return _Gates.apply(sums, a2c_out, c_prev)
+
+
+class _LogSoftmaxNLL(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, target, mask, want_logp):
+        logits = f32c(logits)
+        R, V = logits.shape
+        target = target.to(torch.int64).contiguous()
+        mask = f32c(mask)
+        logp = torch.empty_like(logits) if want_logp else None
+        nll = torch.empty(R, device=logits.device, dtype=torch.float32)
+        call("l2s_logsoftmax_nll_fwd", ptr(logits), ptr(target), ptr(mask), ptr(logp), ptr(nll), R, V, stream())
+        ctx.save_for_backward(logits, target, mask)
+        if logp is None:
+            logp = logits.new_empty(0)
+        ctx.mark_non_differentiable(logp)
+        return nll.sum(), logp
+
+    @staticmethod
+    def backward(ctx, g, _glogp):
+        logits, target, mask = ctx.saved_tensors
+        R, V = logits.shape
+        d = torch.empty_like(logits)
+        gs = f32c(g).reshape(1)
+        call("l2s_logsoftmax_nll_bwd", ptr(logits), ptr(target), ptr(mask), ptr(gs), ptr(d), R, V, stream())
+        return d, None, None, None
+
+
+def logsoftmax_nll(logits, target, mask, want_logp=False):
+    """sum_r -log_softmax(logits)[r,target[r]] * mask[r]  (AttModel.py:98 + misc/utils.py:43-53 numerator)."""
+    return _LogSoftmaxNLL.apply(logits, target, mask, want_logp)
+
+
+def log_softmax(logits):
+    """log_softmax over the last dim of (R,V) logits through the fused kernel (no gradient)."""
+    logits = f32c(logits)
+    R, V = logits.shape
+    logp = torch.empty_like(logits)
+    call("l2s_logsoftmax_nll_fwd", ptr(logits), None, None, ptr(logp), None, R, V, stream())
+    return logp
+
+
+# ------------------------------------------------------------------------------------------------
+# caption feature prep
+# ------------------------------------------------------------------------------------------------
+class _CaptionFeats(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, before, after, S):
+        before, after = f32c(before), f32c(after)
+        B, C, H, W = before.shape
+        fc = torch.empty(B, 2 * C, device=before.device, dtype=torch.float32)
+        att = torch.empty(B, S, S, 2 * C, device=before.device, dtype=torch.float32)
+        call("l2s_caption_feats_fwd", ptr(before), ptr(fc), ptr(att), B, C, H, W, S, 2 * C, 0, stream())
+        call("l2s_caption_feats_fwd", ptr(after), ptr(fc), ptr(att), B, C, H, W, S, 2 * C, C, stream())
+        ctx.meta = (B, C, H, W, S)
+        return fc, att
+
+    @staticmethod
+    def backward(ctx, dfc, datt):
+        B, C, H, W, S = ctx.meta
+        dev = (dfc if dfc is not None else datt).device
+        dfc = f32c(dfc) if dfc is not None else None
+        datt = f32c(datt) if datt is not None else None
+        gb = torch.empty(B, C, H, W, device=dev, dtype=torch.float32)
+        ga = torch.empty(B, C, H, W, device=dev, dtype=torch.float32)
+        call("l2s_caption_feats_bwd", ptr(dfc), ptr(datt), ptr(gb), B, C, H, W, S, 2 * C, 0, stream())
+        call("l2s_caption_feats_bwd", ptr(dfc), ptr(datt), ptr(ga), B, C, H, W, S, 2 * C, C, stream())
+        return gb, ga, None
+
+
+def caption_features(feats_before, feats_after, att_size=14):
+    """network_cycle_response.py:428-438 -> fc (B,2C), att (B,S,S,2C)."""
+    return _CaptionFeats.apply(feats_before, feats_after, att_size)
+
+
+# ------------------------------------------------------------------------------------------------
+# raw GEMM access (tests / benchmarks)
+# ------------------------------------------------------------------------------------------------
+def split_bf16(x, ld_dst=None):
+    x = f32c(x)
+    rows, cols = x.shape
+    ld = ld_dst or cols
+    hi = torch.empty(rows, ld, device=x.device, dtype=torch.bfloat16)
+    lo = torch.empty(rows, ld, device=x.device, dtype=torch.bfloat16)
+    call("l2s_split_bf16", ptr(x), ptr(hi), ptr(lo), rows, cols, cols, ld, stream())
+    return hi, lo
+
+
+def gemm_bf16x3(a_hi, a_lo, b_hi, b_lo, M, N, K, a_mn=False, b_mn=False, epilogue=0, bias=None, bias_div=1,
+                split_k=1, out=None):
+    D = out if out is not None else torch.empty(M, N, device=a_hi.device, dtype=torch.float32)
+    call("l2s_gemm_bf16x3", ptr(a_hi), ptr(a_lo), ptr(b_hi), ptr(b_lo), ptr(D), ptr(bias), bias_div, M, N, K,
+         int(a_mn), int(b_mn), epilogue, split_k, stream())
+    return D
+
+
+def gemm_f32(A, B, accumulate=False, out=None):
+    """D = A @ B.T with A (M,K), B (N,K), exact fp32 FFMA."""
+    A, B = f32c(A), f32c(B)
+    M, K = A.shape
+    N = B.shape[0]
+    D = out if out is not None else torch.empty(M, N, device=A.device, dtype=torch.float32)
+    call("l2s_gemm_f32", ptr(A), ptr(B), ptr(D), M, N, K, K, 1, K, 1, N, int(accumulate), stream())
+    return D

@@ -1,0 +1,35 @@
+"""Filter generator + spatial dynamic-filter response layer.
+
+Drop-in for network_cycle_response.py:510-570 with the parameters of
+resnet_v1_cycle_response.py:313-321 (dynamic_fc_0..6, response_fc) kept under the same names.
+"""
+import torch
+import torch.nn as nn
+
+from .. import functional as L2F
+
+
+def generate_filters(hidden, dynamic_fcs, response_fc):
+    """f_k = tanh(dynamic_fc_k(hidden)) stacked to (E,7,C) ; w = tanh(response_fc(hidden)) (E,7).  (:510-532)"""
+    filt = torch.tanh(torch.stack([fc(hidden) for fc in dynamic_fcs], 1))
+    fuse = torch.tanh(response_fc(hidden))
+    return filt, fuse
+
+
+class DynamicFilterResponse(nn.Module):
+    """Owns dynamic_fc_0..6 / response_fc and applies the fused sm_100a response kernel."""
+
+    def __init__(self, hidden_dim, feat_dim, gate="sigmoid"):
+        super().__init__()
+        for k in range(L2F.NUM_FILTERS):
+            setattr(self, "dynamic_fc_%d" % k, nn.Linear(hidden_dim, feat_dim))
+        self.response_fc = nn.Linear(hidden_dim, L2F.NUM_FILTERS)
+        self.gate = gate
+
+    @property
+    def dynamic_fcs(self):
+        return [getattr(self, "dynamic_fc_%d" % k) for k in range(L2F.NUM_FILTERS)]
+
+    def forward(self, net_conv, hidden, expr2img=None, resp_target=None):
+        filt, fuse = generate_filters(hidden, self.dynamic_fcs, self.response_fc)
+        return L2F.dynamic_filter(net_conv, filt, fuse, expr2img, self.gate, resp_target)

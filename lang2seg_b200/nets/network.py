@@ -1,0 +1,151 @@
+"""Hot-path half of the reference `Network` (pyutils/mask-faster-rcnn/lib/nets/network_cycle_response.py).
+
+Only the methods on the path of SURVEY.md section 8 are provided, under the reference's names and
+argument orders, so that a reference Network subclass can inherit them:
+
+    _crop_pool_layer(bottom, rois, max_pool=True)                  :107-149
+    _crop_pool_layer_align(bottom, rois, im_info, max_pool=True)   :151-182
+    _roi_pool_layer(bottom, rois)                                  :104-105
+    _region_classification(spatial_fc7)                            :277-290
+    _mask_prediction(spatial_fc7)                                  :292-307
+    _dynamic_filter(net_conv, labels | hidden)                     :503-570
+    _add_hot_path_losses(...)                                      :404-422, :443 (mask, response, caption)
+
+`HotPathNet` is the concrete module (parameter names of resnet_v1_cycle_response.py:238-335) used by
+bench.py and the tests; backbone, RPN and res5 are outside this repository's scope and are supplied
+by the caller (`head_to_tail`) or replaced by synthetic tensors.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import caption_models
+from .. import functional as L2F
+from ..layers.dynamic_filter import generate_filters
+from ..layers.lang_encoder import RNNEncoder
+from ..layers.roi_pooling import RoIPoolFunction
+
+POOLING_SIZE = 7      # cfg.POOLING_SIZE  (model/config.py:276)
+MASK_SIZE = 14        # cfg.MASK_SIZE     (model/config.py:285)
+
+
+class Network(nn.Module):
+    def __init__(self, batch_size=1):
+        super().__init__()
+        self._feat_stride = [16, ]
+        self._feat_compress = [1. / 16, ]
+        self._batch_size = batch_size
+        self._predictions = {}
+        self._losses = {}
+        self._proposal_targets = {}
+        self._gate = "sigmoid"
+
+    # ---- ROI pooling -------------------------------------------------------------------------
+    def _roi_pool_layer(self, bottom, rois):
+        return RoIPoolFunction(POOLING_SIZE, POOLING_SIZE, 1. / 16.)(bottom, rois)
+
+    def _crop_pool_layer(self, bottom, rois, max_pool=True):
+        return L2F.roi_crop(bottom, rois, max_pool=max_pool, pool=POOLING_SIZE)
+
+    def _crop_pool_layer_align(self, bottom, rois, im_info, max_pool=True):
+        im_h, im_w = float(im_info[0][0]), float(im_info[0][1])
+        return L2F.roi_crop(bottom, rois, max_pool=max_pool, align_im_hw=(im_h, im_w), pool=POOLING_SIZE)
+
+    # ---- heads ---------------------------------------------------------------------------------
+    def _region_classification(self, spatial_fc7):
+        fc7 = spatial_fc7.mean(3).mean(2)
+        cls_score = self.cls_score_net(fc7)
+        cls_pred = torch.max(cls_score, 1)[1]
+        cls_prob = F.softmax(cls_score, 1)
+        bbox_pred = self.bbox_pred_net(fc7)
+        self._predictions["cls_score"] = cls_score
+        self._predictions["cls_pred"] = cls_pred
+        self._predictions["cls_prob"] = cls_prob
+        self._predictions["bbox_pred"] = bbox_pred
+        return cls_prob, bbox_pred
+
+    def _mask_prediction(self, spatial_fc7):
+        mask_score, mask_prob = L2F.mask_head(spatial_fc7, self.mask_up_sampling.weight, self.mask_up_sampling.bias,
+                                              self.mask_pred_net.weight, self.mask_pred_net.bias)
+        self._predictions["mask_score"] = mask_score
+        self._predictions["mask_prob"] = mask_prob
+        return mask_prob
+
+    # ---- dynamic filter ------------------------------------------------------------------------
+    def _dynamic_filter(self, net_conv, labels=None, hidden=None, expr2img=None, resp_target=None):
+        """net_conv (I,C,H,W) ; labels (E,L) tokens or precomputed hidden (E,Dh).
+
+        Stores _predictions['net_conv_before'] / ['response'] like :504,:568 and returns the gated map."""
+        self._predictions["net_conv_before"] = net_conv
+        if hidden is None:
+            _, hidden, _ = self.rnn_encoder(labels)
+        filt, fuse = generate_filters(hidden, [getattr(self, "dynamic_fc_%d" % k) for k in range(7)], self.response_fc)
+        response, gated, resp_loss = L2F.dynamic_filter(net_conv, filt, fuse, expr2img, self._gate, resp_target)
+        self._predictions["response"] = response
+        self._losses["loss_response_per_expr"] = resp_loss
+        return gated
+
+    # ---- losses on the path ----------------------------------------------------------------------
+    def _mask_loss(self, labels, mask_targets):
+        return L2F.mask_bce_loss(self._predictions["mask_score"], labels, mask_targets)
+
+    def _caption_loss(self, fc_feats, att_feats, cap_labels, cap_masks):
+        return self.caption_model.forward_loss(fc_feats, att_feats, cap_labels, cap_masks)
+
+
+DEFAULT_OPT = dict(
+    vocab_size=1999, word_embedding_size=512, word_vec_size=512, rnn_hidden_size=512, bidirectional=1,
+    word_drop_out=0.5, rnn_drop_out=0.2, rnn_num_layers=1, rnn_type="lstm", variable_lengths=1,
+    C4_feat_dim=1024, cap_loss_weight=1.0, caption_model="att2in2", input_encoding_size=512, rnn_size=512,
+    num_layers=1, drop_prob_lm=0.5, seq_length=10, fc_feat_size=4096, att_feat_size=4096, att_hid_size=512,
+)
+
+
+class HotPathNet(Network):
+    """Modules of resnetv1 (resnet_v1_cycle_response.py:232-335) that lie on the hot path."""
+
+    def __init__(self, opt=None, num_classes=81, fc7_dim=2048, mask_mid=256, head_to_tail=None, batch_size=1):
+        super().__init__(batch_size=batch_size)
+        o = dict(DEFAULT_OPT)
+        o.update(opt or {})
+        self.opt = o
+        self._num_classes = num_classes
+        self.rnn_encoder = RNNEncoder(vocab_size=o["vocab_size"], word_embedding_size=o["word_embedding_size"],
+                                      word_vec_size=o["word_vec_size"], hidden_size=o["rnn_hidden_size"],
+                                      bidirectional=o["bidirectional"] > 0, input_dropout_p=o["word_drop_out"],
+                                      dropout_p=o["rnn_drop_out"], n_layers=o["rnn_num_layers"],
+                                      rnn_type=o["rnn_type"], variable_lengths=o["variable_lengths"] > 0)
+        hid = o["rnn_num_layers"] * (2 if o["bidirectional"] > 0 else 1) * o["rnn_hidden_size"]
+        self._C4_feat_dim = o["C4_feat_dim"]
+        self._cap_loss_weight = o["cap_loss_weight"]
+        self.caption_model = caption_models.setup(o)
+        for k in range(7):
+            setattr(self, "dynamic_fc_%d" % k, nn.Linear(hid, self._C4_feat_dim))
+        self.response_fc = nn.Linear(hid, 7)
+        self.cls_score_net = nn.Linear(fc7_dim, num_classes)
+        self.bbox_pred_net = nn.Linear(fc7_dim, num_classes * 4)
+        self.mask_up_sampling = nn.ConvTranspose2d(fc7_dim, mask_mid, 2, 2)
+        self.mask_pred_net = nn.Conv2d(mask_mid, num_classes, kernel_size=1, stride=1)
+        self._head = head_to_tail
+        self.init_weights()
+
+    def init_weights(self):
+        # network_cycle_response.py:333-355: N(0, 0.01) heads (bbox 0.001), zero bias
+        for m, std in ((self.cls_score_net, 0.01), (self.bbox_pred_net, 0.001), (self.mask_up_sampling, 0.01),
+                       (self.mask_pred_net, 0.01)):
+            m.weight.data.normal_(0, std)
+            m.bias.data.zero_()
+
+    def _head_to_tail(self, pool5):
+        if self._head is None:
+            raise RuntimeError("res5 / fc6-7 is outside this repository's scope: pass head_to_tail=<module>")
+        return self._head(pool5)
+
+    def gradient_groups(self):
+        """The three parameter groups whose gradients are all-reduced (north_star)."""
+        fg = list(self.rnn_encoder.parameters()) + list(self.response_fc.parameters())
+        for k in range(7):
+            fg += list(getattr(self, "dynamic_fc_%d" % k).parameters())
+        heads = [p for m in (self.cls_score_net, self.bbox_pred_net, self.mask_up_sampling, self.mask_pred_net)
+                 for p in m.parameters()]
+        return {"filter_generator": fg, "caption": list(self.caption_model.parameters()), "heads": heads}

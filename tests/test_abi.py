@@ -1,0 +1,63 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol that
+include/l2s.h declares, and the ctypes table mirrors the header (no compute calls: no GPU here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+
+HEADER = os.path.join(ROOT, "include", "l2s.h")
+
+
+def _declared():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(l2s_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_builds_and_exports_header_symbols():
+    from lang2seg_b200 import build
+    lib_path = build.build()
+    lib = ctypes.CDLL(lib_path)
+    names = _declared()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), "libl2s.so does not export %s" % n
+    lib.l2s_version.restype = ctypes.c_int
+    assert lib.l2s_version() >= 100
+    lib.l2s_last_error_string.restype = ctypes.c_char_p
+    assert isinstance(lib.l2s_last_error_string(), bytes)
+
+
+def test_ctypes_table_matches_header():
+    from lang2seg_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == _declared()
+    # argument counts: count top-level commas of each prototype
+    src = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    for name, (_, args) in _lib.SIGNATURES.items():
+        m = re.search(r"\b%s\s*\(([^;]*?)\)\s*;" % name, src, flags=re.S)
+        assert m, name
+        params = m.group(1).strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert n == len(args), "%s: header has %d parameters, ctypes table %d" % (name, n, len(args))
+
+
+def test_error_paths_without_gpu():
+    """Shape / argument validation happens on the host before any CUDA call."""
+    from lang2seg_b200 import _lib
+    lib = _lib.load()
+    rc = lib.l2s_roi_crop_fwd(None, None, None, None, 1, 8, 16, 16, 1, 7, 0, 0.0, 0.0, None, 0, None)
+    assert rc == -5 and b"null" in lib.l2s_last_error_string()
+    rc = lib.l2s_att_step_fwd(*([ctypes.c_void_p(16)] * 7), 1, 4, 6, 8, None)
+    assert rc == -1 and b"multiples of 4" in lib.l2s_last_error_string()
+    with pytest.raises(_lib.L2SError):
+        _lib.call("l2s_mask_head_fwd", *([ctypes.c_void_p(16)] * 8), 1, 30, 24, 5, None, 0, None)
+
+
+def test_cpu_tensors_are_rejected():
+    import torch
+    import lang2seg_b200.functional as F
+    with pytest.raises(AssertionError):
+        F.roi_max_pool(torch.zeros(1, 4, 8, 8), torch.zeros(1, 5))

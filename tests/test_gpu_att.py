@@ -1,0 +1,147 @@
+"""att2in2 kernels and modules vs golden vectors from the reference caption model and the oracle."""
+import pytest
+import torch
+
+from conftest import relerr
+from oracle import restate as R
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
+TOL = 1e-4
+SMALL_OPT = dict(vocab_size=40, input_encoding_size=16, rnn_size=16, att_hid_size=16, fc_feat_size=24,
+                 att_feat_size=24, seq_length=6, num_layers=1, drop_prob_lm=0.5, caption_model="att2in2")
+
+
+def _params(d, prefix="p."):
+    return {k[len(prefix):]: v for k, v in d.items() if k.startswith(prefix)}
+
+
+def test_att2in2_model_golden(golden):
+    from lang2seg_b200 import caption_models
+    from lang2seg_b200.misc.utils import LanguageModelCriterion
+    d = golden("att2in2.npz")
+    model = caption_models.setup(SMALL_OPT).cuda().eval()
+    missing = model.load_state_dict(_params(d), strict=True)      # reference checkpoint keys load as they are
+    att = d["att"].cuda().requires_grad_(True)
+    logp = model(d["fc"].cuda(), att, d["cap"].cuda())
+    assert logp.shape == d["logp"].shape
+    assert relerr(logp, d["logp"]) < TOL
+    loss = LanguageModelCriterion()(logp, d["cap"][:, 1:].cuda(), d["msk"][:, 1:].cuda())
+    assert relerr(loss, d["loss"]) < TOL
+    loss.backward()
+    assert relerr(att.grad, d["d_att"]) < TOL
+    for k, v in model.named_parameters():
+        if k.endswith("alpha_net.bias"):
+            continue
+        assert relerr(v.grad, d["g." + k]) < TOL, k
+    # fused loss path (logit -> log-softmax -> masked NLL per step)
+    model.zero_grad()
+    att2 = d["att"].cuda().requires_grad_(True)
+    loss2 = model.forward_loss(d["fc"].cuda(), att2, d["cap"].cuda(), d["msk"].cuda())
+    assert relerr(loss2, d["loss"]) < TOL
+    loss2.backward()
+    assert relerr(att2.grad, d["d_att"]) < TOL
+    for k, v in model.named_parameters():
+        if k.endswith("alpha_net.bias"):
+            continue
+        assert relerr(v.grad, d["g." + k]) < TOL, k
+    # one isolated Attention.forward
+    res = model.core.attention(d["step.h"].cuda(), d["step.att_feats"].cuda(), d["step.p_att"].cuda())
+    assert relerr(res, d["step.att_res"]) < TOL
+
+
+@pytest.mark.parametrize("B,A,D", [(5, 196, 512), (16, 196, 512), (2, 49, 64), (3, 7, 16)])
+def test_attention_step_vs_oracle(B, A, D):
+    import lang2seg_b200.functional as F
+    g = torch.Generator().manual_seed(B * A)
+    att_h = torch.randn(B, D, generator=g)
+    feats = torch.relu(torch.randn(B, A, D, generator=g))
+    p_att = torch.randn(B, A, D, generator=g)
+    aw = torch.randn(D, generator=g) / D ** 0.5
+    ab = torch.randn(1, generator=g)
+    G = torch.randn(B, D, generator=g)
+
+    def run(dev):
+        ts = [t.to(dev).clone().requires_grad_(True) for t in (att_h, feats, p_att, aw, ab)]
+        if dev == "cpu":
+            dot = torch.tanh(ts[2] + ts[0][:, None, :])
+            e = dot @ ts[3] + ts[4]
+            w = torch.softmax(e, 1)
+            res = torch.bmm(w[:, None], ts[1])[:, 0]
+        else:
+            res, w = F.attention_step(*ts)
+        grads = torch.autograd.grad((res * G.to(dev)).sum(), ts[:4])
+        return [res, w] + list(grads)
+
+    ref, out = run("cpu"), run("cuda")
+    for name, a, b in zip(["res", "w", "datt_h", "dfeats", "dp_att", "dalpha"], out, ref):
+        assert relerr(a, b) < TOL, name
+
+
+def test_gates_and_nll_vs_oracle():
+    import lang2seg_b200.functional as F
+    g = torch.Generator().manual_seed(9)
+    B, D, V = 7, 512, 2000
+    sums, a2c, c0 = torch.randn(B, 5 * D, generator=g), torch.randn(B, 2 * D, generator=g), torch.randn(B, D, generator=g)
+    Gh, Gc = torch.randn(B, D, generator=g), torch.randn(B, D, generator=g)
+
+    def gates(dev):
+        s, a, c = (t.to(dev).clone().requires_grad_(True) for t in (sums, a2c, c0))
+        if dev == "cpu":
+            sg = torch.sigmoid(s[:, :3 * D])
+            i, f, o = sg[:, :D], sg[:, D:2 * D], sg[:, 2 * D:]
+            gg = s[:, 3 * D:] + a
+            gg = torch.max(gg[:, :D], gg[:, D:])
+            c2 = f * c + i * gg
+            h2 = o * torch.tanh(c2)
+        else:
+            h2, c2 = F.att2in2_gates(s, a, c)
+        return [h2, c2] + list(torch.autograd.grad((h2 * Gh.to(dev)).sum() + (c2 * Gc.to(dev)).sum(), [s, a, c]))
+
+    for a, b in zip(gates("cuda"), gates("cpu")):
+        assert relerr(a, b) < TOL
+    logits = torch.randn(B, V, generator=g) * 3
+    tgt = torch.randint(0, V, (B,), generator=g)
+    msk = (torch.rand(B, generator=g) < 0.7).float()
+
+    def nll(dev):
+        l = logits.to(dev).clone().requires_grad_(True)
+        if dev == "cpu":
+            lp = torch.log_softmax(l, 1)
+            val = -(lp.gather(1, tgt[:, None])[:, 0] * msk).sum()
+        else:
+            val, lp = F.logsoftmax_nll(l, tgt.to(dev), msk.to(dev), True)
+        return [val, lp] + list(torch.autograd.grad(val * 0.37, [l]))
+
+    for a, b in zip(nll("cuda"), nll("cpu")):
+        assert relerr(a, b) < TOL
+
+
+def test_caption_features(golden):
+    import lang2seg_b200.functional as F
+    d = golden("caption_features.npz")
+    fb, fa = d["fb"].cuda().requires_grad_(True), d["fa"].cuda().requires_grad_(True)
+    fc, att = F.caption_features(fb, fa)
+    assert relerr(fc, d["fc"]) < TOL and relerr(att, d["att"]) < TOL
+    g = torch.Generator().manual_seed(2)
+    G1, G2 = torch.randn(fc.shape, generator=g), torch.randn(att.shape, generator=g)
+    gb, ga = torch.autograd.grad((fc * G1.cuda()).sum() + (att * G2.cuda()).sum(), [fb, fa])
+    fb2, fa2 = d["fb"].clone().requires_grad_(True), d["fa"].clone().requires_grad_(True)
+    fc2, att2 = R.caption_features(fb2, fa2)
+    rb, ra = torch.autograd.grad((fc2 * G1).sum() + (att2 * G2).sum(), [fb2, fa2])
+    assert relerr(gb, rb) < TOL and relerr(ga, ra) < TOL
+    # 38x63 res5 map, 2048 channels slice
+    x = torch.randn(2, 64, 38, 63, generator=g)
+    fc3, att3 = F.caption_features(x.cuda(), x.cuda() * 2)
+    r1, r2 = R.caption_features(x, x * 2)
+    assert relerr(fc3, r1) < TOL and relerr(att3, r2) < TOL
+
+
+def test_lang_encoder_golden(golden):
+    from lang2seg_b200.layers.lang_encoder import RNNEncoder
+    d = golden("lang_encoder.npz")
+    enc = RNNEncoder(vocab_size=40, word_embedding_size=12, word_vec_size=12, hidden_size=8, bidirectional=True,
+                     input_dropout_p=0.5, dropout_p=0.2, n_layers=1, rnn_type="lstm", variable_lengths=True)
+    enc.load_state_dict(_params(d), strict=True)
+    enc = enc.cuda().eval()
+    out, hid, emb = enc(d["labels"].cuda())
+    assert relerr(out, d["output"]) < TOL and relerr(hid, d["hidden"]) < TOL and relerr(emb, d["embedded"]) < TOL

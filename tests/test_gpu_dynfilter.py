@@ -1,0 +1,86 @@
+"""Dynamic-filter response layer through the C ABI vs golden vectors (reference output) and the oracle."""
+import pytest
+import torch
+
+from conftest import relerr
+from oracle import restate as R
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
+TOL = 1e-4
+
+
+def _params(d, prefix="p."):
+    return {k[len(prefix):]: v for k, v in d.items() if k.startswith(prefix)}
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_golden(golden, tag):
+    import lang2seg_b200.functional as F
+    d = golden("dynfilter.npz")
+    p = _params(d)
+    dyn_w = [p["dynamic_fc_%d.weight" % k].cuda().requires_grad_(True) for k in range(7)]
+    dyn_b = [p["dynamic_fc_%d.bias" % k].cuda().requires_grad_(True) for k in range(7)]
+    rw = p["response_fc.weight"].cuda().requires_grad_(True)
+    rb = p["response_fc.bias"].cuda()
+    X = d[tag + ".X"].cuda().requires_grad_(True)
+    filt, fuse = R.filter_generator(d[tag + ".hidden"].cuda(), dyn_w, dyn_b, rw, rb)   # plain torch ops on GPU
+    r, Y, rl = F.dynamic_filter(X, filt, fuse, resp_target=d[tag + ".tgt"][None].cuda())
+    assert relerr(r, d[tag + ".response"]) < TOL
+    assert relerr(Y, d[tag + ".Y"]) < TOL
+    loss = (Y * d[tag + ".G"].cuda()).sum() + rl.sum()
+    gX, g3, g0b, grw = torch.autograd.grad(loss, [X, dyn_w[3], dyn_b[0], rw])
+    assert relerr(gX, d[tag + ".dX"]) < TOL
+    assert relerr(g3, d[tag + ".d_dyn3_w"]) < TOL
+    assert relerr(g0b, d[tag + ".d_dyn0_b"]) < TOL
+    assert relerr(grw, d[tag + ".d_resp_w"]) < TOL
+
+
+@pytest.mark.parametrize("cfg", [dict(I=3, C=96, H=32, W=32, e2i=[0, 0, 1, 1, 1, 2, 2]),
+                                 dict(I=2, C=512, H=37, W=62, e2i=[0, 1, 1]),
+                                 dict(I=4, C=1024, H=8, W=12, e2i=[0, 2, 2, 3]),      # image 1 has no expression
+                                 dict(I=1, C=20, H=9, W=13, e2i=[0])])
+@pytest.mark.parametrize("gate", ["sigmoid", "linear"])
+def test_vs_oracle(cfg, gate):
+    import lang2seg_b200.functional as F
+    I, C, H, W, e2i = cfg["I"], cfg["C"], cfg["H"], cfg["W"], cfg["e2i"]
+    E = len(e2i)
+    g = torch.Generator().manual_seed(C + H)
+    X = torch.relu(torch.randn(I, C, H, W, generator=g))
+    filt = torch.tanh(torch.randn(E, 7, C, generator=g) * 0.5)
+    fuse = torch.tanh(torch.randn(E, 7, generator=g))
+    if gate == "linear":
+        filt = filt / C ** 0.5
+    G = torch.randn(E, C, H, W, generator=g)
+    Gr = torch.randn(E, 1, H, W, generator=g) * 0.1
+    tgt = (torch.rand(E, H, W, generator=g) < 0.3).float()
+
+    def run(fn, dev):
+        x, f, w = (t.to(dev).clone().requires_grad_(True) for t in (X, filt, fuse))
+        if fn == "oracle":
+            r, Y = R.dynamic_filter(x, f, w, e2i, gate)
+            rl = R.response_loss(r, tgt)
+        else:
+            r, Y, rl = F.dynamic_filter(x, f, w, torch.tensor(e2i), gate, tgt.to(dev))
+        loss = (Y * G.to(dev)).sum() + (r * Gr.to(dev)).sum() + (rl * torch.arange(1, E + 1, device=dev)).sum()
+        return [r, Y, rl] + list(torch.autograd.grad(loss, [x, f, w]))
+
+    ref = run("oracle", "cpu")
+    out = run("kernel", "cuda")
+    for name, a, b in zip(["r", "Y", "rl", "dX", "dfilt", "dfuse"], out, ref):
+        assert relerr(a, b) < TOL, name
+
+
+def test_partition_bounds_contract():
+    """Integer partition boundaries: with X = 1 and one-hot filters r_k is exactly C * M_k."""
+    import lang2seg_b200.functional as F
+    for H, W in [(38, 63), (37, 62), (9, 13), (32, 32)]:
+        C = 8
+        X = torch.ones(1, C, H, W, device="cuda")
+        masks = R.partition_masks(H, W)
+        for k in range(7):
+            filt = torch.zeros(1, 7, C, device="cuda")
+            filt[0, k] = 1.0
+            fuse = torch.zeros(1, 7, device="cuda")
+            fuse[0, k] = 1.0
+            r, _, _ = F.dynamic_filter(X, filt, fuse)
+            assert torch.equal(r[0, 0].cpu(), masks[k] * C), (H, W, k)

@@ -1,0 +1,91 @@
+"""tcgen05 bf16x3 GEMM and the mask head vs fp64 matmul, golden vectors and the oracle."""
+import pytest
+import torch
+
+from conftest import relerr
+from oracle import restate as R
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
+TOL = 1e-4
+
+
+def test_gemm_f32_exact():
+    import lang2seg_b200.functional as F
+    g = torch.Generator().manual_seed(1)
+    A, B = torch.randn(130, 70, generator=g), torch.randn(90, 70, generator=g)
+    D = F.gemm_f32(A.cuda(), B.cuda())
+    assert relerr(D, A.double() @ B.double().t()) < 1e-6
+
+
+def test_split_bf16():
+    import lang2seg_b200.functional as F
+    x = torch.randn(37, 50) * 3
+    hi, lo = F.split_bf16(x.cuda(), 64)
+    rec = hi.float() + lo.float()
+    assert float((rec[:, :50].cpu() - x).abs().max() / x.abs().max()) < 2 ** -15
+    assert float(rec[:, 50:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 512, 2048), (300, 96, 40), (1000, 1024, 136)])
+@pytest.mark.parametrize("layout", ["kk", "mm", "mk", "km"])
+def test_gemm_bf16x3(M, N, K, layout):
+    import lang2seg_b200.functional as F
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g)
+    B = torch.randn(N, K, generator=g)
+    ref = A.double() @ B.double().t()
+    a_mn, b_mn = layout[0] == "m", layout[1] == "m"
+    if (a_mn and M % 8) or (b_mn and N % 8) or ((not a_mn or not b_mn) and K % 8):
+        pytest.skip("row stride not 16-byte aligned for this layout")
+    a_hi, a_lo = F.split_bf16((A.t().contiguous() if a_mn else A).cuda())
+    b_hi, b_lo = F.split_bf16((B.t().contiguous() if b_mn else B).cuda())
+    D = F.gemm_bf16x3(a_hi, a_lo, b_hi, b_lo, M, N, K, a_mn, b_mn)
+    assert relerr(D, ref) < 3e-5, "bf16x3 product should be ~1e-5 from fp64"
+    if layout == "mm":
+        D2 = F.gemm_bf16x3(a_hi, a_lo, b_hi, b_lo, M, N, K, a_mn, b_mn, split_k=3)
+        assert relerr(D2, ref) < 3e-5
+    bias = torch.randn(N // 4 if N % 4 == 0 else N, generator=g)
+    if N % 4 == 0:
+        D3 = F.gemm_bf16x3(a_hi, a_lo, b_hi, b_lo, M, N, K, a_mn, b_mn, epilogue=2, bias=bias.cuda(), bias_div=4)
+        assert relerr(D3, torch.relu(ref + bias.double().repeat_interleave(4)[None])) < 3e-5
+
+
+def test_mask_head_golden(golden):
+    import lang2seg_b200.functional as F
+    d = golden("mask_head.npz")
+    x = d["x"].cuda().requires_grad_(True)
+    ws = [d[k].cuda().requires_grad_(True) for k in ("up_w", "up_b", "pred_w", "pred_b")]
+    score, prob = F.mask_head(x, *ws)
+    assert relerr(score, d["score"]) < TOL and relerr(prob, d["prob"]) < TOL
+    loss = F.mask_bce_loss(score, d["labels"].cuda(), d["tgt"].cuda())
+    assert relerr(loss, d["loss"]) < TOL
+    gs = torch.autograd.grad(loss, [x] + ws)
+    for gk, k in zip(gs, ("dx", "d_up_w", "d_up_b", "d_pred_w", "d_pred_b")):
+        assert relerr(gk, d[k]) < TOL, k
+
+
+@pytest.mark.parametrize("n", [1, 8])
+def test_mask_head_full_size_vs_oracle(n):
+    import lang2seg_b200.functional as F
+    g = torch.Generator().manual_seed(n)
+    x = torch.relu(torch.randn(n, 2048, 7, 7, generator=g))
+    up_w, up_b = torch.randn(2048, 256, 2, 2, generator=g) * 0.01, torch.randn(256, generator=g) * 0.01
+    pw, pb = torch.randn(81, 256, 1, 1, generator=g) * 0.01, torch.randn(81, generator=g) * 0.01
+    labels = torch.randint(1, 81, (n,), generator=g)
+    tgt = (torch.rand(n, 14, 14, generator=g) < 0.5).float()
+    Gs = torch.randn(n, 81, 14, 14, generator=g) * 1e-3
+
+    def run(dev):
+        ts = [t.to(dev).clone().requires_grad_(True) for t in (x, up_w, up_b, pw, pb)]
+        if dev == "cpu":
+            s, p = R.mask_head(*ts)
+            loss = R.mask_loss(s, labels, tgt)
+        else:
+            s, p = F.mask_head(*ts)
+            loss = F.mask_bce_loss(s, labels.to(dev), tgt.to(dev))
+        tot = loss + (s * Gs.to(dev)).sum() + (p * Gs.to(dev)).sum()      # dense dscore and dprob paths too
+        return [s, p, loss] + list(torch.autograd.grad(tot, ts))
+
+    ref, out = run("cpu"), run("cuda")
+    for name, a, b in zip(["score", "prob", "loss", "dx", "d_up_w", "d_up_b", "d_pred_w", "d_pred_b"], out, ref):
+        assert relerr(a, b) < TOL, name

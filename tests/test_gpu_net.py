@@ -1,0 +1,72 @@
+"""End-to-end hot-path step through the reference-facing modules (HotPathNet) vs the oracle."""
+import pytest
+import torch
+
+from conftest import relerr
+from oracle import restate as R
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
+TOL = 1e-4
+
+
+def test_hot_path_step_vs_oracle():
+    from lang2seg_b200 import _lib
+    from lang2seg_b200.nets.network import HotPathNet
+    torch.manual_seed(0)
+    net = HotPathNet().cuda().eval()
+    g = torch.Generator().manual_seed(5)
+    I, E, H, W, Rn, nfg, L = 2, 3, 32, 32, 12, 4, 10
+    e2i = [0, 0, 1]
+    X = torch.relu(torch.randn(I, 1024, H, W, generator=g))
+    labels, lens = R.synth_labels(g, E, L, 1999)
+    cap, msk = R.caption_targets(labels, lens, L)
+    rois = torch.cat([R.synth_rois(g, Rn, 512, 512, e) for e in range(E)])
+    fc7 = torch.relu(torch.randn(E * nfg, 2048, 7, 7, generator=g))
+    mlab = torch.randint(1, 81, (E * nfg,), generator=g)
+    mtgt = (torch.rand(E * nfg, 14, 14, generator=g) < 0.5).float()
+    rtgt = (torch.rand(E, H, W, generator=g) < 0.3).float()
+    fc = torch.randn(E, 4096, generator=g)
+    att = torch.relu(torch.randn(E, 14, 14, 4096, generator=g))
+    Gp = torch.randn(E * Rn, 1024, 7, 7, generator=g) * 1e-3
+
+    before = _lib.launch_count()
+    Xc = X.cuda().requires_grad_(True)
+    fc7c = fc7.cuda().requires_grad_(True)
+    attc = att.cuda().requires_grad_(True)
+    gated = net._dynamic_filter(Xc, labels.cuda(), expr2img=torch.tensor(e2i), resp_target=rtgt.cuda())
+    pool5 = net._crop_pool_layer(gated, rois.cuda(), max_pool=False)
+    net._mask_prediction(fc7c)
+    loss = (net._losses["loss_response_per_expr"].sum() + (pool5 * Gp.cuda()).sum()
+            + net._mask_loss(mlab.cuda(), mtgt.cuda()) + net._caption_loss(fc.cuda(), attc, cap.cuda(), msk.cuda()))
+    loss.backward()
+    assert _lib.launch_count() - before > 20
+
+    # ---- oracle on CPU with the same parameters ----
+    p = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+    Xo = X.clone().requires_grad_(True)
+    fc7o = fc7.clone().requires_grad_(True)
+    atto = att.clone().requires_grad_(True)
+    enc = {k[len("rnn_encoder."):]: v for k, v in p.items() if k.startswith("rnn_encoder.")}
+    _, hidden, _ = R.rnn_encoder(labels, enc)
+    dyn_w = [p["dynamic_fc_%d.weight" % k].clone().requires_grad_(True) for k in range(7)]
+    filt, fuse = R.filter_generator(hidden, dyn_w, [p["dynamic_fc_%d.bias" % k] for k in range(7)],
+                                    p["response_fc.weight"], p["response_fc.bias"])
+    r, Y = R.dynamic_filter(Xo, filt, fuse, e2i)
+    pool5o = R.crop_pool(Y, rois)
+    upw = p["mask_up_sampling.weight"].clone().requires_grad_(True)
+    s, _ = R.mask_head(fc7o, upw, p["mask_up_sampling.bias"], p["mask_pred_net.weight"], p["mask_pred_net.bias"])
+    capp = {k[len("caption_model."):]: v for k, v in p.items() if k.startswith("caption_model.")}
+    capp["logit.weight"] = capp["logit.weight"].clone().requires_grad_(True)
+    lo = (R.response_loss(r, rtgt).sum() + (pool5o * Gp).sum() + R.mask_loss(s, mlab, mtgt)
+          + R.caption_loss(fc, atto, cap, msk, capp))
+    lo.backward()
+    assert relerr(loss, lo) < TOL
+    assert relerr(net._predictions["response"], r) < TOL
+    assert relerr(pool5, pool5o) < TOL
+    assert relerr(net._predictions["mask_score"], s) < TOL
+    assert relerr(Xc.grad, Xo.grad) < TOL
+    assert relerr(fc7c.grad, fc7o.grad) < TOL
+    assert relerr(attc.grad, atto.grad) < TOL
+    assert relerr(net.dynamic_fc_3.weight.grad, dyn_w[3].grad) < TOL
+    assert relerr(net.mask_up_sampling.weight.grad, upw.grad) < TOL
+    assert relerr(net.caption_model.logit.weight.grad, capp["logit.weight"].grad) < TOL

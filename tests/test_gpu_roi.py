@@ -1,0 +1,138 @@
+"""ROI pooling kernels (crop-and-resize and RoI max-pool) through the C ABI vs the oracle / golden vectors."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import relerr
+from oracle import restate as R
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
+TOL = 1e-4   # north_star: fp32 outputs and gradients within 1e-4 relative (norm-wise)
+
+
+def _f():
+    import lang2seg_b200.functional as F
+    return F
+
+
+CASES = {"p7": dict(max_pool=False), "p14max": dict(max_pool=True),
+         "align7": dict(max_pool=False, align=True), "align14max": dict(max_pool=True, align=True)}
+
+
+@pytest.mark.parametrize("tag", list(CASES))
+def test_crop_golden(golden, tag):
+    d = golden("crop.npz")
+    kw = CASES[tag]
+    imhw = (float(d["im_info"][0, 0]), float(d["im_info"][0, 1])) if kw.get("align") else None
+    # C=6 is not a multiple of 4: pad channels (the kernel requires C % 4 == 0) and slice back
+    b = torch.zeros(1, 8, 9, 13)
+    b[:, :6] = d["bottom"]
+    b = b.cuda().requires_grad_(True)
+    out = _f().roi_crop(b, d["rois"].cuda(), max_pool=kw["max_pool"], align_im_hw=imhw)
+    assert relerr(out[:, :6], d[tag + ".out"]) < TOL
+    G = torch.zeros_like(out)
+    G[:, :6] = d[tag + ".G"].cuda()
+    (gb,) = torch.autograd.grad((out * G).sum(), b)
+    assert relerr(gb[:, :6], d[tag + ".dbottom"]) < TOL
+    assert float(gb[:, 6:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("shape", [(3, 40, 32, 32, 70), (2, 64, 38, 63, 33), (2, 16, 50, 80, 20), (1, 8, 80, 120, 9)])
+@pytest.mark.parametrize("max_pool", [False, True])
+def test_crop_vs_oracle(shape, max_pool):
+    B, C, H, W, N = shape
+    g = torch.Generator().manual_seed(B * 1000 + C + H)
+    bottom = torch.randn(B, C, H, W, generator=g)
+    rois = torch.cat([R.synth_rois(g, N, H * 16, W * 16, b) for b in range(B)])
+    rois = rois[torch.randperm(rois.shape[0], generator=g)]          # unsorted batch indices
+    bo = bottom.clone().requires_grad_(True)
+    ref = R.crop_pool(bo, rois, max_pool=max_pool)
+    G = torch.randn(ref.shape, generator=g)
+    (gref,) = torch.autograd.grad((ref * G).sum(), bo)
+    bc = bottom.cuda().requires_grad_(True)
+    out = _f().roi_crop(bc, rois.cuda(), max_pool=max_pool)
+    assert relerr(out, ref) < TOL
+    (gb,) = torch.autograd.grad((out * G.cuda()).sum(), bc)
+    assert relerr(gb, gref) < TOL
+    # deterministic scatter-add: bit-identical on a second run
+    (gb2,) = torch.autograd.grad((_f().roi_crop(bc, rois.cuda(), max_pool=max_pool) * G.cuda()).sum(), bc)
+    assert torch.equal(gb, gb2)
+
+
+def test_crop_index_contract():
+    """Corner indices: a one-hot map makes every output reveal which pixel it sampled."""
+    g = torch.Generator().manual_seed(3)
+    H, W = 32, 32
+    rois = R.synth_rois(g, 40, 512, 512)
+    px, py = R.crop_sample_coords(rois.numpy(), H, W, 7)
+    bottom = torch.zeros(1, 4, H, W)
+    bottom[0, 0] = torch.arange(W, dtype=torch.float32)[None, :].expand(H, W)       # value = x
+    bottom[0, 1] = torch.arange(H, dtype=torch.float32)[:, None].expand(H, W)       # value = y
+    out = _f().roi_crop(bottom.cuda(), rois.cuda()).cpu().double().numpy()
+    inside = (px >= 0) & (px <= W - 1)
+    got_x = out[:, 0][:, 0, :]                       # row i = 0: interpolated x coordinate
+    ok = inside & (py[:, :1] >= 0) & (py[:, :1] <= H - 1)
+    assert np.max(np.abs(got_x - px)[ok]) < 1e-4     # interpolating f(x)=x returns px itself
+
+
+def test_crop_empty_and_errors():
+    F = _f()
+    from lang2seg_b200._lib import L2SError
+    b = torch.randn(1, 8, 16, 16, device="cuda", requires_grad=True)
+    out = F.roi_crop(b, torch.zeros(0, 5, device="cuda"))
+    assert out.shape == (0, 8, 7, 7)
+    with pytest.raises(L2SError):
+        F.roi_crop(torch.randn(1, 6, 16, 16, device="cuda"), torch.zeros(1, 5, device="cuda"))   # C % 4 != 0
+    with pytest.raises(AssertionError):
+        F.roi_crop(torch.randn(1, 8, 16, 16), torch.zeros(1, 5))                                  # CPU tensors
+
+
+@pytest.mark.parametrize("shape", [(2, 5, 12, 17, 9), (1, 64, 38, 63, 50), (3, 32, 32, 32, 40)])
+def test_roi_maxpool_bit_exact(shape):
+    B, C, H, W, N = shape
+    g = torch.Generator().manual_seed(C + N)
+    f = torch.randn(B, C, H, W, generator=g)
+    rois = torch.cat([R.synth_rois(g, N, H * 16, W * 16, b) for b in range(B)])
+    rois = torch.cat([rois, torch.tensor([[0, 5000., 5000., 6000., 6000.], [0, 40., 40., 40., 40.],
+                                          [0, 100., 90., 30., 20.]])])
+    ref, refarg = R.roi_max_pool(f, rois)
+    fc = f.cuda().requires_grad_(True)
+    out, arg = _f().roi_max_pool(fc, rois.cuda(), 7, 7, 1.0 / 16, return_argmax=True)
+    assert torch.equal(out.cpu(), ref)               # integer bins + fp32 max: bit exact
+    assert torch.equal(arg.cpu(), refarg)
+    top = torch.randn(ref.shape, generator=g)
+    (gb,) = torch.autograd.grad((out * top.cuda()).sum(), fc)
+    assert relerr(gb, R.roi_max_pool_backward(top, rois, refarg, f.shape)) < 1e-6
+
+
+def test_roi_maxpool_vs_reference_cuda_kernel():
+    """Bit-exact against the reference's own ROIPoolForward/Backward kernels (roi_pooling_kernel.cu),
+    compiled for sm_100a by oracle/Makefile into oracle/_ref (batch 1, as the reference requires)."""
+    from oracle import clib
+    lib = clib.reference_roi_pool_cuda()
+    if lib is None:
+        pytest.skip("oracle/_ref/libroi_pooling_ref.so not built")
+    g = torch.Generator().manual_seed(17)
+    C, H, W, N = 96, 38, 63, 120
+    f = torch.randn(1, C, H, W, generator=g).cuda()
+    rois = R.synth_rois(g, N, H * 16, W * 16).cuda()
+    out_ref = torch.zeros(N, C, 7, 7, device="cuda")
+    arg_ref = torch.zeros(N, C, 7, 7, device="cuda", dtype=torch.int32)
+    vp = ctypes.c_void_p
+    st = vp(torch.cuda.current_stream().cuda_stream)
+    lib.ROIPoolForwardLaucher(vp(f.data_ptr()), ctypes.c_float(1 / 16.), N, H, W, C, 7, 7, vp(rois.data_ptr()),
+                              vp(out_ref.data_ptr()), vp(arg_ref.data_ptr()), st)
+    out, arg = _f().roi_max_pool(f, rois, 7, 7, 1.0 / 16, return_argmax=True)
+    torch.cuda.synchronize()
+    assert torch.equal(out, out_ref) and torch.equal(arg, arg_ref)
+    top = torch.randn(N, C, 7, 7, generator=g).cuda()
+    gb_ref = torch.zeros(1, C, H, W, device="cuda")
+    lib.ROIPoolBackwardLaucher(vp(top.data_ptr()), ctypes.c_float(1 / 16.), 1, N, H, W, C, 7, 7, vp(rois.data_ptr()),
+                               vp(gb_ref.data_ptr()), vp(arg_ref.data_ptr()), st)
+    fr = f.clone().requires_grad_(True)
+    o2 = _f().roi_max_pool(fr, rois)
+    (gb,) = torch.autograd.grad((o2 * top).sum(), fr)
+    torch.cuda.synchronize()
+    assert relerr(gb, gb_ref) < 1e-6
