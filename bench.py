@@ -1,0 +1,453 @@
+"""bench.py -- expressions/sec of the lang2seg hot path (fwd+bwd) on B200, next to its CPU baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload cfg2|cfg4|tiny]
+
+A "step" is one forward+backward pass of the chained hot path over one batch of synthetic input
+(SURVEY.md section 8d): lang encoder -> filter generator -> dynamic filter (+response BCE) ->
+ROI crop (consumes the gated map) -> mask head (+mask BCE, synthetic res5 features) -> att2in2
+(+LM loss, synthetic fc/att features), gradient all-reduce of the three parameter groups (N>1)
+and the SGD update.  res5 is cuDNN glue outside the graded step.
+
+N>1 is launched by torchrun (one rank per GPU); every rank processes its own shard of images /
+expressions (weak scaling) and only parameter gradients cross NVLink.
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the oracle's torch-CPU port of the
+reference modules on the host cores instead (rank 0 only).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "expressions/sec fwd+bwd (dynfilter+ROIAlign+mask head+att2in2)"
+UNIT = "expressions/s"
+
+WORKLOADS = {
+    # BASELINE.json configs[1] / SURVEY 8d config 2 -- the configuration the metric is quoted on (fits one GPU)
+    "cfg2": dict(name="cfg2: 16 images x 3 expressions, C4 1024x32x32, 256 ROIs + 64 fg per expression, "
+                      "L=10 (T=11), V=1999, 7x7 crop, response+mask+caption losses",
+                 I=16, EPI=3, C=1024, H=32, W=32, R=256, NFG=64, L=10, V=1999),
+    "cfg4": dict(name="cfg4 shard: 16 images x 1 expression, L=20 (T=21)", I=16, EPI=1, C=1024, H=32, W=32, R=256,
+                 NFG=64, L=20, V=1999),
+    "tiny": dict(name="tiny smoke workload", I=2, EPI=2, C=1024, H=32, W=32, R=16, NFG=4, L=10, V=1999),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=float(d["hbm_gbs"]), tf_burst=float(d["bf16_tflops"]),
+                    tf_sust=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), source="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, source="fallback")
+
+
+def make_inputs(wl, seed, device, pinned=False):
+    """Seeded synthetic inputs of SURVEY 8d on the host; moved to `device` unless pinned host copies are wanted."""
+    from oracle import restate as R   # generators only (allowed: bench synthetic inputs share the oracle's helpers)
+    g = torch.Generator().manual_seed(seed)
+    I, EPI, C, H, W, Rn, NFG, L, V = (wl[k] for k in ("I", "EPI", "C", "H", "W", "R", "NFG", "L", "V"))
+    E = I * EPI
+    d = {}
+    d["X"] = torch.relu(torch.randn(I, C, H, W, generator=g))
+    labels, lens = R.synth_labels(g, E, L, V)
+    d["labels"] = labels
+    d["cap"], d["msk"] = R.caption_targets(labels, lens, L)
+    d["e2i"] = torch.arange(I).repeat_interleave(EPI).int()
+    d["rois"] = torch.cat([R.synth_rois(g, Rn, H * 16, W * 16, e) for e in range(E)])
+    d["resp_tgt"] = (torch.rand(E, H, W, generator=g) < 0.3).float()
+    d["fc7"] = torch.relu(torch.randn(E * NFG, 2048, 7, 7, generator=g))
+    d["mlab"] = torch.randint(1, 81, (E * NFG,), generator=g)
+    d["mtgt"] = (torch.rand(E * NFG, 14, 14, generator=g) < 0.5).float()
+    d["fc"] = torch.randn(E, 4096, generator=g)
+    d["att"] = torch.relu(torch.randn(E, 14, 14, 4096, generator=g))
+    if pinned:
+        return {k: v.pin_memory() for k, v in d.items()}
+    return {k: v.to(device) for k, v in d.items()}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# the B200 arm
+# --------------------------------------------------------------------------------------------------
+class HotPathStep:
+    def __init__(self, wl, device, world):
+        from lang2seg_b200.nets.network import HotPathNet
+        from lang2seg_b200.parallel import GradientAllReducer
+        torch.manual_seed(1234)
+        self.wl, self.device = wl, device
+        self.net = HotPathNet(dict(seq_length=wl["L"], vocab_size=wl["V"])).to(device).eval()   # eval: dropout off (D8)
+        self.params = [p for p in self.net.parameters() if p.requires_grad]
+        self.opt = torch.optim.SGD(self.params, lr=1e-5, momentum=0.9, foreach=True)
+        self.reducer = GradientAllReducer(self.net.gradient_groups()) if world > 1 else None
+        E = wl["I"] * wl["EPI"]
+        g = torch.Generator().manual_seed(99)
+        # upstream gradient of pool5: stands in for res5's backward (device resident, not an input)
+        self.g_pool = (torch.randn(E * wl["R"], wl["C"], 7, 7, generator=g) * 1e-4).to(device)
+        self.one = torch.ones((), device=device)
+
+    def __call__(self, d):
+        net = self.net
+        self.opt.zero_grad(set_to_none=True)
+        X = d["X"].requires_grad_(True)
+        fc7 = d["fc7"].requires_grad_(True)
+        att = d["att"].requires_grad_(True)
+        gated = net._dynamic_filter(X, d["labels"], expr2img=d["e2i"], resp_target=d["resp_tgt"])
+        pool5 = net._crop_pool_layer(gated, d["rois"], max_pool=False)
+        net._mask_prediction(fc7)
+        loss = (net._losses["loss_response_per_expr"].sum() + net._mask_loss(d["mlab"], d["mtgt"])
+                + net._cap_loss_weight * net._caption_loss(d["fc"], att, d["cap"], d["msk"]))
+        torch.autograd.backward([loss, pool5], [self.one, self.g_pool])
+        if self.reducer is not None:
+            self.reducer.all_reduce()
+        self.opt.step()
+        X.grad = fc7.grad = att.grad = None
+        return loss
+
+
+def time_region(fn, steps, dist_on):
+    import torch.distributed as dist
+    if dist_on:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(steps):
+        fn()
+    t1.record()
+    torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1)
+    if dist_on:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.barrier()
+        ms = float(t[0])
+    return ms
+
+
+def ev_time(fn, iters=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+def component_rooflines(wl, d, step, pk):
+    """Per-kernel device time (CUDA events, kernel alone => burst peaks) and roofline fractions.
+    Algorithmic bytes / flops per SURVEY 8d (stated again in DESIGN.md)."""
+    import lang2seg_b200.functional as F
+    from lang2seg_b200 import _lib
+    from lang2seg_b200._lib import call, ptr, stream
+    I, EPI, C, H, W, Rn, NFG = (wl[k] for k in ("I", "EPI", "C", "H", "W", "R", "NFG"))
+    E, HW = I * EPI, H * W
+    dev = d["X"].device
+    out = []
+    filt = torch.tanh(torch.randn(E, 7, C, device=dev) * 0.1)
+    fuse = torch.tanh(torch.randn(E, 7, device=dev))
+    # --- dynamic filter
+    resp, Y, rl = F.dynamic_filter(d["X"], filt, fuse, d["e2i"], "sigmoid", d["resp_tgt"])
+    rk = torch.empty(E, 7, H, W, device=dev)
+    lossb = torch.empty(E, device=dev)
+    t = ev_time(lambda: call("l2s_dynfilter_fwd", ptr(d["X"]), ptr(filt), ptr(fuse), ptr(d["e2i"]), ptr(resp), ptr(rk),
+                             ptr(Y), ptr(d["resp_tgt"]), ptr(lossb), I, E, C, H, W, 0, stream()))
+    out.append(dict(kernel="dynfilter_fwd", ms=t, bound="hbm", work=4.0 * C * HW * (I + E)))
+    dY = torch.randn_like(Y) * 1e-3
+    dX, dfilt, dfuse = torch.empty_like(d["X"]), torch.empty_like(filt), torch.empty_like(fuse)
+    gs = torch.ones(E, device=dev)
+    nb = _lib.size("l2s_dynfilter_bwd_workspace_bytes", I, E, C, H, W)
+    ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+    t = ev_time(lambda: call("l2s_dynfilter_bwd", ptr(d["X"]), ptr(filt), ptr(fuse), ptr(d["e2i"]), ptr(resp), ptr(rk),
+                             ptr(dY), None, ptr(d["resp_tgt"]), ptr(gs), ptr(dX), ptr(dfilt), ptr(dfuse), I, E, C, H, W,
+                             0, ptr(ws), nb, stream()))
+    out.append(dict(kernel="dynfilter_bwd", ms=t, bound="hbm", work=4.0 * C * HW * (E + 2 * I)))
+    del dY, dX
+    # --- ROI crop
+    N = E * Rn
+    pool = torch.empty(N, C, 7, 7, device=dev)
+    nb2 = _lib.size("l2s_roi_crop_workspace_bytes", E, N)
+    ws2 = torch.empty(nb2, dtype=torch.uint8, device=dev)
+    t = ev_time(lambda: call("l2s_roi_crop_fwd", ptr(Y), ptr(d["rois"]), ptr(pool), None, E, C, H, W, N, 7, 0, 0.0, 0.0,
+                             ptr(ws2), nb2, stream()))
+    out.append(dict(kernel="roi_crop_fwd", ms=t, bound="hbm", work=4.0 * C * (49 * Rn + HW) * E))
+    dYb = torch.empty_like(Y)
+    t = ev_time(lambda: call("l2s_roi_crop_bwd", ptr(step.g_pool), ptr(d["rois"]), None, ptr(dYb), E, C, H, W, N, 7, 0,
+                             0.0, 0.0, ptr(ws2), nb2, stream()))
+    out.append(dict(kernel="roi_crop_bwd", ms=t, bound="hbm", work=4.0 * C * (49 * Rn + HW) * E))
+    del pool, dYb
+    # --- mask head (tensor bound): fwd 2*n*49*2048*1024 + 2*n*196*256*81 ; bwd = 2x
+    n = E * NFG
+    net = step.net
+    with torch.no_grad():
+        t = ev_time(lambda: F.mask_head(d["fc7"], net.mask_up_sampling.weight, net.mask_up_sampling.bias,
+                                        net.mask_pred_net.weight, net.mask_pred_net.bias), iters=3, warm=1)
+    flops_f = 2.0 * n * 49 * 2048 * 1024 + 2.0 * n * 196 * 256 * 81
+    out.append(dict(kernel="mask_head_fwd (2 GEMM + repack)", ms=t, bound="tensor", work=flops_f))
+    fc7 = d["fc7"].detach().requires_grad_(True)
+    s, p = F.mask_head(fc7, net.mask_up_sampling.weight, net.mask_up_sampling.bias, net.mask_pred_net.weight,
+                       net.mask_pred_net.bias)
+    gsc = torch.randn_like(s) * 1e-4
+    t = ev_time(lambda: torch.autograd.grad(s, [fc7, net.mask_up_sampling.weight, net.mask_pred_net.weight], gsc,
+                                            retain_graph=True), iters=3, warm=1)
+    out.append(dict(kernel="mask_head_bwd (4 GEMM + repack)", ms=t, bound="tensor", work=2 * flops_f))
+    del s, p, gsc
+    # --- the dominant GEMM alone: GEMM1 of the mask head  [49n x 2048] x [1024 x 2048]^T
+    M, Nn, K = n * 49, 1024, 2048
+    a_hi = torch.randn(M, K, device=dev).bfloat16(); a_lo = (torch.randn(M, K, device=dev) * 1e-3).bfloat16()
+    b_hi = torch.randn(Nn, K, device=dev).bfloat16(); b_lo = (torch.randn(Nn, K, device=dev) * 1e-3).bfloat16()
+    D = torch.empty(M, Nn, device=dev)
+    t = ev_time(lambda: F.gemm_bf16x3(a_hi, a_lo, b_hi, b_lo, M, Nn, K, out=D), iters=5, warm=2)
+    out.append(dict(kernel="gemm_bf16x3_kernel<256,K,K> (mask head GEMM1 shape)", ms=t, bound="tensor",
+                    work=2.0 * M * Nn * K))
+    del a_hi, a_lo, b_hi, b_lo, D
+    # --- attention step (L2/HBM bound): one step fwd + bwd
+    A, Dd = 196, 512
+    att_h = torch.randn(E, Dd, device=dev)
+    feats = torch.randn(E, A, Dd, device=dev)
+    p_att = torch.randn(E, A, Dd, device=dev)
+    aw, ab = torch.randn(Dd, device=dev) * 0.04, torch.zeros(1, device=dev)
+    wgt, res = torch.empty(E, A, device=dev), torch.empty(E, Dd, device=dev)
+    t = ev_time(lambda: call("l2s_att_step_fwd", ptr(att_h), ptr(feats), ptr(p_att), ptr(aw), ptr(ab), ptr(wgt), ptr(res),
+                             E, A, Dd, Dd, stream()), iters=20)
+    out.append(dict(kernel="att_step_fwd", ms=t, bound="hbm", work=2.0 * A * Dd * 4 * E))
+    for o in out:
+        sec = o["ms"] * 1e-3
+        if o["bound"] == "hbm":
+            o["achieved"] = o["work"] / sec / 1e9
+            o["peak"], o["unit"] = pk["hbm"], "GB/s"
+        else:
+            o["achieved"] = o["work"] / sec / 1e12
+            o["peak"], o["unit"] = pk["tf_burst"], "TFLOP/s"
+        o["frac"] = o["achieved"] / o["peak"]
+    return out
+
+
+def cpu_sample(wl, repeats=1, threads=None):
+    """The oracle's torch-CPU port of the reference modules on ONE image and its expressions (the reference's
+    native batching), fwd+bwd, timed on the host cores."""
+    from oracle import restate as R
+    from lang2seg_b200.layers.lang_encoder import RNNEncoder    # pure torch (cuDNN/CPU LSTM), as the reference's
+    if threads:
+        torch.set_num_threads(threads)
+    w1 = dict(wl, I=1)
+    d = make_inputs(w1, 4321, "cpu")
+    E, C, V, L = w1["EPI"], w1["C"], w1["V"], w1["L"]
+    torch.manual_seed(7)
+    enc = RNNEncoder(V, 512, 512, 512, bidirectional=True, n_layers=1).eval()
+    P = lambda *s: (torch.randn(*s) * 0.01).requires_grad_(True)      # noqa: E731
+    dyn_w, dyn_b = [P(C, 1024) for _ in range(7)], [P(C) for _ in range(7)]
+    rw, rb = P(7, 1024), P(7)
+    up_w, up_b, pw, pb = P(2048, 256, 2, 2), P(256), P(81, 256, 1, 1), P(81)
+    D = 512
+    cp = {"att_embed.0.weight": P(D, 4096), "att_embed.0.bias": P(D), "ctx2att.weight": P(D, D), "ctx2att.bias": P(D),
+          "embed.0.weight": P(V + 1, D), "logit.weight": P(V + 1, D), "logit.bias": P(V + 1),
+          "core.i2h.weight": P(5 * D, D), "core.i2h.bias": P(5 * D), "core.h2h.weight": P(5 * D, D),
+          "core.h2h.bias": P(5 * D), "core.a2c.weight": P(2 * D, D), "core.a2c.bias": P(2 * D),
+          "core.attention.h2att.weight": P(D, D), "core.attention.h2att.bias": P(D),
+          "core.attention.alpha_net.weight": P(1, D), "core.attention.alpha_net.bias": P(1)}
+    g_pool = torch.randn(E * w1["R"], C, 7, 7) * 1e-4
+    params = list(enc.parameters()) + dyn_w + dyn_b + [rw, rb, up_w, up_b, pw, pb] + list(cp.values())
+
+    def one():
+        for p in params:
+            p.grad = None
+        X = d["X"].clone().requires_grad_(True)
+        fc7 = d["fc7"].clone().requires_grad_(True)
+        att = d["att"].clone().requires_grad_(True)
+        _, hidden, _ = enc(d["labels"])
+        filt, fuse = R.filter_generator(hidden, dyn_w, dyn_b, rw, rb)
+        r, Y = R.dynamic_filter(X, filt, fuse, d["e2i"].tolist())
+        rl = R.response_loss(r, d["resp_tgt"]).sum()
+        pool5 = R.crop_pool(Y, d["rois"])
+        s, _ = R.mask_head(fc7, up_w, up_b, pw, pb)
+        ml = R.mask_loss(s, d["mlab"], d["mtgt"])
+        cl = R.caption_loss(d["fc"], att, d["cap"], d["msk"], cp)
+        torch.autograd.backward([rl + ml + cl, pool5], [torch.ones(()), g_pool])
+
+    one()   # warm-up
+    t0 = time.perf_counter()
+    for _ in range(repeats):
+        one()
+    dt = (time.perf_counter() - t0) / repeats
+    return E / dt, dt, E
+
+
+def run_reference_arm(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    vals = []
+    for _ in range(args.warmup):
+        cpu_sample(wl, 1)
+    t0 = time.perf_counter()
+    n_expr = 0
+    for _ in range(args.steps):
+        v, dt, e = cpu_sample(wl, 1)
+        n_expr += e
+        vals.append(dt)
+    total = sum(vals)
+    value = n_expr / total
+    sample = "1 image x %d expressions of the workload per step (reference's native batching), fwd+bwd, torch CPU" % wl["EPI"]
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": {"workload": wl["name"], "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-components", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    if args.impl == "reference":
+        run_reference_arm(args, wl)
+        return
+
+    import torch.distributed as dist
+    from lang2seg_b200 import _lib
+    _lib.load()          # fails loudly if libl2s.so is missing: there is no fallback
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist_on = world > 1
+    if dist_on:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    pk = peaks()
+    E = wl["I"] * wl["EPI"]
+
+    step = HotPathStep(wl, dev, world)
+    d = make_inputs(wl, 1234 + rank, dev)
+    for _ in range(args.warmup):
+        step(d)
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = _lib.launch_count()
+    ms = time_region(lambda: step(d), args.steps, dist_on)
+    launches = _lib.launch_count() - l0
+    clocks = sampler.stop() if sampler else None
+    value = E * world * args.steps / (ms * 1e-3)
+
+    # ---- e2e: same step through the public modules with HOST (pinned) inputs, H2D + loss D2H every step
+    host = make_inputs(wl, 1234 + rank, dev, pinned=True)
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    losses = []
+
+    def e2e_step():
+        dd = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        losses.append(float(step(dd)))            # .item(): device->host read of the step's result
+
+    for _ in range(2):
+        e2e_step()
+    e2e_steps = max(3, min(args.steps, 10))
+    ms_e2e = time_region(e2e_step, e2e_steps, dist_on)
+    e2e_value = E * world * e2e_steps / (ms_e2e * 1e-3)
+
+    comps = None
+    if rank == 0 and not args.no_components:
+        comps = component_rooflines(wl, d, step, pk)
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        v, dt, e = cpu_sample(wl, repeats=max(1, int(12.0 / max(1.0, 0.7 * wl["EPI"]))))
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "1 image x %d expressions of the workload (reference's native batching), fwd+bwd, "
+                         "oracle torch-CPU port, %.2f s per pass" % (e, dt)}
+    if rank == 0:
+        roof = None
+        if comps:
+            dom = max((c for c in comps if not c["kernel"].startswith("gemm_")), key=lambda c: c["ms"])
+            if dom["bound"] == "tensor":
+                dom = next(c for c in comps if c["kernel"].startswith("gemm_"))
+            roof = {"kernel": dom["kernel"], "bound": dom["bound"], "achieved": dom["achieved"], "peak": dom["peak"],
+                    "unit": dom["unit"], "frac": dom["frac"], "traffic": None, "peak_source": pk["source"],
+                    "ms_per_launch": dom["ms"]}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+                "config": {"workload": wl["name"], "per_gpu_expressions": E, "parallelism": "dp%d" % world,
+                           "l2": "inputs larger than L2 (>= 1.2 GB streamed per step); no flush needed",
+                           "includes": "lang encoder, filter generator, 4 hot components fwd+bwd, grad all-reduce, SGD"},
+                "clocks": clocks, "gpu_launches": launches,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                        "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps},
+                "roofline": roof, "cpu_baseline": cpu,
+                "components": [{k: (round(v, 5) if isinstance(v, float) else v) for k, v in c.items()} for c in comps]
+                if comps else None}
+        print(json.dumps(line), flush=True)
+    if dist_on:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

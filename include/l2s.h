@@ -128,10 +128,11 @@ int l2s_roi_maxpool_bwd(int pooled_height, int pooled_width, float spatial_scale
  * l2s_gemm_bf16x3: D (M,N) fp32, ldd = N.
  *     a_layout/b_layout 0: operand stored K-major  (A: [M][K], B: [N][K])
  *                       1: operand stored MN-major (A: [K][M], B: [K][N])
- *     epilogue  0: D = acc ; 1: D += acc ; 2: D = relu(acc + bias[col/bias_div])
+ *     epilogue  0: D = acc ; 1: D += acc ; 2: D = relu(acc + bias[col/bias_div]) ; 4: D = acc + bias[col/bias_div]
  *     split_k >= 1 (with split_k > 1 the epilogue accumulates atomically; D must be zeroed
  *     or hold the value to accumulate into).
- *     Requirements: M % 128 == 0, N % 64 == 0, K % 32 == 0, 16-byte aligned pointers.
+ *     Any M, N, K (tails use TMA out-of-bounds zero fill); operand row strides and pointers must be
+ *     16-byte aligned (K % 8 == 0 for K-major operands, rows % 8 == 0 for MN-major ones).
  * ------------------------------------------------------------------------------------- */
 int l2s_split_bf16(const float* src, uint16_t* hi, uint16_t* lo, int64_t rows, int64_t cols, int64_t ld_src,
                    int64_t ld_dst, l2s_stream_t stream);

@@ -13,4 +13,10 @@ The package mirrors the reference's module interfaces for that path only (SURVEY
 
 Everything computes through libl2s.so; there is no CPU path and no PyTorch fallback.
 """
+import torch as _torch
+
+# fp32 parity (1e-4) on this path: keep cuDNN (the LSTM of the expression encoder) and cuBLAS off TF32.
+_torch.backends.cudnn.allow_tf32 = False
+_torch.backends.cuda.matmul.allow_tf32 = False
+
 __version__ = "0.1.0"

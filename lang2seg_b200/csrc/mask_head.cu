@@ -106,7 +106,7 @@ struct EpiGeneric {
   int64_t ldd;
   const float* bias;
   int bias_div;
-  int mode;   // 0 store, 1 accumulate (+=), 2 relu(acc+bias), 3 atomic accumulate
+  int mode;   // 0 store, 1 accumulate (+=), 2 relu(acc+bias), 3 atomic accumulate, 4 acc+bias
   __device__ __forceinline__ void operator()(int row, int col0, const float (&v)[32], int M, int N, int) const {
     if (row >= M) return;
     float* d = D + (size_t)row * ldd + col0;
@@ -115,6 +115,7 @@ struct EpiGeneric {
       if (col0 + j < N) {
         float x = v[j];
         if (mode == 2) x = fmaxf(x + (bias ? __ldg(bias + (col0 + j) / bias_div) : 0.f), 0.f);
+        if (mode == 4) x += bias ? __ldg(bias + (col0 + j) / bias_div) : 0.f;
         if (mode == 1) d[j] += x;
         else if (mode == 3) atomicAdd(d + j, x);
         else d[j] = x;
@@ -140,7 +141,9 @@ struct EpiUp {
     if (col0 + 32 <= N) {
       store_split32(hi + (size_t)row * ld + col0, lo + (size_t)row * ld + col0, u);
     } else {
-      for (int j = 0; j < 32 && col0 + j < N; ++j) split2(u[j], hi + (size_t)row * ld + col0 + j, lo + (size_t)row * ld + col0 + j);
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < N) split2(u[j], hi + (size_t)row * ld + col0 + j, lo + (size_t)row * ld + col0 + j);
     }
   }
 };
@@ -169,6 +172,40 @@ struct EpiScore {
   }
 };
 
+// sum over the 32 lanes of a warp for each of 32 per-lane values: 31 shuffles (transpose-reduce butterfly);
+// lane j ends with the total of v[j]
+__device__ __forceinline__ float warp_column_sums(const float (&v)[32]) {
+  const int lane = threadIdx.x & 31;
+  float a[16], b[8], c[4], d[2];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const bool up = lane & 16;
+    const float recv = __shfl_xor_sync(0xffffffffu, up ? v[j] : v[j + 16], 16);
+    a[j] = (up ? v[j + 16] : v[j]) + recv;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const bool up = lane & 8;
+    const float recv = __shfl_xor_sync(0xffffffffu, up ? a[j] : a[j + 8], 8);
+    b[j] = (up ? a[j + 8] : a[j]) + recv;
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const bool up = lane & 4;
+    const float recv = __shfl_xor_sync(0xffffffffu, up ? b[j] : b[j + 4], 4);
+    c[j] = (up ? b[j + 4] : b[j]) + recv;
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const bool up = lane & 2;
+    const float recv = __shfl_xor_sync(0xffffffffu, up ? c[j] : c[j + 2], 2);
+    d[j] = (up ? c[j + 2] : c[j]) + recv;
+  }
+  const bool up = lane & 1;
+  const float recv = __shfl_xor_sync(0xffffffffu, up ? d[0] : d[1], 1);
+  return (up ? d[1] : d[0]) + recv;
+}
+
 // dU = acc * [U > 0] -> bf16 planes [4M][Cmid] (same memory order as U) ; column sums -> d_up_b
 struct EpiDU {
   uint16_t *hi, *lo;
@@ -178,29 +215,40 @@ struct EpiDU {
   __device__ __forceinline__ void operator()(int row, int col0, const float (&v)[32], int M, int N, int) const {
     float d[32];
     const bool ok = row < M;
+    const bool full = col0 + 32 <= N;
+    if (ok && full) {
+      // 32 bf16 of this row = 64 contiguous bytes
+      const uint4* up = reinterpret_cast<const uint4*>(u_hi + (size_t)row * Cmid + col0);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int col = col0 + j;
-      float x = 0.f;
-      if (ok && col < N) {
-        const __nv_bfloat16 u = __ushort_as_bfloat16(u_hi[(size_t)row * Cmid + col]);
-        x = (__bfloat162float(u) > 0.f) ? v[j] : 0.f;
+      for (int q = 0; q < 4; ++q) {
+        const uint4 w = __ldg(up + q);
+        const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          // bf16 > 0  <=>  sign bit clear and magnitude non-zero
+          const uint32_t lo16 = ws[e] & 0xffffu, hi16 = ws[e] >> 16;
+          d[q * 8 + 2 * e] = (lo16 != 0 && lo16 < 0x8000u) ? v[q * 8 + 2 * e] : 0.f;
+          d[q * 8 + 2 * e + 1] = (hi16 != 0 && hi16 < 0x8000u) ? v[q * 8 + 2 * e + 1] : 0.f;
+        }
       }
-      d[j] = x;
-    }
-    if (ok) {
-      if (col0 + 32 <= N) store_split32(hi + (size_t)row * Cmid + col0, lo + (size_t)row * Cmid + col0, d);
-      else
-        for (int j = 0; j < 32 && col0 + j < N; ++j)
-          split2(d[j], hi + (size_t)row * Cmid + col0 + j, lo + (size_t)row * Cmid + col0 + j);
-    }
-    // bias gradient: sum over the 32 rows of this warp, one atomic per column
-    const int lane = threadIdx.x & 31;
+      store_split32(hi + (size_t)row * Cmid + col0, lo + (size_t)row * Cmid + col0, d);
+    } else {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const float s = warp_sum(d[j]);
-      if (lane == j && col0 + j < N) atomicAdd(d_up_b + col0 + j, s);
+      for (int j = 0; j < 32; ++j) {
+        const int col = col0 + j;
+        float x = 0.f;
+        if (ok && col < N) {
+          const uint32_t u = u_hi[(size_t)row * Cmid + col];
+          x = (u != 0 && u < 0x8000u) ? v[j] : 0.f;
+          split2(x, hi + (size_t)row * Cmid + col, lo + (size_t)row * Cmid + col);
+        }
+        d[j] = x;
+      }
     }
+    // bias gradient: column sums over the 32 rows of this warp, one atomic per column
+    const float tot = warp_column_sums(d);
+    const int lane = threadIdx.x & 31;
+    if (col0 + lane < N) atomicAdd(d_up_b + col0 + lane, tot);
   }
 };
 
@@ -463,12 +511,12 @@ extern "C" int l2s_gemm_bf16x3(const uint16_t* a_hi, const uint16_t* a_lo, const
                                int b_layout, int epilogue, int split_k, l2s_stream_t stream) {
   L2S_REQUIRE(a_hi && a_lo && b_hi && b_lo && D, L2S_ERR_ARG, "gemm_bf16x3: null pointer");
   L2S_REQUIRE(M > 0 && N > 0 && K > 0, L2S_ERR_SHAPE, "gemm_bf16x3: bad shape");
-  L2S_REQUIRE(epilogue >= 0 && epilogue <= 2, L2S_ERR_ARG, "gemm_bf16x3: unknown epilogue %d", epilogue);
+  L2S_REQUIRE((epilogue >= 0 && epilogue <= 2) || epilogue == 4, L2S_ERR_ARG, "gemm_bf16x3: unknown epilogue %d", epilogue);
   cudaStream_t st = (cudaStream_t)stream;
 
   EpiGeneric epi{D, N, bias, bias_div > 0 ? bias_div : 1, epilogue};
   if (split_k > 1) {
-    L2S_REQUIRE(epilogue != 2, L2S_ERR_ARG, "gemm_bf16x3: split-K cannot be combined with the bias/ReLU epilogue");
+    L2S_REQUIRE(epilogue < 2, L2S_ERR_ARG, "gemm_bf16x3: split-K cannot be combined with a bias epilogue");
     if (epilogue == 0) L2S_CUDA_OK(cudaMemsetAsync(D, 0, sizeof(float) * (size_t)M * N, st));
     epi.mode = 3;
   }

@@ -26,6 +26,7 @@ namespace {
 constexpr int kSlotP = 56;          // sample slots per ROI in the forward kernel (49 used)
 constexpr int kFwdThreads = 896;    // RPI * CGN * kSlotP with RPI * CGN == 16
 constexpr int kBwdStages = 4;
+constexpr int kBoxChunk = 256;      // ROI boxes staged per pass in the forward kernel
 
 __device__ __forceinline__ int swz_key(int px) { return (px ^ (px >> 3) ^ (px >> 6)) & 7; }
 
@@ -163,6 +164,8 @@ roi_crop_fwd_kernel(const float* __restrict__ bottom, const float* __restrict__ 
   float* tiles = map + (size_t)HW * CC;                        // [2][RPI][TILE]
   uint8_t* atile = reinterpret_cast<uint8_t*>(tiles + 2 * RPI * TILE);   // [2][RPI][TILE] (max-pool only)
   __shared__ int s_n[2][RPI];
+  __shared__ float4 s_box[kBoxChunk];
+  __shared__ int s_ni[kBoxChunk];
 
   const int b = blockIdx.y, c0 = blockIdx.x * CC;
   const int t = threadIdx.x;
@@ -201,20 +204,25 @@ roi_crop_fwd_kernel(const float* __restrict__ bottom, const float* __restrict__ 
   };
 
   int it = 0;
-  for (int gi = beg; gi < end; gi += RPI, ++it) {
+  for (int cb0 = beg; cb0 < end; cb0 += kBoxChunk) {
+    // stage the boxes (already scaled to feature pixels) and ROI ids of this chunk of the segment
+    __syncthreads();
+    for (int i = t; i < min(kBoxChunk, end - cb0); i += blockDim.x) {
+      const int n = __ldg(order + cb0 + i);
+      const float* rp = rois + 5 * (size_t)n;
+      s_ni[i] = n;
+      s_box[i] = make_float4(__ldg(rp + 1) * g.sx, __ldg(rp + 2) * g.sy, __ldg(rp + 3) * g.sx, __ldg(rp + 4) * g.sy);
+    }
+    __syncthreads();
+    const int cend = min(end, cb0 + kBoxChunk);
+  for (int gi = cb0; gi < cend; gi += RPI, ++it) {
     const int buf = it & 1;
     const int ri = gi + slot;
     float* tile = tiles + (size_t)(buf * RPI + slot) * TILE;
     uint8_t* at = atile + (size_t)(buf * RPI + slot) * TILE;
-    if (ri < end && p < PP) {
-      const int n = __ldg(order + ri);
-      if (r == 0) s_n[buf][slot] = n;
-      const float* rp = rois + 5 * (size_t)n;
-      float4 box;
-      box.x = __ldg(rp + 1) * g.sx;
-      box.y = __ldg(rp + 2) * g.sy;
-      box.z = __ldg(rp + 3) * g.sx;
-      box.w = __ldg(rp + 4) * g.sy;
+    if (ri < cend && p < PP) {
+      if (r == 0) s_n[buf][slot] = s_ni[ri - cb0];
+      const float4 box = s_box[ri - cb0];
       float4 o;
       if (!g.maxpool) {
         o = gather(sample_at(box, pi, pj, inv));
@@ -247,7 +255,7 @@ roi_crop_fwd_kernel(const float* __restrict__ bottom, const float* __restrict__ 
     if (t == 0) bulk_wait_read<0>();      // the previous iteration's stores have left the other buffer
     __syncthreads();
     if (t == 0) {
-      const int cnt = min(RPI, end - gi);
+      const int cnt = min(RPI, cend - gi);
       for (int s = 0; s < cnt; ++s) {
         const int n = s_n[buf][s];
         bulk_s2g(out + ((size_t)n * g.C + c0) * PP, tiles + (size_t)(buf * RPI + s) * TILE,
@@ -257,7 +265,7 @@ roi_crop_fwd_kernel(const float* __restrict__ bottom, const float* __restrict__ 
     }
     if (g.maxpool && argmax != nullptr) {
       // winners: plain 32-bit copies (tile byte count and global offset are multiples of 4)
-      const int cnt = min(RPI, end - gi);
+      const int cnt = min(RPI, cend - gi);
       const int words = cvalid * PP / 4;
       for (int w = t; w < cnt * words; w += blockDim.x) {
         const int s = w / words, k = w % words;
@@ -266,6 +274,7 @@ roi_crop_fwd_kernel(const float* __restrict__ bottom, const float* __restrict__ 
             reinterpret_cast<const uint32_t*>(atile + (size_t)(buf * RPI + s) * TILE)[k];
       }
     }
+  }
   }
   if (t == 0) bulk_wait<0>();
 }
@@ -410,6 +419,142 @@ roi_crop_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ ro
   unstage_map<CC>(map, dbottom + (size_t)b * g.C * HW, c0, g.C, HW);
 }
 
+
+// ------------------------------------------------------------------ backward, fast path (no max-pool)
+// Geometry is channel independent, so the PRODUCER warp computes it once per ROI: for each of the 49
+// samples the corner index, the two fractions and a collision rank (samples whose (y0,x0) coincide get
+// ranks 0,1,2,.. by match.any), next to issuing the TMA load of the gradient tile.  Consumer warp cg owns
+// channel quad cg of the accumulator map: lanes = samples, 4 corners of a sample are 4 distinct pixels,
+// equal-rank samples never share a pixel through the same corner => plain float4 read-modify-write.
+struct __align__(16) SampleEnt {
+  int yx;        // (y0 << 16) | (x0 & 0xffff)
+  float ly, lx;
+  int rank;
+};
+
+template <int CC>
+__global__ void __launch_bounds__((CC / 4 + 1) * 32, 1)
+roi_crop_bwd_fast_kernel(const float* __restrict__ dout, const float* __restrict__ rois,
+                         const int* __restrict__ seg, const int* __restrict__ order, float* __restrict__ dbottom,
+                         CropGeom g) {
+  constexpr int CGN = CC / 4;
+  constexpr int PP = 49;
+  constexpr int TILE = CC * PP;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int HW = g.H * g.W;
+  float* map = reinterpret_cast<float*>(smem_raw);
+  float* tiles = map + (size_t)HW * CC;                          // [kBwdStages][TILE]
+  __shared__ uint64_t full_bar[kBwdStages], empty_bar[kBwdStages];
+  __shared__ SampleEnt s_tab[kBwdStages][64];
+  __shared__ int s_maxrank[kBwdStages][2];
+
+  const int b = blockIdx.y, c0 = blockIdx.x * CC;
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  const int cvalid = min(CC, g.C - c0);
+  const unsigned lt = (1u << lane) - 1u;
+
+  for (int i = t; i < HW * CC; i += blockDim.x) map[i] = 0.f;
+  if (t == 0) {
+    for (int s = 0; s < kBwdStages; ++s) {
+      mbar_init(&full_bar[s], 2);          // TMA issue (expect_tx) + "table written"
+      mbar_init(&empty_bar[s], CGN);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  const int beg = seg[b], end = seg[b + 1];
+  const uint32_t tile_bytes = (uint32_t)(cvalid * PP * sizeof(float));
+  const float inv = 1.0f / (float)(g.S - 1);
+
+  if (wid == CGN) {
+    // ---------------- producer warp ----------------
+    for (int ri = beg, k = 0; ri < end; ++ri, ++k) {
+      const int s = k % kBwdStages;
+      if (k >= kBwdStages) mbar_wait(&empty_bar[s], ((k / kBwdStages) - 1) & 1);
+      const int n = __ldg(order + ri);
+      if (lane == 0) {
+        mbar_arrive_expect_tx(&full_bar[s], tile_bytes);
+        bulk_g2s(tiles + (size_t)s * TILE, dout + ((size_t)n * g.C + c0) * PP, tile_bytes, &full_bar[s]);
+      }
+      const float* rp = rois + 5 * (size_t)n;
+      float4 box;
+      box.x = __ldg(rp + 1) * g.sx;
+      box.y = __ldg(rp + 2) * g.sy;
+      box.z = __ldg(rp + 3) * g.sx;
+      box.w = __ldg(rp + 4) * g.sy;
+#pragma unroll
+      for (int pass = 0; pass < 2; ++pass) {
+        const int p = pass * 32 + lane;
+        const bool valid = p < PP;
+        const Corner c = sample_at(box, p / 7, p % 7, inv);
+        const int y0 = min(max(c.y0, -2), 30000), x0 = min(max(c.x0, -2), 30000);
+        const int key = valid ? ((y0 << 16) | (x0 & 0xffff)) : (int)(0x80000000u | (unsigned)lane);
+        const unsigned grp = __match_any_sync(0xffffffffu, key);
+        const int rank = __popc(grp & lt);
+        const int mr = __reduce_max_sync(0xffffffffu, valid ? rank : 0);
+        SampleEnt e;
+        e.yx = key; e.ly = c.ly; e.lx = c.lx; e.rank = rank;
+        s_tab[s][p] = e;
+        if (lane == 0) s_maxrank[s][pass] = mr;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full_bar[s]);
+    }
+  } else {
+    // ---------------- consumer warps ----------------
+    const int cg = wid;
+    const int W = g.W, H = g.H;
+    const bool ch_ok = cg * 4 < cvalid;
+    float4* map4 = reinterpret_cast<float4*>(map);
+    for (int ri = beg, k = 0; ri < end; ++ri, ++k) {
+      const int s = k % kBwdStages;
+      mbar_wait(&full_bar[s], (k / kBwdStages) & 1);
+      const float* tile = tiles + (size_t)s * TILE;
+#pragma unroll
+      for (int pass = 0; pass < 2; ++pass) {
+        const int p = pass * 32 + lane;
+        const bool act = p < PP && ch_ok;
+        const SampleEnt e = s_tab[s][p];
+        const int mr = s_maxrank[s][pass];
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (act) {
+          const int cb = cg * 4;
+          v.x = tile[(cb + 0) * PP + p];
+          v.y = tile[(cb + 1) * PP + p];
+          v.z = tile[(cb + 2) * PP + p];
+          v.w = tile[(cb + 3) * PP + p];
+        }
+        const int y0 = e.yx >> 16, x0 = (int)(short)(e.yx & 0xffff);
+        const bool vx0 = (unsigned)x0 < (unsigned)W, vx1 = (unsigned)(x0 + 1) < (unsigned)W;
+        const bool vy0 = (unsigned)y0 < (unsigned)H, vy1 = (unsigned)(y0 + 1) < (unsigned)H;
+        const float wy0 = 1.f - e.ly, wy1 = e.ly, wx0 = 1.f - e.lx, wx1 = e.lx;
+        const int pbase = y0 * W + x0;
+        for (int rr = 0; rr <= mr; ++rr) {
+          if (act && e.rank == rr) {
+            float4 m00, m01, m10, m11;
+            int o00 = 0, o01 = 0, o10 = 0, o11 = 0;
+            const bool b00 = vy0 && vx0, b01 = vy0 && vx1, b10 = vy1 && vx0, b11 = vy1 && vx1;
+            if (b00) { o00 = map_off<CC>(pbase, cg) >> 2; m00 = map4[o00]; }
+            if (b01) { o01 = map_off<CC>(pbase + 1, cg) >> 2; m01 = map4[o01]; }
+            if (b10) { o10 = map_off<CC>(pbase + W, cg) >> 2; m10 = map4[o10]; }
+            if (b11) { o11 = map_off<CC>(pbase + W + 1, cg) >> 2; m11 = map4[o11]; }
+            if (b00) { const float w = wy0 * wx0; m00.x = fmaf(w, v.x, m00.x); m00.y = fmaf(w, v.y, m00.y); m00.z = fmaf(w, v.z, m00.z); m00.w = fmaf(w, v.w, m00.w); map4[o00] = m00; }
+            if (b01) { const float w = wy0 * wx1; m01.x = fmaf(w, v.x, m01.x); m01.y = fmaf(w, v.y, m01.y); m01.z = fmaf(w, v.z, m01.z); m01.w = fmaf(w, v.w, m01.w); map4[o01] = m01; }
+            if (b10) { const float w = wy1 * wx0; m10.x = fmaf(w, v.x, m10.x); m10.y = fmaf(w, v.y, m10.y); m10.z = fmaf(w, v.z, m10.z); m10.w = fmaf(w, v.w, m10.w); map4[o10] = m10; }
+            if (b11) { const float w = wy1 * wx1; m11.x = fmaf(w, v.x, m11.x); m11.y = fmaf(w, v.y, m11.y); m11.z = fmaf(w, v.z, m11.z); m11.w = fmaf(w, v.w, m11.w); map4[o11] = m11; }
+          }
+          __syncwarp();
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[s]);
+    }
+  }
+  __syncthreads();
+  unstage_map<CC>(map, dbottom + (size_t)b * g.C * HW, c0, g.C, HW);
+}
+
 // ------------------------------------------------------------------ host side
 struct Plan {
   int cc;
@@ -501,6 +646,18 @@ int launch_bwd(const float* dout, const float* rois, const int* seg, const int* 
   return L2S_OK;
 }
 
+template <int CC>
+int launch_bwd_fast(const float* dout, const float* rois, const int* seg, const int* order, float* dbottom,
+                    const CropGeom& g, size_t smem, cudaStream_t st) {
+  auto kern = roi_crop_bwd_fast_kernel<CC>;
+  L2S_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((g.C + CC - 1) / CC, g.B);
+  kern<<<grid, (CC / 4 + 1) * 32, smem, st>>>(dout, rois, seg, order, dbottom, g);
+  L2S_LAUNCH_OK("roi_crop_bwd_fast_kernel");
+  count_launch();
+  return L2S_OK;
+}
+
 }  // namespace
 }  // namespace l2s
 
@@ -513,9 +670,9 @@ extern "C" size_t l2s_roi_crop_workspace_bytes(int B, int N) {
 extern "C" int l2s_roi_crop_fwd(const float* bottom, const float* rois, float* out, uint8_t* argmax, int B,
                                 int C, int H, int W, int N, int pool, int flags, float im_h, float im_w,
                                 void* workspace, size_t workspace_bytes, l2s_stream_t stream) {
+  if (N == 0) return L2S_OK;
   int rc = check_common(bottom, rois, out, B, C, H, W, N, pool, flags, im_h, im_w, workspace, workspace_bytes);
   if (rc) return rc;
-  if (N == 0) return L2S_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const CropGeom g = make_geom(B, C, H, W, N, pool, flags, im_h, im_w);
   Plan pl;
@@ -535,14 +692,15 @@ extern "C" int l2s_roi_crop_fwd(const float* bottom, const float* rois, float* o
 extern "C" int l2s_roi_crop_bwd(const float* dout, const float* rois, const uint8_t* argmax, float* dbottom,
                                 int B, int C, int H, int W, int N, int pool, int flags, float im_h, float im_w,
                                 void* workspace, size_t workspace_bytes, l2s_stream_t stream) {
-  int rc = check_common(dbottom, rois, dout ? (const void*)dout : (const void*)dbottom, B, C, H, W, N, pool, flags,
-                        im_h, im_w, workspace, workspace_bytes);
-  if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   if (N == 0) {
+    L2S_REQUIRE(dbottom && B > 0 && C > 0 && H > 0 && W > 0, L2S_ERR_ARG, "roi_crop_bwd: bad arguments");
     L2S_CUDA_OK(cudaMemsetAsync(dbottom, 0, (size_t)B * C * H * W * sizeof(float), st));
     return L2S_OK;
   }
+  int rc = check_common(dbottom, rois, dout ? (const void*)dout : (const void*)dbottom, B, C, H, W, N, pool, flags,
+                        im_h, im_w, workspace, workspace_bytes);
+  if (rc) return rc;
   L2S_REQUIRE(dout, L2S_ERR_ARG, "roi_crop_bwd: null dout");
   const CropGeom g = make_geom(B, C, H, W, N, pool, flags, im_h, im_w);
   L2S_REQUIRE(!g.maxpool || argmax, L2S_ERR_ARG, "roi_crop_bwd: max-pool mode needs the argmax of the forward");
@@ -552,6 +710,14 @@ extern "C" int l2s_roi_crop_bwd(const float* dout, const float* rois, const uint
   int *seg, *order;
   rc = bin_rois(rois, B, N, workspace, st, &seg, &order);
   if (rc) return rc;
+  if (!g.maxpool) {
+    switch (pl.cc) {
+      case 32: return launch_bwd_fast<32>(dout, rois, seg, order, dbottom, g, pl.smem_bwd, st);
+      case 16: return launch_bwd_fast<16>(dout, rois, seg, order, dbottom, g, pl.smem_bwd, st);
+      case 8: return launch_bwd_fast<8>(dout, rois, seg, order, dbottom, g, pl.smem_bwd, st);
+      default: return launch_bwd_fast<4>(dout, rois, seg, order, dbottom, g, pl.smem_bwd, st);
+    }
+  }
   switch (pl.cc) {
     case 32: return launch_bwd<32, 2>(dout, rois, seg, order, argmax, dbottom, g, pl.smem_bwd, st);
     case 16: return launch_bwd<16, 4>(dout, rois, seg, order, argmax, dbottom, g, pl.smem_bwd, st);

@@ -395,6 +395,47 @@ def gemm_bf16x3(a_hi, a_lo, b_hi, b_lo, M, N, K, a_mn=False, b_mn=False, epilogu
     return D
 
 
+class _LinearTC(torch.autograd.Function):
+    """y = x @ w.T + b on the tcgen05 bf16x3 GEMM; both gradients read the saved bf16 planes in place
+    through MN-major descriptors (no transposes)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        x, w = f32c(x), f32c(w)
+        M, K = x.shape
+        N = w.shape[0]
+        xh, xl = split_bf16(x)
+        wh, wl = split_bf16(w)
+        bias = f32c(b) if b is not None else None
+        y = gemm_bf16x3(xh, xl, wh, wl, M, N, K, epilogue=4 if bias is not None else 0, bias=bias)
+        ctx.save_for_backward(xh, xl, wh, wl)
+        ctx.has_bias = b is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xh, xl, wh, wl = ctx.saved_tensors
+        M, K = xh.shape
+        N = wh.shape[0]
+        dy = f32c(dy)
+        dyh, dyl = split_bf16(dy)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = gemm_bf16x3(dyh, dyl, wh, wl, M, K, N, a_mn=False, b_mn=True)           # dY [M,N] . W [N,K]
+        if ctx.needs_input_grad[1]:
+            tiles = ((N + 127) // 128) * ((K + 255) // 256)
+            dw = gemm_bf16x3(dyh, dyl, xh, xl, N, K, M, a_mn=True, b_mn=True,
+                             split_k=max(1, min(16, 296 // max(tiles, 1))))                # dY^T [N,M] . X [M,K]
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dy.sum(0)
+        return dx, dw, db
+
+
+def linear(x, weight, bias=None):
+    """nn.Linear forward/backward for large row counts on the tensor pipe at fp32 accuracy (bf16x3)."""
+    return _LinearTC.apply(x, weight, bias)
+
+
 def gemm_f32(A, B, accumulate=False, out=None):
     """D = A @ B.T with A (M,K), B (N,K), exact fp32 FFMA."""
     A, B = f32c(A), f32c(B)

@@ -24,18 +24,28 @@ class RNNEncoder(nn.Module):
                                                  dropout=dropout_p if n_layers > 1 else 0)
         self.num_dirs = 2 if bidirectional else 1
 
+    def train(self, mode=True):
+        # cuDNN refuses RNN backward in eval mode; with one layer the LSTM has no dropout, so keeping the
+        # LSTM itself in training mode changes nothing numerically (parity runs use eval())
+        super().train(mode)
+        if self.rnn.num_layers == 1:
+            self.rnn.train(True)
+        return self
+
     def forward(self, input_labels):
         """input_labels (B,L) int64 zero padded -> output (B,L,H*dirs), hidden (B,layers*dirs*H), embedded (B,L,Dw)"""
         B, L = input_labels.shape
         vec = self.mlp(self.input_dropout(self.embedding(input_labels)))
         if not self.variable_lengths:
-            output, hidden = self.rnn(vec)
+            with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+                output, hidden = self.rnn(vec)
             return output, hidden, vec
         lengths = (input_labels != 0).sum(1)
         lens_cpu = lengths.cpu()
         assert int(lens_cpu.max()) == L, "labels must be trimmed to the longest expression (lang_encoder.py:45)"
         packed = pack_padded_sequence(vec, lens_cpu, batch_first=True, enforce_sorted=False)
-        output, hidden = self.rnn(packed)
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):     # fp32 parity: no TF32 inside cuDNN
+            output, hidden = self.rnn(packed)
         output, _ = pad_packed_sequence(output, batch_first=True, total_length=L)
         if self.rnn_type == "lstm":
             hidden = hidden[0]

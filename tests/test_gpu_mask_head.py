@@ -89,3 +89,21 @@ def test_mask_head_full_size_vs_oracle(n):
     ref, out = run("cpu"), run("cuda")
     for name, a, b in zip(["score", "prob", "loss", "dx", "d_up_w", "d_up_b", "d_pred_w", "d_pred_b"], out, ref):
         assert relerr(a, b) < TOL, name
+
+
+def test_linear_tc_vs_fp64():
+    import lang2seg_b200.functional as F
+    g = torch.Generator().manual_seed(4)
+    M, K, N = 1960, 4096, 512
+    x = torch.relu(torch.randn(M, K, generator=g))
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g)
+    G = torch.randn(M, N, generator=g)
+    xs, ws, bs = (t.cuda().requires_grad_(True) for t in (x, w, b))
+    y = F.linear(xs, ws, bs)
+    gx, gw, gb = torch.autograd.grad((y * G.cuda()).sum(), [xs, ws, bs])
+    xd, wd, bd, Gd = x.double(), w.double(), b.double(), G.double()
+    assert relerr(y, xd @ wd.t() + bd) < 3e-5
+    assert relerr(gx, Gd @ wd) < 3e-5
+    assert relerr(gw, Gd.t() @ xd) < 3e-5
+    assert relerr(gb, Gd.sum(0)) < 1e-5

@@ -50,6 +50,14 @@ def test_crop_vs_oracle(shape, max_pool):
     bo = bottom.clone().requires_grad_(True)
     ref = R.crop_pool(bo, rois, max_pool=max_pool)
     G = torch.randn(ref.shape, generator=g)
+    if max_pool:
+        # max-pool routing is discontinuous: where the two best samples of a 2x2 window are closer than the
+        # coordinate rounding noise, the winner may legitimately differ -- give those windows no gradient
+        with torch.no_grad():
+            s14 = R.crop_pool(bottom, rois, max_pool=False, pool=14)
+            win = s14.unfold(2, 2, 2).unfold(3, 2, 2).reshape(*ref.shape, 4)
+            top2 = win.topk(2, dim=-1).values
+            G = G * ((top2[..., 0] - top2[..., 1]) > 1e-3)
     (gref,) = torch.autograd.grad((ref * G).sum(), bo)
     bc = bottom.cuda().requires_grad_(True)
     out = _f().roi_crop(bc, rois.cuda(), max_pool=max_pool)
