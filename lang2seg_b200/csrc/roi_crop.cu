@@ -530,21 +530,29 @@ roi_crop_bwd_fast_kernel(const float* __restrict__ dout, const float* __restrict
         const bool vy0 = (unsigned)y0 < (unsigned)H, vy1 = (unsigned)(y0 + 1) < (unsigned)H;
         const float wy0 = 1.f - e.ly, wy1 = e.ly, wx0 = 1.f - e.lx, wx1 = e.lx;
         const int pbase = y0 * W + x0;
-        for (int rr = 0; rr <= mr; ++rr) {
-          if (act && e.rank == rr) {
-            float4 m00, m01, m10, m11;
-            int o00 = 0, o01 = 0, o10 = 0, o11 = 0;
-            const bool b00 = vy0 && vx0, b01 = vy0 && vx1, b10 = vy1 && vx0, b11 = vy1 && vx1;
-            if (b00) { o00 = map_off<CC>(pbase, cg) >> 2; m00 = map4[o00]; }
-            if (b01) { o01 = map_off<CC>(pbase + 1, cg) >> 2; m01 = map4[o01]; }
-            if (b10) { o10 = map_off<CC>(pbase + W, cg) >> 2; m10 = map4[o10]; }
-            if (b11) { o11 = map_off<CC>(pbase + W + 1, cg) >> 2; m11 = map4[o11]; }
-            if (b00) { const float w = wy0 * wx0; m00.x = fmaf(w, v.x, m00.x); m00.y = fmaf(w, v.y, m00.y); m00.z = fmaf(w, v.z, m00.z); m00.w = fmaf(w, v.w, m00.w); map4[o00] = m00; }
-            if (b01) { const float w = wy0 * wx1; m01.x = fmaf(w, v.x, m01.x); m01.y = fmaf(w, v.y, m01.y); m01.z = fmaf(w, v.z, m01.z); m01.w = fmaf(w, v.w, m01.w); map4[o01] = m01; }
-            if (b10) { const float w = wy1 * wx0; m10.x = fmaf(w, v.x, m10.x); m10.y = fmaf(w, v.y, m10.y); m10.z = fmaf(w, v.z, m10.z); m10.w = fmaf(w, v.w, m10.w); map4[o10] = m10; }
-            if (b11) { const float w = wy1 * wx1; m11.x = fmaf(w, v.x, m11.x); m11.y = fmaf(w, v.y, m11.y); m11.z = fmaf(w, v.z, m11.z); m11.w = fmaf(w, v.w, m11.w); map4[o11] = m11; }
+        // Two samples of equal rank have different (y0,x0) but may still meet in one pixel through
+        // DIFFERENT corners (A's (y0+1,x0+1) is B's (y0,x0)); so the four corners are four separate
+        // read-modify-write phases with a warp barrier between them.  Inside one phase a pixel is
+        // reached only by samples of the same (y0,x0), which carry distinct ranks.
+        const bool b00 = vy0 && vx0, b01 = vy0 && vx1, b10 = vy1 && vx0, b11 = vy1 && vx1;
+        auto rmw = [&](bool on, int px, float w) {
+          if (on) {
+            const int o = map_off<CC>(px, cg) >> 2;
+            float4 m = map4[o];
+            m.x = fmaf(w, v.x, m.x);
+            m.y = fmaf(w, v.y, m.y);
+            m.z = fmaf(w, v.z, m.z);
+            m.w = fmaf(w, v.w, m.w);
+            map4[o] = m;
           }
           __syncwarp();
+        };
+        for (int rr = 0; rr <= mr; ++rr) {
+          const bool sel = act && e.rank == rr;
+          rmw(sel && b00, pbase, wy0 * wx0);
+          rmw(sel && b01, pbase + 1, wy0 * wx1);
+          rmw(sel && b10, pbase + W, wy1 * wx0);
+          rmw(sel && b11, pbase + W + 1, wy1 * wx1);
         }
       }
       __syncwarp();
