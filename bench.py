@@ -219,7 +219,7 @@ def component_rooflines(wl, d, step, pk):
     # --- ROI crop
     N = E * Rn
     pool = torch.empty(N, C, 7, 7, device=dev)
-    nb2 = _lib.size("l2s_roi_crop_workspace_bytes", E, N)
+    nb2 = _lib.size("l2s_roi_crop_workspace_bytes", E, N, 0)
     ws2 = torch.empty(nb2, dtype=torch.uint8, device=dev)
     t = ev_time(lambda: call("l2s_roi_crop_fwd", ptr(Y), ptr(d["rois"]), ptr(pool), None, E, C, H, W, N, 7, 0, 0.0, 0.0,
                              ptr(ws2), nb2, stream()))

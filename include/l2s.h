@@ -41,6 +41,8 @@ typedef void* l2s_stream_t; /* cudaStream_t */
 #define L2S_GATE_LINEAR 1   /* Y = X * r           network_7f.py:534, network_cycle_res5_2.py:562 */
 #define L2S_CROP_MAX_POOL 1 /* 2S x 2S samples then 2x2 max (network_cycle_response.py:140-144) */
 #define L2S_CROP_ALIGN 2    /* _crop_pool_layer_align (network_cycle_response.py:151-182)  */
+#define L2S_CROP_BWD_RANKED 4 /* backward only: force the sample-per-lane (ranked) kernel even where the row-owner
+                               * kernel applies (maps <= ~1700 pixels, no max-pool); for tests / comparison */
 
 int l2s_version(void);
 const char* l2s_last_error_string(void);
@@ -91,9 +93,10 @@ int l2s_dynfilter_bwd(const float* X, const float* filt, const float* fuse, cons
  *   out (N,C,pool,pool) ; argmax (N,C,pool,pool) uint8 winner of each 2x2 block, only with
  *   L2S_CROP_MAX_POOL (may be NULL when no backward is needed) ;
  *   im_h, im_w: image size, used only with L2S_CROP_ALIGN.
- *   workspace: l2s_roi_crop_workspace_bytes(B,N).
+ *   workspace: l2s_roi_crop_workspace_bytes(B,N,flags), 16-byte aligned: ROI binning by batch index and one
+ *   geometry record per ROI (corner slots + bilinear fractions + collision ranks), rebuilt by every call.
  * ------------------------------------------------------------------------------------- */
-size_t l2s_roi_crop_workspace_bytes(int B, int N);
+size_t l2s_roi_crop_workspace_bytes(int B, int N, int flags);
 int l2s_roi_crop_fwd(const float* bottom, const float* rois, float* out, uint8_t* argmax, int B, int C,
                      int H, int W, int N, int pool, int flags, float im_h, float im_w, void* workspace,
                      size_t workspace_bytes, l2s_stream_t stream);
@@ -200,6 +203,48 @@ int l2s_att2in2_gates_fwd(const float* sums, const float* a2c_out, const float* 
 int l2s_att2in2_gates_bwd(const float* sums, const float* a2c_out, const float* c_prev, const float* c,
                           const float* dh, const float* dc, float* dsums, float* da2c, float* dc_prev,
                           int B, int D, l2s_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * att2in2 decode loop.  Replaces the T-step recurrence of AttModel.forward
+ * (lib/caption_models/AttModel.py:75-99) with Att2in2Core.forward (:446-466) and Attention.forward
+ * (:406-423) inside it, as one call per direction (4 kernel launches per token, issued by the library).
+ * The caller hoists what does not depend on the state: i2h(xt) for all t, logit/log-softmax/NLL for
+ * all t, and every weight gradient (GEMMs over the stacked T*B rows of the buffers below).
+ *
+ *   LC = Dh + 5*D ; requires D == Dh (both rnn_size = att_hid_size = 512 in att2in2).
+ *   cat_all  (T,B,LC)  in/out: on entry row (t,b) = [ b_h2att | i2h(x_t)+b_i2h+b_h2h ] ; on exit
+ *                      [ att_h_t | sums_t ] (h_{t-1} . [W_h2att;W_h2h]^T added for t >= 1) -- kept for bwd
+ *   w_cat    (LC,D)    rows [h2att.weight ; h2h.weight] ;  w_a2c (2D,D), b_a2c (2D)
+ *   alpha_w (Dh), alpha_b (1) ; att_feats (B,A,D), p_att (B,A,Dh)
+ *   outputs / saved: h_all, c_all (T,B,D) ; a2c_all (T,B,2D) ; pi_all (T,B,A) softmax weights ;
+ *                    att_res_all (T,B,D)
+ * backward: dh_all (T,B,D) gradient on every h_t (from the logit layer) ;
+ *   w_cat_t (D,LC) and w_a2c_t (D,2D) are the TRANSPOSED weights ;
+ *   dcat_all (T,B,LC) = [datt_h_t | dsums_t] ; da2c_all (T,B,2D) ; dres_all (T,B,D) = datt_res_t ;
+ *   de_all (T,B,A) score gradients ; dp_att, datt_feats (B,A,D) and dalpha_w (Dh) are OVERWRITTEN.
+ *   Weight gradients follow as  dW_cat = dcat_all[1:]^T . h_all[:-1],  dW_a2c = da2c_all^T . att_res_all,
+ *   db_h2att = sum dcat[:, :Dh], d(i2h) = dcat[:, Dh:], db_a2c = sum da2c, dalpha_b = sum de_all.
+ * workspace: l2s_att2in2_decode_workspace_bytes() for both directions.
+ * ------------------------------------------------------------------------------------- */
+size_t l2s_att2in2_decode_workspace_bytes(int T, int B, int A, int D, int Dh);
+int l2s_att2in2_decode_fwd(float* cat_all, const float* att_feats, const float* p_att, const float* w_cat,
+                           const float* w_a2c, const float* b_a2c, const float* alpha_w, const float* alpha_b,
+                           float* h_all, float* c_all, float* a2c_all, float* pi_all, float* att_res_all, int T,
+                           int B, int A, int D, int Dh, void* workspace, size_t workspace_bytes,
+                           l2s_stream_t stream);
+int l2s_att2in2_decode_bwd(const float* dh_all, const float* cat_all, const float* att_feats, const float* p_att,
+                           const float* w_cat_t, const float* w_a2c_t, const float* alpha_w, const float* c_all,
+                           const float* a2c_all, const float* pi_all, float* dcat_all, float* da2c_all,
+                           float* dres_all, float* de_all, float* dp_att, float* datt_feats, float* dalpha_w, int T,
+                           int B, int A, int D, int Dh, void* workspace, size_t workspace_bytes,
+                           l2s_stream_t stream);
+
+/* Skinny exact-fp32 linear layer used inside the decode loop (nn.Linear on a batch of <= a few hundred
+ * rows): D[M,N] (+)= A[M,K] . W[N,K]^T + bias[N].  K, lda, ldw multiples of 4; deterministic split-K. */
+size_t l2s_linear_small_workspace_bytes(int M, int N, int K);
+int l2s_linear_small(const float* A, const float* W, const float* bias, float* D, int M, int N, int K, int lda,
+                     int ldw, int ldd, int accumulate, void* workspace, size_t workspace_bytes,
+                     l2s_stream_t stream);
 
 /* log-softmax + masked NLL (AttModel.py:98 + lib/misc/utils.py:43-53) on logits (R,V):
  *   logp = log_softmax(logits) (written when non-NULL) ; nll[r] = -logp[r,target[r]]*mask[r]

@@ -20,7 +20,7 @@ SIGNATURES = {
     "l2s_dynfilter_fwd": (_i, [_vp] * 9 + [_i] * 6 + [_vp]),
     "l2s_dynfilter_bwd_workspace_bytes": (_sz, [_i] * 5),
     "l2s_dynfilter_bwd": (_i, [_vp] * 13 + [_i] * 6 + [_vp, _sz, _vp]),
-    "l2s_roi_crop_workspace_bytes": (_sz, [_i, _i]),
+    "l2s_roi_crop_workspace_bytes": (_sz, [_i, _i, _i]),
     "l2s_roi_crop_fwd": (_i, [_vp] * 4 + [_i] * 7 + [_f, _f, _vp, _sz, _vp]),
     "l2s_roi_crop_bwd": (_i, [_vp] * 4 + [_i] * 7 + [_f, _f, _vp, _sz, _vp]),
     "l2s_roi_maxpool_fwd": (_i, [_i, _i, _f] + [_vp] * 4 + [_i] * 5 + [_vp]),
@@ -38,6 +38,11 @@ SIGNATURES = {
     "l2s_att_step_bwd": (_i, [_vp] * 11 + [_i] * 4 + [_vp]),
     "l2s_att2in2_gates_fwd": (_i, [_vp] * 5 + [_i] * 2 + [_vp]),
     "l2s_att2in2_gates_bwd": (_i, [_vp] * 9 + [_i] * 2 + [_vp]),
+    "l2s_att2in2_decode_workspace_bytes": (_sz, [_i] * 5),
+    "l2s_att2in2_decode_fwd": (_i, [_vp] * 13 + [_i] * 5 + [_vp, _sz, _vp]),
+    "l2s_att2in2_decode_bwd": (_i, [_vp] * 17 + [_i] * 5 + [_vp, _sz, _vp]),
+    "l2s_linear_small_workspace_bytes": (_sz, [_i] * 3),
+    "l2s_linear_small": (_i, [_vp] * 4 + [_i] * 7 + [_vp, _sz, _vp]),
     "l2s_logsoftmax_nll_fwd": (_i, [_vp] * 5 + [_i] * 2 + [_vp]),
     "l2s_logsoftmax_nll_bwd": (_i, [_vp] * 5 + [_i] * 2 + [_vp]),
     "l2s_caption_feats_fwd": (_i, [_vp] * 3 + [_i] * 7 + [_vp]),

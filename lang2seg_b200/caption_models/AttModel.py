@@ -111,27 +111,63 @@ class AttModel(nn.Module):
         p_att = p_att.view(*(att.size()[:-1] + (self.att_hid_size,)))
         return fc_feats, att, p_att
 
-    def forward(self, fc_feats, att_feats, seq):
-        """fc_feats (B,F) ; att_feats (B,14,14,F) ; seq (B,L+2) -> log-probs (B,T,V+1)."""
+    def _fast_decode_ok(self, att):
+        core = self.core
+        return (att.is_cuda and isinstance(core, Att2in2Core) and self.num_layers == 1
+                and self.rnn_size == self.att_hid_size and self.rnn_size % 4 == 0 and self.rnn_size <= 1024)
+
+    def _decode(self, att, p_att, seq, T):
+        """All T steps of the recurrence through l2s_att2in2_decode_{fwd,bwd}: i2h(x_t) for every t is one GEMM,
+        the state-dependent part is four launches per token inside the library.  Returns dropout(h_t) (T,B,D)."""
+        core = self.core
+        B = att.size(0)
+        xt = self.embed(seq[:, :T].t())                                   # (T,B,E): Embedding+ReLU+Dropout (:95)
+        bias = core.i2h.bias + core.h2h.bias
+        x2 = xt.reshape(T * B, -1)
+        if x2.shape[0] >= 512 and x2.shape[1] % 8 == 0:
+            i2h_all = L2F.linear(x2, core.i2h.weight, bias)
+        else:
+            i2h_all = F.linear(x2, core.i2h.weight, bias)
+        att3 = att.reshape(B, -1, self.rnn_size)
+        h_all = L2F.att2in2_decode(i2h_all.view(T, B, -1), att3, p_att.reshape(B, -1, self.att_hid_size),
+                                   core.attention.h2att.weight, core.attention.h2att.bias, core.h2h.weight,
+                                   core.a2c.weight, core.a2c.bias, core.attention.alpha_net.weight,
+                                   core.attention.alpha_net.bias)
+        return core.dropout(h_all)
+
+    def forward(self, fc_feats, att_feats, seq, steps=None):
+        """fc_feats (B,F) ; att_feats (B,14,14,F) ; seq (B,L+2) -> log-probs (B,T,V+1).
+        `steps`: host-known T (skips the device->host read of decode_steps)."""
         B = fc_feats.size(0)
-        state = self.init_hidden(B)
         fc_feats, att, p_att = self._prepare(fc_feats, att_feats)
+        T = int(steps) if steps is not None else self.decode_steps(seq)
+        if self._fast_decode_ok(att):
+            out = self._decode(att, p_att, seq, T)                        # (T,B,D)
+            logits = self._big_linear(self.logit, out.reshape(T * B, -1))
+            logp = F.log_softmax(logits, dim=1) if torch.is_grad_enabled() else L2F.log_softmax(logits)
+            return logp.view(T, B, -1).transpose(0, 1)
+        state = self.init_hidden(B)
         outputs = []
-        for i in range(self.decode_steps(seq)):
+        for i in range(T):
             xt = self.embed(seq[:, i])
             output, state = self.core(xt, fc_feats, att, p_att, state)
             outputs.append(L2F.log_softmax(self.logit(output)) if not torch.is_grad_enabled()
                            else F.log_softmax(self.logit(output), dim=1))
         return torch.stack(outputs, 1)
 
-    def forward_loss(self, fc_feats, att_feats, seq, masks):
+    def forward_loss(self, fc_feats, att_feats, seq, masks, steps=None):
         """crit(model(fc, att, seq), seq[:,1:], masks[:,1:]) of network_cycle_response.py:443 without
-        materialising the (B,T,V+1) log-probs: per step logit -> fused log-softmax + masked NLL."""
+        materialising the (B,T,V+1) log-probs: logit for all steps -> fused log-softmax + masked NLL."""
         B = fc_feats.size(0)
-        state = self.init_hidden(B)
         fc_feats, att, p_att = self._prepare(fc_feats, att_feats)
-        T = self.decode_steps(seq)
+        T = int(steps) if steps is not None else self.decode_steps(seq)
         masks = masks.to(att.dtype)
+        if self._fast_decode_ok(att):
+            out = self._decode(att, p_att, seq, T)
+            logits = self._big_linear(self.logit, out.reshape(T * B, -1))
+            nll, _ = L2F.logsoftmax_nll(logits, seq[:, 1:T + 1].t().reshape(-1), masks[:, 1:T + 1].t().reshape(-1))
+            return nll / masks[:, 1:T + 1].sum()
+        state = self.init_hidden(B)
         total = att.new_zeros(())
         for i in range(T):
             xt = self.embed(seq[:, i])

@@ -25,6 +25,8 @@ constexpr int kMaxLoc = 256;   // locations per CTA slice held in smem
 
 struct AttGeom {
   int B, A, D, Dh;
+  int ldh;     // row stride of att_h (>= Dh): the decode loop reads it in place from the [att_h | sums] buffer
+  int ld_dah;  // row stride of the datt_h output
 };
 
 __device__ __forceinline__ void slice(int A, int rank, int* a0, int* a1) {
@@ -55,7 +57,7 @@ att_step_fwd_kernel(const float* __restrict__ att_h, const float* __restrict__ a
   slice(g.A, rank, &a0, &a1);
   const int na = a1 - a0;
   for (int d = t; d < g.Dh; d += kAttThreads) {
-    s_ah[d] = __ldg(att_h + (size_t)b * g.Dh + d);
+    s_ah[d] = __ldg(att_h + (size_t)b * g.ldh + d);
     s_aw[d] = __ldg(alpha_w + d);
   }
   __syncthreads();
@@ -171,7 +173,7 @@ att_step_bwd_kernel(const float* __restrict__ datt_res, const float* __restrict_
   slice(g.A, rank, &a0, &a1);
   const int na = a1 - a0;
   for (int d = t; d < g.Dh; d += kAttThreads) {
-    s_ah[d] = __ldg(att_h + (size_t)b * g.Dh + d);
+    s_ah[d] = __ldg(att_h + (size_t)b * g.ldh + d);
     s_aw[d] = __ldg(alpha_w + d);
   }
   for (int d = t; d < g.D; d += kAttThreads) s_do[d] = __ldg(datt_res + (size_t)b * g.D + d);
@@ -223,11 +225,20 @@ att_step_bwd_kernel(const float* __restrict__ datt_res, const float* __restrict_
   }
   __syncthreads();
   // g[a,d] = de_a * alpha_d * (1 - th^2): column sums -> d att_h ; de_a*th -> d alpha_w ; += d p_att
-  for (int q = t; q < g.Dh / 4; q += kAttThreads) {
+  // thread = (float4 column group q, location phase ph): nph phases split the locations of the slice so
+  // that all 256 threads work when Dh/4 < 256; the phases' column sums meet in shared memory.
+  const int nq = g.Dh / 4;
+  const int nph = (nq <= kAttThreads / 2) ? 2 : 1;
+  const int items = nq * nph;
+  for (int base = 0; base < items; base += kAttThreads) {      // uniform trip count: barriers inside
+    const int qq = base + t;
+    const bool on = qq < items;
+    const int q = on ? qq % nq : 0, ph = on ? qq / nq : 0;
     const float4 h = reinterpret_cast<const float4*>(s_ah)[q];
     const float4 w = reinterpret_cast<const float4*>(s_aw)[q];
     float4 dah = make_float4(0.f, 0.f, 0.f, 0.f), daw = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int a = 0; a < na; ++a) {
+#pragma unroll 2
+    for (int a = on ? ph : na; a < na; a += nph) {
       const size_t off = ((size_t)b * g.A + a0 + a) * g.Dh;
       const float4 p = __ldg(reinterpret_cast<const float4*>(p_att + off) + q);
       const float de = s_dpi[a];
@@ -246,8 +257,15 @@ att_step_bwd_kernel(const float* __restrict__ datt_res, const float* __restrict_
         *gp = o;
       }
     }
-    reinterpret_cast<float4*>(s_dah)[q] = dah;
-    if (dalpha_w) {
+    // two phases at most: phase 1 adds after phase 0 stored (ordered by the barrier below)
+    if (on && ph == 0) reinterpret_cast<float4*>(s_dah)[q] = dah;
+    __syncthreads();
+    if (on && ph == 1) {
+      float4 o = reinterpret_cast<float4*>(s_dah)[q];
+      o.x += dah.x; o.y += dah.y; o.z += dah.z; o.w += dah.w;
+      reinterpret_cast<float4*>(s_dah)[q] = o;
+    }
+    if (on && dalpha_w) {
       atomicAdd(dalpha_w + 4 * q + 0, daw.x);
       atomicAdd(dalpha_w + 4 * q + 1, daw.y);
       atomicAdd(dalpha_w + 4 * q + 2, daw.z);
@@ -260,48 +278,51 @@ att_step_bwd_kernel(const float* __restrict__ datt_res, const float* __restrict_
     float v = 0.f;
 #pragma unroll
     for (int r = 0; r < kCluster; ++r) v += cluster.map_shared_rank(s_dah, r)[d];
-    datt_h[(size_t)b * g.Dh + d] = v;
+    datt_h[(size_t)b * g.ld_dah + d] = v;
   }
   cluster.sync();
 }
 
 // ------------------------------------------------------------------------------- gates
-__global__ void gates_fwd_kernel(const float* __restrict__ sums, const float* __restrict__ a2c,
+// sums has row stride lds (the decode loop keeps [att_h | sums] rows in one buffer); c_prev may be
+// NULL (zero state at t = 0); dh = dh_a + dh_b (either may be NULL); dsums has row stride ld_ds.
+__global__ void gates_fwd_kernel(const float* __restrict__ sums, int lds, const float* __restrict__ a2c,
                                  const float* __restrict__ c_prev, float* __restrict__ h, float* __restrict__ c,
                                  int B, int D) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * D) return;
   const int b = idx / D, d = idx - b * D;
-  const float* s = sums + (size_t)b * 5 * D;
+  const float* s = sums + (size_t)b * lds;
   const float ig = sigmoidf_acc(s[d]), fg = sigmoidf_acc(s[D + d]), og = sigmoidf_acc(s[2 * D + d]);
   const float g1 = s[3 * D + d] + a2c[(size_t)b * 2 * D + d];
   const float g2 = s[4 * D + d] + a2c[(size_t)b * 2 * D + D + d];
   const float gg = fmaxf(g1, g2);
-  const float cn = fmaf(fg, c_prev[idx], ig * gg);
+  const float cp = c_prev ? c_prev[idx] : 0.f;
+  const float cn = fmaf(fg, cp, ig * gg);
   c[idx] = cn;
   h[idx] = og * tanhf(cn);
 }
 
-__global__ void gates_bwd_kernel(const float* __restrict__ sums, const float* __restrict__ a2c,
+__global__ void gates_bwd_kernel(const float* __restrict__ sums, int lds, const float* __restrict__ a2c,
                                  const float* __restrict__ c_prev, const float* __restrict__ c,
-                                 const float* __restrict__ dh, const float* __restrict__ dc,
-                                 float* __restrict__ dsums, float* __restrict__ da2c, float* __restrict__ dc_prev,
-                                 int B, int D) {
+                                 const float* __restrict__ dh_a, const float* __restrict__ dh_b,
+                                 const float* __restrict__ dc, float* __restrict__ dsums, int ld_ds,
+                                 float* __restrict__ da2c, float* __restrict__ dc_prev, int B, int D) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * D) return;
   const int b = idx / D, d = idx - b * D;
-  const float* s = sums + (size_t)b * 5 * D;
-  float* ds = dsums + (size_t)b * 5 * D;
+  const float* s = sums + (size_t)b * lds;
+  float* ds = dsums + (size_t)b * ld_ds;
   const float ig = sigmoidf_acc(s[d]), fg = sigmoidf_acc(s[D + d]), og = sigmoidf_acc(s[2 * D + d]);
   const float g1 = s[3 * D + d] + a2c[(size_t)b * 2 * D + d];
   const float g2 = s[4 * D + d] + a2c[(size_t)b * 2 * D + D + d];
   const bool first = g1 >= g2;
   const float gg = first ? g1 : g2;
   const float tc = tanhf(c[idx]);
-  const float gh = dh[idx];
+  const float gh = (dh_a ? dh_a[idx] : 0.f) + (dh_b ? dh_b[idx] : 0.f);
   const float dct = (dc ? dc[idx] : 0.f) + gh * og * (1.f - tc * tc);
   ds[d] = dct * gg * ig * (1.f - ig);
-  ds[D + d] = dct * c_prev[idx] * fg * (1.f - fg);
+  ds[D + d] = dct * (c_prev ? c_prev[idx] : 0.f) * fg * (1.f - fg);
   ds[2 * D + d] = gh * tc * og * (1.f - og);
   const float dg = dct * ig;
   ds[3 * D + d] = first ? dg : 0.f;
@@ -481,55 +502,88 @@ int check_att(int B, int A, int D, int Dh) {
 
 using namespace l2s;
 
-extern "C" int l2s_att_step_fwd(const float* att_h, const float* att_feats, const float* p_att, const float* alpha_w,
-                                const float* alpha_b, float* weight, float* att_res, int B, int A, int D, int Dh,
-                                l2s_stream_t stream) {
+// ---- internal launchers (also used by the decode loop in decode.cu; declared in common.cuh) ----
+namespace l2s {
+
+int launch_att_step_fwd(const float* att_h, int ldh, const float* att_feats, const float* p_att, const float* alpha_w,
+                        const float* alpha_b, float* weight, float* att_res, int B, int A, int D, int Dh,
+                        cudaStream_t st) {
   L2S_REQUIRE(att_h && att_feats && p_att && alpha_w && alpha_b && weight && att_res, L2S_ERR_ARG, "att_step_fwd: null pointer");
   int rc = check_att(B, A, D, Dh);
   if (rc) return rc;
+  L2S_REQUIRE(ldh >= Dh, L2S_ERR_SHAPE, "att_step_fwd: att_h row stride %d < Dh %d", ldh, Dh);
   L2S_REQUIRE(aligned16(att_feats) && aligned16(p_att), L2S_ERR_ALIGN, "att_step_fwd: att_feats / p_att must be 16-byte aligned");
-  AttGeom g{B, A, D, Dh};
+  AttGeom g{B, A, D, Dh, ldh, Dh};
   void* args[] = {&att_h, &att_feats, &p_att, &alpha_w, &alpha_b, &weight, &att_res, &g};
-  return launch_cluster((const void*)att_step_fwd_kernel, dim3(B * kCluster), (size_t)(2 * Dh + D) * 4,
-                        (cudaStream_t)stream, args);
+  return launch_cluster((const void*)att_step_fwd_kernel, dim3(B * kCluster), (size_t)(2 * Dh + D) * 4, st, args);
 }
 
-extern "C" int l2s_att_step_bwd(const float* datt_res, const float* att_h, const float* att_feats, const float* p_att,
-                                const float* alpha_w, const float* weight, float* datt_h, float* de, float* dp_att,
-                                float* datt_feats, float* dalpha_w, int B, int A, int D, int Dh, l2s_stream_t stream) {
+int launch_att_step_bwd(const float* datt_res, const float* att_h, int ldh, const float* att_feats, const float* p_att,
+                        const float* alpha_w, const float* weight, float* datt_h, int ld_dah, float* de, float* dp_att,
+                        float* datt_feats, float* dalpha_w, int B, int A, int D, int Dh, cudaStream_t st) {
   L2S_REQUIRE(datt_res && att_h && att_feats && p_att && alpha_w && weight && datt_h && de, L2S_ERR_ARG,
               "att_step_bwd: null pointer");
   int rc = check_att(B, A, D, Dh);
   if (rc) return rc;
+  L2S_REQUIRE(ldh >= Dh && ld_dah >= Dh, L2S_ERR_SHAPE, "att_step_bwd: row strides must be >= Dh");
   L2S_REQUIRE(aligned16(att_feats) && aligned16(p_att) && aligned16(dp_att) && aligned16(datt_feats), L2S_ERR_ALIGN,
               "att_step_bwd: feature pointers must be 16-byte aligned");
-  AttGeom g{B, A, D, Dh};
+  AttGeom g{B, A, D, Dh, ldh, ld_dah};
   void* args[] = {&datt_res, &att_h, &att_feats, &p_att, &alpha_w, &weight, &datt_h, &de, &dp_att, &datt_feats,
                   &dalpha_w, &g};
-  return launch_cluster((const void*)att_step_bwd_kernel, dim3(B * kCluster), (size_t)(3 * Dh + D) * 4,
-                        (cudaStream_t)stream, args);
+  return launch_cluster((const void*)att_step_bwd_kernel, dim3(B * kCluster), (size_t)(3 * Dh + D) * 4, st, args);
 }
 
-extern "C" int l2s_att2in2_gates_fwd(const float* sums, const float* a2c_out, const float* c_prev, float* h, float* c,
-                                     int B, int D, l2s_stream_t stream) {
-  L2S_REQUIRE(sums && a2c_out && c_prev && h && c, L2S_ERR_ARG, "gates_fwd: null pointer");
-  L2S_REQUIRE(B > 0 && D > 0, L2S_ERR_SHAPE, "gates_fwd: bad shape");
-  gates_fwd_kernel<<<(B * D + 255) / 256, 256, 0, (cudaStream_t)stream>>>(sums, a2c_out, c_prev, h, c, B, D);
+int launch_gates_fwd(const float* sums, int lds, const float* a2c_out, const float* c_prev, float* h, float* c, int B,
+                     int D, cudaStream_t st) {
+  L2S_REQUIRE(sums && a2c_out && h && c, L2S_ERR_ARG, "gates_fwd: null pointer");
+  L2S_REQUIRE(B > 0 && D > 0 && lds >= 5 * D, L2S_ERR_SHAPE, "gates_fwd: bad shape");
+  gates_fwd_kernel<<<(B * D + 255) / 256, 256, 0, st>>>(sums, lds, a2c_out, c_prev, h, c, B, D);
   L2S_LAUNCH_OK("gates_fwd_kernel");
   count_launch();
   return L2S_OK;
 }
 
-extern "C" int l2s_att2in2_gates_bwd(const float* sums, const float* a2c_out, const float* c_prev, const float* c,
-                                     const float* dh, const float* dc, float* dsums, float* da2c, float* dc_prev,
-                                     int B, int D, l2s_stream_t stream) {
-  L2S_REQUIRE(sums && a2c_out && c_prev && c && dh && dsums && da2c && dc_prev, L2S_ERR_ARG, "gates_bwd: null pointer");
-  L2S_REQUIRE(B > 0 && D > 0, L2S_ERR_SHAPE, "gates_bwd: bad shape");
-  gates_bwd_kernel<<<(B * D + 255) / 256, 256, 0, (cudaStream_t)stream>>>(sums, a2c_out, c_prev, c, dh, dc, dsums,
-                                                                         da2c, dc_prev, B, D);
+int launch_gates_bwd(const float* sums, int lds, const float* a2c_out, const float* c_prev, const float* c,
+                     const float* dh_a, const float* dh_b, const float* dc, float* dsums, int ld_ds, float* da2c,
+                     float* dc_prev, int B, int D, cudaStream_t st) {
+  L2S_REQUIRE(sums && a2c_out && c && (dh_a || dh_b) && dsums && da2c && dc_prev, L2S_ERR_ARG, "gates_bwd: null pointer");
+  L2S_REQUIRE(B > 0 && D > 0 && lds >= 5 * D && ld_ds >= 5 * D, L2S_ERR_SHAPE, "gates_bwd: bad shape");
+  gates_bwd_kernel<<<(B * D + 255) / 256, 256, 0, st>>>(sums, lds, a2c_out, c_prev, c, dh_a, dh_b, dc, dsums, ld_ds,
+                                                        da2c, dc_prev, B, D);
   L2S_LAUNCH_OK("gates_bwd_kernel");
   count_launch();
   return L2S_OK;
+}
+
+}  // namespace l2s
+
+extern "C" int l2s_att_step_fwd(const float* att_h, const float* att_feats, const float* p_att, const float* alpha_w,
+                                const float* alpha_b, float* weight, float* att_res, int B, int A, int D, int Dh,
+                                l2s_stream_t stream) {
+  return launch_att_step_fwd(att_h, Dh, att_feats, p_att, alpha_w, alpha_b, weight, att_res, B, A, D, Dh,
+                             (cudaStream_t)stream);
+}
+
+extern "C" int l2s_att_step_bwd(const float* datt_res, const float* att_h, const float* att_feats, const float* p_att,
+                                const float* alpha_w, const float* weight, float* datt_h, float* de, float* dp_att,
+                                float* datt_feats, float* dalpha_w, int B, int A, int D, int Dh, l2s_stream_t stream) {
+  return launch_att_step_bwd(datt_res, att_h, Dh, att_feats, p_att, alpha_w, weight, datt_h, Dh, de, dp_att,
+                             datt_feats, dalpha_w, B, A, D, Dh, (cudaStream_t)stream);
+}
+
+extern "C" int l2s_att2in2_gates_fwd(const float* sums, const float* a2c_out, const float* c_prev, float* h, float* c,
+                                     int B, int D, l2s_stream_t stream) {
+  L2S_REQUIRE(c_prev, L2S_ERR_ARG, "gates_fwd: null pointer");
+  return launch_gates_fwd(sums, 5 * D, a2c_out, c_prev, h, c, B, D, (cudaStream_t)stream);
+}
+
+extern "C" int l2s_att2in2_gates_bwd(const float* sums, const float* a2c_out, const float* c_prev, const float* c,
+                                     const float* dh, const float* dc, float* dsums, float* da2c, float* dc_prev,
+                                     int B, int D, l2s_stream_t stream) {
+  L2S_REQUIRE(c_prev && dh, L2S_ERR_ARG, "gates_bwd: null pointer");
+  return launch_gates_bwd(sums, 5 * D, a2c_out, c_prev, c, dh, nullptr, dc, dsums, 5 * D, da2c, dc_prev, B, D,
+                          (cudaStream_t)stream);
 }
 
 extern "C" int l2s_logsoftmax_nll_fwd(const float* logits, const int64_t* target, const float* mask, float* logp,

@@ -39,6 +39,19 @@ int  sm_count();
 int  max_smem_optin();
 void count_launch(int n = 1);          // feeds l2s_launch_count()
 
+// ---- internal launchers shared between translation units (att.cu <-> decode.cu) -----------
+int launch_att_step_fwd(const float* att_h, int ldh, const float* att_feats, const float* p_att, const float* alpha_w,
+                        const float* alpha_b, float* weight, float* att_res, int B, int A, int D, int Dh,
+                        cudaStream_t st);
+int launch_att_step_bwd(const float* datt_res, const float* att_h, int ldh, const float* att_feats, const float* p_att,
+                        const float* alpha_w, const float* weight, float* datt_h, int ld_dah, float* de, float* dp_att,
+                        float* datt_feats, float* dalpha_w, int B, int A, int D, int Dh, cudaStream_t st);
+int launch_gates_fwd(const float* sums, int lds, const float* a2c_out, const float* c_prev, float* h, float* c, int B,
+                     int D, cudaStream_t st);
+int launch_gates_bwd(const float* sums, int lds, const float* a2c_out, const float* c_prev, const float* c,
+                     const float* dh_a, const float* dh_b, const float* dc, float* dsums, int ld_ds, float* da2c,
+                     float* dc_prev, int B, int D, cudaStream_t st);
+
 // ---- device helpers --------------------------------------------------------------------
 #ifdef __CUDACC__
 

@@ -6,27 +6,32 @@
 // the map, optional 2x2 max over a 2S x 2S sample grid.  Closed form: SURVEY.md appendix A.2.
 //
 // Design (HBM-bound; the output / upstream gradient is ~12x the size of the map):
-//   * one CTA owns (batch index b, chunk of CC channels) and stages that slice of the map ONCE
-//     in shared memory, transposed to [pixel][channel] with a 16-byte XOR swizzle, then loops
-//     over all ROIs of b.  Map bytes therefore cross L2->SM exactly once per CTA.
-//   * forward: thread = (4-channel group, sample position); four LDS.128 gathers per output
-//     float4, results staged in a [channel][49] tile that is written to HBM with one 1-D TMA
-//     bulk store per ROI (cp.async.bulk.global.shared::cta), double buffered.
-//   * backward: upstream-gradient tiles arrive by TMA bulk loads (mbarrier pipeline, producer
-//     warp).  Every consumer warp exclusively OWNS one (4-channel group, pixel-parity class) of
-//     the shared-memory accumulator map, so plain vectorised read-modify-write is race free
-//     across warps; lanes are sample positions and collisions inside a warp are resolved with
-//     match.any + ranked rounds (warp-aggregated, fixed order => bit-reproducible sums).
-//     No floating-point atomics anywhere (shared fp32 atomicAdd is a CAS loop on sm_100).
+//   * ROIs are binned by batch index (roi_count/order_kernel) and roi_geom_kernel writes ONE geometry
+//     record per ROI: for every sample the four shared-memory slots of its corners (zero slot when the
+//     corner is outside the map) and the two bilinear fractions; for the 7x7 variant also a collision
+//     rank per sample (samples of equal rank never share a corner cell).  Sample geometry does not depend
+//     on the channel, so the 32 channel-chunk CTAs of an expression read it instead of recomputing it.
+//   * one CTA owns (batch index b, chunk of CC channels) and stages that slice of the map ONCE in shared
+//     memory, transposed to [pixel][channel] with a 16-byte XOR swizzle, then loops over all ROIs of b.
+//   * forward: thread = (4-channel group, sample); geometry records arrive by 1-D TMA bulk loads one
+//     iteration ahead; four LDS.128 gathers per output float4; results staged in [channel][49] tiles
+//     that leave by one TMA bulk store per ROI, double buffered.
+//   * backward: upstream-gradient tiles and geometry records arrive by TMA bulk loads through an
+//     mbarrier ring fed by a producer warp.  Consumer warp cg exclusively OWNS channel quad cg of the
+//     shared-memory accumulator map, so plain vectorised read-modify-write is race free across warps;
+//     lanes are samples, the four corners are four phases, and equal-cell samples are serialised by their
+//     precomputed rank (fixed order => bit-reproducible sums).  No floating-point atomics anywhere
+//     (shared fp32 atomicAdd costs 2 cycles per lane on sm_100).
 #include "common.cuh"
 
 namespace l2s {
 namespace {
 
-constexpr int kSlotP = 56;          // sample slots per ROI in the forward kernel (49 used)
-constexpr int kFwdThreads = 896;    // RPI * CGN * kSlotP with RPI * CGN == 16
-constexpr int kBwdStages = 4;
-constexpr int kBoxChunk = 256;      // ROI boxes staged per pass in the forward kernel
+constexpr int kPP = 49;             // outputs per (ROI, channel): cfg.POOLING_SIZE^2
+constexpr int kFwdItems = 32 * kPP; // (ROI, sample, channel quad) items per forward iteration pass: RPI * CGN == 32
+constexpr int kFwdThreads = 800;    // 25 warps: items t and t + 784 ... of an iteration (784 = kFwdItems / 2)
+constexpr int kBwdStages = 6;
+constexpr int kRecTail = 64;        // bytes after the entries of a geometry record: ranks[49], maxrank, ROI id
 
 __device__ __forceinline__ int swz_key(int px) { return (px ^ (px >> 3) ^ (px >> 6)) & 7; }
 
@@ -85,11 +90,13 @@ __global__ void roi_order_kernel(const float* __restrict__ rois, int N, const in
   }
 }
 
+
 struct CropGeom {
   int C, H, W, N, B;
   int S;        // samples per side (pool or 2*pool)
   int maxpool;  // 0/1
   float sx, sy; // image -> feature scale
+  int rec;      // bytes per geometry record = S*S*16 + kRecTail
 };
 
 // sample coordinate -> corner index / weights.  px = x1 + (x2-x1) * j/(S-1) in feature pixels.
@@ -110,8 +117,97 @@ __device__ __forceinline__ Corner sample_at(const float4& box, int i, int j, flo
   return c;
 }
 
+// ------------------------------------------------------------------ geometry records
+// record r (position in `order`):  entries[S*S] | ranks[49] u8 | ... | maxrank u8 @ +60 | ROI id i32 @ +56
+// entry: 4 x u16 float4-slot of the corners (00, 01, 10, 11) for channel quad 0 -- the consumer XORs its
+// quad index in -- or the zero slot HW*CGN when the corner lies outside the map; then ly, lx.
+struct __align__(16) GeomEntry {
+  uint16_t s00, s01, s10, s11;
+  float ly, lx;
+};
+
+// Separable form of the same geometry for the row-owner backward: sample (i,j) sits at (py_i, px_j).
+struct __align__(16) SepRec {
+  int16_t x0[8];
+  float lx[8];
+  int16_t y0[8];
+  float ly[8];
+  int n, ymin, ymax, pad;
+};
+static_assert(sizeof(SepRec) == 112, "SepRec layout");
+
+__global__ void __launch_bounds__(256)
+roi_geom_kernel(const float* __restrict__ rois, const int* __restrict__ order, unsigned char* __restrict__ table,
+                SepRec* __restrict__ sep, CropGeom g, int CGN) {
+  const int r = blockIdx.x, p = threadIdx.x;
+  const int n = __ldg(order + r);
+  const int SS = g.S * g.S;
+  __shared__ int s_key[64];
+  unsigned char* rec = table + (size_t)r * g.rec;
+  const float* rp = rois + 5 * (size_t)n;
+  float4 box;
+  box.x = __ldg(rp + 1) * g.sx;
+  box.y = __ldg(rp + 2) * g.sy;
+  box.z = __ldg(rp + 3) * g.sx;
+  box.w = __ldg(rp + 4) * g.sy;
+  const float inv = 1.0f / (float)(g.S - 1);
+  int key = 0;
+  if (p < SS) {
+    const Corner c = sample_at(box, p / g.S, p % g.S, inv);
+    const int W = g.W, H = g.H, zs = H * W * CGN;
+    const bool vx0 = (unsigned)c.x0 < (unsigned)W, vx1 = (unsigned)(c.x0 + 1) < (unsigned)W;
+    const bool vy0 = (unsigned)c.y0 < (unsigned)H, vy1 = (unsigned)(c.y0 + 1) < (unsigned)H;
+    auto slot = [&](bool ok, int yy, int xx) -> uint16_t {
+      if (!ok) return (uint16_t)zs;
+      const int px = yy * W + xx;
+      return (uint16_t)(px * CGN + (swz_key(px) & (CGN - 1)));
+    };
+    GeomEntry e;
+    e.s00 = slot(vy0 && vx0, c.y0, c.x0);
+    e.s01 = slot(vy0 && vx1, c.y0, c.x0 + 1);
+    e.s10 = slot(vy1 && vx0, c.y0 + 1, c.x0);
+    e.s11 = slot(vy1 && vx1, c.y0 + 1, c.x0 + 1);
+    e.ly = c.ly;
+    e.lx = c.lx;
+    reinterpret_cast<GeomEntry*>(rec)[p] = e;
+    const int y0 = min(max(c.y0, -2), 30000), x0 = min(max(c.x0, -2), 30000);
+    key = (y0 << 16) | (x0 & 0xffff);
+  }
+  if (g.S == 7) {   // launched with 64 threads
+    // collision rank over all 49 samples: number of earlier samples in the same (y0,x0) cell
+    s_key[p] = (p < SS) ? key : (int)(0x80000000u | (unsigned)p);
+    __syncthreads();
+    int rank = 0;
+    if (p < SS)
+      for (int q = 0; q < p; ++q) rank += (s_key[q] == key);
+    __syncthreads();
+    const int mr = __reduce_max_sync(0xffffffffu, p < SS ? rank : 0);
+    if ((p & 31) == 0) s_key[p >> 5] = mr;
+    __syncthreads();
+    unsigned char* tail = rec + (size_t)SS * 16;
+    if (p < SS) tail[p] = (unsigned char)rank;
+    if (p == 0) tail[60] = (unsigned char)max(s_key[0], s_key[1]);
+  }
+  if (p == 0) *reinterpret_cast<int*>(rec + (size_t)SS * 16 + 56) = n;
+  if (sep != nullptr && g.S == 7 && p < 8) {
+    SepRec* sr = sep + r;
+    const Corner c = sample_at(box, min(p, 6), min(p, 6), inv);
+    const int y0 = min(max(c.y0, -2), 30000), x0 = min(max(c.x0, -2), 30000);
+    sr->x0[p] = (int16_t)x0; sr->lx[p] = c.lx;
+    sr->y0[p] = (int16_t)y0; sr->ly[p] = c.ly;
+    if (p == 0) {
+      const Corner c6 = sample_at(box, 6, 6, inv);
+      const int y6 = min(max(c6.y0, -2), 30000);
+      sr->n = n;
+      sr->ymin = min(y0, y6);
+      sr->ymax = max(y0, y6) + 1;
+      sr->pad = 0;
+    }
+  }
+}
+
 // ------------------------------------------------------------------ staging the map slice
-// smem map layout: element (px, c) at px*CC + ((c/4 ^ key(px)) & (CGN-1))*4 + (c&3)
+// smem map: float4 slot (px, cgrp) at px*CGN + ((cgrp ^ key(px)) & (CGN-1)); CGN zero slots follow at px = HW.
 template <int CC>
 __device__ __forceinline__ int map_off(int px, int cgrp) {
   constexpr int CGN = CC / 4;
@@ -122,17 +218,29 @@ template <int CC>
 __device__ void stage_map(float* __restrict__ map, const float* __restrict__ src /* (C,HW) of batch b */,
                           int c0, int C, int HW) {
   constexpr int CGN = CC / 4;
+  constexpr int U = 8;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const int pl = lane & 7, cl = lane >> 3;
   const int nblk = (HW + 7) >> 3;
-  for (int it = wid; it < nblk * CGN; it += nw) {
-    const int g = it % CGN, blk = it / CGN;
-    const int px = blk * 8 + pl, c = c0 + g * 4 + cl;
-    if (px < HW) {
-      const float v = (c < C) ? __ldg(src + (size_t)c * HW + px) : 0.f;
-      map[map_off<CC>(px, g) + cl] = v;
+  const int total = nblk * CGN;
+  for (int it0 = wid; it0 < total; it0 += nw * U) {
+    float v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {       // U independent loads in flight per lane
+      const int it = it0 + u * nw;
+      const int gq = it % CGN, blk = it / CGN;
+      const int px = blk * 8 + pl, c = c0 + gq * 4 + cl;
+      v[u] = (it < total && px < HW && c < C) ? __ldg(src + (size_t)c * HW + px) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int it = it0 + u * nw;
+      const int gq = it % CGN, blk = it / CGN;
+      const int px = blk * 8 + pl;
+      if (it < total && px < HW) map[map_off<CC>(px, gq) + cl] = v[u];
     }
   }
+  for (int i = threadIdx.x; i < CC; i += blockDim.x) map[(size_t)HW * CC + i] = 0.f;   // the zero slots
 }
 
 template <int CC>
@@ -142,321 +250,188 @@ __device__ void unstage_map(const float* __restrict__ map, float* __restrict__ d
   const int pl = lane & 7, cl = lane >> 3;
   const int nblk = (HW + 7) >> 3;
   for (int it = wid; it < nblk * CGN; it += nw) {
-    const int g = it % CGN, blk = it / CGN;
-    const int px = blk * 8 + pl, c = c0 + g * 4 + cl;
-    if (px < HW && c < C) dst[(size_t)c * HW + px] = map[map_off<CC>(px, g) + cl];
+    const int gq = it % CGN, blk = it / CGN;
+    const int px = blk * 8 + pl, c = c0 + gq * 4 + cl;
+    if (px < HW && c < C) dst[(size_t)c * HW + px] = map[map_off<CC>(px, gq) + cl];
   }
 }
 
+__device__ __forceinline__ float4 bilerp4(const float4* __restrict__ map4, const uint4& e, int cg) {
+  const float ly = __uint_as_float(e.z), lx = __uint_as_float(e.w);
+  const float4 a = map4[(e.x & 0xffffu) ^ cg];
+  const float4 b = map4[(e.x >> 16) ^ cg];
+  const float4 c = map4[(e.y & 0xffffu) ^ cg];
+  const float4 d = map4[(e.y >> 16) ^ cg];
+  const float wy0 = 1.f - ly, wx0 = 1.f - lx;
+  const float w00 = wy0 * wx0, w01 = wy0 * lx, w10 = ly * wx0, w11 = ly * lx;
+  float4 o;
+  o.x = fmaf(w11, d.x, fmaf(w10, c.x, fmaf(w01, b.x, w00 * a.x)));
+  o.y = fmaf(w11, d.y, fmaf(w10, c.y, fmaf(w01, b.y, w00 * a.y)));
+  o.z = fmaf(w11, d.z, fmaf(w10, c.z, fmaf(w01, b.z, w00 * a.z)));
+  o.w = fmaf(w11, d.w, fmaf(w10, c.w, fmaf(w01, b.w, w00 * a.w)));
+  return o;
+}
+
 // ------------------------------------------------------------------ forward
-template <int CC>
+// Iteration = kRPI ROIs: kRPI * 49 * CGN (ROI, sample, channel quad) items, up to two per thread.
+// Geometry records arrive through a ring of NT buffers, loaded NT-1 iterations ahead (a bulk load from L2/HBM
+// takes longer than one iteration).
+constexpr int kRPI = 4;
+template <int CC, bool MAXPOOL>
 __global__ void __launch_bounds__(kFwdThreads, 1)
-roi_crop_fwd_kernel(const float* __restrict__ bottom, const float* __restrict__ rois,
-                    const int* __restrict__ seg, const int* __restrict__ order, float* __restrict__ out,
+roi_crop_fwd_kernel(const float* __restrict__ bottom, const int* __restrict__ seg,
+                    const unsigned char* __restrict__ table, float* __restrict__ out,
                     uint8_t* __restrict__ argmax, CropGeom g) {
   constexpr int CGN = CC / 4;
-  constexpr int RPI = 16 / CGN;            // ROIs per iteration
-  constexpr int PP = 49;
-  constexpr int TILE = CC * PP;            // floats per ROI tile
+  constexpr int RPI = kRPI;
+  constexpr int NT = MAXPOOL ? 2 : 4;      // table ring depth
+  constexpr int ITEMS = RPI * kPP * CGN;
+  constexpr int HALF = kFwdItems / 2;      // 784
+  constexpr int TILE = CC * kPP;           // floats per ROI tile
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int HW = g.H * g.W;
   float* map = reinterpret_cast<float*>(smem_raw);
-  float* tiles = map + (size_t)HW * CC;                        // [2][RPI][TILE]
-  uint8_t* atile = reinterpret_cast<uint8_t*>(tiles + 2 * RPI * TILE);   // [2][RPI][TILE] (max-pool only)
+  float* tiles = map + (size_t)(HW + 1) * CC;                               // [2][RPI][TILE]
+  unsigned char* tabs = reinterpret_cast<unsigned char*>(tiles + 2 * RPI * TILE);   // [NT][RPI * rec]
+  uint8_t* atile = tabs + (size_t)NT * RPI * g.rec;                         // [2][RPI][TILE] (max-pool only)
+  __shared__ uint64_t tab_bar[NT];
   __shared__ int s_n[2][RPI];
-  __shared__ float4 s_box[kBoxChunk];
-  __shared__ int s_ni[kBoxChunk];
 
   const int b = blockIdx.y, c0 = blockIdx.x * CC;
   const int t = threadIdx.x;
-  const int slot = t / (CGN * kSlotP), r = t % (CGN * kSlotP);
-  const int cg = r % CGN, p = r / CGN;
-  const int pi = p / 7, pj = p % 7;
   const int cvalid = min(CC, g.C - c0);
+  const int beg = seg[b], end = seg[b + 1];
+  const int nit = (end - beg + RPI - 1) / RPI;
 
+  if (t == 0) {
+    for (int i = 0; i < NT; ++i) mbar_init(&tab_bar[i], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  auto load_tab = [&](int it) {
+    const int gi = beg + it * RPI;
+    const uint32_t bytes = (uint32_t)(min(RPI, end - gi) * g.rec);
+    mbar_arrive_expect_tx(&tab_bar[it % NT], bytes);
+    bulk_g2s(tabs + (size_t)(it % NT) * RPI * g.rec, table + (size_t)gi * g.rec, bytes, &tab_bar[it % NT]);
+  };
+  if (t == 0)
+    for (int i = 0; i < NT - 1 && i < nit; ++i) load_tab(i);
   stage_map<CC>(map, bottom + (size_t)b * g.C * HW, c0, g.C, HW);
   __syncthreads();
 
-  const int beg = seg[b], end = seg[b + 1];
-  const float inv = 1.0f / (float)(g.S - 1);
   const float4* map4 = reinterpret_cast<const float4*>(map);
-  const int W = g.W, H = g.H;
-
-  auto gather = [&](const Corner& c) -> float4 {
-    const bool vx0 = (unsigned)c.x0 < (unsigned)W, vx1 = (unsigned)(c.x0 + 1) < (unsigned)W;
-    const bool vy0 = (unsigned)c.y0 < (unsigned)H, vy1 = (unsigned)(c.y0 + 1) < (unsigned)H;
-    const int xa = min(max(c.x0, 0), W - 1), xb = min(max(c.x0 + 1, 0), W - 1);
-    const int ya = min(max(c.y0, 0), H - 1), yb = min(max(c.y0 + 1, 0), H - 1);
-    const float wy0 = vy0 ? 1.f - c.ly : 0.f, wy1 = vy1 ? c.ly : 0.f;
-    const float wx0 = vx0 ? 1.f - c.lx : 0.f, wx1 = vx1 ? c.lx : 0.f;
-    const int p00 = ya * W + xa, p01 = ya * W + xb, p10 = yb * W + xa, p11 = yb * W + xb;
-    const float4 a = map4[map_off<CC>(p00, cg) >> 2];
-    const float4 bq = map4[map_off<CC>(p01, cg) >> 2];
-    const float4 cq = map4[map_off<CC>(p10, cg) >> 2];
-    const float4 d = map4[map_off<CC>(p11, cg) >> 2];
-    const float w00 = wy0 * wx0, w01 = wy0 * wx1, w10 = wy1 * wx0, w11 = wy1 * wx1;
-    float4 o;
-    o.x = fmaf(w11, d.x, fmaf(w10, cq.x, fmaf(w01, bq.x, w00 * a.x)));
-    o.y = fmaf(w11, d.y, fmaf(w10, cq.y, fmaf(w01, bq.y, w00 * a.y)));
-    o.z = fmaf(w11, d.z, fmaf(w10, cq.z, fmaf(w01, bq.z, w00 * a.z)));
-    o.w = fmaf(w11, d.w, fmaf(w10, cq.w, fmaf(w01, bq.w, w00 * a.w)));
-    return o;
-  };
-
-  int it = 0;
-  for (int cb0 = beg; cb0 < end; cb0 += kBoxChunk) {
-    // stage the boxes (already scaled to feature pixels) and ROI ids of this chunk of the segment
-    __syncthreads();
-    for (int i = t; i < min(kBoxChunk, end - cb0); i += blockDim.x) {
-      const int n = __ldg(order + cb0 + i);
-      const float* rp = rois + 5 * (size_t)n;
-      s_ni[i] = n;
-      s_box[i] = make_float4(__ldg(rp + 1) * g.sx, __ldg(rp + 2) * g.sy, __ldg(rp + 3) * g.sx, __ldg(rp + 4) * g.sy);
-    }
-    __syncthreads();
-    const int cend = min(end, cb0 + kBoxChunk);
-  for (int gi = cb0; gi < cend; gi += RPI, ++it) {
-    const int buf = it & 1;
-    const int ri = gi + slot;
-    float* tile = tiles + (size_t)(buf * RPI + slot) * TILE;
-    uint8_t* at = atile + (size_t)(buf * RPI + slot) * TILE;
-    if (ri < cend && p < PP) {
-      if (r == 0) s_n[buf][slot] = s_ni[ri - cb0];
-      const float4 box = s_box[ri - cb0];
-      float4 o;
-      if (!g.maxpool) {
-        o = gather(sample_at(box, pi, pj, inv));
-      } else {
-        // 2x2 block of the 2S x 2S sample grid; first strict maximum in row-major order wins,
-        // as in max_pool2d's backward (network_cycle_response.py:144)
-        o = gather(sample_at(box, 2 * pi, 2 * pj, inv));
-        uint32_t am = 0;   // 4 x 8-bit winners
+  // this thread's (up to) two items of every iteration
+  int i_slot[2], i_p[2], i_cg[2];
+  bool i_on[2];
 #pragma unroll
-        for (int q = 1; q < 4; ++q) {
-          const float4 v = gather(sample_at(box, 2 * pi + (q >> 1), 2 * pj + (q & 1), inv));
-          if (v.x > o.x) { o.x = v.x; am = (am & ~0xffu) | (uint32_t)q; }
-          if (v.y > o.y) { o.y = v.y; am = (am & ~0xff00u) | ((uint32_t)q << 8); }
-          if (v.z > o.z) { o.z = v.z; am = (am & ~0xff0000u) | ((uint32_t)q << 16); }
-          if (v.w > o.w) { o.w = v.w; am = (am & ~0xff000000u) | ((uint32_t)q << 24); }
+  for (int k = 0; k < 2; ++k) {
+    const int item = t + k * HALF;
+    i_on[k] = t < HALF && item < ITEMS;
+    i_cg[k] = item % CGN;
+    const int sp = item / CGN;
+    i_slot[k] = sp / kPP;
+    i_p[k] = sp - i_slot[k] * kPP;
+  }
+
+  for (int it = 0; it < nit; ++it) {
+    const int buf = it & 1;
+    const int gi = beg + it * RPI;
+    const int cnt = min(RPI, end - gi);
+    // ring slot (it-1) % NT was last read in iteration it-1, i.e. before the previous barrier
+    if (t == 0 && it + NT - 1 < nit) load_tab(it + NT - 1);
+    mbar_wait(&tab_bar[it % NT], (it / NT) & 1);
+    const unsigned char* tab = tabs + (size_t)(it % NT) * RPI * g.rec;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int slot = i_slot[k], p = i_p[k], cg = i_cg[k];
+      if (i_on[k] && slot < cnt) {
+        const unsigned char* rec = tab + (size_t)slot * g.rec;
+        const uint4* ent = reinterpret_cast<const uint4*>(rec);
+        float* tile = tiles + (size_t)(buf * RPI + slot) * TILE;
+        float4 o;
+        if (!MAXPOOL) {
+          o = bilerp4(map4, ent[p], cg);
+        } else {
+          // 2x2 block of the 2S x 2S sample grid; first strict maximum in row-major order wins,
+          // as in max_pool2d's backward (network_cycle_response.py:144)
+          const int pi = p / 7, pj = p - pi * 7;
+          const int e0 = (2 * pi) * 14 + 2 * pj;
+          o = bilerp4(map4, ent[e0], cg);
+          uint32_t am = 0;   // 4 x 8-bit winners
+#pragma unroll
+          for (int q = 1; q < 4; ++q) {
+            const float4 v = bilerp4(map4, ent[e0 + (q >> 1) * 14 + (q & 1)], cg);
+            if (v.x > o.x) { o.x = v.x; am = (am & ~0xffu) | (uint32_t)q; }
+            if (v.y > o.y) { o.y = v.y; am = (am & ~0xff00u) | ((uint32_t)q << 8); }
+            if (v.z > o.z) { o.z = v.z; am = (am & ~0xff0000u) | ((uint32_t)q << 16); }
+            if (v.w > o.w) { o.w = v.w; am = (am & ~0xff000000u) | ((uint32_t)q << 24); }
+          }
+          uint8_t* at = atile + (size_t)(buf * RPI + slot) * TILE;
+          const int cb = cg * 4;
+          at[(cb + 0) * kPP + p] = (uint8_t)(am & 0xff);
+          at[(cb + 1) * kPP + p] = (uint8_t)((am >> 8) & 0xff);
+          at[(cb + 2) * kPP + p] = (uint8_t)((am >> 16) & 0xff);
+          at[(cb + 3) * kPP + p] = (uint8_t)(am >> 24);
         }
         const int cb = cg * 4;
-        at[(cb + 0) * PP + p] = (uint8_t)(am & 0xff);
-        at[(cb + 1) * PP + p] = (uint8_t)((am >> 8) & 0xff);
-        at[(cb + 2) * PP + p] = (uint8_t)((am >> 16) & 0xff);
-        at[(cb + 3) * PP + p] = (uint8_t)(am >> 24);
+        tile[(cb + 0) * kPP + p] = o.x;
+        tile[(cb + 1) * kPP + p] = o.y;
+        tile[(cb + 2) * kPP + p] = o.z;
+        tile[(cb + 3) * kPP + p] = o.w;
+        if (p == 0 && cg == 0) s_n[buf][slot] = *reinterpret_cast<const int*>(rec + (size_t)g.S * g.S * 16 + 56);
       }
-      const int cb = cg * 4;
-      tile[(cb + 0) * PP + p] = o.x;
-      tile[(cb + 1) * PP + p] = o.y;
-      tile[(cb + 2) * PP + p] = o.z;
-      tile[(cb + 3) * PP + p] = o.w;
     }
     fence_proxy_async_smem();
     if (t == 0) bulk_wait_read<0>();      // the previous iteration's stores have left the other buffer
     __syncthreads();
     if (t == 0) {
-      const int cnt = min(RPI, cend - gi);
       for (int s = 0; s < cnt; ++s) {
         const int n = s_n[buf][s];
-        bulk_s2g(out + ((size_t)n * g.C + c0) * PP, tiles + (size_t)(buf * RPI + s) * TILE,
-                 (uint32_t)(cvalid * PP * sizeof(float)));
+        bulk_s2g(out + ((size_t)n * g.C + c0) * kPP, tiles + (size_t)(buf * RPI + s) * TILE,
+                 (uint32_t)(cvalid * kPP * sizeof(float)));
       }
       bulk_commit();
     }
-    if (g.maxpool && argmax != nullptr) {
+    if (MAXPOOL && argmax != nullptr) {
       // winners: plain 32-bit copies (tile byte count and global offset are multiples of 4)
-      const int cnt = min(RPI, cend - gi);
-      const int words = cvalid * PP / 4;
+      const int words = cvalid * kPP / 4;
       for (int w = t; w < cnt * words; w += blockDim.x) {
         const int s = w / words, k = w % words;
         const int n = s_n[buf][s];
-        reinterpret_cast<uint32_t*>(argmax + ((size_t)n * g.C + c0) * PP)[k] =
+        reinterpret_cast<uint32_t*>(argmax + ((size_t)n * g.C + c0) * kPP)[k] =
             reinterpret_cast<const uint32_t*>(atile + (size_t)(buf * RPI + s) * TILE)[k];
       }
     }
-  }
   }
   if (t == 0) bulk_wait<0>();
 }
 
 // ------------------------------------------------------------------ backward
-// warps: CGN * NCLS consumers + 1 producer.  Consumer warp (cg, q) owns the accumulator entries
-// of channel group cg at pixels of parity class q.
-template <int CC, int NCLS>
-__global__ void __launch_bounds__((CC / 4 * NCLS + 1) * 32, 1)
-roi_crop_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ rois,
-                    const int* __restrict__ seg, const int* __restrict__ order,
-                    const uint8_t* __restrict__ argmax, float* __restrict__ dbottom, CropGeom g) {
+// warps: CGN consumers + 1 producer.  Consumer warp cg owns channel quad cg of the accumulator map.
+// Stage = gradient tile [CC][49] (+ winners [CC][49] u8 with max-pool) + the ROI's geometry record.
+template <int CC, bool MAXPOOL>
+__global__ void __launch_bounds__((CC / 4 + 1) * 32, 1)
+roi_crop_bwd_kernel(const float* __restrict__ dout, const int* __restrict__ seg,
+                    const unsigned char* __restrict__ table, const uint8_t* __restrict__ argmax,
+                    float* __restrict__ dbottom, CropGeom g) {
   constexpr int CGN = CC / 4;
-  constexpr int NCONS = CGN * NCLS;
-  constexpr int PP = 49;
-  constexpr int TILE = CC * PP;
+  constexpr int TILE = CC * kPP;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int HW = g.H * g.W;
   float* map = reinterpret_cast<float*>(smem_raw);
-  float* tiles = map + (size_t)HW * CC;                          // [kBwdStages][TILE]
+  float* tiles = map + (size_t)(HW + 1) * CC;                                 // [kBwdStages][TILE]
+  unsigned char* recs = reinterpret_cast<unsigned char*>(tiles + kBwdStages * TILE);   // [kBwdStages][rec]
+  uint8_t* atiles = recs + (size_t)kBwdStages * g.rec;                        // [kBwdStages][TILE] (max-pool)
   __shared__ uint64_t full_bar[kBwdStages], empty_bar[kBwdStages];
-  __shared__ int s_n[kBwdStages];
 
   const int b = blockIdx.y, c0 = blockIdx.x * CC;
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
   const int cvalid = min(CC, g.C - c0);
 
-  for (int i = t; i < HW * CC; i += blockDim.x) map[i] = 0.f;
+  for (int i = t; i < (HW + 1) * CC; i += blockDim.x) map[i] = 0.f;
   if (t == 0) {
     for (int s = 0; s < kBwdStages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], NCONS);
-    }
-    mbar_fence_init();
-  }
-  __syncthreads();
-
-  const int beg = seg[b], end = seg[b + 1];
-  const uint32_t tile_bytes = (uint32_t)(cvalid * PP * sizeof(float));
-
-  if (wid == NCONS) {
-    // ---------------- producer: one lane streams the upstream-gradient tiles ----------------
-    if (lane == 0) {
-      for (int ri = beg, k = 0; ri < end; ++ri, ++k) {
-        const int s = k % kBwdStages;
-        if (k >= kBwdStages) mbar_wait(&empty_bar[s], ((k / kBwdStages) - 1) & 1);
-        const int n = __ldg(order + ri);
-        s_n[s] = n;
-        mbar_arrive_expect_tx(&full_bar[s], tile_bytes);
-        bulk_g2s(tiles + (size_t)s * TILE, dout + ((size_t)n * g.C + c0) * PP, tile_bytes, &full_bar[s]);
-      }
-    }
-  } else {
-    // ---------------- consumers ----------------
-    const int cg = wid % CGN, q = wid / CGN;
-    const int qy = (NCLS >= 2) ? (q & 1) : 0;
-    const int qx = (NCLS == 4) ? (q >> 1) : 0;
-    const float inv = 1.0f / (float)(g.S - 1);
-    const int W = g.W, H = g.H;
-    const bool ch_ok = cg * 4 < cvalid;
-    float4* map4 = reinterpret_cast<float4*>(map);
-    const unsigned lt = (1u << lane) - 1u;
-
-    for (int ri = beg, k = 0; ri < end; ++ri, ++k) {
-      const int s = k % kBwdStages;
-      mbar_wait(&full_bar[s], (k / kBwdStages) & 1);
-      const int n = s_n[s];
-      const float* tile = tiles + (size_t)s * TILE;
-      const float* rp = rois + 5 * (size_t)n;
-      float4 box;
-      box.x = __ldg(rp + 1) * g.sx;
-      box.y = __ldg(rp + 2) * g.sy;
-      box.z = __ldg(rp + 3) * g.sx;
-      box.w = __ldg(rp + 4) * g.sy;
-#pragma unroll 1
-      for (int round = 0; round < 2; ++round) {
-        const int p = round * 32 + lane;
-        const bool act = p < PP && ch_ok;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (act) {
-          const int cb = cg * 4;
-          v.x = tile[(cb + 0) * PP + p];
-          v.y = tile[(cb + 1) * PP + p];
-          v.z = tile[(cb + 2) * PP + p];
-          v.w = tile[(cb + 3) * PP + p];
-        }
-        const int pi = p / 7, pj = p % 7;
-        uint32_t am = 0;
-        if (g.maxpool && act) {
-          const uint8_t* ap = argmax + ((size_t)n * g.C + c0 + cg * 4) * PP + p;
-          am = (uint32_t)ap[0] | ((uint32_t)ap[PP] << 8) | ((uint32_t)ap[2 * PP] << 16) |
-               ((uint32_t)ap[3 * PP] << 24);
-        }
-        // with max-pool the 4 channels of a lane may route to different samples: handle them as
-        // 4 scalar streams; otherwise one float4 stream.
-        const int nstream = g.maxpool ? 4 : 1;
-#pragma unroll 1
-        for (int e = 0; e < nstream; ++e) {
-          const int a = (am >> (8 * e)) & 3;
-          const Corner c = g.maxpool ? sample_at(box, 2 * pi + (a >> 1), 2 * pj + (a & 1), inv)
-                                     : sample_at(box, pi, pj, inv);
-#pragma unroll
-          for (int sub = 0; sub < 4 / NCLS; ++sub) {
-            // the corner(s) of this sample that fall into this warp's parity class
-            int dy, dx;
-            if (NCLS == 4) { dy = (qy ^ c.y0) & 1; dx = (qx ^ c.x0) & 1; }
-            else if (NCLS == 2) { dy = (qy ^ c.y0) & 1; dx = sub; }
-            else { dy = sub >> 1; dx = sub & 1; }
-            const int yy = c.y0 + dy, xx = c.x0 + dx;
-            const bool ok = act && (unsigned)yy < (unsigned)H && (unsigned)xx < (unsigned)W;
-            const float wgt = (dy ? c.ly : 1.f - c.ly) * (dx ? c.lx : 1.f - c.lx);
-            const int px = yy * W + xx;
-            const int key = ok ? px : -1 - lane;
-            const unsigned grp = __match_any_sync(0xffffffffu, key);
-            const int rank = __popc(grp & lt);
-            const int maxrank = __reduce_max_sync(0xffffffffu, ok ? rank : 0);
-            for (int rr = 0; rr <= maxrank; ++rr) {
-              if (ok && rank == rr) {
-                const int off = map_off<CC>(px, cg);
-                if (g.maxpool) {
-                  const float val = e == 0 ? v.x : (e == 1 ? v.y : (e == 2 ? v.z : v.w));
-                  map[off + e] = fmaf(wgt, val, map[off + e]);
-                } else {
-                  float4 m = map4[off >> 2];
-                  m.x = fmaf(wgt, v.x, m.x);
-                  m.y = fmaf(wgt, v.y, m.y);
-                  m.z = fmaf(wgt, v.z, m.z);
-                  m.w = fmaf(wgt, v.w, m.w);
-                  map4[off >> 2] = m;
-                }
-              }
-              __syncwarp();
-            }
-          }
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty_bar[s]);
-    }
-  }
-  __syncthreads();
-  unstage_map<CC>(map, dbottom + (size_t)b * g.C * HW, c0, g.C, HW);
-}
-
-
-// ------------------------------------------------------------------ backward, fast path (no max-pool)
-// Geometry is channel independent, so the PRODUCER warp computes it once per ROI: for each of the 49
-// samples the corner index, the two fractions and a collision rank (samples whose (y0,x0) coincide get
-// ranks 0,1,2,.. by match.any), next to issuing the TMA load of the gradient tile.  Consumer warp cg owns
-// channel quad cg of the accumulator map: lanes = samples, 4 corners of a sample are 4 distinct pixels,
-// equal-rank samples never share a pixel through the same corner => plain float4 read-modify-write.
-struct __align__(16) SampleEnt {
-  int yx;        // (y0 << 16) | (x0 & 0xffff)
-  float ly, lx;
-  int rank;
-};
-
-template <int CC>
-__global__ void __launch_bounds__((CC / 4 + 1) * 32, 1)
-roi_crop_bwd_fast_kernel(const float* __restrict__ dout, const float* __restrict__ rois,
-                         const int* __restrict__ seg, const int* __restrict__ order, float* __restrict__ dbottom,
-                         CropGeom g) {
-  constexpr int CGN = CC / 4;
-  constexpr int PP = 49;
-  constexpr int TILE = CC * PP;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int HW = g.H * g.W;
-  float* map = reinterpret_cast<float*>(smem_raw);
-  float* tiles = map + (size_t)HW * CC;                          // [kBwdStages][TILE]
-  __shared__ uint64_t full_bar[kBwdStages], empty_bar[kBwdStages];
-  __shared__ SampleEnt s_tab[kBwdStages][64];
-  __shared__ int s_maxrank[kBwdStages][2];
-
-  const int b = blockIdx.y, c0 = blockIdx.x * CC;
-  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
-  const int cvalid = min(CC, g.C - c0);
-  const unsigned lt = (1u << lane) - 1u;
-
-  for (int i = t; i < HW * CC; i += blockDim.x) map[i] = 0.f;
-  if (t == 0) {
-    for (int s = 0; s < kBwdStages; ++s) {
-      mbar_init(&full_bar[s], 2);          // TMA issue (expect_tx) + "table written"
       mbar_init(&empty_bar[s], CGN);
     }
     mbar_fence_init();
@@ -464,95 +439,258 @@ roi_crop_bwd_fast_kernel(const float* __restrict__ dout, const float* __restrict
   __syncthreads();
 
   const int beg = seg[b], end = seg[b + 1];
-  const uint32_t tile_bytes = (uint32_t)(cvalid * PP * sizeof(float));
-  const float inv = 1.0f / (float)(g.S - 1);
+  const uint32_t tile_bytes = (uint32_t)(cvalid * kPP * sizeof(float));
+  const uint32_t arg_bytes = (uint32_t)(cvalid * kPP);
+  // winners travel by TMA only when their rows are 16-byte sized / aligned (C % 16 == 0); otherwise read in place
+  const bool arg_smem = MAXPOOL && (g.C % 16 == 0) && (cvalid % 16 == 0);
 
   if (wid == CGN) {
-    // ---------------- producer warp ----------------
-    for (int ri = beg, k = 0; ri < end; ++ri, ++k) {
-      const int s = k % kBwdStages;
-      if (k >= kBwdStages) mbar_wait(&empty_bar[s], ((k / kBwdStages) - 1) & 1);
-      const int n = __ldg(order + ri);
-      if (lane == 0) {
-        mbar_arrive_expect_tx(&full_bar[s], tile_bytes);
-        bulk_g2s(tiles + (size_t)s * TILE, dout + ((size_t)n * g.C + c0) * PP, tile_bytes, &full_bar[s]);
+    // ---------------- producer warp: streams tiles + records (ROI ids fetched 32 at a time) ----------------
+    for (int r0 = beg, k = 0; r0 < end; r0 += 32) {
+      const int mine = r0 + lane;
+      int nl = 0;
+      if (mine < end) nl = __ldg(reinterpret_cast<const int*>(table + (size_t)mine * g.rec + (size_t)g.S * g.S * 16 + 56));
+      const int cnt = min(32, end - r0);
+      for (int j = 0; j < cnt; ++j, ++k) {
+        const int n = __shfl_sync(0xffffffffu, nl, j);
+        if (lane == 0) {
+          const int s = k % kBwdStages;
+          if (k >= kBwdStages) mbar_wait(&empty_bar[s], ((k / kBwdStages) - 1) & 1);
+          const unsigned char* rec = table + (size_t)(r0 + j) * g.rec;
+          mbar_arrive_expect_tx(&full_bar[s], tile_bytes + (uint32_t)g.rec + (arg_smem ? arg_bytes : 0u));
+          bulk_g2s(recs + (size_t)s * g.rec, rec, (uint32_t)g.rec, &full_bar[s]);
+          bulk_g2s(tiles + (size_t)s * TILE, dout + ((size_t)n * g.C + c0) * kPP, tile_bytes, &full_bar[s]);
+          if (arg_smem)
+            bulk_g2s(atiles + (size_t)s * TILE, argmax + ((size_t)n * g.C + c0) * kPP, arg_bytes, &full_bar[s]);
+        }
       }
-      const float* rp = rois + 5 * (size_t)n;
-      float4 box;
-      box.x = __ldg(rp + 1) * g.sx;
-      box.y = __ldg(rp + 2) * g.sy;
-      box.z = __ldg(rp + 3) * g.sx;
-      box.w = __ldg(rp + 4) * g.sy;
-#pragma unroll
-      for (int pass = 0; pass < 2; ++pass) {
-        const int p = pass * 32 + lane;
-        const bool valid = p < PP;
-        const Corner c = sample_at(box, p / 7, p % 7, inv);
-        const int y0 = min(max(c.y0, -2), 30000), x0 = min(max(c.x0, -2), 30000);
-        const int key = valid ? ((y0 << 16) | (x0 & 0xffff)) : (int)(0x80000000u | (unsigned)lane);
-        const unsigned grp = __match_any_sync(0xffffffffu, key);
-        const int rank = __popc(grp & lt);
-        const int mr = __reduce_max_sync(0xffffffffu, valid ? rank : 0);
-        SampleEnt e;
-        e.yx = key; e.ly = c.ly; e.lx = c.lx; e.rank = rank;
-        s_tab[s][p] = e;
-        if (lane == 0) s_maxrank[s][pass] = mr;
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&full_bar[s]);
     }
   } else {
-    // ---------------- consumer warps ----------------
+    // ---------------- consumers ----------------
     const int cg = wid;
-    const int W = g.W, H = g.H;
     const bool ch_ok = cg * 4 < cvalid;
     float4* map4 = reinterpret_cast<float4*>(map);
+    const unsigned lt = (1u << lane) - 1u;
+    const int zs = HW * CGN;
+    const int p0 = lane, p1 = 32 + lane;
+    const bool on1 = p1 < kPP;
     for (int ri = beg, k = 0; ri < end; ++ri, ++k) {
       const int s = k % kBwdStages;
       mbar_wait(&full_bar[s], (k / kBwdStages) & 1);
       const float* tile = tiles + (size_t)s * TILE;
-#pragma unroll
-      for (int pass = 0; pass < 2; ++pass) {
-        const int p = pass * 32 + lane;
-        const bool act = p < PP && ch_ok;
-        const SampleEnt e = s_tab[s][p];
-        const int mr = s_maxrank[s][pass];
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (act) {
-          const int cb = cg * 4;
-          v.x = tile[(cb + 0) * PP + p];
-          v.y = tile[(cb + 1) * PP + p];
-          v.z = tile[(cb + 2) * PP + p];
-          v.w = tile[(cb + 3) * PP + p];
+      const unsigned char* rec = recs + (size_t)s * g.rec;
+      const uint4* ent = reinterpret_cast<const uint4*>(rec);
+      const int cb = cg * 4;
+      if (!MAXPOOL) {
+        const unsigned char* tail = rec + kPP * 16;
+        const int mr = tail[60];
+        const uint4 e0 = ent[p0];
+        const uint4 e1 = on1 ? ent[p1] : make_uint4(0, 0, 0, 0);
+        const int r0 = ch_ok ? (int)tail[p0] : -1, r1 = (ch_ok && on1) ? (int)tail[p1] : -1;
+        float4 v0, v1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        v0.x = tile[(cb + 0) * kPP + p0]; v0.y = tile[(cb + 1) * kPP + p0];
+        v0.z = tile[(cb + 2) * kPP + p0]; v0.w = tile[(cb + 3) * kPP + p0];
+        if (on1) {
+          v1.x = tile[(cb + 0) * kPP + p1]; v1.y = tile[(cb + 1) * kPP + p1];
+          v1.z = tile[(cb + 2) * kPP + p1]; v1.w = tile[(cb + 3) * kPP + p1];
         }
-        const int y0 = e.yx >> 16, x0 = (int)(short)(e.yx & 0xffff);
-        const bool vx0 = (unsigned)x0 < (unsigned)W, vx1 = (unsigned)(x0 + 1) < (unsigned)W;
-        const bool vy0 = (unsigned)y0 < (unsigned)H, vy1 = (unsigned)(y0 + 1) < (unsigned)H;
-        const float wy0 = 1.f - e.ly, wy1 = e.ly, wx0 = 1.f - e.lx, wx1 = e.lx;
-        const int pbase = y0 * W + x0;
-        // Two samples of equal rank have different (y0,x0) but may still meet in one pixel through
-        // DIFFERENT corners (A's (y0+1,x0+1) is B's (y0,x0)); so the four corners are four separate
-        // read-modify-write phases with a warp barrier between them.  Inside one phase a pixel is
-        // reached only by samples of the same (y0,x0), which carry distinct ranks.
-        const bool b00 = vy0 && vx0, b01 = vy0 && vx1, b10 = vy1 && vx0, b11 = vy1 && vx1;
-        auto rmw = [&](bool on, int px, float w) {
+        const float ly0 = __uint_as_float(e0.z), lx0 = __uint_as_float(e0.w);
+        const float ly1 = __uint_as_float(e1.z), lx1 = __uint_as_float(e1.w);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[s]);     // everything of this stage is in registers now
+        // Samples of equal rank lie in different (y0,x0) cells but may still meet in one pixel through
+        // DIFFERENT corners; so the four corners are four read-modify-write phases with a warp barrier
+        // between them.  Inside a phase a pixel is reached only by samples of one cell => distinct ranks.
+        // Corners outside the map point at the zero slot, whose content is never written back.
+        auto rmw = [&](bool on, uint32_t slot, float w, const float4& v) {
           if (on) {
-            const int o = map_off<CC>(px, cg) >> 2;
-            float4 m = map4[o];
+            float4 m = map4[slot ^ cg];
             m.x = fmaf(w, v.x, m.x);
             m.y = fmaf(w, v.y, m.y);
             m.z = fmaf(w, v.z, m.z);
             m.w = fmaf(w, v.w, m.w);
-            map4[o] = m;
+            map4[slot ^ cg] = m;
           }
-          __syncwarp();
         };
         for (int rr = 0; rr <= mr; ++rr) {
-          const bool sel = act && e.rank == rr;
-          rmw(sel && b00, pbase, wy0 * wx0);
-          rmw(sel && b01, pbase + 1, wy0 * wx1);
-          rmw(sel && b10, pbase + W, wy1 * wx0);
-          rmw(sel && b11, pbase + W + 1, wy1 * wx1);
+          const bool a0 = r0 == rr, a1 = r1 == rr;
+          rmw(a0, e0.x & 0xffffu, (1.f - ly0) * (1.f - lx0), v0);
+          rmw(a1, e1.x & 0xffffu, (1.f - ly1) * (1.f - lx1), v1);
+          __syncwarp();
+          rmw(a0, e0.x >> 16, (1.f - ly0) * lx0, v0);
+          rmw(a1, e1.x >> 16, (1.f - ly1) * lx1, v1);
+          __syncwarp();
+          rmw(a0, e0.y & 0xffffu, ly0 * (1.f - lx0), v0);
+          rmw(a1, e1.y & 0xffffu, ly1 * (1.f - lx1), v1);
+          __syncwarp();
+          rmw(a0, e0.y >> 16, ly0 * lx0, v0);
+          rmw(a1, e1.y >> 16, ly1 * lx1, v1);
+          __syncwarp();
+        }
+      } else {
+        // max-pool: the 4 channels of a lane may route to different samples of the 2x2 block, so they
+        // are 4 scalar streams; collisions (same slot, same channel) are ranked on the fly by match.any.
+        const int n = *reinterpret_cast<const int*>(rec + (size_t)g.S * g.S * 16 + 56);
+        const uint8_t* at = arg_smem ? atiles + (size_t)s * TILE : argmax + ((size_t)n * g.C + c0) * kPP;
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+          const int p = pass * 32 + lane;
+          const bool act = p < kPP && ch_ok;
+          const int pi = p / 7, pj = p - pi * 7;
+#pragma unroll 1
+          for (int e = 0; e < 4; ++e) {
+            float val = 0.f;
+            uint4 en = make_uint4(0, 0, 0, 0);
+            if (act) {
+              val = tile[(cb + e) * kPP + p];
+              const int a = at[(cb + e) * kPP + p] & 3;
+              en = ent[(2 * pi + (a >> 1)) * 14 + 2 * pj + (a & 1)];
+            }
+            const float ly = __uint_as_float(en.z), lx = __uint_as_float(en.w);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const uint32_t slot = (c == 0) ? (en.x & 0xffffu) : (c == 1) ? (en.x >> 16) : (c == 2) ? (en.y & 0xffffu) : (en.y >> 16);
+              const float w = ((c & 2) ? ly : 1.f - ly) * ((c & 1) ? lx : 1.f - lx);
+              const bool ok = act && (int)slot < zs;
+              const int key = ok ? (int)slot : -1 - lane;
+              const unsigned grp = __match_any_sync(0xffffffffu, key);
+              const int rank = __popc(grp & lt);
+              const int mr = __reduce_max_sync(0xffffffffu, ok ? rank : 0);
+              for (int rr = 0; rr <= mr; ++rr) {
+                if (ok && rank == rr) {
+                  float* mp = map + (size_t)((slot ^ cg) << 2) + e;
+                  *mp = fmaf(w, val, *mp);
+                }
+                __syncwarp();
+              }
+            }
+          }
+        }
+      }
+      if (MAXPOOL) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[s]);
+      }
+    }
+  }
+  __syncthreads();
+  unstage_map<CC>(map, dbottom + (size_t)b * g.C * HW, c0, g.C, HW);
+}
+
+// ------------------------------------------------------------------ backward, row-owner variant (CC = 32, 7x7)
+// lane = channel, warp w owns map rows y = w (mod 31): every read-modify-write of the accumulator map is a
+// conflict-free 128-byte row segment, control flow is warp uniform (geometry does not depend on the channel),
+// there are no collisions to rank and no barriers inside a ROI.  Per sample row i and map row y the 7 samples
+// are swept left to right with the two live column sums in registers, so a column is written once per sweep
+// (<= 14 RMW per (ROI, sample row, map row) instead of 28).
+constexpr int kRowWarps = 31;
+constexpr int kRowStages = 8;
+
+__global__ void __launch_bounds__(1024, 1)
+roi_crop_bwd_rows_kernel(const float* __restrict__ dout, const int* __restrict__ seg,
+                         const SepRec* __restrict__ sep, float* __restrict__ dbottom, CropGeom g) {
+  constexpr int CC = 32;
+  constexpr int TILE = CC * kPP;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int HW = g.H * g.W, W = g.W, H = g.H;
+  float* map = reinterpret_cast<float*>(smem_raw);
+  float* tiles = map + (size_t)(HW + 1) * CC;                                // [kRowStages][TILE]
+  SepRec* recs = reinterpret_cast<SepRec*>(tiles + kRowStages * TILE);       // [kRowStages]
+  __shared__ uint64_t full_bar[kRowStages], empty_bar[kRowStages];
+
+  const int b = blockIdx.y, c0 = blockIdx.x * CC;
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  const int cvalid = min(CC, g.C - c0);
+
+  for (int i = t; i < (HW + 1) * CC; i += blockDim.x) map[i] = 0.f;
+  if (t == 0) {
+    for (int s = 0; s < kRowStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], kRowWarps);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  const int beg = seg[b], end = seg[b + 1];
+  const uint32_t tile_bytes = (uint32_t)(cvalid * kPP * sizeof(float));
+
+  if (wid == kRowWarps) {
+    // ---------------- producer warp ----------------
+    for (int r0 = beg, k = 0; r0 < end; r0 += 32) {
+      const int mine = r0 + lane;
+      const int nl = (mine < end) ? __ldg(&sep[mine].n) : 0;
+      const int cnt = min(32, end - r0);
+      for (int j = 0; j < cnt; ++j, ++k) {
+        const int n = __shfl_sync(0xffffffffu, nl, j);
+        if (lane == 0) {
+          const int s = k % kRowStages;
+          if (k >= kRowStages) mbar_wait(&empty_bar[s], ((k / kRowStages) - 1) & 1);
+          mbar_arrive_expect_tx(&full_bar[s], tile_bytes + (uint32_t)sizeof(SepRec));
+          bulk_g2s(recs + s, sep + r0 + j, (uint32_t)sizeof(SepRec), &full_bar[s]);
+          bulk_g2s(tiles + (size_t)s * TILE, dout + ((size_t)n * g.C + c0) * kPP, tile_bytes, &full_bar[s]);
+        }
+      }
+    }
+  } else {
+    // ---------------- consumers: warp = rows, lane = channel ----------------
+    const bool act = lane < cvalid;
+    const int cgq = lane >> 2, csub = lane & 3;
+    for (int ri = beg, k = 0; ri < end; ++ri, ++k) {
+      const int s = k % kRowStages;
+      mbar_wait(&full_bar[s], (k / kRowStages) & 1);
+      const SepRec* rec = recs + s;
+      const int ymin = rec->ymin, ymax = rec->ymax;
+      bool any = false;
+      for (int y = wid; y < H; y += kRowWarps) any |= (y >= ymin && y <= ymax);
+      if (any) {
+        const float* tcol = tiles + (size_t)s * TILE + (size_t)(act ? lane : 0) * kPP;
+        int x0[7];
+        float lx[7];
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+          x0[j] = rec->x0[j];
+          lx[j] = rec->lx[j];
+        }
+#pragma unroll 1
+        for (int i = 0; i < 7; ++i) {
+          const int y0 = rec->y0[i];
+          const float ly = rec->ly[i];
+#pragma unroll 1
+          for (int dy = 0; dy < 2; ++dy) {
+            const int y = y0 + dy;
+            if ((unsigned)y >= (unsigned)H || (y % kRowWarps) != wid) continue;   // warp uniform
+            const float wy = dy ? ly : 1.f - ly;
+            const int rowpx = y * W;
+            auto add = [&](int col, float v) {
+              if ((unsigned)col < (unsigned)W && act) {
+                float* m = map + map_off<CC>(rowpx + col, cgq) + csub;
+                *m += v;
+              }
+            };
+            float a = 0.f, bsum = 0.f;
+            int cur = x0[0];
+#pragma unroll
+            for (int j = 0; j < 7; ++j) {
+              const float v = tcol[i * 7 + j] * wy;
+              const int xj = x0[j];
+              if (xj != cur) {                    // warp uniform
+                add(cur, a);
+                if (xj == cur + 1) {
+                  a = bsum;
+                } else {
+                  add(cur + 1, bsum);
+                  a = 0.f;
+                }
+                bsum = 0.f;
+                cur = xj;
+              }
+              a = fmaf(1.f - lx[j], v, a);
+              bsum = fmaf(lx[j], v, bsum);
+            }
+            add(cur, a);
+            add(cur + 1, bsum);
+          }
         }
       }
       __syncwarp();
@@ -566,25 +704,30 @@ roi_crop_bwd_fast_kernel(const float* __restrict__ dout, const float* __restrict
 // ------------------------------------------------------------------ host side
 struct Plan {
   int cc;
-  size_t smem_fwd, smem_bwd;
+  size_t smem_fwd, smem_bwd, smem_rows;
 };
 
-bool make_plan(int HW, bool maxpool, Plan* pl) {
+bool make_plan(int HW, bool maxpool, int rec, Plan* pl) {
   const size_t cap = (size_t)max_smem_optin() - 1024;
   for (int cc = 32; cc >= 4; cc >>= 1) {
-    const size_t map = (size_t)HW * cc * 4;
-    const size_t tile = (size_t)cc * 49;
-    const int rpi = 16 / (cc / 4);
-    const size_t fwd = map + 2 * rpi * tile * 4 + (maxpool ? 2 * rpi * tile : 0) + 128;
-    const size_t bwd = map + kBwdStages * tile * 4 + 128;
-    if (fwd <= cap && bwd <= cap) {
+    const size_t map = (size_t)(HW + 1) * cc * 4;
+    const size_t tile = (size_t)cc * kPP;
+    const int rpi = kRPI;
+    const size_t fwd = map + 2 * rpi * tile * 4 + (size_t)(maxpool ? 2 : 4) * rpi * rec + (maxpool ? 2 * rpi * tile : 0) + 128;
+    const size_t bwd = map + kBwdStages * (tile * 4 + (size_t)rec + (maxpool ? tile : 0)) + 128;
+    if (fwd <= cap && bwd <= cap && (size_t)(HW + 1) * (cc / 4) <= 65535) {
       pl->cc = cc;
       pl->smem_fwd = fwd;
       pl->smem_bwd = bwd;
+      pl->smem_rows = map + kRowStages * (tile * 4 + sizeof(SepRec)) + 128;
       return true;
     }
   }
   return false;
+}
+
+size_t table_offset(int B, int N) {
+  return (((size_t)2 * B + 1 + (size_t)(N > 0 ? N : 0)) * sizeof(int) + 255) & ~(size_t)255;
 }
 
 int check_common(const void* a, const void* rois, const void* o, int B, int C, int H, int W, int N, int pool,
@@ -595,11 +738,13 @@ int check_common(const void* a, const void* rois, const void* o, int B, int C, i
   L2S_REQUIRE(pool == 7, L2S_ERR_SHAPE, "roi_crop: pool must be 7 (cfg.POOLING_SIZE), got %d", pool);
   L2S_REQUIRE(C % 4 == 0, L2S_ERR_SHAPE, "roi_crop: C must be a multiple of 4, got %d", C);
   L2S_REQUIRE(aligned16(a) && aligned16(o), L2S_ERR_ALIGN, "roi_crop: map / pooled pointers must be 16-byte aligned");
-  L2S_REQUIRE((flags & ~(L2S_CROP_MAX_POOL | L2S_CROP_ALIGN)) == 0, L2S_ERR_ARG, "roi_crop: unknown flags %d", flags);
+  L2S_REQUIRE((flags & ~(L2S_CROP_MAX_POOL | L2S_CROP_ALIGN | L2S_CROP_BWD_RANKED)) == 0, L2S_ERR_ARG,
+              "roi_crop: unknown flags %d", flags);
   if (flags & L2S_CROP_ALIGN)
     L2S_REQUIRE(im_h > 1.f && im_w > 1.f, L2S_ERR_ARG, "roi_crop: align mode needs the image size");
-  L2S_REQUIRE(ws && ws_bytes >= l2s_roi_crop_workspace_bytes(B, N), L2S_ERR_WORKSPACE,
-              "roi_crop: workspace too small (%zu < %zu)", ws_bytes, l2s_roi_crop_workspace_bytes(B, N));
+  L2S_REQUIRE(ws && ws_bytes >= l2s_roi_crop_workspace_bytes(B, N, flags) && aligned16(ws), L2S_ERR_WORKSPACE,
+              "roi_crop: workspace missing, misaligned or too small (%zu < %zu)", ws_bytes,
+              l2s_roi_crop_workspace_bytes(B, N, flags));
   return L2S_OK;
 }
 
@@ -608,6 +753,7 @@ CropGeom make_geom(int B, int C, int H, int W, int N, int pool, int flags, float
   g.B = B; g.C = C; g.H = H; g.W = W; g.N = N;
   g.maxpool = (flags & L2S_CROP_MAX_POOL) ? 1 : 0;
   g.S = g.maxpool ? 2 * pool : pool;
+  g.rec = g.S * g.S * 16 + kRecTail;
   if (flags & L2S_CROP_ALIGN) {
     g.sx = (float)(W - 1) / (im_w - 1.f);
     g.sy = (float)(H - 1) / (im_h - 1.f);
@@ -618,50 +764,44 @@ CropGeom make_geom(int B, int C, int H, int W, int N, int pool, int flags, float
   return g;
 }
 
-int bin_rois(const float* rois, int B, int N, void* ws, cudaStream_t st, int** seg, int** order) {
+// bins the ROIs by batch index and writes the geometry records (3 small launches)
+int prepare(const float* rois, const CropGeom& g, int cgn, void* ws, cudaStream_t st, int** seg,
+            unsigned char** table, SepRec** sep) {
   int* counts = reinterpret_cast<int*>(ws);
-  *seg = counts + B;
-  *order = counts + 2 * B + 1;
-  roi_count_kernel<<<B, 256, 0, st>>>(rois, N, counts);
+  *seg = counts + g.B;
+  int* order = counts + 2 * g.B + 1;
+  *table = reinterpret_cast<unsigned char*>(ws) + table_offset(g.B, g.N);
+  roi_count_kernel<<<g.B, 256, 0, st>>>(rois, g.N, counts);
   L2S_LAUNCH_OK("roi_count_kernel");
-  roi_order_kernel<<<B, 256, 0, st>>>(rois, N, counts, *seg, *order);
+  roi_order_kernel<<<g.B, 256, 0, st>>>(rois, g.N, counts, *seg, order);
   L2S_LAUNCH_OK("roi_order_kernel");
-  count_launch(2);
+  *sep = g.maxpool ? nullptr : reinterpret_cast<SepRec*>(*table + (size_t)g.N * g.rec);
+  roi_geom_kernel<<<g.N, g.S == 7 ? 64 : 256, 0, st>>>(rois, order, *table, *sep, g, cgn);
+  L2S_LAUNCH_OK("roi_geom_kernel");
+  count_launch(3);
   return L2S_OK;
 }
 
-template <int CC>
-int launch_fwd(const float* bottom, const float* rois, const int* seg, const int* order, float* out,
-               uint8_t* argmax, const CropGeom& g, size_t smem, cudaStream_t st) {
-  auto kern = roi_crop_fwd_kernel<CC>;
+template <int CC, bool MP>
+int launch_fwd(const float* bottom, const int* seg, const unsigned char* table, float* out, uint8_t* argmax,
+               const CropGeom& g, size_t smem, cudaStream_t st) {
+  auto kern = roi_crop_fwd_kernel<CC, MP>;
   L2S_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((g.C + CC - 1) / CC, g.B);
-  kern<<<grid, kFwdThreads, smem, st>>>(bottom, rois, seg, order, out, argmax, g);
+  kern<<<grid, kFwdThreads, smem, st>>>(bottom, seg, table, out, argmax, g);
   L2S_LAUNCH_OK("roi_crop_fwd_kernel");
   count_launch();
   return L2S_OK;
 }
 
-template <int CC, int NCLS>
-int launch_bwd(const float* dout, const float* rois, const int* seg, const int* order, const uint8_t* argmax,
-               float* dbottom, const CropGeom& g, size_t smem, cudaStream_t st) {
-  auto kern = roi_crop_bwd_kernel<CC, NCLS>;
+template <int CC, bool MP>
+int launch_bwd(const float* dout, const int* seg, const unsigned char* table, const uint8_t* argmax, float* dbottom,
+               const CropGeom& g, size_t smem, cudaStream_t st) {
+  auto kern = roi_crop_bwd_kernel<CC, MP>;
   L2S_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((g.C + CC - 1) / CC, g.B);
-  kern<<<grid, (CC / 4 * NCLS + 1) * 32, smem, st>>>(dout, rois, seg, order, argmax, dbottom, g);
+  kern<<<grid, (CC / 4 + 1) * 32, smem, st>>>(dout, seg, table, argmax, dbottom, g);
   L2S_LAUNCH_OK("roi_crop_bwd_kernel");
-  count_launch();
-  return L2S_OK;
-}
-
-template <int CC>
-int launch_bwd_fast(const float* dout, const float* rois, const int* seg, const int* order, float* dbottom,
-                    const CropGeom& g, size_t smem, cudaStream_t st) {
-  auto kern = roi_crop_bwd_fast_kernel<CC>;
-  L2S_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((g.C + CC - 1) / CC, g.B);
-  kern<<<grid, (CC / 4 + 1) * 32, smem, st>>>(dout, rois, seg, order, dbottom, g);
-  L2S_LAUNCH_OK("roi_crop_bwd_fast_kernel");
   count_launch();
   return L2S_OK;
 }
@@ -671,9 +811,28 @@ int launch_bwd_fast(const float* dout, const float* rois, const int* seg, const 
 
 using namespace l2s;
 
-extern "C" size_t l2s_roi_crop_workspace_bytes(int B, int N) {
-  return ((size_t)2 * B + 1 + (size_t)(N > 0 ? N : 0)) * sizeof(int) + 64;
+extern "C" size_t l2s_roi_crop_workspace_bytes(int B, int N, int flags) {
+  const int S = (flags & L2S_CROP_MAX_POOL) ? 14 : 7;
+  return table_offset(B, N) + (size_t)(N > 0 ? N : 0) * (S * S * 16 + kRecTail + (S == 7 ? sizeof(SepRec) : 0)) + 256;
 }
+
+#define L2S_CROP_DISPATCH(FN, ...)                                                      \
+  do {                                                                                  \
+    if (g.maxpool) {                                                                    \
+      switch (pl.cc) {                                                                  \
+        case 32: return FN<32, true>(__VA_ARGS__);                                      \
+        case 16: return FN<16, true>(__VA_ARGS__);                                      \
+        case 8: return FN<8, true>(__VA_ARGS__);                                        \
+        default: return FN<4, true>(__VA_ARGS__);                                       \
+      }                                                                                 \
+    }                                                                                   \
+    switch (pl.cc) {                                                                    \
+      case 32: return FN<32, false>(__VA_ARGS__);                                       \
+      case 16: return FN<16, false>(__VA_ARGS__);                                       \
+      case 8: return FN<8, false>(__VA_ARGS__);                                         \
+      default: return FN<4, false>(__VA_ARGS__);                                        \
+    }                                                                                   \
+  } while (0)
 
 extern "C" int l2s_roi_crop_fwd(const float* bottom, const float* rois, float* out, uint8_t* argmax, int B,
                                 int C, int H, int W, int N, int pool, int flags, float im_h, float im_w,
@@ -684,17 +843,14 @@ extern "C" int l2s_roi_crop_fwd(const float* bottom, const float* rois, float* o
   cudaStream_t st = (cudaStream_t)stream;
   const CropGeom g = make_geom(B, C, H, W, N, pool, flags, im_h, im_w);
   Plan pl;
-  L2S_REQUIRE(make_plan(H * W, g.maxpool, &pl), L2S_ERR_SHAPE,
-              "roi_crop: feature map %dx%d does not fit the shared-memory staging (max 12800 pixels)", H, W);
-  int *seg, *order;
-  rc = bin_rois(rois, B, N, workspace, st, &seg, &order);
+  L2S_REQUIRE(make_plan(H * W, g.maxpool, g.rec, &pl), L2S_ERR_SHAPE,
+              "roi_crop: feature map %dx%d does not fit the shared-memory staging", H, W);
+  int* seg;
+  unsigned char* table;
+  SepRec* sep;
+  rc = prepare(rois, g, pl.cc / 4, workspace, st, &seg, &table, &sep);
   if (rc) return rc;
-  switch (pl.cc) {
-    case 32: return launch_fwd<32>(bottom, rois, seg, order, out, argmax, g, pl.smem_fwd, st);
-    case 16: return launch_fwd<16>(bottom, rois, seg, order, out, argmax, g, pl.smem_fwd, st);
-    case 8: return launch_fwd<8>(bottom, rois, seg, order, out, argmax, g, pl.smem_fwd, st);
-    default: return launch_fwd<4>(bottom, rois, seg, order, out, argmax, g, pl.smem_fwd, st);
-  }
+  L2S_CROP_DISPATCH(launch_fwd, bottom, seg, table, out, argmax, g, pl.smem_fwd, st);
 }
 
 extern "C" int l2s_roi_crop_bwd(const float* dout, const float* rois, const uint8_t* argmax, float* dbottom,
@@ -711,25 +867,24 @@ extern "C" int l2s_roi_crop_bwd(const float* dout, const float* rois, const uint
   if (rc) return rc;
   L2S_REQUIRE(dout, L2S_ERR_ARG, "roi_crop_bwd: null dout");
   const CropGeom g = make_geom(B, C, H, W, N, pool, flags, im_h, im_w);
-  L2S_REQUIRE(!g.maxpool || argmax, L2S_ERR_ARG, "roi_crop_bwd: max-pool mode needs the argmax of the forward");
+  L2S_REQUIRE(!g.maxpool || (argmax && aligned16(argmax)), L2S_ERR_ARG,
+              "roi_crop_bwd: max-pool mode needs the (16-byte aligned) argmax of the forward");
   Plan pl;
-  L2S_REQUIRE(make_plan(H * W, g.maxpool, &pl), L2S_ERR_SHAPE,
-              "roi_crop: feature map %dx%d does not fit the shared-memory staging (max 12800 pixels)", H, W);
-  int *seg, *order;
-  rc = bin_rois(rois, B, N, workspace, st, &seg, &order);
+  L2S_REQUIRE(make_plan(H * W, g.maxpool, g.rec, &pl), L2S_ERR_SHAPE,
+              "roi_crop: feature map %dx%d does not fit the shared-memory staging", H, W);
+  int* seg;
+  unsigned char* table;
+  SepRec* sep;
+  rc = prepare(rois, g, pl.cc / 4, workspace, st, &seg, &table, &sep);
   if (rc) return rc;
-  if (!g.maxpool) {
-    switch (pl.cc) {
-      case 32: return launch_bwd_fast<32>(dout, rois, seg, order, dbottom, g, pl.smem_bwd, st);
-      case 16: return launch_bwd_fast<16>(dout, rois, seg, order, dbottom, g, pl.smem_bwd, st);
-      case 8: return launch_bwd_fast<8>(dout, rois, seg, order, dbottom, g, pl.smem_bwd, st);
-      default: return launch_bwd_fast<4>(dout, rois, seg, order, dbottom, g, pl.smem_bwd, st);
-    }
+  if (!g.maxpool && pl.cc == 32 && !(flags & L2S_CROP_BWD_RANKED)) {
+    auto kern = roi_crop_bwd_rows_kernel;
+    L2S_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_rows));
+    dim3 grid((g.C + 31) / 32, g.B);
+    kern<<<grid, (kRowWarps + 1) * 32, pl.smem_rows, st>>>(dout, seg, sep, dbottom, g);
+    L2S_LAUNCH_OK("roi_crop_bwd_rows_kernel");
+    count_launch();
+    return L2S_OK;
   }
-  switch (pl.cc) {
-    case 32: return launch_bwd<32, 2>(dout, rois, seg, order, argmax, dbottom, g, pl.smem_bwd, st);
-    case 16: return launch_bwd<16, 4>(dout, rois, seg, order, argmax, dbottom, g, pl.smem_bwd, st);
-    case 8: return launch_bwd<8, 4>(dout, rois, seg, order, argmax, dbottom, g, pl.smem_bwd, st);
-    default: return launch_bwd<4, 4>(dout, rois, seg, order, argmax, dbottom, g, pl.smem_bwd, st);
-  }
+  L2S_CROP_DISPATCH(launch_bwd, dout, seg, table, argmax, dbottom, g, pl.smem_bwd, st);
 }

@@ -13,7 +13,7 @@ from ._lib import call, f32c, ptr, stream
 
 NUM_FILTERS = 7
 GATE_SIGMOID, GATE_LINEAR = 0, 1
-CROP_MAX_POOL, CROP_ALIGN = 1, 2
+CROP_MAX_POOL, CROP_ALIGN, CROP_BWD_RANKED = 1, 2, 4
 
 
 def _ws(nbytes, device):
@@ -91,7 +91,7 @@ class _RoICrop(torch.autograd.Function):
         assert rois.dim() == 2 and rois.shape[1] == 5, "rois must be (N,5) [batch,x1,y1,x2,y2]"
         out = torch.empty(N, C, pool, pool, device=bottom.device, dtype=torch.float32)
         arg = torch.empty(N, C, pool, pool, device=bottom.device, dtype=torch.uint8) if flags & CROP_MAX_POOL else None
-        nbytes = _lib.size("l2s_roi_crop_workspace_bytes", B, N)
+        nbytes = _lib.size("l2s_roi_crop_workspace_bytes", B, N, flags)
         ws = _ws(nbytes, bottom.device)
         call("l2s_roi_crop_fwd", ptr(bottom), ptr(rois), ptr(out), ptr(arg), B, C, H, W, N, pool, flags,
              float(im_h), float(im_w), ptr(ws), nbytes, stream())
@@ -105,16 +105,18 @@ class _RoICrop(torch.autograd.Function):
         B, C, H, W, N, pool, flags, im_h, im_w = ctx.meta
         dout = f32c(dout)
         dbottom = torch.empty(B, C, H, W, device=dout.device, dtype=torch.float32)
-        nbytes = _lib.size("l2s_roi_crop_workspace_bytes", B, N)
+        nbytes = _lib.size("l2s_roi_crop_workspace_bytes", B, N, flags)
         ws = _ws(nbytes, dout.device)
         call("l2s_roi_crop_bwd", ptr(dout), ptr(rois), ptr(arg), ptr(dbottom), B, C, H, W, N, pool, flags,
              im_h, im_w, ptr(ws), nbytes, stream())
         return dbottom, None, None, None, None, None
 
 
-def roi_crop(bottom, rois, max_pool=False, align_im_hw=None, pool=7):
-    """Network._crop_pool_layer / _crop_pool_layer_align (network_cycle_response.py:107-182)."""
-    flags = (CROP_MAX_POOL if max_pool else 0) | (CROP_ALIGN if align_im_hw is not None else 0)
+def roi_crop(bottom, rois, max_pool=False, align_im_hw=None, pool=7, bwd_ranked=False):
+    """Network._crop_pool_layer / _crop_pool_layer_align (network_cycle_response.py:107-182).
+    bwd_ranked forces the sample-per-lane backward kernel where the row-owner one would be used (tests)."""
+    flags = (CROP_MAX_POOL if max_pool else 0) | (CROP_ALIGN if align_im_hw is not None else 0) | \
+            (CROP_BWD_RANKED if bwd_ranked else 0)
     im_h, im_w = align_im_hw if align_im_hw is not None else (0.0, 0.0)
     return _RoICrop.apply(bottom, rois, flags, im_h, im_w, pool)
 
@@ -299,6 +301,86 @@ class _Gates(torch.autograd.Function):
 def att2in2_gates(sums, a2c_out, c_prev):
     """Att2in2Core gate epilogue (AttModel.py:450-462) -> (next_h, next_c)."""
     return _Gates.apply(sums, a2c_out, c_prev)
+
+
+class _Att2in2Decode(torch.autograd.Function):
+    """The whole T-step att2in2 recurrence (AttModel.py:75-99 around Att2in2Core :446-466) as one call per
+    direction: l2s_att2in2_decode_{fwd,bwd}.  Weight gradients are GEMMs over the stacked T*B rows."""
+
+    @staticmethod
+    def forward(ctx, i2h_all, att, p_att, w_h2att, b_h2att, w_h2h, w_a2c, b_a2c, alpha_w, alpha_b):
+        i2h_all, att, p_att = f32c(i2h_all), f32c(att), f32c(p_att)
+        T, B, _ = i2h_all.shape
+        A, D = att.shape[1], att.shape[2]
+        Dh = p_att.shape[2]
+        LC = Dh + 5 * D
+        dev = att.device
+        ctx.shapes = (T, B, A, D, Dh, alpha_w.shape, alpha_b.shape)
+        cat_all = torch.empty(T, B, LC, device=dev, dtype=torch.float32)
+        cat_all[:, :, :Dh] = f32c(b_h2att)
+        cat_all[:, :, Dh:] = i2h_all
+        w_cat = torch.cat([f32c(w_h2att), f32c(w_h2h)], 0).contiguous()
+        w_a2c, b_a2c = f32c(w_a2c), f32c(b_a2c)
+        aw, ab = f32c(alpha_w).reshape(-1), f32c(alpha_b).reshape(-1)
+        h_all = torch.empty(T, B, D, device=dev, dtype=torch.float32)
+        c_all = torch.empty_like(h_all)
+        a2c_all = torch.empty(T, B, 2 * D, device=dev, dtype=torch.float32)
+        pi_all = torch.empty(T, B, A, device=dev, dtype=torch.float32)
+        res_all = torch.empty_like(h_all)
+        nbytes = _lib.size("l2s_att2in2_decode_workspace_bytes", T, B, A, D, Dh)
+        ws = _ws(nbytes, dev)
+        call("l2s_att2in2_decode_fwd", ptr(cat_all), ptr(att), ptr(p_att), ptr(w_cat), ptr(w_a2c), ptr(b_a2c), ptr(aw),
+             ptr(ab), ptr(h_all), ptr(c_all), ptr(a2c_all), ptr(pi_all), ptr(res_all), T, B, A, D, Dh, ptr(ws), nbytes,
+             stream())
+        ctx.save_for_backward(cat_all, att, p_att, w_cat, w_a2c, aw, h_all, c_all, a2c_all, pi_all, res_all)
+        return h_all
+
+    @staticmethod
+    def backward(ctx, dh_all):
+        cat_all, att, p_att, w_cat, w_a2c, aw, h_all, c_all, a2c_all, pi_all, res_all = ctx.saved_tensors
+        T, B, A, D, Dh, aw_shape, ab_shape = ctx.shapes
+        LC = Dh + 5 * D
+        dev = att.device
+        dh_all = f32c(dh_all)
+        w_cat_t = w_cat.t().contiguous()
+        w_a2c_t = w_a2c.t().contiguous()
+        dcat_all = torch.empty(T, B, LC, device=dev, dtype=torch.float32)
+        da2c_all = torch.empty(T, B, 2 * D, device=dev, dtype=torch.float32)
+        dres_all = torch.empty(T, B, D, device=dev, dtype=torch.float32)
+        de_all = torch.empty(T, B, A, device=dev, dtype=torch.float32)
+        dp_att = torch.empty_like(p_att)
+        datt = torch.empty_like(att)
+        dalpha = torch.empty(Dh, device=dev, dtype=torch.float32)
+        nbytes = _lib.size("l2s_att2in2_decode_workspace_bytes", T, B, A, D, Dh)
+        ws = _ws(nbytes, dev)
+        call("l2s_att2in2_decode_bwd", ptr(dh_all), ptr(cat_all), ptr(att), ptr(p_att), ptr(w_cat_t), ptr(w_a2c_t),
+             ptr(aw), ptr(c_all), ptr(a2c_all), ptr(pi_all), ptr(dcat_all), ptr(da2c_all), ptr(dres_all), ptr(de_all),
+             ptr(dp_att), ptr(datt), ptr(dalpha), T, B, A, D, Dh, ptr(ws), nbytes, stream())
+        # weight gradients: one GEMM each over the stacked rows (h_{-1} = 0 contributes nothing)
+        dw_cat = dcat_all[1:].reshape(-1, LC).t() @ h_all[:-1].reshape(-1, D)
+        dw_a2c = da2c_all.reshape(-1, 2 * D).t() @ res_all.reshape(-1, D)
+        return (dcat_all[:, :, Dh:], datt, dp_att, dw_cat[:Dh], dcat_all[:, :, :Dh].sum((0, 1)), dw_cat[Dh:], dw_a2c,
+                da2c_all.sum((0, 1)), dalpha.view(aw_shape), de_all.sum().reshape(ab_shape))
+
+
+def att2in2_decode(i2h_all, att_feats, p_att, w_h2att, b_h2att, w_h2h, w_a2c, b_a2c, alpha_w, alpha_b):
+    """h_t for t = 0..T-1 of the att2in2 recurrence from zero state.
+
+    i2h_all (T,B,5D) = i2h(x_t) + b_i2h + b_h2h ; att_feats (B,A,D) ; p_att (B,A,Dh), Dh == D -> h_all (T,B,D)."""
+    return _Att2in2Decode.apply(i2h_all, att_feats, p_att, w_h2att, b_h2att, w_h2h, w_a2c, b_a2c, alpha_w, alpha_b)
+
+
+def linear_small(x, weight, bias=None, out=None, accumulate=False):
+    """out (+)= x @ weight.T + bias, exact fp32, for a small number of rows (no gradient)."""
+    x, weight = f32c(x), f32c(weight)
+    M, K = x.shape
+    N = weight.shape[0]
+    D = out if out is not None else torch.empty(M, N, device=x.device, dtype=torch.float32)
+    nbytes = _lib.size("l2s_linear_small_workspace_bytes", M, N, K)
+    ws = _ws(nbytes, x.device)
+    call("l2s_linear_small", ptr(x), ptr(weight), ptr(f32c(bias) if bias is not None else None), ptr(D), M, N, K, K, K,
+         D.stride(0), int(accumulate), ptr(ws), nbytes, stream())
+    return D
 
 
 class _LogSoftmaxNLL(torch.autograd.Function):

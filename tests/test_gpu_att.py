@@ -145,3 +145,78 @@ def test_lang_encoder_golden(golden):
     enc = enc.cuda().eval()
     out, hid, emb = enc(d["labels"].cuda())
     assert relerr(out, d["output"]) < TOL and relerr(hid, d["hidden"]) < TOL and relerr(emb, d["embedded"]) < TOL
+
+
+@pytest.mark.parametrize("M,N,K,acc", [(48, 3072, 512, True), (48, 1024, 512, False), (48, 512, 1024, False),
+                                         (48, 512, 3072, False), (16, 3072, 512, True), (5, 96, 16, False),
+                                         (70, 40, 1028, True), (1, 8, 4, False), (130, 2000, 512, False)])
+def test_linear_small_vs_fp64(M, N, K, acc):
+    """skinny exact-fp32 linear of the decode loop, incl. deterministic split-K (K > 512) and row blocks (M > 64)"""
+    import lang2seg_b200.functional as F
+    g = torch.Generator().manual_seed(M * 7 + N)
+    x, w, b = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) / K ** 0.5, torch.randn(N, generator=g)
+    d0 = torch.randn(M, N, generator=g)
+    ref = x.double() @ w.double().t() + b.double() + (d0.double() if acc else 0)
+    out = d0.clone().cuda() if acc else torch.full((M, N), float("nan")).cuda()
+    F.linear_small(x.cuda(), w.cuda(), b.cuda(), out=out, accumulate=acc)
+    assert relerr(out, ref) < 2e-6
+    out2 = d0.clone().cuda() if acc else torch.empty(M, N).cuda()
+    F.linear_small(x.cuda(), w.cuda(), b.cuda(), out=out2, accumulate=acc)
+    assert torch.equal(out, out2), "split-K reduction must be deterministic"
+
+
+@pytest.mark.parametrize("B,L,opt", [(5, 10, {}), (16, 20, {}), (3, 6, SMALL_OPT)])
+def test_att2in2_decode_fast_path_vs_stepwise_and_oracle(B, L, opt):
+    """l2s_att2in2_decode_{fwd,bwd} (the whole recurrence in two calls) against the per-step modules and the
+    CPU oracle, at the reference's sizes (rnn 512, 196 locations, vocab 1999)."""
+    from lang2seg_b200 import caption_models
+    o = dict(vocab_size=1999, input_encoding_size=512, rnn_size=512, att_hid_size=512, fc_feat_size=4096,
+             att_feat_size=4096, seq_length=L, num_layers=1, drop_prob_lm=0.5, caption_model="att2in2")
+    o.update(opt)
+    o["seq_length"] = L
+    torch.manual_seed(3)
+    model = caption_models.setup(o).cuda().eval()
+    g = torch.Generator().manual_seed(11)
+    labels, lens = R.synth_labels(g, B, L, o["vocab_size"])
+    cap, msk = R.caption_targets(labels, lens, L)
+    A = 196 if not opt else 9
+    side = 14 if not opt else 3
+    att0 = torch.relu(torch.randn(B, side, side, o["att_feat_size"], generator=g))
+    fc = torch.randn(B, o["fc_feat_size"], generator=g)
+
+    def run(fast):
+        model.zero_grad()
+        att = att0.cuda().requires_grad_(True)
+        if not fast:
+            model._fast_decode_ok = lambda a: False
+        else:
+            model.__dict__.pop("_fast_decode_ok", None)
+        loss = model.forward_loss(fc.cuda(), att, cap.cuda(), msk.cuda())
+        loss.backward()
+        return loss.detach(), att.grad, {k: v.grad.clone() for k, v in model.named_parameters()}
+
+    lf, gf, pf = run(True)
+    ls, gs, ps = run(False)
+    assert relerr(lf, ls) < TOL and relerr(gf, gs) < TOL
+    for k in pf:
+        if k.endswith("alpha_net.bias"):      # softmax is shift invariant: gradient is exactly 0 up to rounding
+            assert float(pf[k].abs().max()) < 1e-6
+            continue
+        assert relerr(pf[k], ps[k]) < TOL, k
+    # oracle (CPU restatement of AttModel.py / misc/utils.py)
+    params = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in model.named_parameters()}
+    atto = att0.clone().requires_grad_(True)
+    lo = R.caption_loss(fc, atto, cap, msk, params)
+    lo.backward()
+    assert relerr(lf, lo) < TOL and relerr(gf, atto.grad) < TOL
+    for k in pf:
+        if k.endswith("alpha_net.bias"):      # softmax is shift invariant: gradient is exactly 0 up to rounding
+            continue
+        assert relerr(pf[k], params[k].grad) < TOL, k
+    # log-prob interface
+    with torch.no_grad():
+        lp = model(fc.cuda(), att0.cuda(), cap.cuda())
+        model._fast_decode_ok = lambda a: False
+        lp2 = model(fc.cuda(), att0.cuda(), cap.cuda())
+        model.__dict__.pop("_fast_decode_ok", None)
+    assert lp.shape == lp2.shape and relerr(lp, lp2) < TOL

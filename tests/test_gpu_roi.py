@@ -40,9 +40,11 @@ def test_crop_golden(golden, tag):
 
 
 @pytest.mark.parametrize("shape", [(3, 40, 32, 32, 70), (2, 64, 38, 63, 33), (2, 16, 50, 80, 20), (1, 8, 80, 120, 9)])
-@pytest.mark.parametrize("max_pool", [False, True])
+@pytest.mark.parametrize("max_pool", [False, True, "ranked"])
 def test_crop_vs_oracle(shape, max_pool):
     B, C, H, W, N = shape
+    ranked = max_pool == "ranked"          # 7x7 crop through the sample-per-lane backward kernel
+    max_pool = max_pool is True
     g = torch.Generator().manual_seed(B * 1000 + C + H)
     bottom = torch.randn(B, C, H, W, generator=g)
     rois = torch.cat([R.synth_rois(g, N, H * 16, W * 16, b) for b in range(B)])
@@ -60,13 +62,43 @@ def test_crop_vs_oracle(shape, max_pool):
             G = G * ((top2[..., 0] - top2[..., 1]) > 1e-3)
     (gref,) = torch.autograd.grad((ref * G).sum(), bo)
     bc = bottom.cuda().requires_grad_(True)
-    out = _f().roi_crop(bc, rois.cuda(), max_pool=max_pool)
+    out = _f().roi_crop(bc, rois.cuda(), max_pool=max_pool, bwd_ranked=ranked)
     assert relerr(out, ref) < TOL
     (gb,) = torch.autograd.grad((out * G.cuda()).sum(), bc)
     assert relerr(gb, gref) < TOL
     # deterministic scatter-add: bit-identical on a second run
-    (gb2,) = torch.autograd.grad((_f().roi_crop(bc, rois.cuda(), max_pool=max_pool) * G.cuda()).sum(), bc)
+    (gb2,) = torch.autograd.grad((_f().roi_crop(bc, rois.cuda(), max_pool=max_pool, bwd_ranked=ranked) * G.cuda()).sum(), bc)
     assert torch.equal(gb, gb2)
+
+
+@pytest.mark.parametrize("max_pool", [False, True, "ranked"])
+def test_crop_degenerate_boxes(max_pool):
+    """Zero-area, sub-pixel, out-of-map and whole-map boxes: all 49 samples of a box may fall into one cell
+    (collision ranks up to 48 in the backward) or entirely into the zero padding."""
+    ranked = max_pool == "ranked"
+    max_pool = max_pool is True
+    g = torch.Generator().manual_seed(5)
+    B, C, H, W = 2, 32, 32, 32
+    bottom = torch.randn(B, C, H, W, generator=g)
+    boxes = [[0, 100., 100., 100., 100.], [0, 37., 41., 39., 43.], [1, 0., 0., 511., 511.], [1, 600., 600., 900., 900.],
+             [0, -50., -50., 20., 20.], [1, 496., 496., 511., 511.], [0, 8., 8., 24., 8.], [1, 16., 300., 16., 420.],
+             [0, 255.5, 255.5, 256.5, 256.5], [1, 0., 0., 15., 15.]]
+    rois = torch.tensor(boxes * 3)
+    bo = bottom.clone().requires_grad_(True)
+    ref = R.crop_pool(bo, rois, max_pool=max_pool)
+    G = torch.randn(ref.shape, generator=g)
+    if max_pool:
+        with torch.no_grad():
+            s14 = R.crop_pool(bottom, rois, max_pool=False, pool=14)
+            win = s14.unfold(2, 2, 2).unfold(3, 2, 2).reshape(*ref.shape, 4)
+            top2 = win.topk(2, dim=-1).values
+            G = G * ((top2[..., 0] - top2[..., 1]) > 1e-3)
+    (gref,) = torch.autograd.grad((ref * G).sum(), bo)
+    bc = bottom.cuda().requires_grad_(True)
+    out = _f().roi_crop(bc, rois.cuda(), max_pool=max_pool, bwd_ranked=ranked)
+    assert relerr(out, ref) < TOL
+    (gb,) = torch.autograd.grad((out * G.cuda()).sum(), bc)
+    assert relerr(gb, gref) < TOL
 
 
 def test_crop_index_contract():
