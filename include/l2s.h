@@ -41,8 +41,8 @@ typedef void* l2s_stream_t; /* cudaStream_t */
 #define L2S_GATE_LINEAR 1   /* Y = X * r           network_7f.py:534, network_cycle_res5_2.py:562 */
 #define L2S_CROP_MAX_POOL 1 /* 2S x 2S samples then 2x2 max (network_cycle_response.py:140-144) */
 #define L2S_CROP_ALIGN 2    /* _crop_pool_layer_align (network_cycle_response.py:151-182)  */
-#define L2S_CROP_BWD_RANKED 4 /* backward only: force the sample-per-lane (ranked) kernel even where the row-owner
-                               * kernel applies (maps <= ~1700 pixels, no max-pool); for tests / comparison */
+#define L2S_CROP_BWD_RANKED 4 /* backward only: force the sample-per-lane (ranked) kernel where the row-owner kernel
+                               * (lane = channel, warp = map rows; 7x7 crops of maps <= ~1300 pixels) is the default */
 
 int l2s_version(void);
 const char* l2s_last_error_string(void);

@@ -124,6 +124,10 @@ __device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint3
                "r"(smem_u32(smem_src)), "r"(bytes)
                : "memory");
 }
+// pull a global range into L2 ahead of the shared-memory ring (decouples DRAM latency from the ring depth)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gsrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() {

@@ -31,7 +31,7 @@ constexpr int kPP = 49;             // outputs per (ROI, channel): cfg.POOLING_S
 constexpr int kFwdItems = 32 * kPP; // (ROI, sample, channel quad) items per forward iteration pass: RPI * CGN == 32
 constexpr int kFwdThreads = 800;    // 25 warps: items t and t + 784 ... of an iteration (784 = kFwdItems / 2)
 constexpr int kBwdStages = 6;
-constexpr int kRecTail = 64;        // bytes after the entries of a geometry record: ranks[49], maxrank, ROI id
+constexpr int kRecTail = 128;       // bytes after the entries of a geometry record (see roi_geom_kernel)
 
 __device__ __forceinline__ int swz_key(int px) { return (px ^ (px >> 3) ^ (px >> 6)) & 7; }
 
@@ -174,25 +174,34 @@ roi_geom_kernel(const float* __restrict__ rois, const int* __restrict__ order, u
     key = (y0 << 16) | (x0 & 0xffff);
   }
   if (g.S == 7) {   // launched with 64 threads
-    // collision rank over all 49 samples: number of earlier samples in the same (y0,x0) cell
-    s_key[p] = (p < SS) ? key : (int)(0x80000000u | (unsigned)p);
-    __syncthreads();
-    int rank = 0;
-    if (p < SS)
-      for (int q = 0; q < p; ++q) rank += (s_key[q] == key);
-    __syncthreads();
-    const int mr = __reduce_max_sync(0xffffffffu, p < SS ? rank : 0);
-    if ((p & 31) == 0) s_key[p >> 5] = mr;
-    __syncthreads();
+    // The ranked backward splits the corners of a sample between two warps by the PARITY h of the map row
+    // (row y0 or y0+1).  Inside warp h two samples meet in a pixel through the same (left/right) corner iff they
+    // agree in (row_h, x0): rank_h = number of earlier samples with the same key.  tail layout:
+    //   [0..48] rank_0 | bit 7: parity of y0      [64..112] rank_1      [56..59] ROI id   [60],[61] max rank_0/1
+    const int yq = key >> 16, xq = (int)(short)(key & 0xffff);
     unsigned char* tail = rec + (size_t)SS * 16;
-    if (p < SS) tail[p] = (unsigned char)rank;
-    if (p == 0) tail[60] = (unsigned char)max(s_key[0], s_key[1]);
+    for (int h = 0; h < 2; ++h) {
+      const int row = yq + (((yq & 1) ^ h) & 1);
+      const int kh = (p < SS) ? ((row << 16) | (xq & 0xffff)) : (int)(0x80000000u | (unsigned)p);
+      __syncthreads();
+      s_key[p] = kh;
+      __syncthreads();
+      int rank = 0;
+      if (p < SS)
+        for (int q = 0; q < p; ++q) rank += (s_key[q] == kh);
+      __syncthreads();
+      const int mr = __reduce_max_sync(0xffffffffu, p < SS ? rank : 0);
+      if ((p & 31) == 0) s_key[p >> 5] = mr;
+      __syncthreads();
+      if (p < SS) tail[h * 64 + p] = (unsigned char)(rank | (h == 0 ? ((yq & 1) << 7) : 0));
+      if (p == 0) tail[60 + h] = (unsigned char)max(s_key[0], s_key[1]);
+    }
   }
   if (p == 0) *reinterpret_cast<int*>(rec + (size_t)SS * 16 + 56) = n;
   if (sep != nullptr && g.S == 7 && p < 8) {
     SepRec* sr = sep + r;
     const Corner c = sample_at(box, min(p, 6), min(p, 6), inv);
-    const int y0 = min(max(c.y0, -2), 30000), x0 = min(max(c.x0, -2), 30000);
+    const int y0 = min(max(c.y0, -2), 30000), x0 = min(max(c.x0, -2), g.W);
     sr->x0[p] = (int16_t)x0; sr->lx[p] = c.lx;
     sr->y0[p] = (int16_t)y0; sr->ly[p] = c.ly;
     if (p == 0) {
@@ -410,11 +419,13 @@ roi_crop_fwd_kernel(const float* __restrict__ bottom, const int* __restrict__ se
 // warps: CGN consumers + 1 producer.  Consumer warp cg owns channel quad cg of the accumulator map.
 // Stage = gradient tile [CC][49] (+ winners [CC][49] u8 with max-pool) + the ROI's geometry record.
 template <int CC, bool MAXPOOL>
-__global__ void __launch_bounds__((CC / 4 + 1) * 32, 1)
+__global__ void __launch_bounds__(((MAXPOOL ? 1 : 2) * CC / 4 + 1) * 32, 1)
 roi_crop_bwd_kernel(const float* __restrict__ dout, const int* __restrict__ seg,
                     const unsigned char* __restrict__ table, const uint8_t* __restrict__ argmax,
                     float* __restrict__ dbottom, CropGeom g) {
   constexpr int CGN = CC / 4;
+  constexpr int NH = MAXPOOL ? 1 : 2;        // consumer warps per channel quad (row-parity split)
+  constexpr int NCONS = NH * CGN;
   constexpr int TILE = CC * kPP;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int HW = g.H * g.W;
@@ -432,7 +443,7 @@ roi_crop_bwd_kernel(const float* __restrict__ dout, const int* __restrict__ seg,
   if (t == 0) {
     for (int s = 0; s < kBwdStages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], CGN);
+      mbar_init(&empty_bar[s], NCONS);
     }
     mbar_fence_init();
   }
@@ -444,12 +455,20 @@ roi_crop_bwd_kernel(const float* __restrict__ dout, const int* __restrict__ seg,
   // winners travel by TMA only when their rows are 16-byte sized / aligned (C % 16 == 0); otherwise read in place
   const bool arg_smem = MAXPOOL && (g.C % 16 == 0) && (cvalid % 16 == 0);
 
-  if (wid == CGN) {
+  if (wid == NCONS) {
     // ---------------- producer warp: streams tiles + records (ROI ids fetched 32 at a time) ----------------
     for (int r0 = beg, k = 0; r0 < end; r0 += 32) {
       const int mine = r0 + lane;
       int nl = 0;
       if (mine < end) nl = __ldg(reinterpret_cast<const int*>(table + (size_t)mine * g.rec + (size_t)g.S * g.S * 16 + 56));
+      {   // L2 prefetch of the group after this one (the first group is prefetched before the loop)
+        const int ahead = mine + (r0 == beg ? 0 : 32);
+        for (int a = ahead; a < end && a <= mine + 32; a += 32) {
+          const int na = __ldg(reinterpret_cast<const int*>(table + (size_t)a * g.rec + (size_t)g.S * g.S * 16 + 56));
+          bulk_prefetch_l2(dout + ((size_t)na * g.C + c0) * kPP, tile_bytes);
+          bulk_prefetch_l2(table + (size_t)a * g.rec, (uint32_t)g.rec);
+        }
+      }
       const int cnt = min(32, end - r0);
       for (int j = 0; j < cnt; ++j, ++k) {
         const int n = __shfl_sync(0xffffffffu, nl, j);
@@ -467,7 +486,7 @@ roi_crop_bwd_kernel(const float* __restrict__ dout, const int* __restrict__ seg,
     }
   } else {
     // ---------------- consumers ----------------
-    const int cg = wid;
+    const int cg = wid % CGN, hpar = wid / CGN;
     const bool ch_ok = cg * 4 < cvalid;
     float4* map4 = reinterpret_cast<float4*>(map);
     const unsigned lt = (1u << lane) - 1u;
@@ -482,11 +501,14 @@ roi_crop_bwd_kernel(const float* __restrict__ dout, const int* __restrict__ seg,
       const uint4* ent = reinterpret_cast<const uint4*>(rec);
       const int cb = cg * 4;
       if (!MAXPOOL) {
+        // warp (cg, hpar): of every sample the two corners that lie in the map row of parity hpar
         const unsigned char* tail = rec + kPP * 16;
-        const int mr = tail[60];
+        const int mr = tail[60 + hpar];
         const uint4 e0 = ent[p0];
         const uint4 e1 = on1 ? ent[p1] : make_uint4(0, 0, 0, 0);
-        const int r0 = ch_ok ? (int)tail[p0] : -1, r1 = (ch_ok && on1) ? (int)tail[p1] : -1;
+        const int top0 = ((tail[p0] >> 7) == hpar), top1 = on1 ? ((tail[p1] >> 7) == hpar) : 0;
+        const int r0 = ch_ok ? (int)(tail[hpar * 64 + p0] & 0x7f) : -1;
+        const int r1 = (ch_ok && on1) ? (int)(tail[hpar * 64 + p1] & 0x7f) : -1;
         float4 v0, v1 = make_float4(0.f, 0.f, 0.f, 0.f);
         v0.x = tile[(cb + 0) * kPP + p0]; v0.y = tile[(cb + 1) * kPP + p0];
         v0.z = tile[(cb + 2) * kPP + p0]; v0.w = tile[(cb + 3) * kPP + p0];
@@ -498,10 +520,11 @@ roi_crop_bwd_kernel(const float* __restrict__ dout, const int* __restrict__ seg,
         const float ly1 = __uint_as_float(e1.z), lx1 = __uint_as_float(e1.w);
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty_bar[s]);     // everything of this stage is in registers now
-        // Samples of equal rank lie in different (y0,x0) cells but may still meet in one pixel through
-        // DIFFERENT corners; so the four corners are four read-modify-write phases with a warp barrier
-        // between them.  Inside a phase a pixel is reached only by samples of one cell => distinct ranks.
-        // Corners outside the map point at the zero slot, whose content is never written back.
+        const uint32_t pair0 = top0 ? e0.x : e0.y, pair1 = top1 ? e1.x : e1.y;   // slots of (x0, x0+1) in my row
+        const float wy0 = top0 ? 1.f - ly0 : ly0, wy1 = top1 ? 1.f - ly1 : ly1;
+        // Equal-rank samples differ in (row, x0) but may still meet in a pixel through DIFFERENT corners
+        // (A's right pixel is B's left pixel): left and right corners are two read-modify-write phases with a
+        // warp barrier between them.  Corners outside the map point at the zero slot, never written back.
         auto rmw = [&](bool on, uint32_t slot, float w, const float4& v) {
           if (on) {
             float4 m = map4[slot ^ cg];
@@ -514,17 +537,11 @@ roi_crop_bwd_kernel(const float* __restrict__ dout, const int* __restrict__ seg,
         };
         for (int rr = 0; rr <= mr; ++rr) {
           const bool a0 = r0 == rr, a1 = r1 == rr;
-          rmw(a0, e0.x & 0xffffu, (1.f - ly0) * (1.f - lx0), v0);
-          rmw(a1, e1.x & 0xffffu, (1.f - ly1) * (1.f - lx1), v1);
+          rmw(a0, pair0 & 0xffffu, wy0 * (1.f - lx0), v0);
+          rmw(a1, pair1 & 0xffffu, wy1 * (1.f - lx1), v1);
           __syncwarp();
-          rmw(a0, e0.x >> 16, (1.f - ly0) * lx0, v0);
-          rmw(a1, e1.x >> 16, (1.f - ly1) * lx1, v1);
-          __syncwarp();
-          rmw(a0, e0.y & 0xffffu, ly0 * (1.f - lx0), v0);
-          rmw(a1, e1.y & 0xffffu, ly1 * (1.f - lx1), v1);
-          __syncwarp();
-          rmw(a0, e0.y >> 16, ly0 * lx0, v0);
-          rmw(a1, e1.y >> 16, ly1 * lx1, v1);
+          rmw(a0, pair0 >> 16, wy0 * lx0, v0);
+          rmw(a1, pair1 >> 16, wy1 * lx1, v1);
           __syncwarp();
         }
       } else {
@@ -578,23 +595,27 @@ roi_crop_bwd_kernel(const float* __restrict__ dout, const int* __restrict__ seg,
 }
 
 // ------------------------------------------------------------------ backward, row-owner variant (CC = 32, 7x7)
-// lane = channel, warp w owns map rows y = w (mod 31): every read-modify-write of the accumulator map is a
-// conflict-free 128-byte row segment, control flow is warp uniform (geometry does not depend on the channel),
-// there are no collisions to rank and no barriers inside a ROI.  Per sample row i and map row y the 7 samples
-// are swept left to right with the two live column sums in registers, so a column is written once per sweep
-// (<= 14 RMW per (ROI, sample row, map row) instead of 28).
+// lane = channel, warp w owns map rows y = w (mod kRowWarps): every read-modify-write of the accumulator map
+// is a conflict-free 128-byte segment, control flow is warp uniform (geometry does not depend on the channel),
+// there are no collisions to rank and no barriers inside a ROI.  The accumulator is stored [row][col+2][33]:
+// the odd channel stride keeps both the channel-wise updates and the pixel-wise final read-out conflict free,
+// and two guard columns on each side absorb the corners that fall outside the map (x0 is clamped to
+// [-2, W] in the record), so the inner loop has no bounds checks and no branches.
 constexpr int kRowWarps = 31;
 constexpr int kRowStages = 8;
+constexpr int kRowLd = 33;
 
-__global__ void __launch_bounds__(1024, 1)
+__global__ void __launch_bounds__((kRowWarps + 1) * 32, 1)
 roi_crop_bwd_rows_kernel(const float* __restrict__ dout, const int* __restrict__ seg,
                          const SepRec* __restrict__ sep, float* __restrict__ dbottom, CropGeom g) {
   constexpr int CC = 32;
   constexpr int TILE = CC * kPP;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int HW = g.H * g.W, W = g.W, H = g.H;
-  float* map = reinterpret_cast<float*>(smem_raw);
-  float* tiles = map + (size_t)(HW + 1) * CC;                                // [kRowStages][TILE]
+  const int WP = W + 4;                                                      // padded row length
+  float* map = reinterpret_cast<float*>(smem_raw);                           // [H][WP][33]
+  const int map_floats = (H * WP * kRowLd + 3) & ~3;
+  float* tiles = map + map_floats;                                           // [kRowStages][TILE]
   SepRec* recs = reinterpret_cast<SepRec*>(tiles + kRowStages * TILE);       // [kRowStages]
   __shared__ uint64_t full_bar[kRowStages], empty_bar[kRowStages];
 
@@ -602,7 +623,7 @@ roi_crop_bwd_rows_kernel(const float* __restrict__ dout, const int* __restrict__
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
   const int cvalid = min(CC, g.C - c0);
 
-  for (int i = t; i < (HW + 1) * CC; i += blockDim.x) map[i] = 0.f;
+  for (int i = t; i < map_floats; i += blockDim.x) map[i] = 0.f;
   if (t == 0) {
     for (int s = 0; s < kRowStages; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -620,6 +641,11 @@ roi_crop_bwd_rows_kernel(const float* __restrict__ dout, const int* __restrict__
     for (int r0 = beg, k = 0; r0 < end; r0 += 32) {
       const int mine = r0 + lane;
       const int nl = (mine < end) ? __ldg(&sep[mine].n) : 0;
+      {   // L2 prefetch of the group after this one (and of the first group itself)
+        const int ahead = mine + (r0 == beg ? 0 : 32);
+        for (int a = ahead; a < end && a <= mine + 32; a += 32)
+          bulk_prefetch_l2(dout + ((size_t)__ldg(&sep[a].n) * g.C + c0) * kPP, tile_bytes);
+      }
       const int cnt = min(32, end - r0);
       for (int j = 0; j < cnt; ++j, ++k) {
         const int n = __shfl_sync(0xffffffffu, nl, j);
@@ -634,62 +660,43 @@ roi_crop_bwd_rows_kernel(const float* __restrict__ dout, const int* __restrict__
     }
   } else {
     // ---------------- consumers: warp = rows, lane = channel ----------------
-    const bool act = lane < cvalid;
-    const int cgq = lane >> 2, csub = lane & 3;
+    const int cl = lane < cvalid ? lane : 0;          // idle lanes shadow channel 0 into their own column
+    float* mlane = map + 2 * kRowLd + lane;           // (row 0, col 0, my channel); lanes >= cvalid never unstaged
     for (int ri = beg, k = 0; ri < end; ++ri, ++k) {
       const int s = k % kRowStages;
       mbar_wait(&full_bar[s], (k / kRowStages) & 1);
       const SepRec* rec = recs + s;
       const int ymin = rec->ymin, ymax = rec->ymax;
-      bool any = false;
-      for (int y = wid; y < H; y += kRowWarps) any |= (y >= ymin && y <= ymax);
-      if (any) {
-        const float* tcol = tiles + (size_t)s * TILE + (size_t)(act ? lane : 0) * kPP;
-        int x0[7];
-        float lx[7];
+      bool loaded = false;
+      int xoff[7];
+      float wa[7], wb[7];
+#pragma unroll 1
+      for (int yy = wid; yy < H; yy += kRowWarps) {
+        if (yy < ymin || yy > ymax) continue;          // warp uniform
+        if (!loaded) {
 #pragma unroll
-        for (int j = 0; j < 7; ++j) {
-          x0[j] = rec->x0[j];
-          lx[j] = rec->lx[j];
+          for (int j = 0; j < 7; ++j) {
+            xoff[j] = (int)rec->x0[j] * kRowLd;
+            wb[j] = rec->lx[j];
+            wa[j] = 1.f - wb[j];
+          }
+          loaded = true;
         }
+        const float* tcol = tiles + (size_t)s * TILE + (size_t)cl * kPP;
+        float* mrow = mlane + (size_t)yy * WP * kRowLd;
 #pragma unroll 1
         for (int i = 0; i < 7; ++i) {
-          const int y0 = rec->y0[i];
+          const int d = yy - (int)rec->y0[i];
+          if (d != 0 && d != 1) continue;              // warp uniform
           const float ly = rec->ly[i];
-#pragma unroll 1
-          for (int dy = 0; dy < 2; ++dy) {
-            const int y = y0 + dy;
-            if ((unsigned)y >= (unsigned)H || (y % kRowWarps) != wid) continue;   // warp uniform
-            const float wy = dy ? ly : 1.f - ly;
-            const int rowpx = y * W;
-            auto add = [&](int col, float v) {
-              if ((unsigned)col < (unsigned)W && act) {
-                float* m = map + map_off<CC>(rowpx + col, cgq) + csub;
-                *m += v;
-              }
-            };
-            float a = 0.f, bsum = 0.f;
-            int cur = x0[0];
+          const float wy = d ? ly : 1.f - ly;
+          const float* trow = tcol + i * 7;
 #pragma unroll
-            for (int j = 0; j < 7; ++j) {
-              const float v = tcol[i * 7 + j] * wy;
-              const int xj = x0[j];
-              if (xj != cur) {                    // warp uniform
-                add(cur, a);
-                if (xj == cur + 1) {
-                  a = bsum;
-                } else {
-                  add(cur + 1, bsum);
-                  a = 0.f;
-                }
-                bsum = 0.f;
-                cur = xj;
-              }
-              a = fmaf(1.f - lx[j], v, a);
-              bsum = fmaf(lx[j], v, bsum);
-            }
-            add(cur, a);
-            add(cur + 1, bsum);
+          for (int j = 0; j < 7; ++j) {
+            const float v = trow[j] * wy;
+            float* m = mrow + xoff[j];
+            m[0] = fmaf(wa[j], v, m[0]);
+            m[kRowLd] = fmaf(wb[j], v, m[kRowLd]);
           }
         }
       }
@@ -698,7 +705,15 @@ roi_crop_bwd_rows_kernel(const float* __restrict__ dout, const int* __restrict__
     }
   }
   __syncthreads();
-  unstage_map<CC>(map, dbottom + (size_t)b * g.C * HW, c0, g.C, HW);
+  // read-out: warp = (channel, 32 consecutive pixels of a row)
+  float* dst = dbottom + ((size_t)b * g.C + c0) * HW;
+  const int nw = blockDim.x >> 5;
+  const int xblocks = (W + 31) >> 5;
+  for (int it = wid; it < cvalid * H * xblocks; it += nw) {
+    const int c = it % cvalid, rest = it / cvalid;
+    const int y = rest / xblocks, x = (rest % xblocks) * 32 + lane;
+    if (x < W) dst[(size_t)c * HW + y * W + x] = map[((size_t)y * WP + x + 2) * kRowLd + c];
+  }
 }
 
 // ------------------------------------------------------------------ host side
@@ -709,6 +724,7 @@ struct Plan {
 
 bool make_plan(int HW, bool maxpool, int rec, Plan* pl) {
   const size_t cap = (size_t)max_smem_optin() - 1024;
+  pl->smem_rows = 0;
   for (int cc = 32; cc >= 4; cc >>= 1) {
     const size_t map = (size_t)(HW + 1) * cc * 4;
     const size_t tile = (size_t)cc * kPP;
@@ -719,7 +735,6 @@ bool make_plan(int HW, bool maxpool, int rec, Plan* pl) {
       pl->cc = cc;
       pl->smem_fwd = fwd;
       pl->smem_bwd = bwd;
-      pl->smem_rows = map + kRowStages * (tile * 4 + sizeof(SepRec)) + 128;
       return true;
     }
   }
@@ -800,7 +815,7 @@ int launch_bwd(const float* dout, const int* seg, const unsigned char* table, co
   auto kern = roi_crop_bwd_kernel<CC, MP>;
   L2S_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((g.C + CC - 1) / CC, g.B);
-  kern<<<grid, (CC / 4 + 1) * 32, smem, st>>>(dout, seg, table, argmax, dbottom, g);
+  kern<<<grid, ((MP ? 1 : 2) * CC / 4 + 1) * 32, smem, st>>>(dout, seg, table, argmax, dbottom, g);
   L2S_LAUNCH_OK("roi_crop_bwd_kernel");
   count_launch();
   return L2S_OK;
@@ -877,7 +892,9 @@ extern "C" int l2s_roi_crop_bwd(const float* dout, const float* rois, const uint
   SepRec* sep;
   rc = prepare(rois, g, pl.cc / 4, workspace, st, &seg, &table, &sep);
   if (rc) return rc;
-  if (!g.maxpool && pl.cc == 32 && !(flags & L2S_CROP_BWD_RANKED)) {
+  // row-owner kernel: needs the whole 32-channel accumulator with guard columns + the tile ring in shared memory
+  pl.smem_rows = (((size_t)H * (W + 4) * kRowLd + 3) & ~(size_t)3) * 4 + kRowStages * ((size_t)32 * kPP * 4 + sizeof(SepRec)) + 128;
+  if (!g.maxpool && pl.cc == 32 && pl.smem_rows <= (size_t)max_smem_optin() - 1024 && !(flags & L2S_CROP_BWD_RANKED)) {
     auto kern = roi_crop_bwd_rows_kernel;
     L2S_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_rows));
     dim3 grid((g.C + 31) / 32, g.B);

@@ -114,7 +114,7 @@ class _RoICrop(torch.autograd.Function):
 
 def roi_crop(bottom, rois, max_pool=False, align_im_hw=None, pool=7, bwd_ranked=False):
     """Network._crop_pool_layer / _crop_pool_layer_align (network_cycle_response.py:107-182).
-    bwd_ranked forces the sample-per-lane backward kernel where the row-owner one would be used (tests)."""
+    bwd_ranked forces the sample-per-lane backward kernel where the row-owner one (lane = channel) is the default."""
     flags = (CROP_MAX_POOL if max_pool else 0) | (CROP_ALIGN if align_im_hw is not None else 0) | \
             (CROP_BWD_RANKED if bwd_ranked else 0)
     im_h, im_w = align_im_hw if align_im_hw is not None else (0.0, 0.0)

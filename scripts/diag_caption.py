@@ -6,8 +6,6 @@ sys.path.insert(0, ROOT)
 import torch
 from oracle import restate as R
 from lang2seg_b200 import caption_models
-import importlib
-AM = importlib.import_module('lang2seg_b200.caption_models.AttModel')
 
 def rel(a, b):
     a, b = a.detach().double().cpu(), b.detach().double().cpu()
@@ -28,14 +26,13 @@ for B, L in [(5, 10), (16, 10), (5, 20), (16, 20), (48, 10)]:
     lo = R.caption_loss(fc, atto, cap, msk, params)
     lo.backward()
     for big in (True, False):
-        orig = AM.AttModel._big_linear
         if not big:
-            AM.AttModel._big_linear = staticmethod(lambda lin, x: lin(x))
+            model._big_linear = lambda lin, x: lin(x)      # instance attribute shadows the staticmethod
         model.zero_grad()
         att = att0.cuda().requires_grad_(True)
         loss = model.forward_loss(fc.cuda(), att, cap.cuda(), msk.cuda())
         loss.backward()
-        AM.AttModel._big_linear = orig
+        model.__dict__.pop("_big_linear", None)
         worst = sorted(((rel(v.grad, params[k].grad), k) for k, v in model.named_parameters()
                         if not k.endswith("alpha_net.bias")), reverse=True)[:4]
         print("B=%d L=%d tc_linear=%s loss %.2e datt %.2e worst %s" % (B, L, big, rel(loss, lo), rel(att.grad, atto.grad),

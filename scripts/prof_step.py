@@ -1,0 +1,55 @@
+#!/usr/bin/env python
+"""Per-kernel device time of the bench step measured in situ (warm caches, real overlap) with torch.profiler/CUPTI.
+
+    python scripts/prof_step.py [--workload cfg2] [--steps 3] > gpurun_out/step_kernels.txt
+"""
+import argparse
+import collections
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+from torch.profiler import ProfilerActivity, profile  # noqa: E402
+
+from bench import WORKLOADS, HotPathStep, make_inputs  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="cfg2")
+    ap.add_argument("--steps", type=int, default=3)
+    a = ap.parse_args()
+    wl = WORKLOADS[a.workload]
+    dev = torch.device("cuda:0")
+    step = HotPathStep(wl, dev, 1)
+    d = make_inputs(wl, 1234, dev)
+    for _ in range(3):
+        step(d)
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(a.steps):
+        step(d)
+    t1.record()
+    torch.cuda.synchronize()
+    print("# un-profiled: %.3f ms/step" % (t0.elapsed_time(t1) / a.steps))
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+        for _ in range(a.steps):
+            step(d)
+        torch.cuda.synchronize()
+    agg = collections.defaultdict(lambda: [0, 0.0])
+    for ev in prof.events():
+        if ev.device_type == torch.autograd.DeviceType.CUDA:
+            agg[ev.name[:110]][0] += 1
+            agg[ev.name[:110]][1] += ev.device_time if hasattr(ev, "device_time") else ev.cuda_time
+    tot = sum(v[1] for v in agg.values())
+    print("# %d steps, %.1f us of kernel time per step (sum over kernels)" % (a.steps, tot / a.steps))
+    print("%-110s %8s %12s %7s" % ("kernel", "n/step", "us/step", "share"))
+    for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:70]:
+        print("%-110s %8.1f %12.1f %6.2f%%" % (k, v[0] / a.steps, v[1] / a.steps, 100 * v[1] / tot))
+
+
+if __name__ == "__main__":
+    main()

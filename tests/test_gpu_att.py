@@ -203,14 +203,21 @@ def test_att2in2_decode_fast_path_vs_stepwise_and_oracle(B, L, opt):
             assert float(pf[k].abs().max()) < 1e-6
             continue
         assert relerr(pf[k], ps[k]) < TOL, k
-    # oracle (CPU restatement of AttModel.py / misc/utils.py)
+    # oracle (CPU restatement of AttModel.py / misc/utils.py).  The network is piecewise linear (ReLU after
+    # att_embed, maxout in the cell): a pre-activation that sits within rounding of a kink can take the other branch
+    # and changes single gradient entries by O(1).  The bf16x3 tensor-core Linear (1e-5 from fp32, checked on its own
+    # in test_linear_tc_vs_fp64) perturbs ~10^6 pre-activations and makes such flips likely, so the comparison
+    # against the CPU oracle runs the two big projections in exact fp32 (cuBLAS); seeds are fixed.
+    model._big_linear = lambda lin, x: lin(x)
+    lf, gf, pf = run(True)
+    model.__dict__.pop("_big_linear", None)
     params = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in model.named_parameters()}
     atto = att0.clone().requires_grad_(True)
     lo = R.caption_loss(fc, atto, cap, msk, params)
     lo.backward()
     assert relerr(lf, lo) < TOL and relerr(gf, atto.grad) < TOL
     for k in pf:
-        if k.endswith("alpha_net.bias"):      # softmax is shift invariant: gradient is exactly 0 up to rounding
+        if k.endswith("alpha_net.bias"):
             continue
         assert relerr(pf[k], params[k].grad) < TOL, k
     # log-prob interface

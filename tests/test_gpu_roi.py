@@ -43,7 +43,7 @@ def test_crop_golden(golden, tag):
 @pytest.mark.parametrize("max_pool", [False, True, "ranked"])
 def test_crop_vs_oracle(shape, max_pool):
     B, C, H, W, N = shape
-    ranked = max_pool == "ranked"          # 7x7 crop through the sample-per-lane backward kernel
+    ranked = max_pool == "ranked"          # 7x7 crop through the sample-per-lane (ranked) backward kernel
     max_pool = max_pool is True
     g = torch.Generator().manual_seed(B * 1000 + C + H)
     bottom = torch.randn(B, C, H, W, generator=g)
