@@ -314,6 +314,125 @@ dynfilter_bwd_kernel(const float* __restrict__ X, const float* __restrict__ filt
   }
 }
 
+// ------------------------------------------------------------------------------- backward (A'), register accumulators
+// Same arithmetic as dynfilter_bwd_kernel for the common case C <= 16 * (256 / (TP/4)) and float4-aligned maps:
+// the dX tile lives in registers (thread (pixel quad, channel slot) owns <= 16 channels x 4 pixels) instead of a
+// second [C x TP] shared-memory tile, which halves the shared-memory footprint (2 CTAs per SM instead of 1) and
+// removes the read-modify-write traffic of the accumulation.
+constexpr int kRegCh = 16;
+template <int TP>
+__global__ void __launch_bounds__(kThreads, 2)
+dynfilter_bwd_reg_kernel(const float* __restrict__ X, const float* __restrict__ filt, const float* __restrict__ fuse,
+                         const int* __restrict__ e2i, const float* __restrict__ response,
+                         const float* __restrict__ dY, const float* __restrict__ dresp,
+                         const float* __restrict__ target, const float* __restrict__ gscale,
+                         float* __restrict__ dX, float* __restrict__ drbuf, DfGeom g) {
+  constexpr int Q = TP / 4;
+  constexpr int CSTEP = kThreads / Q;
+  extern __shared__ __align__(16) float smem[];
+  float* xs = smem;                         // [C][TP]
+  float* fs = xs + (size_t)g.C * TP;        // [7][C]
+  float* red = fs + (size_t)NF * g.C;       // [8][1][TP]
+  float* ds = red + 8 * TP;                 // [TP]
+  float* gate = ds + TP;                    // [TP]
+  float* mwdr = gate + TP;                  // [7][TP]  w_k * M_k[p] * dr[p]
+
+  const int i = blockIdx.y, p0 = blockIdx.x * TP, t = threadIdx.x;
+  const int pq = t % Q, cs = t / Q;
+  int e0, e1;
+  expr_range(e2i, g.E, i, &e0, &e1);
+
+  load_tile<TP, true>(xs, X + (size_t)i * g.C * g.HW, g.C, g.HW, p0);
+  float4 dacc[kRegCh];
+#pragma unroll
+  for (int j = 0; j < kRegCh; ++j) dacc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int p = p0 + 4 * pq;
+  const bool pin = p < g.HW;
+  __syncthreads();
+
+  for (int e = e0; e < e1; ++e) {
+    for (int idx = t; idx < NF * g.C; idx += kThreads) fs[idx] = __ldg(filt + (size_t)e * NF * g.C + idx);
+    if (t < TP) {
+      const int pp = p0 + t;
+      const float r = (pp < g.HW) ? __ldg(response + (size_t)e * g.HW + pp) : 0.f;
+      gate[t] = g.linear ? r : sigmoidf_acc(r);
+    }
+    __syncthreads();
+    // pass 1: stream dY once; ds partials and the gate term of dX
+    float acc[1][4] = {{0.f, 0.f, 0.f, 0.f}};
+    const float* dYe = dY + (size_t)e * g.C * g.HW;
+    const float4 gq = reinterpret_cast<const float4*>(gate)[pq];
+    if (pin) {
+#pragma unroll
+      for (int h = 0; h < kRegCh; h += 8) {      // 8 streaming loads of the thread in flight at once
+        float4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int c = cs + (h + j) * CSTEP;
+          v[j] = (c < g.C) ? __ldcs(reinterpret_cast<const float4*>(dYe + (size_t)c * g.HW + p))
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int c = cs + (h + j) * CSTEP;
+          if (c < g.C) {
+            const float4 x = reinterpret_cast<const float4*>(xs)[c * Q + pq];
+            acc[0][0] = fmaf(v[j].x, x.x, acc[0][0]);
+            acc[0][1] = fmaf(v[j].y, x.y, acc[0][1]);
+            acc[0][2] = fmaf(v[j].z, x.z, acc[0][2]);
+            acc[0][3] = fmaf(v[j].w, x.w, acc[0][3]);
+            float4& d = dacc[h + j];
+            d.x = fmaf(v[j].x, gq.x, d.x); d.y = fmaf(v[j].y, gq.y, d.y);
+            d.z = fmaf(v[j].z, gq.z, d.z); d.w = fmaf(v[j].w, gq.w, d.w);
+          }
+        }
+      }
+    }
+    reduce_quads<TP, 1>(acc, red, ds);
+    if (t < TP) {
+      const int pp = p0 + t;
+      float dr = 0.f;
+      if (pp < g.HW) {
+        const float r = __ldg(response + (size_t)e * g.HW + pp);
+        const float sg = sigmoidf_acc(r);
+        dr = g.linear ? ds[t] : ds[t] * sg * (1.f - sg);
+        if (dresp) dr += __ldg(dresp + (size_t)e * g.HW + pp);
+        if (target && gscale) dr += __ldg(gscale + e) * (sg - __ldg(target + (size_t)e * g.HW + pp)) / (float)g.HW;
+        drbuf[(size_t)e * g.HW + pp] = dr;
+      }
+#pragma unroll
+      for (int k = 0; k < NF; ++k)
+        mwdr[k * TP + t] = (pp < g.HW) ? __ldg(fuse + e * NF + k) * mask_k(g, k, pp) * dr : 0.f;
+    }
+    __syncthreads();
+    // pass 2: dX += dr[p] * sum_k w_k M_k[p] f_k[c]
+    float4 m[NF];
+#pragma unroll
+    for (int k = 0; k < NF; ++k) m[k] = reinterpret_cast<const float4*>(mwdr)[k * Q + pq];
+#pragma unroll
+    for (int j = 0; j < kRegCh; ++j) {
+      const int c = cs + j * CSTEP;
+      if (c < g.C) {
+#pragma unroll
+        for (int k = 0; k < NF; ++k) {
+          const float f = fs[k * g.C + c];
+          dacc[j].x = fmaf(f, m[k].x, dacc[j].x); dacc[j].y = fmaf(f, m[k].y, dacc[j].y);
+          dacc[j].z = fmaf(f, m[k].z, dacc[j].z); dacc[j].w = fmaf(f, m[k].w, dacc[j].w);
+        }
+      }
+    }
+    __syncthreads();
+  }
+  float* dXi = dX + (size_t)i * g.C * g.HW;
+  if (pin) {
+#pragma unroll
+    for (int j = 0; j < kRegCh; ++j) {
+      const int c = cs + j * CSTEP;
+      if (c < g.C) *reinterpret_cast<float4*>(dXi + (size_t)c * g.HW + p) = dacc[j];
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------- backward (B)
 // df[e,k,c] = w_k * sum_p M_k[p] dr[e,p] X[img(e),c,p].  CTA = (image, 8 channels); warp = channel;
 // lanes stride over pixels; expressions of the image in chunks of EB.
@@ -422,6 +541,7 @@ DfGeom make_geom(int I, int E, int C, int H, int W, int flags) {
 }
 
 size_t fwd_smem(int C, int TP) { return ((size_t)C * TP + (size_t)NF * C + 8 * NF * TP + NF * TP + TP) * 4; }
+size_t bwd_reg_smem(int C, int TP) { return ((size_t)C * TP + (size_t)NF * C + 8 * TP + 2 * TP + NF * TP) * 4; }
 size_t bwd_smem(int C, int TP) { return ((size_t)2 * C * TP + (size_t)NF * C + 8 * TP + 2 * TP + NF * TP) * 4; }
 
 template <int TP, bool VEC>
@@ -511,7 +631,16 @@ extern "C" int l2s_dynfilter_bwd(const float* X, const float* filt, const float*
   float* rk_ws = drbuf + (size_t)E * g.HW;
   const bool vec = (g.HW % 4 == 0) && aligned16(X) && aligned16(dY) && aligned16(dX);
   const size_t cap = (size_t)max_smem_optin();
-  if (bwd_smem(C, 16) <= cap && vec)
+  if (vec && C <= kRegCh * (kThreads / 4) && bwd_reg_smem(C, 16) <= cap) {
+    auto kern = dynfilter_bwd_reg_kernel<16>;
+    const size_t smem = bwd_reg_smem(C, 16);
+    L2S_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((g.HW + 15) / 16, I);
+    kern<<<grid, kThreads, smem, st>>>(X, filt, fuse, expr2img, response, dY, dresponse, resp_target, resp_gscale, dX,
+                                       drbuf, g);
+    L2S_LAUNCH_OK("dynfilter_bwd_reg_kernel");
+    count_launch();
+  } else if (bwd_smem(C, 16) <= cap && vec)
     rc = launch_bwd<16, true>(X, filt, fuse, expr2img, response, dY, dresponse, resp_target, resp_gscale, dX, drbuf, g, st);
   else if (bwd_smem(C, 16) <= cap)
     rc = launch_bwd<16, false>(X, filt, fuse, expr2img, response, dY, dresponse, resp_target, resp_gscale, dX, drbuf, g, st);

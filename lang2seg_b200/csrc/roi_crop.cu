@@ -666,30 +666,29 @@ roi_crop_bwd_rows_kernel(const float* __restrict__ dout, const int* __restrict__
       const int s = k % kRowStages;
       mbar_wait(&full_bar[s], (k / kRowStages) & 1);
       const SepRec* rec = recs + s;
-      const int ymin = rec->ymin, ymax = rec->ymax;
-      bool loaded = false;
-      int xoff[7];
-      float wa[7], wb[7];
-#pragma unroll 1
-      for (int yy = wid; yy < H; yy += kRowWarps) {
-        if (yy < ymin || yy > ymax) continue;          // warp uniform
-        if (!loaded) {
+      // lanes 0..13 test the 14 (sample row i, upper/lower map row) pairs of the ROI against this warp's rows
+      int yrow = -1;
+      if (lane < 14) yrow = (int)rec->y0[lane >> 1] + (lane & 1);
+      const bool hit = (unsigned)yrow < (unsigned)H && (yrow % kRowWarps) == wid;
+      unsigned hits = __ballot_sync(0xffffffffu, hit);
+      if (hits) {
+        int xoff[7];
+        float wa[7], wb[7];
 #pragma unroll
-          for (int j = 0; j < 7; ++j) {
-            xoff[j] = (int)rec->x0[j] * kRowLd;
-            wb[j] = rec->lx[j];
-            wa[j] = 1.f - wb[j];
-          }
-          loaded = true;
+        for (int j = 0; j < 7; ++j) {
+          xoff[j] = (int)rec->x0[j] * kRowLd;
+          wb[j] = rec->lx[j];
+          wa[j] = 1.f - wb[j];
         }
         const float* tcol = tiles + (size_t)s * TILE + (size_t)cl * kPP;
-        float* mrow = mlane + (size_t)yy * WP * kRowLd;
-#pragma unroll 1
-        for (int i = 0; i < 7; ++i) {
-          const int d = yy - (int)rec->y0[i];
-          if (d != 0 && d != 1) continue;              // warp uniform
+        while (hits) {
+          const int bsel = __ffs(hits) - 1;
+          hits &= hits - 1;
+          const int i = bsel >> 1;
+          const int yy = __shfl_sync(0xffffffffu, yrow, bsel);
           const float ly = rec->ly[i];
-          const float wy = d ? ly : 1.f - ly;
+          const float wy = (bsel & 1) ? ly : 1.f - ly;
+          float* mrow = mlane + (size_t)yy * WP * kRowLd;
           const float* trow = tcol + i * 7;
 #pragma unroll
           for (int j = 0; j < 7; ++j) {

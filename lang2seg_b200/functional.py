@@ -370,6 +370,36 @@ def att2in2_decode(i2h_all, att_feats, p_att, w_h2att, b_h2att, w_h2h, w_a2c, b_
     return _Att2in2Decode.apply(i2h_all, att_feats, p_att, w_h2att, b_h2att, w_h2h, w_a2c, b_a2c, alpha_w, alpha_b)
 
 
+class _LinearSmallFn(torch.autograd.Function):
+    """nn.Linear on a small batch (rows <= a few hundred) in exact fp32 through l2s_linear_small, fwd and dX;
+    the weight gradient is one rank-`rows` update (cuBLAS)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        x, w = f32c(x), f32c(w)
+        ctx.save_for_backward(x, w)
+        ctx.has_bias = b is not None
+        return linear_small(x, w, b)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dy = f32c(dy)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = linear_small(dy, w.t().contiguous())
+        if ctx.needs_input_grad[1]:
+            dw = dy.t() @ x
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = dy.sum(0)
+        return dx, dw, db
+
+
+def linear_small_fn(x, weight, bias=None):
+    """Differentiable x @ weight.T + bias for small row counts (exact fp32, no cuBLAS SIMT launches)."""
+    return _LinearSmallFn.apply(x, weight, bias)
+
+
 def linear_small(x, weight, bias=None, out=None, accumulate=False):
     """out (+)= x @ weight.T + bias, exact fp32, for a small number of rows (no gradient)."""
     x, weight = f32c(x), f32c(weight)

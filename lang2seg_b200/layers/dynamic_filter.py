@@ -10,8 +10,18 @@ from .. import functional as L2F
 
 
 def generate_filters(hidden, dynamic_fcs, response_fc):
-    """f_k = tanh(dynamic_fc_k(hidden)) stacked to (E,7,C) ; w = tanh(response_fc(hidden)) (E,7).  (:510-532)"""
-    filt = torch.tanh(torch.stack([fc(hidden) for fc in dynamic_fcs], 1))
+    """f_k = tanh(dynamic_fc_k(hidden)) stacked to (E,7,C) ; w = tanh(response_fc(hidden)) (E,7).  (:510-532)
+
+    The reference issues 8 separate Linears per expression; on the GPU the seven (C x Dh) projections run as ONE
+    skinny exact-fp32 GEMM over the stacked weights (l2s_linear_small), forward and backward."""
+    E, Dh = hidden.shape
+    C = dynamic_fcs[0].out_features
+    if hidden.is_cuda and Dh % 4 == 0 and (len(dynamic_fcs) * C) % 4 == 0 and E <= 512:
+        W = torch.cat([fc.weight for fc in dynamic_fcs], 0)
+        b = torch.cat([fc.bias for fc in dynamic_fcs], 0)
+        filt = torch.tanh(L2F.linear_small_fn(hidden, W, b)).view(E, len(dynamic_fcs), C)
+    else:
+        filt = torch.tanh(torch.stack([fc(hidden) for fc in dynamic_fcs], 1))
     fuse = torch.tanh(response_fc(hidden))
     return filt, fuse
 

@@ -84,3 +84,26 @@ def test_partition_bounds_contract():
             fuse[0, k] = 1.0
             r, _, _ = F.dynamic_filter(X, filt, fuse)
             assert torch.equal(r[0, 0].cpu(), masks[k] * C), (H, W, k)
+
+
+@pytest.mark.parametrize("E,C,Dh", [(48, 1024, 1024), (3, 512, 1024), (70, 64, 32)])
+def test_filter_generator_fused_vs_oracle(E, C, Dh):
+    """generate_filters: the seven dynamic_fc projections as one skinny exact-fp32 GEMM (fwd, dX) vs 8 torch Linears."""
+    from lang2seg_b200.layers.dynamic_filter import DynamicFilterResponse, generate_filters
+    torch.manual_seed(E + C)
+    mod = DynamicFilterResponse(Dh, C).cuda()
+    g = torch.Generator().manual_seed(1)
+    hidden = torch.randn(E, Dh, generator=g)
+    Gf, Gw = torch.randn(E, 7, C, generator=g), torch.randn(E, 7, generator=g)
+    h = hidden.cuda().requires_grad_(True)
+    filt, fuse = generate_filters(h, mod.dynamic_fcs, mod.response_fc)
+    ((filt * Gf.cuda()).sum() + (fuse * Gw.cuda()).sum()).backward()
+    p = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in mod.named_parameters()}
+    ho = hidden.clone().requires_grad_(True)
+    fo, wo = R.filter_generator(ho, [p["dynamic_fc_%d.weight" % k] for k in range(7)],
+                                [p["dynamic_fc_%d.bias" % k] for k in range(7)], p["response_fc.weight"], p["response_fc.bias"])
+    ((fo * Gf).sum() + (wo * Gw).sum()).backward()
+    assert relerr(filt, fo) < TOL and relerr(fuse, wo) < TOL
+    assert relerr(h.grad, ho.grad) < TOL
+    for k, v in mod.named_parameters():
+        assert relerr(v.grad, p[k].grad) < TOL, k
