@@ -64,6 +64,7 @@ def make_inputs(wl, seed, device, pinned=False):
     d["X"] = torch.relu(torch.randn(I, C, H, W, generator=g))
     labels, lens = R.synth_labels(g, E, L, V)
     d["labels"] = labels
+    host_meta = {"lens": lens.clone(), "steps": int(lens.max()) + 1}    # host-side facts about the batch (never copied)
     d["cap"], d["msk"] = R.caption_targets(labels, lens, L)
     d["e2i"] = torch.arange(I).repeat_interleave(EPI).int()
     d["rois"] = torch.cat([R.synth_rois(g, Rn, H * 16, W * 16, e) for e in range(E)])
@@ -74,8 +75,11 @@ def make_inputs(wl, seed, device, pinned=False):
     d["fc"] = torch.randn(E, 4096, generator=g)
     d["att"] = torch.relu(torch.randn(E, 14, 14, 4096, generator=g))
     if pinned:
-        return {k: v.pin_memory() for k, v in d.items()}
-    return {k: v.to(device) for k, v in d.items()}
+        out = {k: v.pin_memory() for k, v in d.items()}
+    else:
+        out = {k: v.to(device) for k, v in d.items()}
+    out["_meta"] = host_meta
+    return out
 
 
 class ClockSampler:
@@ -135,17 +139,19 @@ class HotPathStep:
         self.g_pool = (torch.randn(E * wl["R"], wl["C"], 7, 7, generator=g) * 1e-4).to(device)
         self.one = torch.ones((), device=device)
 
-    def __call__(self, d):
+    def __call__(self, d, meta=None):
         net = self.net
+        meta = meta if meta is not None else d.get("_meta", {})
         self.opt.zero_grad(set_to_none=True)
         X = d["X"].requires_grad_(True)
         fc7 = d["fc7"].requires_grad_(True)
         att = d["att"].requires_grad_(True)
-        gated = net._dynamic_filter(X, d["labels"], expr2img=d["e2i"], resp_target=d["resp_tgt"])
+        gated = net._dynamic_filter(X, d["labels"], expr2img=d["e2i"], resp_target=d["resp_tgt"],
+                                    lengths=meta.get("lens"))
         pool5 = net._crop_pool_layer(gated, d["rois"], max_pool=False)
         net._mask_prediction(fc7)
         loss = (net._losses["loss_response_per_expr"].sum() + net._mask_loss(d["mlab"], d["mtgt"])
-                + net._cap_loss_weight * net._caption_loss(d["fc"], att, d["cap"], d["msk"]))
+                + net._cap_loss_weight * net._caption_loss(d["fc"], att, d["cap"], d["msk"], steps=meta.get("steps")))
         torch.autograd.backward([loss, pool5], [self.one, self.g_pool])
         if self.reducer is not None:
             self.reducer.all_reduce()
@@ -406,6 +412,7 @@ def main():
     # of step i) and reads its loss back (device->host) inside the timed region.
     from lang2seg_b200.pipeline import HostBatchPipeline
     host = make_inputs(wl, 1234 + rank, dev, pinned=True)
+    host_meta = host.pop("_meta")
     h2d = sum(v.numel() * v.element_size() for v in host.values())
     losses = []
     pipe = HostBatchPipeline(dev, depth=2)
@@ -416,7 +423,7 @@ def main():
             if i + 1 < n:
                 pipe.submit(host)
             dd = pipe.get()
-            losses.append(float(step(dd).detach()))     # device->host read of the step's result
+            losses.append(float(step(dd, host_meta).detach()))     # device->host read of the step's result
             pipe.release()
 
     e2e_run(2)

@@ -30,10 +30,11 @@ constexpr int kLinThreads = 256;
 constexpr int kLinKC = 512;      // K chunk held in shared memory (lane owns 4 float4 of it)
 constexpr int kLinMaxRows = 64;  // rows of A per CTA
 
-// transpose-reduce: lane l ends with sum over lanes of v[l]
-__device__ __forceinline__ float transpose_reduce32(float (&v)[32], int lane) {
+// transpose-reduce: lane l ends with the sum over all lanes of v[l % NR]  (NR = 32 or 16)
+template <int NR>
+__device__ __forceinline__ float transpose_reduce(float (&v)[NR], int lane) {
 #pragma unroll
-  for (int s = 16; s >= 1; s >>= 1) {
+  for (int s = NR / 2; s >= 1; s >>= 1) {
     const bool up = (lane & s) != 0;
 #pragma unroll
     for (int i = 0; i < s; ++i) {
@@ -42,7 +43,9 @@ __device__ __forceinline__ float transpose_reduce32(float (&v)[32], int lane) {
       v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
     }
   }
-  return v[0];
+  float r = v[0];
+  if (NR == 16) r += __shfl_xor_sync(0xffffffffu, r, 16);   // the two half-warps hold the two halves of the K sum
+  return r;
 }
 
 struct LinGeom {
@@ -53,8 +56,37 @@ struct LinGeom {
   int rows_pad;    // rows of A staged per CTA (32 or 64)
 };
 
+// NR rows of the staged A chunk against this warp's CPW weight rows; lane (l % NR) ends with row mg + l % NR
+template <int CPW, int NR, class Store>
+__device__ __forceinline__ void row_group(const float4* __restrict__ As4, const float4 (&w)[CPW][4], int mg, int lane,
+                                          int n0, Store& store) {
+  float p[CPW][NR];
+#pragma unroll
+  for (int mi = 0; mi < NR; ++mi) {
+    const float4* row = As4 + (size_t)(mg + mi) * (kLinKC / 4) + lane;
+    const float4 a0 = row[0], a1 = row[32], a2 = row[64], a3 = row[96];
+#pragma unroll
+    for (int c = 0; c < CPW; ++c) {
+      float acc = a0.x * w[c][0].x;
+      acc = fmaf(a0.y, w[c][0].y, acc); acc = fmaf(a0.z, w[c][0].z, acc); acc = fmaf(a0.w, w[c][0].w, acc);
+      acc = fmaf(a1.x, w[c][1].x, acc); acc = fmaf(a1.y, w[c][1].y, acc);
+      acc = fmaf(a1.z, w[c][1].z, acc); acc = fmaf(a1.w, w[c][1].w, acc);
+      acc = fmaf(a2.x, w[c][2].x, acc); acc = fmaf(a2.y, w[c][2].y, acc);
+      acc = fmaf(a2.z, w[c][2].z, acc); acc = fmaf(a2.w, w[c][2].w, acc);
+      acc = fmaf(a3.x, w[c][3].x, acc); acc = fmaf(a3.y, w[c][3].y, acc);
+      acc = fmaf(a3.z, w[c][3].z, acc); acc = fmaf(a3.w, w[c][3].w, acc);
+      p[c][mi] = acc;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < CPW; ++c) {
+    const float tot = transpose_reduce<NR>(p[c], lane);
+    if (NR == 32 || lane < 16) store(mg + (lane % NR), n0 + c, tot);
+  }
+}
+
 template <int CPW>
-__global__ void __launch_bounds__(kLinThreads, 1)
+__global__ void __launch_bounds__(kLinThreads, 2)
 linear_small_kernel(const float* __restrict__ A, const float* __restrict__ W, const float* __restrict__ bias,
                     float* __restrict__ D, float* __restrict__ partials, unsigned int* __restrict__ counters,
                     LinGeom g) {
@@ -94,41 +126,22 @@ linear_small_kernel(const float* __restrict__ A, const float* __restrict__ W, co
   __syncthreads();
 
   const float4* As4 = reinterpret_cast<const float4*>(As);
-  for (int mg = 0; mg < g.rows_pad; mg += 32) {
-    float p[CPW][32];
-#pragma unroll
-    for (int mi = 0; mi < 32; ++mi) {
-      const float4* row = As4 + (size_t)(mg + mi) * (kLinKC / 4) + lane;
-      const float4 a0 = row[0], a1 = row[32], a2 = row[64], a3 = row[96];
-#pragma unroll
-      for (int c = 0; c < CPW; ++c) {
-        float acc = a0.x * w[c][0].x;
-        acc = fmaf(a0.y, w[c][0].y, acc); acc = fmaf(a0.z, w[c][0].z, acc); acc = fmaf(a0.w, w[c][0].w, acc);
-        acc = fmaf(a1.x, w[c][1].x, acc); acc = fmaf(a1.y, w[c][1].y, acc);
-        acc = fmaf(a1.z, w[c][1].z, acc); acc = fmaf(a1.w, w[c][1].w, acc);
-        acc = fmaf(a2.x, w[c][2].x, acc); acc = fmaf(a2.y, w[c][2].y, acc);
-        acc = fmaf(a2.z, w[c][2].z, acc); acc = fmaf(a2.w, w[c][2].w, acc);
-        acc = fmaf(a3.x, w[c][3].x, acc); acc = fmaf(a3.y, w[c][3].y, acc);
-        acc = fmaf(a3.z, w[c][3].z, acc); acc = fmaf(a3.w, w[c][3].w, acc);
-        p[c][mi] = acc;
+  auto store = [&](int mrow, int n, float tot) {
+    const int m = m0 + mrow;
+    if (mrow < rows && n < g.N) {
+      if (g.ks == 1) {
+        float* dp = D + (size_t)m * g.ldd + n;
+        float v = tot + (bias ? __ldg(bias + n) : 0.f);
+        if (g.accumulate) v += *dp;
+        *dp = v;
+      } else {
+        partials[((size_t)s * g.M + m) * g.N + n] = tot;
       }
     }
-#pragma unroll
-    for (int c = 0; c < CPW; ++c) {
-      const float tot = transpose_reduce32(p[c], lane);
-      const int m = m0 + mg + lane, n = n0 + c;
-      if (mg + lane < rows && n < g.N) {
-        if (g.ks == 1) {
-          float* dp = D + (size_t)m * g.ldd + n;
-          float v = tot + (bias ? __ldg(bias + n) : 0.f);
-          if (g.accumulate) v += *dp;
-          *dp = v;
-        } else {
-          partials[((size_t)s * g.M + m) * g.N + n] = tot;
-        }
-      }
-    }
-  }
+  };
+  int mg = 0;
+  for (; mg + 32 <= g.rows_pad; mg += 32) row_group<CPW, 32>(As4, w, mg, lane, n0, store);
+  if (mg < g.rows_pad) row_group<CPW, 16>(As4, w, mg, lane, n0, store);
   if (g.ks == 1) return;
 
   // ---- split-K: the last CTA of this (column block, row block) sums the partials in split order
@@ -190,7 +203,10 @@ int launch_linear_small(const float* A, int lda, const float* W, int ldw, const 
   g.ks = (K + kLinKC - 1) / kLinKC;
   g.accumulate = accumulate;
   const int mblocks = (M + kLinMaxRows - 1) / kLinMaxRows;
-  g.rows_pad = (M <= 32) ? 32 : kLinMaxRows;
+  {
+    const int mrows = M < kLinMaxRows ? M : kLinMaxRows;
+    g.rows_pad = (mrows + 15) & ~15;      // staged rows per CTA: 16..64 (two CTAs per SM fit up to 48)
+  }
   const int cpw = pick_cpw(N, g.ks, mblocks);
   const int cbs = (N + 8 * cpw - 1) / (8 * cpw);
   L2S_REQUIRE((size_t)cbs * mblocks * sizeof(unsigned int) <= kLinCounterBytes, L2S_ERR_SHAPE,

@@ -32,16 +32,23 @@ class RNNEncoder(nn.Module):
             self.rnn.train(True)
         return self
 
-    def forward(self, input_labels):
-        """input_labels (B,L) int64 zero padded -> output (B,L,H*dirs), hidden (B,layers*dirs*H), embedded (B,L,Dw)"""
+    def forward(self, input_labels, lengths=None):
+        """input_labels (B,L) int64 zero padded -> output (B,L,H*dirs), hidden (B,layers*dirs*H), embedded (B,L,Dw)
+
+        `lengths`: optional HOST tensor / list of the expression lengths.  The reference computes them on the host
+        from the labels (lang_encoder.py:38-40, a device->host sync per call); passing them in keeps the launch
+        queue asynchronous when the labels already live on the GPU."""
         B, L = input_labels.shape
         vec = self.mlp(self.input_dropout(self.embedding(input_labels)))
         if not self.variable_lengths:
             with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
                 output, hidden = self.rnn(vec)
             return output, hidden, vec
-        lengths = (input_labels != 0).sum(1)
-        lens_cpu = lengths.cpu()
+        if lengths is None:
+            lens_cpu = (input_labels != 0).sum(1).cpu()
+        else:
+            lens_cpu = torch.as_tensor(lengths, dtype=torch.int64, device="cpu")
+        lengths = lens_cpu.to(vec.device, non_blocking=True)
         assert int(lens_cpu.max()) == L, "labels must be trimmed to the longest expression (lang_encoder.py:45)"
         packed = pack_padded_sequence(vec, lens_cpu, batch_first=True, enforce_sorted=False)
         with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):     # fp32 parity: no TF32 inside cuDNN

@@ -72,13 +72,13 @@ class Network(nn.Module):
         return mask_prob
 
     # ---- dynamic filter ------------------------------------------------------------------------
-    def _dynamic_filter(self, net_conv, labels=None, hidden=None, expr2img=None, resp_target=None):
+    def _dynamic_filter(self, net_conv, labels=None, hidden=None, expr2img=None, resp_target=None, lengths=None):
         """net_conv (I,C,H,W) ; labels (E,L) tokens or precomputed hidden (E,Dh).
 
         Stores _predictions['net_conv_before'] / ['response'] like :504,:568 and returns the gated map."""
         self._predictions["net_conv_before"] = net_conv
         if hidden is None:
-            _, hidden, _ = self.rnn_encoder(labels)
+            _, hidden, _ = self.rnn_encoder(labels, lengths)
         filt, fuse = generate_filters(hidden, [getattr(self, "dynamic_fc_%d" % k) for k in range(7)], self.response_fc)
         response, gated, resp_loss = L2F.dynamic_filter(net_conv, filt, fuse, expr2img, self._gate, resp_target)
         self._predictions["response"] = response
@@ -89,8 +89,9 @@ class Network(nn.Module):
     def _mask_loss(self, labels, mask_targets):
         return L2F.mask_bce_loss(self._predictions["mask_score"], labels, mask_targets)
 
-    def _caption_loss(self, fc_feats, att_feats, cap_labels, cap_masks):
-        return self.caption_model.forward_loss(fc_feats, att_feats, cap_labels, cap_masks)
+    def _caption_loss(self, fc_feats, att_feats, cap_labels, cap_masks, steps=None):
+        """`steps`: host-known number of decode steps (max caption length + 1); None reads it from the labels."""
+        return self.caption_model.forward_loss(fc_feats, att_feats, cap_labels, cap_masks, steps=steps)
 
 
 DEFAULT_OPT = dict(

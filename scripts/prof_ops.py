@@ -69,6 +69,12 @@ def main():
             ab = torch.zeros(1, device=dev, requires_grad=True)
             res, _ = F.attention_step(att_h, feats, p_att, aw, ab)
             torch.autograd.grad(res, [att_h, feats, p_att, aw, ab], torch.randn_like(res))
+        if "lin" in only:
+            for (M, N, K) in [(48, 3072, 512), (48, 1024, 512), (48, 512, 1024), (48, 512, 3072), (48, 7168, 1024)]:
+                x = torch.randn(M, K, device=dev)
+                w = torch.randn(N, K, device=dev)
+                for _ in range(3):
+                    F.linear_small(x, w)
     torch.cuda.synchronize()
     print("prof_ops done")
 
