@@ -157,7 +157,12 @@ class HotPathStep:
             self.reducer.all_reduce()
         self.opt.step()
         X.grad = fc7.grad = att.grad = None
-        return loss
+        # drop the references into this step's autograd graph (the reference keeps them in _predictions/_losses for its
+        # tensorboard summaries): a graph kept alive across steps pins AccumulateGrad nodes to the stream they were
+        # created on, which breaks CUDA-graph capture on another stream
+        net._predictions.clear()
+        net._losses.clear()
+        return loss.detach()
 
 
 def time_region(fn, steps, dist_on):
@@ -373,6 +378,7 @@ def main():
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-components", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a captured CUDA graph")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -400,10 +406,36 @@ def main():
     d = make_inputs(wl, 1234 + rank, dev)
     for _ in range(args.warmup):
         step(d)
-    sampler = ClockSampler(local) if rank == 0 else None
+    torch.cuda.synchronize()
     l0 = _lib.launch_count()
-    ms = time_region(lambda: step(d), args.steps, dist_on)
-    launches = _lib.launch_count() - l0
+    step(d)
+    launches_per_step = _lib.launch_count() - l0          # kernels of libl2s.so per step (counted on an eager step)
+    # The whole step (lang encoder .. SGD update, ~650 launches, shapes static for a given batch geometry) is captured
+    # once in a CUDA graph and replayed: the timed region then measures the kernels, not Python/launch latency.
+    run, graphed = (lambda: step(d)), False
+    if not args.no_graph:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                step(d)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                static_loss = step(d)
+            graph.replay()
+            torch.cuda.synchronize()
+            assert torch.isfinite(static_loss).all()
+            run, graphed = graph.replay, True
+        except Exception as exc:      # capture is an optimisation: fall back to eager launches and say so
+            print("bench: CUDA graph capture failed (%s); timing eager launches" % str(exc).splitlines()[0], file=sys.stderr)
+            torch.cuda.synchronize()
+    for _ in range(args.warmup):
+        run()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms = time_region(run, args.steps, dist_on)
+    launches = launches_per_step * args.steps
     clocks = sampler.stop() if sampler else None
     value = E * world * args.steps / (ms * 1e-3)
 
@@ -457,7 +489,8 @@ def main():
                 "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
                 "config": {"workload": wl["name"], "per_gpu_expressions": E, "parallelism": "dp%d" % world,
                            "l2": "inputs larger than L2 (>= 1.2 GB streamed per step); no flush needed",
-                           "includes": "lang encoder, filter generator, 4 hot components fwd+bwd, grad all-reduce, SGD"},
+                           "includes": "lang encoder, filter generator, 4 hot components fwd+bwd, grad all-reduce, SGD",
+                           "launch": "one CUDA graph replay per step" if graphed else "eager launches"},
                 "clocks": clocks, "gpu_launches": launches,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                         "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,

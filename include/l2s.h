@@ -239,6 +239,28 @@ int l2s_att2in2_decode_bwd(const float* dh_all, const float* cat_all, const floa
                            int B, int A, int D, int Dh, void* workspace, size_t workspace_bytes,
                            l2s_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Variable-length bidirectional LSTM recurrence of the expression encoder.  Replaces
+ * pack_padded_sequence -> nn.LSTM(bidirectional, 1 layer) -> pad_packed_sequence in RNNEncoder.forward
+ * (lib/layers/lang_encoder.py:38-80) by masking: sequence b advances only while t < lens[b].
+ *
+ *   G     (B,L,2,4H) in/out: on entry x_t W_ih^T + b_ih + b_hh per direction (gate order i,f,g,o); on exit the
+ *                            full pre-activations (h W_hh^T added) -- kept for the backward call
+ *   w_hh  (2,4H,H)   weight_hh_l0, weight_hh_l0_reverse ;  lens (B) int32 expression lengths (1..L)
+ *   c_all, h_all (L,2,B,H) states after every TIME step (saved) ; out (B,L,2H) zero where t >= lens[b] ;
+ *   hidden (B,2H) = [h_fwd(last) | h_bwd(first)]
+ * backward: dout (B,L,2H) and/or dhidden (B,2H) -> dG (B,L,2,4H) gradient on the pre-activations (= gradient on
+ *   the entry value of G) ; w_hh_t (2,H,4H) TRANSPOSED recurrent weights.
+ *   dW_hh[dir] = sum_t dG[:,t,dir]^T . h_prev(t,dir) is left to the caller (one GEMM per direction).
+ * ------------------------------------------------------------------------------------- */
+size_t l2s_bilstm_workspace_bytes(int L, int B, int H);
+int l2s_bilstm_fwd(float* G, const float* w_hh, const int32_t* lens, float* c_all, float* h_all, float* out,
+                   float* hidden, int L, int B, int H, void* workspace, size_t workspace_bytes,
+                   l2s_stream_t stream);
+int l2s_bilstm_bwd(const float* dout, const float* dhidden, const float* G, const float* w_hh_t,
+                   const int32_t* lens, const float* c_all, float* dG, int L, int B, int H, void* workspace,
+                   size_t workspace_bytes, l2s_stream_t stream);
+
 /* Skinny exact-fp32 linear layer used inside the decode loop (nn.Linear on a batch of <= a few hundred
  * rows): D[M,N] (+)= A[M,K] . W[N,K]^T + bias[N].  K, lda, ldw multiples of 4; deterministic split-K. */
 size_t l2s_linear_small_workspace_bytes(int M, int N, int K);

@@ -52,6 +52,11 @@ int launch_gates_bwd(const float* sums, int lds, const float* a2c_out, const flo
                      const float* dh_a, const float* dh_b, const float* dc, float* dsums, int ld_ds, float* da2c,
                      float* dc_prev, int B, int D, cudaStream_t st);
 
+size_t linear_small_workspace_bytes(int M, int N, int K);
+// D[M,N] (+)= A[M,K] . W[N,K]^T + bias ; workspace = [4096 B of zeroed counters | split-K partials]
+int launch_linear_small(const float* A, int lda, const float* W, int ldw, const float* bias, float* D, int ldd, int M,
+                        int N, int K, int accumulate, void* workspace, size_t ws_bytes, cudaStream_t st);
+
 // ---- device helpers --------------------------------------------------------------------
 #ifdef __CUDACC__
 

@@ -413,6 +413,59 @@ def linear_small(x, weight, bias=None, out=None, accumulate=False):
     return D
 
 
+class _BiLSTM(torch.autograd.Function):
+    """Masked variable-length bidirectional LSTM recurrence (l2s_bilstm_{fwd,bwd}); the input projection and the
+    weight gradients are GEMMs over all (b,t) rows outside the time loop."""
+
+    @staticmethod
+    def forward(ctx, xg, w_hh_f, w_hh_b, lens):
+        B, L, H8 = xg.shape
+        H = H8 // 8
+        dev = xg.device
+        G = f32c(xg).clone()
+        w_hh = torch.stack([f32c(w_hh_f), f32c(w_hh_b)], 0).contiguous()
+        lens = lens.to(device=dev, dtype=torch.int32).contiguous()
+        c_all = torch.empty(L, 2, B, H, device=dev, dtype=torch.float32)
+        h_all = torch.empty_like(c_all)
+        out = torch.empty(B, L, 2 * H, device=dev, dtype=torch.float32)
+        hidden = torch.empty(B, 2 * H, device=dev, dtype=torch.float32)
+        nbytes = _lib.size("l2s_bilstm_workspace_bytes", L, B, H)
+        ws = _ws(nbytes, dev)
+        call("l2s_bilstm_fwd", ptr(G), ptr(w_hh), ptr(lens), ptr(c_all), ptr(h_all), ptr(out), ptr(hidden), L, B, H,
+             ptr(ws), nbytes, stream())
+        ctx.save_for_backward(G, w_hh, lens, c_all, h_all)
+        return out, hidden
+
+    @staticmethod
+    def backward(ctx, dout, dhidden):
+        G, w_hh, lens, c_all, h_all = ctx.saved_tensors
+        B, L, H8 = G.shape
+        H = H8 // 8
+        dev = G.device
+        dout = f32c(dout) if dout is not None else None
+        dhidden = f32c(dhidden) if dhidden is not None else None
+        w_hh_t = w_hh.transpose(1, 2).contiguous()
+        dG = torch.empty_like(G)
+        nbytes = _lib.size("l2s_bilstm_workspace_bytes", L, B, H)
+        ws = _ws(nbytes, dev)
+        call("l2s_bilstm_bwd", ptr(dout), ptr(dhidden), ptr(G), ptr(w_hh_t), ptr(lens), ptr(c_all), ptr(dG), L, B, H,
+             ptr(ws), nbytes, stream())
+        # recurrent weight gradients: one GEMM per direction over all (t,b) rows against the previous state
+        dG5 = dG.view(B, L, 2, 4 * H)
+        zero = h_all.new_zeros(1, B, H)
+        hp_f = torch.cat([zero, h_all[:-1, 0]], 0)           # state before time t, forward direction
+        hp_b = torch.cat([h_all[1:, 1], zero], 0)            # ... backward direction (previous = time t+1)
+        dw_f = dG5[:, :, 0].transpose(0, 1).reshape(L * B, 4 * H).t() @ hp_f.reshape(L * B, H)
+        dw_b = dG5[:, :, 1].transpose(0, 1).reshape(L * B, 4 * H).t() @ hp_b.reshape(L * B, H)
+        return dG, dw_f, dw_b, None
+
+
+def bilstm(xg, w_hh_f, w_hh_b, lens):
+    """xg (B,L,8H) = x W_ih^T + b for [forward | backward] direction (gate order i,f,g,o) ; lens (B) ->
+    (out (B,L,2H) zero padded, hidden (B,2H) = [h_fwd(last) | h_bwd(first)])."""
+    return _BiLSTM.apply(xg, w_hh_f, w_hh_b, lens)
+
+
 class _LogSoftmaxNLL(torch.autograd.Function):
     @staticmethod
     def forward(ctx, logits, target, mask, want_logp):

@@ -1,13 +1,18 @@
 """Expression encoder -- drop-in for lib/layers/lang_encoder.py:RNNEncoder.
 
-Stays on torch (cuDNN LSTM): it is the input of the filter generator, not one of the hot kernels.
-Parameter names (embedding, mlp.0, rnn) and the returned triple match the reference so that its
-checkpoints load.  Differences: sorting by length is left to pack_padded_sequence
-(enforce_sorted=False) instead of the host-side numpy argsort at lang_encoder.py:38-52.
+Parameter names (embedding, mlp.0, rnn.*) and the returned triple match the reference so that its checkpoints
+load (`self.rnn` is still an nn.LSTM: it owns the weights).  On the GPU the reference configuration (1 layer,
+bidirectional LSTM, variable lengths) does not go through cuDNN: the input projection of all tokens and both
+directions is one GEMM and the recurrence runs in l2s_bilstm_{fwd,bwd} with MASKING instead of packing -- no
+host-side argsort (lang_encoder.py:38-52), no device->host read of the lengths, CUDA-graph capturable.  Other
+configurations fall back to torch's LSTM with pack_padded_sequence(enforce_sorted=False).
 """
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 from torch.nn.utils.rnn import pack_padded_sequence, pad_packed_sequence
+
+from .. import functional as L2F
 
 
 class RNNEncoder(nn.Module):
@@ -44,6 +49,18 @@ class RNNEncoder(nn.Module):
             with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
                 output, hidden = self.rnn(vec)
             return output, hidden, vec
+        if (vec.is_cuda and self.rnn_type == "lstm" and self.rnn.num_layers == 1 and self.num_dirs == 2
+                and self.rnn.hidden_size % 4 == 0):
+            # masked recurrence: lengths stay on the device (the caller guarantees max length == L, lang_encoder.py:45)
+            lens = lengths if (torch.is_tensor(lengths) and lengths.is_cuda) else (input_labels != 0).sum(1)
+            r = self.rnn
+            w_ih = torch.cat([r.weight_ih_l0, r.weight_ih_l0_reverse], 0)
+            b = torch.cat([r.bias_ih_l0 + r.bias_hh_l0, r.bias_ih_l0_reverse + r.bias_hh_l0_reverse], 0)
+            x2 = vec.reshape(B * L, -1)
+            xg = L2F.linear(x2, w_ih, b) if (B * L >= 256 and x2.shape[1] % 8 == 0) else F.linear(x2, w_ih, b)
+            output, hidden = L2F.bilstm(xg.view(B, L, -1), r.weight_hh_l0, r.weight_hh_l0_reverse, lens)
+            keep = (torch.arange(L, device=vec.device)[None, :] < lens[:, None]).unsqueeze(-1)
+            return output, hidden, vec * keep
         if lengths is None:
             lens_cpu = (input_labels != 0).sum(1).cpu()
         else:

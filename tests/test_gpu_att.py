@@ -227,3 +227,25 @@ def test_att2in2_decode_fast_path_vs_stepwise_and_oracle(B, L, opt):
         lp2 = model(fc.cuda(), att0.cuda(), cap.cuda())
         model.__dict__.pop("_fast_decode_ok", None)
     assert lp.shape == lp2.shape and relerr(lp, lp2) < TOL
+
+
+@pytest.mark.parametrize("B,L,H", [(48, 10, 512), (7, 20, 512), (3, 5, 8)])
+def test_lang_encoder_masked_bilstm_vs_oracle(B, L, H):
+    """RNNEncoder through l2s_bilstm_{fwd,bwd} (masking instead of pack/unpack) against the per-token loops of the
+    oracle, outputs and every parameter gradient."""
+    from lang2seg_b200.layers.lang_encoder import RNNEncoder
+    torch.manual_seed(B + L)
+    V = 1999 if H == 512 else 40
+    enc = RNNEncoder(vocab_size=V, word_embedding_size=H, word_vec_size=H, hidden_size=H, bidirectional=True,
+                     input_dropout_p=0.5, dropout_p=0.2, n_layers=1, rnn_type="lstm", variable_lengths=True).cuda().eval()
+    g = torch.Generator().manual_seed(L)
+    labels, lens = R.synth_labels(g, B, L, V)
+    Go, Gh = torch.randn(B, L, 2 * H, generator=g), torch.randn(B, 2 * H, generator=g)
+    out, hid, emb = enc(labels.cuda())
+    ((out * Go.cuda()).sum() + (hid * Gh.cuda()).sum()).backward()
+    p = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in enc.named_parameters()}
+    oo, ho, eo = R.rnn_encoder(labels, p)
+    ((oo * Go).sum() + (ho * Gh).sum()).backward()
+    assert relerr(out, oo) < TOL and relerr(hid, ho) < TOL and relerr(emb, eo) < TOL
+    for k, v in enc.named_parameters():
+        assert relerr(v.grad, p[k].grad) < TOL, k
