@@ -139,7 +139,8 @@ class HotPathStep:
         self.g_pool = (torch.randn(E * wl["R"], wl["C"], 7, 7, generator=g) * 1e-4).to(device)
         self.one = torch.ones((), device=device)
 
-    def __call__(self, d, meta=None):
+    def fwd_bwd(self, d, meta=None):
+        """forward + backward of the chained hot path; leaves the gradients in p.grad"""
         net = self.net
         meta = meta if meta is not None else d.get("_meta", {})
         self.opt.zero_grad(set_to_none=True)
@@ -153,9 +154,6 @@ class HotPathStep:
         loss = (net._losses["loss_response_per_expr"].sum() + net._mask_loss(d["mlab"], d["mtgt"])
                 + net._cap_loss_weight * net._caption_loss(d["fc"], att, d["cap"], d["msk"], steps=meta.get("steps")))
         torch.autograd.backward([loss, pool5], [self.one, self.g_pool])
-        if self.reducer is not None:
-            self.reducer.all_reduce()
-        self.opt.step()
         X.grad = fc7.grad = att.grad = None
         # drop the references into this step's autograd graph (the reference keeps them in _predictions/_losses for its
         # tensorboard summaries): a graph kept alive across steps pins AccumulateGrad nodes to the stream they were
@@ -163,6 +161,17 @@ class HotPathStep:
         net._predictions.clear()
         net._losses.clear()
         return loss.detach()
+
+    def update(self):
+        """gradient all-reduce of the three parameter groups (N > 1) and the SGD update"""
+        if self.reducer is not None:
+            self.reducer.all_reduce()
+        self.opt.step()
+
+    def __call__(self, d, meta=None):
+        loss = self.fwd_bwd(d, meta)
+        self.update()
+        return loss
 
 
 def time_region(fn, steps, dist_on):
@@ -398,6 +407,9 @@ def main():
     dev = torch.device("cuda", local)
     dist_on = world > 1
     if dist_on:
+        # keep stdout to the ONE JSON line: NCCL prints its version banner there when NCCL_DEBUG=VERSION
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     pk = peaks()
     E = wl["I"] * wl["EPI"]
@@ -412,22 +424,32 @@ def main():
     launches_per_step = _lib.launch_count() - l0          # kernels of libl2s.so per step (counted on an eager step)
     # The whole step (lang encoder .. SGD update, ~650 launches, shapes static for a given batch geometry) is captured
     # once in a CUDA graph and replayed: the timed region then measures the kernels, not Python/launch latency.
+    # N = 1: the whole step is one graph.  N > 1: forward+backward is the graph; the NCCL all-reduce and the SGD update
+    # (a handful of launches) stay eager -- NCCL work captured together with its stream/event hand-offs hung here.
+    whole = world == 1
+    body = (lambda: step(d)) if whole else (lambda: step.fwd_bwd(d))
     run, graphed = (lambda: step(d)), False
     if not args.no_graph:
         try:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
-                step(d)
+                body()
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                static_loss = step(d)
+                static_loss = body()
             graph.replay()
             torch.cuda.synchronize()
             assert torch.isfinite(static_loss).all()
-            run, graphed = graph.replay, True
+            if whole:
+                run = graph.replay
+            else:
+                def run():
+                    graph.replay()
+                    step.update()
+            graphed = True
         except Exception as exc:      # capture is an optimisation: fall back to eager launches and say so
             print("bench: CUDA graph capture failed (%s); timing eager launches" % str(exc).splitlines()[0], file=sys.stderr)
             torch.cuda.synchronize()
@@ -490,7 +512,8 @@ def main():
                 "config": {"workload": wl["name"], "per_gpu_expressions": E, "parallelism": "dp%d" % world,
                            "l2": "inputs larger than L2 (>= 1.2 GB streamed per step); no flush needed",
                            "includes": "lang encoder, filter generator, 4 hot components fwd+bwd, grad all-reduce, SGD",
-                           "launch": "one CUDA graph replay per step" if graphed else "eager launches"},
+                           "launch": ("one CUDA graph replay per step" + ("" if world == 1 else " (fwd+bwd) + eager all-reduce/SGD"))
+                           if graphed else "eager launches"},
                 "clocks": clocks, "gpu_launches": launches,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                         "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
