@@ -5,12 +5,22 @@
 // The dropped terms are O(2^-16) relative, so results sit ~1e-5 from an fp32 GEMM -- inside the
 // 1e-4 parity budget that rules out single-pass TF32/bf16 (hard parts).
 //
-// Persistent, warp-specialised CTA (192 threads):
-//   warp 0      TMA producer: 4-stage ring of {A_hi, A_lo, B_hi, B_lo} tiles, one mbarrier per stage
+// Persistent, warp-specialised CTA (64 + 128*MH*EW threads), CTA tile = (128*MH) x BN:
+//   warp 0      TMA producer: ring of {A_hi, A_lo, B_hi, B_lo} tiles, one mbarrier per stage
 //   warp 1      allocates TMEM, single elected lane issues tcgen05.mma (kind::f16, M=128, N=BN),
 //               tcgen05.commit releases smem stages and publishes the accumulator
-//   warps 2..5  epilogue: tcgen05.ld the fp32 accumulator (two TMEM buffers, so the epilogue of
-//               tile i overlaps the main loop of tile i+1) and apply an Epi functor
+//   warps 2..   epilogue (4 warps per 128-row half): tcgen05.ld the fp32 accumulator (lane = row, 32 columns per
+//               load), apply an Epi functor.  Row-major outputs go through a per-warp 32x33 shared-memory transpose
+//               tile so that every global store instruction writes whole 128-byte lines (a lane-per-row store
+//               touches 32 sectors per instruction).
+// MH = 1: 128 x BN tile, 4 stages, two TMEM accumulators (the epilogue of tile i overlaps the main loop of
+//         tile i+1).  Operand traffic: 24 KB of L2->SM bytes per 3 MMAs (BN = 256) = 64 B/clk/SM at the
+//         tensor peak, above the ~42 B/clk/SM the L2 can deliver chip-wide -- this shape is L2-bound.
+// MH = 2: 256 x BN tile as two 128-row accumulators that share every B tile: 32 KB per 6 MMAs = 42.7 B/clk/SM.
+//         3 stages of 64 KB; the two accumulators fill TMEM (2 x 256 columns), so the epilogue is not
+//         overlapped -- 8 epilogue warps keep it short (a few % of a K = 2048 main loop).
+// EW = 2 (with MH = 1): two epilogue warps per TMEM lane quadrant, splitting the column chunks -- for the GEMMs
+//         whose K is so short that the epilogue (global loads / scattered stores) is the critical path.
 // Operands may be K-major ([rows][K], 64B-swizzled TMA boxes) or MN-major ([K][rows], 128B
 // swizzle) so the weight-gradient GEMMs read activations in place.  M/N/K tails rely on TMA
 // out-of-bounds zero fill; the epilogue guards rows/cols.
@@ -22,10 +32,8 @@
 namespace l2s {
 namespace tc {
 
-constexpr int BM = 128;
+constexpr int BM = 128;       // rows per MMA / per accumulator
 constexpr int BK = 32;        // bf16 elements per k-block (64 bytes)
-constexpr int STAGES = 4;
-constexpr int THREADS = 192;
 
 // ---- PTX wrappers -------------------------------------------------------------------------
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar) {
@@ -90,34 +98,44 @@ __host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
          ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
-template <int BN>
+template <int BN, int MH, int EW = 1>
 struct SmemPlan {
-  static constexpr uint32_t A_BYTES = BM * BK * 2;
+  static constexpr int STAGES = MH == 1 ? 4 : 3;
+  static constexpr int EPI_WARPS = 4 * MH * EW;
+  static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+  static constexpr int NACC = MH == 1 ? 2 : 1;       // TMEM accumulator buffers (each MH * BN columns)
+  static constexpr uint32_t HALF_BYTES = BM * BK * 2;          // one 128-row half of an A plane
+  static constexpr uint32_t A_BYTES = MH * HALF_BYTES;
   static constexpr uint32_t B_BYTES = BN * BK * 2;
   static constexpr uint32_t STAGE = 2 * A_BYTES + 2 * B_BYTES;
-  static constexpr uint32_t TOTAL = STAGES * STAGE + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr uint32_t SCRATCH = 32 * 33 * 4;             // per epilogue warp: a 32 x 32 fp32 transpose tile (padded)
+  static constexpr uint32_t TOTAL = STAGES * STAGE + 1024 /*align slack*/ + 256 /*barriers*/ + EPI_WARPS * SCRATCH;
 };
 
 struct Maps {
   CUtensorMap a_hi, a_lo, b_hi, b_lo;
 };
 
-template <int BN, bool A_MN, bool B_MN, class Epi>
-__global__ void __launch_bounds__(THREADS, 1)
+template <int BN, int MH, int EW, bool A_MN, bool B_MN, class Epi>
+__global__ void __launch_bounds__(64 + 128 * MH * EW, 1)
 gemm_bf16x3_kernel(const __grid_constant__ Maps maps, int M, int N, int K, int nsplit, int kb_per_split, Epi epi) {
-  using P = SmemPlan<BN>;
+  using P = SmemPlan<BN, MH, EW>;
+  constexpr int STAGES = P::STAGES;
+  constexpr int NACC = P::NACC;
+  constexpr int TM = BM * MH;            // rows per CTA tile
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* tiles = smem_raw + (base - smem_u32(smem_raw));
   uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + STAGES * P::STAGE);
   uint64_t* full = bars;                 // [STAGES]
   uint64_t* empty = bars + STAGES;       // [STAGES]
-  uint64_t* tfull = bars + 2 * STAGES;   // [2]
+  uint64_t* tfull = bars + 2 * STAGES;   // [2] (NACC used)
   uint64_t* tempty = tfull + 2;          // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* scratch_all = reinterpret_cast<float*>(tiles + STAGES * P::STAGE + 256);   // [EPI_WARPS][32][33]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
+  const int tiles_m = (M + TM - 1) / TM, tiles_n = (N + BN - 1) / BN;
   const int kblocks = (K + BK - 1) / BK;
   const int total = tiles_m * tiles_n * nsplit;
 
@@ -128,11 +146,11 @@ gemm_bf16x3_kernel(const __grid_constant__ Maps maps, int M, int N, int K, int n
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 4);     // one arrive per epilogue warp
+      mbar_init(&tempty[a], P::EPI_WARPS);     // one arrive per epilogue warp
     }
     mbar_fence_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
+  if (warp == 1) tmem_alloc(tmem_slot, NACC * MH * BN);
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -153,13 +171,13 @@ gemm_bf16x3_kernel(const __grid_constant__ Maps maps, int M, int N, int K, int n
           if (it >= STAGES) mbar_wait(&empty[s], ((it / STAGES) - 1) & 1);
           uint8_t* st = tiles + s * P::STAGE;
           mbar_arrive_expect_tx(&full[s], P::STAGE);
-          const int k0 = kb * BK, m0 = tm * BM, n0 = tn * BN;
+          const int k0 = kb * BK, m0 = tm * TM, n0 = tn * BN;
           if (!A_MN) {
             tma_load_2d(st, &maps.a_hi, k0, m0, &full[s]);
             tma_load_2d(st + P::A_BYTES, &maps.a_lo, k0, m0, &full[s]);
           } else {
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j) {
+            for (int j = 0; j < TM / 64; ++j) {
               tma_load_2d(st + j * (BK * 128), &maps.a_hi, m0 + 64 * j, k0, &full[s]);
               tma_load_2d(st + P::A_BYTES + j * (BK * 128), &maps.a_lo, m0 + 64 * j, k0, &full[s]);
             }
@@ -185,10 +203,10 @@ gemm_bf16x3_kernel(const __grid_constant__ Maps maps, int M, int N, int K, int n
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++tcount) {
       const int split = tile % nsplit;
       const int kb0 = split * kb_per_split, kb1 = min(kblocks, kb0 + kb_per_split);
-      const int acc = tcount & 1;
-      if (tcount >= 2) mbar_wait(&tempty[acc], ((tcount >> 1) - 1) & 1);
+      const int acc = tcount % NACC;
+      if (tcount >= NACC) mbar_wait(&tempty[acc], ((tcount / NACC) - 1) & 1);
       fence_after_sync();
-      const uint32_t d_tmem = tmem_base + acc * BN;
+      const uint32_t d_tmem = tmem_base + acc * MH * BN;
       for (int kb = kb0; kb < kb1; ++kb, ++it) {
         const int s = it % STAGES;
         mbar_wait(&full[s], (it / STAGES) & 1);
@@ -197,14 +215,7 @@ gemm_bf16x3_kernel(const __grid_constant__ Maps maps, int M, int N, int K, int n
           const uint32_t sa = base + s * P::STAGE, sb = sa + 2 * P::A_BYTES;
 #pragma unroll
           for (int kk = 0; kk < BK / 16; ++kk) {
-            uint64_t ahi, alo, bhi, blo;
-            if (!A_MN) {
-              ahi = make_desc(sa + kk * 32, 0, 512, kLayoutSW64);
-              alo = make_desc(sa + P::A_BYTES + kk * 32, 0, 512, kLayoutSW64);
-            } else {
-              ahi = make_desc(sa + kk * 2048, BK * 128, 1024, kLayoutSW128);
-              alo = make_desc(sa + P::A_BYTES + kk * 2048, BK * 128, 1024, kLayoutSW128);
-            }
+            uint64_t bhi, blo;
             if (!B_MN) {
               bhi = make_desc(sb + kk * 32, 0, 512, kLayoutSW64);
               blo = make_desc(sb + P::B_BYTES + kk * 32, 0, 512, kLayoutSW64);
@@ -212,9 +223,23 @@ gemm_bf16x3_kernel(const __grid_constant__ Maps maps, int M, int N, int K, int n
               bhi = make_desc(sb + kk * 2048, BK * 128, 1024, kLayoutSW128);
               blo = make_desc(sb + P::B_BYTES + kk * 2048, BK * 128, 1024, kLayoutSW128);
             }
-            umma_f16(d_tmem, alo, bhi, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
-            umma_f16(d_tmem, ahi, blo, idesc, 1u);
-            umma_f16(d_tmem, ahi, bhi, idesc, 1u);
+#pragma unroll
+            for (int h = 0; h < MH; ++h) {
+              // a 128-row half of an A plane is HALF_BYTES (8 KB) in both layouts
+              const uint32_t sh = sa + h * P::HALF_BYTES;
+              uint64_t ahi, alo;
+              if (!A_MN) {
+                ahi = make_desc(sh + kk * 32, 0, 512, kLayoutSW64);
+                alo = make_desc(sh + P::A_BYTES + kk * 32, 0, 512, kLayoutSW64);
+              } else {
+                ahi = make_desc(sh + kk * 2048, BK * 128, 1024, kLayoutSW128);
+                alo = make_desc(sh + P::A_BYTES + kk * 2048, BK * 128, 1024, kLayoutSW128);
+              }
+              const uint32_t d_half = d_tmem + h * BN;
+              umma_f16(d_half, alo, bhi, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+              umma_f16(d_half, ahi, blo, idesc, 1u);
+              umma_f16(d_half, ahi, bhi, idesc, 1u);
+            }
           }
           umma_commit(&empty[s]);                 // smem stage free once these MMAs retire
           if (kb == kb1 - 1) umma_commit(&tfull[acc]);
@@ -223,24 +248,27 @@ gemm_bf16x3_kernel(const __grid_constant__ Maps maps, int M, int N, int K, int n
       }
     }
   } else {
-    // ================= epilogue (warps 2..5 -> TMEM lane quadrants 2,3,0,1) =================
-    const int q = warp & 3;
+    // ================= epilogue (warps 2..5 [, 6..9] -> TMEM lane quadrants 2,3,0,1 of half 0 [, 1]) =================
+    // warp set = (warp - 2) / 4: the 128-row half it serves (MH = 2) or its share of the column chunks (EW = 2)
+    const int q = warp & 3, wset = (warp - 2) >> 2;
+    const int h = wset % MH, cs = wset / MH;
+    float* scratch = scratch_all + (size_t)(warp - 2) * (P::SCRATCH / 4);
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++tcount) {
       const int split = tile % nsplit;
       const int tn = (tile / nsplit) % tiles_n;
       const int tm = tile / (nsplit * tiles_n);
-      const int acc = tcount & 1;
-      mbar_wait(&tfull[acc], (tcount >> 1) & 1);
+      const int acc = tcount % NACC;
+      mbar_wait(&tfull[acc], (tcount / NACC) & 1);
       fence_after_sync();
-      const int row = tm * BM + q * 32 + lane;
+      const int row = tm * TM + h * BM + q * 32 + lane;
 #pragma unroll 1
-      for (int ch = 0; ch < BN / 32; ++ch) {
+      for (int ch = cs; ch < BN / 32; ch += EW) {
         const int col0 = tn * BN + ch * 32;
         if (col0 >= N) break;             // warp-uniform
         float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + ch * 32, v);
-        epi(row, col0, v, M, N, split);
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (acc * MH + h) * BN + ch * 32, v);
+        epi(row, col0, v, M, N, split, scratch);
       }
       fence_before_sync();
       __syncwarp();
@@ -251,7 +279,7 @@ gemm_bf16x3_kernel(const __grid_constant__ Maps maps, int M, int N, int K, int n
   __syncthreads();
   if (warp == 1) {
     fence_after_sync();
-    tmem_dealloc(tmem_base, 2 * BN);
+    tmem_dealloc(tmem_base, NACC * MH * BN);
   }
 }
 
@@ -265,28 +293,67 @@ EncodeTiledFn encode_fn();
 int make_operand_map(CUtensorMap* out, const void* ptr, int64_t rows, int64_t K, int64_t ld, bool mn_major,
                      int box_rows);
 
-template <int BN, bool A_MN, bool B_MN, class Epi>
-int launch_gemm(const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda, const uint16_t* b_hi, const uint16_t* b_lo,
-                int64_t ldb, int M, int N, int K, int split_k, const Epi& epi, cudaStream_t st) {
+// split-K factor that fills the machine: minimises  waves * (k-blocks per split + epilogue) ; `epi_kb` is the cost of
+// one (atomic) epilogue in k-block units
+int auto_split(int tiles, int kblocks, int epi_kb);
+
+template <int BN, int MH, int EW, bool A_MN, bool B_MN, class Epi>
+int launch_gemm_mh(const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda, const uint16_t* b_hi, const uint16_t* b_lo,
+                   int64_t ldb, int M, int N, int K, int split_k, const Epi& epi, cudaStream_t st) {
+  using P = SmemPlan<BN, MH, EW>;
   Maps maps;
   int rc;
-  if ((rc = make_operand_map(&maps.a_hi, a_hi, M, K, lda, A_MN, BM))) return rc;
-  if ((rc = make_operand_map(&maps.a_lo, a_lo, M, K, lda, A_MN, BM))) return rc;
+  // K-major A: one box of all 128*MH rows; MN-major boxes are always 64 rows wide
+  if ((rc = make_operand_map(&maps.a_hi, a_hi, M, K, lda, A_MN, BM * MH))) return rc;
+  if ((rc = make_operand_map(&maps.a_lo, a_lo, M, K, lda, A_MN, BM * MH))) return rc;
   if ((rc = make_operand_map(&maps.b_hi, b_hi, N, K, ldb, B_MN, BN))) return rc;
   if ((rc = make_operand_map(&maps.b_lo, b_lo, N, K, ldb, B_MN, BN))) return rc;
   const int kblocks = (K + BK - 1) / BK;
+  const int tiles_mn = ((M + BM * MH - 1) / (BM * MH)) * ((N + BN - 1) / BN);
+  if (split_k == 0) split_k = auto_split(tiles_mn, kblocks, 8 * MH);
   split_k = split_k < 1 ? 1 : (split_k > kblocks ? kblocks : split_k);
   const int kb_per = (kblocks + split_k - 1) / split_k;
   const int nsplit = (kblocks + kb_per - 1) / kb_per;
-  const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN) * nsplit;
-  auto kern = gemm_bf16x3_kernel<BN, A_MN, B_MN, Epi>;
-  const size_t smem = SmemPlan<BN>::TOTAL;
+  const int tiles = tiles_mn * nsplit;
+  auto kern = gemm_bf16x3_kernel<BN, MH, EW, A_MN, B_MN, Epi>;
+  const size_t smem = P::TOTAL;
   L2S_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  kern<<<grid, THREADS, smem, st>>>(maps, M, N, K, nsplit, kb_per, epi);
+  kern<<<grid, P::THREADS, smem, st>>>(maps, M, N, K, nsplit, kb_per, epi);
   L2S_LAUNCH_OK("gemm_bf16x3_kernel");
   count_launch();
   return L2S_OK;
+}
+
+// CTA shape of a launch: 0 = (128 rows, 4 epilogue warps), 1 = (128 rows, 8 epilogue warps), 2 = (256 rows, 8 warps)
+enum Shape { kShapeAuto = -1, kShape128 = 0, kShape128E2 = 1, kShape256 = 2 };
+// the L2S_GEMM_SHAPE environment override (diagnostics / parity tests), -1 = none
+int forced_shape();
+
+// split_k: >= 1 as given (the epilogue must then accumulate atomically), 0 = choose (split-K epilogues only).
+// shape: kShapeAuto picks by the measured behaviour on B200 (profiles/): 256-row tiles pay off when a work item's
+// K range is long (split-K weight gradients: the un-overlapped epilogue is amortised and a 256 x 256 tile moves 2/3
+// of the L2->SM bytes per flop); 8 epilogue warps when K is so short that the epilogue is the critical path.
+template <int BN, bool A_MN, bool B_MN, class Epi>
+int launch_gemm(const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda, const uint16_t* b_hi, const uint16_t* b_lo,
+                int64_t ldb, int M, int N, int K, int split_k, const Epi& epi, cudaStream_t st, int shape = kShapeAuto) {
+  const int kblocks = (K + BK - 1) / BK;
+  if (shape == kShapeAuto) {
+    shape = kShape128E2;        // 8 epilogue warps: with 4 the epilogue of a 128 x 256 tile outlasts a K <= 2048 main loop
+    if (BN == 256 && split_k == 0 && M >= 2 * BM) {
+      const int tn = (N + BN - 1) / BN;
+      const int t2 = ((M + 2 * BM - 1) / (2 * BM)) * tn;
+      const int s2 = auto_split(t2, kblocks, 16);
+      if (kblocks / s2 >= 128) shape = kShape256;
+    }
+  }
+  if (forced_shape() >= 0) shape = forced_shape();
+  if (BN != 256 && shape == kShape256) shape = kShape128;
+  if (shape == kShape256)
+    return launch_gemm_mh<BN, (BN == 256 ? 2 : 1), 1, A_MN, B_MN, Epi>(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, split_k, epi, st);
+  if (shape == kShape128E2)
+    return launch_gemm_mh<BN, 1, 2, A_MN, B_MN, Epi>(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, split_k, epi, st);
+  return launch_gemm_mh<BN, 1, 1, A_MN, B_MN, Epi>(a_hi, a_lo, lda, b_hi, b_lo, ldb, M, N, K, split_k, epi, st);
 }
 
 }  // namespace tc

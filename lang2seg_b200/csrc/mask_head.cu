@@ -13,6 +13,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 
 #include "gemm_tc.cuh"
@@ -60,6 +61,30 @@ int make_operand_map(CUtensorMap* out, const void* ptr, int64_t rows, int64_t K,
   return L2S_OK;
 }
 
+int auto_split(int tiles, int kblocks, int epi_kb) {
+  const int sms = sm_count();
+  int best = 1;
+  double best_cost = 1e300;
+  const int smax = std::min(kblocks, 2 * sms);
+  for (int s = 1; s <= smax; ++s) {
+    const int kb_per = (kblocks + s - 1) / s;
+    const int ns = (kblocks + kb_per - 1) / kb_per;      // splits actually launched
+    if (ns != s) continue;
+    const int waves = (tiles * ns + sms - 1) / sms;
+    const double cost = (double)waves * (kb_per + epi_kb);
+    if (cost < best_cost * 0.995) {                        // prefer fewer splits on (near) ties
+      best_cost = cost;
+      best = s;
+    }
+  }
+  return best;
+}
+
+int forced_shape() {   // read on every call so that the parity tests can pin every CTA shape on any GEMM
+  const char* e = getenv("L2S_GEMM_SHAPE");
+  return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : -1;
+}
+
 }  // namespace tc
 
 namespace {
@@ -72,22 +97,64 @@ __device__ __forceinline__ void split2(float v, uint16_t* hi, uint16_t* lo) {
   *lo = __bfloat16_as_ushort(l);
 }
 
-// pack 32 floats of one accumulator row into hi / lo bf16 and store 64 contiguous bytes each
-__device__ __forceinline__ void store_split32(uint16_t* hi, uint16_t* lo, const float (&v)[32]) {
-  uint32_t ph[16], pl[16];
+// ---- staged (coalesced) epilogue stores --------------------------------------------------------
+// Each epilogue lane holds 32 consecutive columns of ONE row.  Writing that directly is a 32-sector store per
+// instruction; going through the warp's private 32 x 33 shared tile turns it into stores of whole 128-byte lines.
+constexpr int kScr = 33;
+
+// fp32 row-major: D[row0 + r][col0 .. col0+31] = f(acc + badd).  mode 0 store, 1 +=, 2 relu then store, 3 atomicAdd.
+// `badd` is the bias of THIS lane's column (col0 + lane): it is applied after the transpose, where lane = column.
+__device__ __forceinline__ void staged_store_f32(float* scratch, float* D, int64_t ldd, int row0, int col0, int M, int N,
+                                                 const float (&v)[32], int mode, float badd) {
+  const int lane = threadIdx.x & 31;
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    uint16_t h0, l0, h1, l1;
-    split2(v[2 * j], &h0, &l0);
-    split2(v[2 * j + 1], &h1, &l1);
-    ph[j] = (uint32_t)h0 | ((uint32_t)h1 << 16);
-    pl[j] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+  for (int j = 0; j < 32; ++j) scratch[lane * kScr + j] = v[j];
+  __syncwarp();
+  const int nr = min(32, M - row0);
+  if (col0 + lane < N) {
+    float* d = D + (size_t)row0 * ldd + col0 + lane;
+#pragma unroll 4
+    for (int r = 0; r < nr; ++r, d += ldd) {
+      float x = scratch[r * kScr + lane] + badd;
+      if (mode == 2) x = fmaxf(x, 0.f);
+      if (mode == 1) *d += x;
+      else if (mode == 3) atomicAdd(d, x);
+      else *d = x;
+    }
   }
+  __syncwarp();
+}
+
+// bf16 planes.  The raw accumulators are staged as float2 column pairs (rotation swizzle: pair p of row r sits at
+// r*16 + ((p + r) & 15), conflict free for the row-wise 64-bit writes and the column-wise 64-bit reads).  After the
+// transpose lane (half, w) owns the column pair (col0 + 2w, +1) of rows i + 16*half, i = 0..15: store instruction i
+// writes the 64-byte segments of two rows.  `fx(x, o, valid, i)` edits the pair in place (bias, ReLU, masks, sums);
+// o indexes the planes in 32-bit words.
+template <class F>
+__device__ __forceinline__ void staged_store_planes(float* scratch, uint16_t* hi, uint16_t* lo, int64_t ld, int row0,
+                                                    int col0, int M, const float (&v)[32], F&& fx) {
+  float2* s2 = reinterpret_cast<float2*>(scratch);
+  const int lane = threadIdx.x & 31;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    reinterpret_cast<uint4*>(hi)[j] = make_uint4(ph[4 * j], ph[4 * j + 1], ph[4 * j + 2], ph[4 * j + 3]);
-    reinterpret_cast<uint4*>(lo)[j] = make_uint4(pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
+  for (int k = 0; k < 16; ++k) s2[lane * 16 + ((k + lane) & 15)] = make_float2(v[2 * k], v[2 * k + 1]);
+  __syncwarp();
+  const int w = lane & 15, half = lane >> 4;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int r = i + 16 * half;
+    float2 x = s2[r * 16 + ((w + r) & 15)];
+    const bool valid = row0 + r < M;
+    const size_t o = ((size_t)(row0 + r) * ld + col0) / 2 + w;       // ld and col0 are even
+    fx(x, o, valid, i);
+    if (valid) {
+      uint16_t h0, l0, h1, l1;
+      split2(x.x, &h0, &l0);
+      split2(x.y, &h1, &l1);
+      reinterpret_cast<uint32_t*>(hi)[o] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+      reinterpret_cast<uint32_t*>(lo)[o] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+    }
   }
+  __syncwarp();
 }
 
 __global__ void split_kernel(const float* __restrict__ src, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
@@ -107,20 +174,14 @@ struct EpiGeneric {
   const float* bias;
   int bias_div;
   int mode;   // 0 store, 1 accumulate (+=), 2 relu(acc+bias), 3 atomic accumulate, 4 acc+bias
-  __device__ __forceinline__ void operator()(int row, int col0, const float (&v)[32], int M, int N, int) const {
-    if (row >= M) return;
-    float* d = D + (size_t)row * ldd + col0;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      if (col0 + j < N) {
-        float x = v[j];
-        if (mode == 2) x = fmaxf(x + (bias ? __ldg(bias + (col0 + j) / bias_div) : 0.f), 0.f);
-        if (mode == 4) x += bias ? __ldg(bias + (col0 + j) / bias_div) : 0.f;
-        if (mode == 1) d[j] += x;
-        else if (mode == 3) atomicAdd(d + j, x);
-        else d[j] = x;
-      }
-    }
+  __device__ __forceinline__ void operator()(int row, int col0, const float (&v)[32], int M, int N, int,
+                                             float* scratch) const {
+    const int lane = threadIdx.x & 31;
+    const int row0 = row - lane;
+    if (row0 >= M) return;                 // warp-uniform
+    float badd = 0.f;
+    if ((mode == 2 || mode == 4) && bias && col0 + lane < N) badd = __ldg(bias + (col0 + lane) / bias_div);
+    staged_store_f32(scratch, D, ldd, row0, col0, M, N, v, mode == 4 ? 0 : mode, badd);
   }
 };
 
@@ -130,20 +191,25 @@ struct EpiUp {
   uint16_t *hi, *lo;
   const float* bias;
   int Cmid, ld;
-  __device__ __forceinline__ void operator()(int row, int col0, const float (&v)[32], int M, int N, int) const {
-    if (row >= M) return;
-    float u[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int col = col0 + j;
-      u[j] = col < N ? fmaxf(v[j] + __ldg(bias + col % Cmid), 0.f) : 0.f;
-    }
-    if (col0 + 32 <= N) {
-      store_split32(hi + (size_t)row * ld + col0, lo + (size_t)row * ld + col0, u);
-    } else {
+  __device__ __forceinline__ void operator()(int row, int col0, const float (&v)[32], int M, int N, int,
+                                             float* scratch) const {
+    const int lane = threadIdx.x & 31;
+    const int row0 = row - lane;
+    if (row0 >= M) return;                 // warp-uniform
+    if (col0 + 32 <= N && Cmid % 2 == 0) {
+      const int cb = (col0 + 2 * (lane & 15)) % Cmid;           // this lane's column pair after the transpose
+      const float b0 = __ldg(bias + cb), b1 = __ldg(bias + cb + 1);
+      staged_store_planes(scratch, hi, lo, ld, row0, col0, M, v, [&](float2& x, size_t, bool, int) {
+        x.x = fmaxf(x.x + b0, 0.f);
+        x.y = fmaxf(x.y + b1, 0.f);
+      });
+    } else if (row < M) {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        if (col0 + j < N) split2(u[j], hi + (size_t)row * ld + col0 + j, lo + (size_t)row * ld + col0 + j);
+        if (col0 + j < N) {
+          const float u = fmaxf(v[j] + __ldg(bias + (col0 + j) % Cmid), 0.f);
+          split2(u, hi + (size_t)row * ld + col0 + j, lo + (size_t)row * ld + col0 + j);
+        }
     }
   }
 };
@@ -153,22 +219,33 @@ struct EpiScore {
   float *score, *prob;
   const float* bias;
   int ncls;
-  __device__ __forceinline__ void operator()(int row, int col0, const float (&v)[32], int M, int N, int) const {
-    if (row >= M) return;
-    const int m = row >> 2, q = row & 3;
+  // The 32 rows of a warp are 8 map positions (y,x) x 4 sub-pixels (dy,dx).  Written lane-per-row, one class is 16
+  // two-float runs; through the transpose tile the lanes are re-ordered to output order (dy, x, dx), so one class
+  // becomes (mostly) two 64-byte runs.
+  __device__ __forceinline__ void operator()(int row, int col0, const float (&v)[32], int M, int N, int,
+                                             float* scratch) const {
+    const int lane = threadIdx.x & 31;
+    const int row0 = row - lane;
+    if (row0 >= M) return;                 // warp-uniform
+#pragma unroll
+    for (int j = 0; j < 32; ++j) scratch[lane * kScr + j] = v[j] + ((col0 + j < ncls) ? __ldg(bias + col0 + j) : 0.f);
+    __syncwarp();
+    const int pr = 4 * ((lane & 15) >> 1) + ((lane >> 4) << 1) + (lane & 1);      // source row of this store lane
+    const int grow = row0 + pr;
+    const int m = grow >> 2, q = grow & 3;
     const int n = m / 49, yx = m - n * 49;
     const int y = yx / 7, x = yx - y * 7;
     const int pos = (2 * y + (q >> 1)) * 14 + 2 * x + (q & 1);
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      const int cls = col0 + j;
-      if (cls < ncls) {
-        const float s = v[j] + __ldg(bias + cls);
-        const size_t o = ((size_t)n * ncls + cls) * 196 + pos;
-        score[o] = s;
-        if (prob) prob[o] = sigmoidf_acc(s);
+    const size_t base = ((size_t)n * ncls + col0) * 196 + pos;
+    const int nc = min(32, ncls - col0);
+    if (grow < M) {
+      for (int j = 0; j < nc; ++j) {
+        const float sc = scratch[pr * kScr + j];
+        score[base + (size_t)j * 196] = sc;
+        if (prob) prob[base + (size_t)j * 196] = sigmoidf_acc(sc);
       }
     }
+    __syncwarp();
   }
 };
 
@@ -212,42 +289,53 @@ struct EpiDU {
   const uint16_t* u_hi;
   float* d_up_b;
   int Cmid;
-  __device__ __forceinline__ void operator()(int row, int col0, const float (&v)[32], int M, int N, int) const {
+  __device__ __forceinline__ void operator()(int row, int col0, const float (&v)[32], int M, int N, int,
+                                             float* scratch) const {
+    const int lane = threadIdx.x & 31;
+    const int row0 = row - lane;
+    if (row0 >= M) return;                 // warp-uniform
+    if (col0 + 32 <= N) {
+      // after the transpose a lane owns a column pair: the ReLU mask is one coalesced 32-bit load of the saved U_hi
+      // plane per row, and the bias gradient is a private running sum over the lane's 16 rows
+      const uint32_t* u32 = reinterpret_cast<const uint32_t*>(u_hi);
+      uint32_t uu[16];        // all 16 mask words are requested up front (independent loads, overlapped with the staging)
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int r = row0 + i + 16 * (lane >> 4);
+        uu[i] = r < M ? __ldg(u32 + ((size_t)r * Cmid + col0) / 2 + (lane & 15)) : 0u;
+      }
+      float s0 = 0.f, s1 = 0.f;
+      staged_store_planes(scratch, hi, lo, Cmid, row0, col0, M, v, [&](float2& x, size_t, bool, int i) {
+        const uint32_t u = uu[i];
+        const uint32_t lo16 = u & 0xffffu, hi16 = u >> 16;     // bf16 > 0  <=>  sign bit clear and magnitude non-zero
+        x.x = (lo16 != 0 && lo16 < 0x8000u) ? x.x : 0.f;
+        x.y = (hi16 != 0 && hi16 < 0x8000u) ? x.y : 0.f;
+        s0 += x.x;
+        s1 += x.y;
+      });
+      s0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+      s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+      if (lane < 16) {
+        atomicAdd(d_up_b + col0 + 2 * lane, s0);
+        atomicAdd(d_up_b + col0 + 2 * lane + 1, s1);
+      }
+      return;
+    }
     float d[32];
     const bool ok = row < M;
-    const bool full = col0 + 32 <= N;
-    if (ok && full) {
-      // 32 bf16 of this row = 64 contiguous bytes
-      const uint4* up = reinterpret_cast<const uint4*>(u_hi + (size_t)row * Cmid + col0);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const uint4 w = __ldg(up + q);
-        const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          // bf16 > 0  <=>  sign bit clear and magnitude non-zero
-          const uint32_t lo16 = ws[e] & 0xffffu, hi16 = ws[e] >> 16;
-          d[q * 8 + 2 * e] = (lo16 != 0 && lo16 < 0x8000u) ? v[q * 8 + 2 * e] : 0.f;
-          d[q * 8 + 2 * e + 1] = (hi16 != 0 && hi16 < 0x8000u) ? v[q * 8 + 2 * e + 1] : 0.f;
-        }
+    for (int j = 0; j < 32; ++j) {
+      const int col = col0 + j;
+      float x = 0.f;
+      if (ok && col < N) {
+        const uint32_t u = u_hi[(size_t)row * Cmid + col];
+        x = (u != 0 && u < 0x8000u) ? v[j] : 0.f;
+        split2(x, hi + (size_t)row * Cmid + col, lo + (size_t)row * Cmid + col);
       }
-      store_split32(hi + (size_t)row * Cmid + col0, lo + (size_t)row * Cmid + col0, d);
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int col = col0 + j;
-        float x = 0.f;
-        if (ok && col < N) {
-          const uint32_t u = u_hi[(size_t)row * Cmid + col];
-          x = (u != 0 && u < 0x8000u) ? v[j] : 0.f;
-          split2(x, hi + (size_t)row * Cmid + col, lo + (size_t)row * Cmid + col);
-        }
-        d[j] = x;
-      }
+      d[j] = x;
     }
     // bias gradient: column sums over the 32 rows of this warp, one atomic per column
     const float tot = warp_column_sums(d);
-    const int lane = threadIdx.x & 31;
     if (col0 + lane < N) atomicAdd(d_up_b + col0 + lane, tot);
   }
 };
@@ -256,7 +344,7 @@ struct EpiDU {
 struct EpiDx {
   float* dx;
   int Cin;
-  __device__ __forceinline__ void operator()(int row, int col0, const float (&v)[32], int M, int N, int) const {
+  __device__ __forceinline__ void operator()(int row, int col0, const float (&v)[32], int M, int N, int, float*) const {
     if (row >= M) return;
     const int n = row / 49, yx = row - n * 49;
     float* d = dx + ((size_t)n * Cin + col0) * 49 + yx;
@@ -270,7 +358,7 @@ struct EpiDx {
 struct EpiDWd {
   float* dw;
   int Cmid;
-  __device__ __forceinline__ void operator()(int row, int col0, const float (&v)[32], int M, int N, int) const {
+  __device__ __forceinline__ void operator()(int row, int col0, const float (&v)[32], int M, int N, int, float*) const {
     if (row >= M) return;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
@@ -287,7 +375,7 @@ struct EpiDWd {
 struct EpiDWp {
   float* dw;
   int ncls, Cmid;
-  __device__ __forceinline__ void operator()(int row, int col0, const float (&v)[32], int M, int N, int) const {
+  __device__ __forceinline__ void operator()(int row, int col0, const float (&v)[32], int M, int N, int, float*) const {
     if (row >= ncls) return;
 #pragma unroll
     for (int j = 0; j < 32; ++j)
@@ -362,16 +450,26 @@ repack_dscore_kernel(const float* __restrict__ ds, uint16_t* __restrict__ hi, ui
       a = warp_sum(a);
       if (lane == 0) atomicAdd(d_pred_b + cls, a);
     }
-  for (int i = t; i < 196 * KP; i += 256) {
-    const int r = i / KP, cls = i - r * KP;
+  // item = (row r, group of 8 classes): one 16-byte store per plane, 12 consecutive threads cover a 192-byte row
+  const int G = KP >> 3;
+  for (int i = t; i < 196 * G; i += 256) {
+    const int r = i / G, g8 = (i - r * G) << 3;
     const int yx = r >> 2, q = r & 3;
     const int y = yx / 7, x = yx - y * 7;
     const int pos = (2 * y + (q >> 1)) * 14 + 2 * x + (q & 1);
-    uint16_t h = 0, l = 0;
-    if (cls < ncls) split2(s[cls * 197 + pos], &h, &l);
-    const size_t o = ((size_t)n * 196 + r) * KP + cls;
-    hi[o] = h;
-    lo[o] = l;
+    uint32_t ph[4], pl[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      uint16_t h0 = 0, l0 = 0, h1 = 0, l1 = 0;
+      const int c0 = g8 + 2 * k;
+      if (c0 < ncls) split2(s[c0 * 197 + pos], &h0, &l0);
+      if (c0 + 1 < ncls) split2(s[(c0 + 1) * 197 + pos], &h1, &l1);
+      ph[k] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+      pl[k] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+    }
+    const size_t o = ((size_t)n * 196 + r) * KP + g8;
+    *reinterpret_cast<uint4*>(hi + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+    *reinterpret_cast<uint4*>(lo + o) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
   }
 }
 
@@ -484,11 +582,6 @@ int check_head(int n, int Cin, int Cmid, int ncls) {
   return L2S_OK;
 }
 
-int split_for(int tiles) {
-  const int sms = sm_count();
-  return tiles >= sms ? 1 : (2 * sms + tiles - 1) / tiles;
-}
-
 }  // namespace
 }  // namespace l2s
 
@@ -514,8 +607,10 @@ extern "C" int l2s_gemm_bf16x3(const uint16_t* a_hi, const uint16_t* a_lo, const
   L2S_REQUIRE((epilogue >= 0 && epilogue <= 2) || epilogue == 4, L2S_ERR_ARG, "gemm_bf16x3: unknown epilogue %d", epilogue);
   cudaStream_t st = (cudaStream_t)stream;
 
+  L2S_REQUIRE(split_k >= 0, L2S_ERR_ARG, "gemm_bf16x3: split_k must be >= 0 (0 = choose)");
   EpiGeneric epi{D, N, bias, bias_div > 0 ? bias_div : 1, epilogue};
-  if (split_k > 1) {
+  if (split_k == 0 && epilogue >= 2) split_k = 1;     // a bias epilogue cannot be split
+  if (split_k != 1) {
     L2S_REQUIRE(epilogue < 2, L2S_ERR_ARG, "gemm_bf16x3: split-K cannot be combined with a bias epilogue");
     if (epilogue == 0) L2S_CUDA_OK(cudaMemsetAsync(D, 0, sizeof(float) * (size_t)M * N, st));
     epi.mode = 3;
@@ -595,11 +690,11 @@ extern "C" int l2s_mask_head_fwd(const float* x, const float* up_w, const float*
   count_launch(3);
   // GEMM1: [M x Cin] * [4Cmid x Cin]^T -> U planes
   EpiUp e1{sv.u_hi, sv.u_lo, up_b, Cmid, 4 * Cmid};
-  rc = tc::launch_gemm<256, false, false>(sv.a_hi, sv.a_lo, Cin, w.b1h, w.b1l, Cin, M, 4 * Cmid, Cin, 1, e1, st);
+  rc = tc::launch_gemm<256, false, false>(sv.a_hi, sv.a_lo, Cin, w.b1h, w.b1l, Cin, M, 4 * Cmid, Cin, 1, e1, st, tc::kShape128E2);
   if (rc) return rc;
   // GEMM2: [4M x Cmid] * [ncls x Cmid]^T -> score / prob
   EpiScore e2{score, prob, pred_b, ncls};
-  return tc::launch_gemm<128, false, false>(sv.u_hi, sv.u_lo, Cmid, w.b2h, w.b2l, Cmid, 4 * M, ncls, Cmid, 1, e2, st);
+  return tc::launch_gemm<128, false, false>(sv.u_hi, sv.u_lo, Cmid, w.b2h, w.b2l, Cmid, 4 * M, ncls, Cmid, 1, e2, st, tc::kShape128E2);
 }
 
 extern "C" int l2s_mask_head_bwd(const float* dscore, const float* up_w, const float* pred_w, const void* saved,
@@ -633,22 +728,19 @@ extern "C" int l2s_mask_head_bwd(const float* dscore, const float* up_w, const f
   count_launch(3);
   // dU[4M x Cmid] = dS[4M x KP] * Wp^T[Cmid x KP]^T, masked by U > 0
   EpiDU e3{w.duh, w.dul, sv.u_hi, d_up_b, Cmid};
-  rc = tc::launch_gemm<256, false, false>(w.dsh, w.dsl, KP, w.b4h, w.b4l, KP, 4 * M, Cmid, KP, 1, e3, st);
+  rc = tc::launch_gemm<256, false, false>(w.dsh, w.dsl, KP, w.b4h, w.b4l, KP, 4 * M, Cmid, KP, 1, e3, st, tc::kShape256);
   if (rc) return rc;
   // dWp[KP x Cmid] = dS^T * U   (both MN-major, K = 4M)
   EpiDWp e4{d_pred_w, ncls, Cmid};
-  rc = tc::launch_gemm<256, true, true>(w.dsh, w.dsl, KP, sv.u_hi, sv.u_lo, Cmid, KP, Cmid, 4 * M,
-                                        split_for(((Cmid + 255) / 256)), e4, st);
+  rc = tc::launch_gemm<256, true, true>(w.dsh, w.dsl, KP, sv.u_hi, sv.u_lo, Cmid, KP, Cmid, 4 * M, 0, e4, st, tc::kShape128);
   if (rc) return rc;
   // dF[M x Cin] = dU[M x 4Cmid] * Wd[Cin x 4Cmid]^T -> dx NCHW
   EpiDx e5{dx, Cin};
-  rc = tc::launch_gemm<256, false, false>(w.duh, w.dul, 4 * Cmid, w.b3h, w.b3l, 4 * Cmid, M, Cin, 4 * Cmid, 1, e5, st);
+  rc = tc::launch_gemm<256, false, false>(w.duh, w.dul, 4 * Cmid, w.b3h, w.b3l, 4 * Cmid, M, Cin, 4 * Cmid, 1, e5, st, tc::kShape256);
   if (rc) return rc;
   // dWd[Cin x 4Cmid] = F^T * dU   (both MN-major, K = M)
   EpiDWd e6{d_up_w, Cmid};
-  const int tiles = ((Cin + 127) / 128) * ((4 * Cmid + 255) / 256);
-  return tc::launch_gemm<256, true, true>(sv.a_hi, sv.a_lo, Cin, w.duh, w.dul, 4 * Cmid, Cin, 4 * Cmid, M,
-                                          split_for(tiles), e6, st);
+  return tc::launch_gemm<256, true, true>(sv.a_hi, sv.a_lo, Cin, w.duh, w.dul, 4 * Cmid, Cin, 4 * Cmid, M, 0, e6, st, tc::kShape256);
 }
 
 extern "C" int l2s_mask_bce_fwd(const float* score, const int64_t* labels, const float* target, float* loss, int n,

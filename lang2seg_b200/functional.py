@@ -588,9 +588,7 @@ class _LinearTC(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             dx = gemm_bf16x3(dyh, dyl, wh, wl, M, K, N, a_mn=False, b_mn=True)           # dY [M,N] . W [N,K]
         if ctx.needs_input_grad[1]:
-            tiles = ((N + 127) // 128) * ((K + 255) // 256)
-            dw = gemm_bf16x3(dyh, dyl, xh, xl, N, K, M, a_mn=True, b_mn=True,
-                             split_k=max(1, min(16, 296 // max(tiles, 1))))                # dY^T [N,M] . X [M,K]
+            dw = gemm_bf16x3(dyh, dyl, xh, xl, N, K, M, a_mn=True, b_mn=True, split_k=0)  # dY^T [N,M] . X [M,K]; split chosen by the library
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = dy.sum(0)
         return dx, dw, db

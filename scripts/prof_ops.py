@@ -69,6 +69,14 @@ def main():
             ab = torch.zeros(1, device=dev, requires_grad=True)
             res, _ = F.attention_step(att_h, feats, p_att, aw, ab)
             torch.autograd.grad(res, [att_h, feats, p_att, aw, ab], torch.randn_like(res))
+        if "cap" in only:
+            # the caption-side projections that run on the tensor-core Linear (att_embed, ctx2att, logit, i2h)
+            for (M, N, K) in [(E * 196, 512, 4096), (E * 196, 512, 512), (E * 11, 2000, 512), (E * 11, 2560, 512)]:
+                x = torch.relu(torch.randn(M, K, device=dev)).requires_grad_(True)
+                w = (torch.randn(N, K, device=dev) * 0.02).requires_grad_(True)
+                b = torch.zeros(N, device=dev, requires_grad=True)
+                y = F.linear(x, w, b)
+                torch.autograd.grad(y, [x, w, b], torch.randn_like(y))
         if "lin" in only:
             for (M, N, K) in [(48, 3072, 512), (48, 1024, 512), (48, 512, 1024), (48, 512, 3072), (48, 7168, 1024)]:
                 x = torch.randn(M, K, device=dev)

@@ -26,9 +26,23 @@ def test_split_bf16():
     assert float(rec[:, 50:].abs().max()) == 0.0
 
 
-@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 512, 2048), (300, 96, 40), (1000, 1024, 136)])
+@pytest.fixture
+def gemm_shape(request, monkeypatch):
+    """L2S_GEMM_SHAPE pins the CTA shape of every tcgen05 GEMM launch (0: 128-row tile / 4 epilogue warps,
+    1: 128 rows / 8 epilogue warps, 2: 256 rows / 8 epilogue warps) so that each variant sees every problem shape;
+    None leaves the library's own choice."""
+    shape = getattr(request, "param", None)
+    if shape is None:
+        monkeypatch.delenv("L2S_GEMM_SHAPE", raising=False)
+    else:
+        monkeypatch.setenv("L2S_GEMM_SHAPE", str(shape))
+    return shape
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 512, 2048), (300, 96, 40), (1000, 1024, 136), (2600, 520, 264)])
 @pytest.mark.parametrize("layout", ["kk", "mm", "mk", "km"])
-def test_gemm_bf16x3(M, N, K, layout):
+@pytest.mark.parametrize("gemm_shape", [0, 1, 2], indirect=True)
+def test_gemm_bf16x3(M, N, K, layout, gemm_shape):
     import lang2seg_b200.functional as F
     g = torch.Generator().manual_seed(M + N + K)
     A = torch.randn(M, K, generator=g)
@@ -42,12 +56,35 @@ def test_gemm_bf16x3(M, N, K, layout):
     D = F.gemm_bf16x3(a_hi, a_lo, b_hi, b_lo, M, N, K, a_mn, b_mn)
     assert relerr(D, ref) < 3e-5, "bf16x3 product should be ~1e-5 from fp64"
     if layout == "mm":
-        D2 = F.gemm_bf16x3(a_hi, a_lo, b_hi, b_lo, M, N, K, a_mn, b_mn, split_k=3)
-        assert relerr(D2, ref) < 3e-5
+        for sk in (3, 0):       # 0: the library chooses the split
+            D2 = F.gemm_bf16x3(a_hi, a_lo, b_hi, b_lo, M, N, K, a_mn, b_mn, split_k=sk)
+            assert relerr(D2, ref) < 3e-5
     bias = torch.randn(N // 4 if N % 4 == 0 else N, generator=g)
     if N % 4 == 0:
         D3 = F.gemm_bf16x3(a_hi, a_lo, b_hi, b_lo, M, N, K, a_mn, b_mn, epilogue=2, bias=bias.cuda(), bias_div=4)
         assert relerr(D3, torch.relu(ref + bias.double().repeat_interleave(4)[None])) < 3e-5
+
+
+@pytest.mark.parametrize("gemm_shape", [0, 1, 2], indirect=True)
+def test_gemm_bf16x3_many_tiles_per_cta(gemm_shape):
+    """More tiles than CTAs: the persistent loop, the smem ring wrap-around and the TMEM accumulator hand-off
+    between the MMA issuer and the epilogue warps are all exercised several times per CTA."""
+    import lang2seg_b200.functional as F
+    M, N, K = 30008, 1000, 200
+    g = torch.Generator().manual_seed(7)
+    A = torch.randn(M, K, generator=g)
+    B = torch.randn(N, K, generator=g)
+    bias = torch.randn(N, generator=g)
+    ref = A.double() @ B.double().t()
+    a_hi, a_lo = F.split_bf16(A.cuda())
+    b_hi, b_lo = F.split_bf16(B.cuda())
+    D = F.gemm_bf16x3(a_hi, a_lo, b_hi, b_lo, M, N, K)
+    assert relerr(D, ref) < 3e-5
+    D = F.gemm_bf16x3(a_hi, a_lo, b_hi, b_lo, M, N, K, epilogue=4, bias=bias.cuda())
+    assert relerr(D, ref + bias.double()[None]) < 3e-5
+    D0 = torch.randn(M, N, generator=g)
+    D = F.gemm_bf16x3(a_hi, a_lo, b_hi, b_lo, M, N, K, epilogue=1, out=D0.cuda())
+    assert relerr(D, ref + D0.double()) < 3e-5
 
 
 def test_mask_head_golden(golden):
@@ -64,8 +101,8 @@ def test_mask_head_golden(golden):
         assert relerr(gk, d[k]) < TOL, k
 
 
-@pytest.mark.parametrize("n", [1, 8])
-def test_mask_head_full_size_vs_oracle(n):
+@pytest.mark.parametrize("n,gemm_shape", [(1, None), (8, None), (8, 0), (8, 1), (8, 2)], indirect=["gemm_shape"])
+def test_mask_head_full_size_vs_oracle(n, gemm_shape):
     import lang2seg_b200.functional as F
     g = torch.Generator().manual_seed(n)
     x = torch.relu(torch.randn(n, 2048, 7, 7, generator=g))
@@ -91,7 +128,8 @@ def test_mask_head_full_size_vs_oracle(n):
         assert relerr(a, b) < TOL, name
 
 
-def test_linear_tc_vs_fp64():
+@pytest.mark.parametrize("gemm_shape", [None, 1, 2], indirect=True)
+def test_linear_tc_vs_fp64(gemm_shape):
     import lang2seg_b200.functional as F
     g = torch.Generator().manual_seed(4)
     M, K, N = 1960, 4096, 512
