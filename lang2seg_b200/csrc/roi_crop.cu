@@ -22,8 +22,6 @@
 //     lanes are samples, the four corners are four phases, and equal-cell samples are serialised by their
 //     precomputed rank (fixed order => bit-reproducible sums).  No floating-point atomics anywhere
 //     (shared fp32 atomicAdd costs 2 cycles per lane on sm_100).
-#include <cstdlib>
-
 #include "common.cuh"
 
 namespace l2s {
@@ -129,15 +127,19 @@ struct __align__(16) GeomEntry {
 };
 
 // Separable form of the same geometry for the row-owner backward: sample (i,j) sits at (py_i, px_j).
+constexpr int kRowWarps = 31;       // consumer warps of the row-owner backward: warp w owns map rows y = w (mod 31)
+constexpr int kRowLd = 33;          // channel stride of its accumulator map (odd: conflict free both ways)
 struct __align__(16) SepRec {
-  int16_t x0[8];
+  int xoff[8];          // (clamped x0_j) * kRowLd : float offset of the left corner inside a padded accumulator row
   float lx[8];
-  int16_t y0[8];
   float ly[8];
-  int n, ymin, ymax;
-  int mode;   // column pattern of the 7 samples: 2 = all 14 corner columns distinct, 1 = x0 strictly increasing, 0 = general
+  int16_t y0[8];        // clamped to [-2, 30000]
+  uint16_t wmask[32];   // per consumer warp: bit 2i+d set <=> map row y0_i + d is inside the map and owned by the warp
+  int n;                // ROI index
+  int mode;             // column pattern: 2 = all 14 corner columns distinct, 1 = x0 strictly increasing, 0 = general
+  int pad[2];
 };
-static_assert(sizeof(SepRec) == 112, "SepRec layout");
+static_assert(sizeof(SepRec) == 192, "SepRec layout");
 
 __global__ void __launch_bounds__(256)
 roi_geom_kernel(const float* __restrict__ rois, const int* __restrict__ order, unsigned char* __restrict__ table,
@@ -201,30 +203,42 @@ roi_geom_kernel(const float* __restrict__ rois, const int* __restrict__ order, u
     }
   }
   if (p == 0) *reinterpret_cast<int*>(rec + (size_t)SS * 16 + 56) = n;
-  if (sep != nullptr && g.S == 7 && p < 8) {
+  if (sep != nullptr && g.S == 7 && p < 32) {
     SepRec* sr = sep + r;
-    const Corner c = sample_at(box, min(p, 6), min(p, 6), inv);
-    const int y0 = min(max(c.y0, -2), 30000), x0 = min(max(c.x0, -2), g.W);
-    sr->x0[p] = (int16_t)x0; sr->lx[p] = c.lx;
-    sr->y0[p] = (int16_t)y0; sr->ly[p] = c.ly;
+    int y0c[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) y0c[i] = min(max(sample_at(box, i, i, inv).y0, -2), 30000);
+    // consumer warp p: which of the 14 (sample row, upper/lower) pairs land in one of its rows
+    unsigned m = 0;
+#pragma unroll
+    for (int i = 0; i < 7; ++i)
+#pragma unroll
+      for (int d = 0; d < 2; ++d) {
+        const int row = y0c[i] + d;
+        if (row >= 0 && row < g.H && (row % kRowWarps) == p) m |= 1u << (2 * i + d);
+      }
+    sr->wmask[p] = (uint16_t)(p < kRowWarps ? m : 0u);
+    if (p < 8) {
+      const Corner c = sample_at(box, min(p, 6), min(p, 6), inv);
+      sr->xoff[p] = min(max(c.x0, -2), g.W) * kRowLd;
+      sr->lx[p] = c.lx;
+      sr->ly[p] = c.ly;
+      sr->y0[p] = (int16_t)min(max(c.y0, -2), 30000);
+    }
     if (p == 0) {
-      const Corner c6 = sample_at(box, 6, 6, inv);
-      const int y6 = min(max(c6.y0, -2), 30000);
-      sr->n = n;
-      sr->ymin = min(y0, y6);
-      sr->ymax = max(y0, y6) + 1;
       // column pattern on the CLAMPED x0 (several samples clamped to the same guard column fall back to mode 0)
       int mode = 2, prev = 0;
       for (int j = 0; j < 7; ++j) {
-        const Corner cj = sample_at(box, j, j, inv);
-        const int xj = min(max(cj.x0, -2), g.W);
+        const int xj = min(max(sample_at(box, j, j, inv).x0, -2), g.W);
         if (j > 0) {
           if (xj <= prev) mode = 0;
           else if (xj == prev + 1) mode = min(mode, 1);
         }
         prev = xj;
       }
+      sr->n = n;
       sr->mode = mode;
+      sr->pad[0] = sr->pad[1] = 0;
     }
   }
 }
@@ -609,15 +623,25 @@ roi_crop_bwd_kernel(const float* __restrict__ dout, const int* __restrict__ seg,
 }
 
 // ------------------------------------------------------------------ backward, row-owner variant (CC = 32, 7x7)
-// lane = channel, warp w owns map rows y = w (mod kRowWarps): every read-modify-write of the accumulator map
-// is a conflict-free 128-byte segment, control flow is warp uniform (geometry does not depend on the channel),
-// there are no collisions to rank and no barriers inside a ROI.  The accumulator is stored [row][col+2][33]:
-// the odd channel stride keeps both the channel-wise updates and the pixel-wise final read-out conflict free,
-// and two guard columns on each side absorb the corners that fall outside the map (x0 is clamped to
-// [-2, W] in the record), so the inner loop has no bounds checks and no branches.
-constexpr int kRowWarps = 31;
-constexpr int kRowStages = 8;
-constexpr int kRowLd = 33;
+// lane = channel, warp w owns map rows y = w (mod kRowWarps): every read-modify-write of the accumulator map is a
+// conflict-free 128-byte segment, control flow is warp uniform (geometry does not depend on the channel), there are
+// no collisions to rank and no barriers inside a ROI.  The accumulator is stored [row][col+2][33]: the odd channel
+// stride keeps both the channel-wise updates and the pixel-wise final read-out conflict free, and two guard columns
+// on each side absorb the corners that fall outside the map (x0 is clamped to [-2, W] in the record), so the inner
+// loop has no bounds checks.
+//
+// The kernel is ISSUE bound (ncu, first version: 86 % of the issue slots, ~4000 warp instructions per ROI of which
+// ~2500 were the 31 warps' per-ROI bookkeeping: mbarrier wait, 14 row tests with a modulo, ballot, shuffles).  So the
+// bookkeeping is done ONCE per ROI by roi_geom_kernel and shipped in the record:
+//   * wmask[w]: the (sample row, upper/lower) pairs that land in warp w's rows -- a warp reads one 16-bit word per
+//     ROI and skips the ROI when it is zero;
+//   * a stage of the TMA ring carries TWO ROIs (one mbarrier round trip per pair);
+//   * sample rows that fall into the same map row are first combined in registers (v_j = sum_i wy_i g_ij: the column
+//     geometry does not depend on i) and written with ONE set of 14 read-modify-writes;
+//   * mode: whether the 14 corner columns are pairwise distinct (one batch of 14 independent loads / FMAs / stores),
+//     or x0 is strictly increasing (two batches: left corners, right corners), or neither (serial chain).
+// Bit-reproducible (fixed order, no atomics).
+constexpr int kRowStages = 6;       // stages of two ROIs
 
 __global__ void __launch_bounds__((kRowWarps + 1) * 32, 1)
 roi_crop_bwd_rows_kernel(const float* __restrict__ dout, const int* __restrict__ seg,
@@ -629,8 +653,8 @@ roi_crop_bwd_rows_kernel(const float* __restrict__ dout, const int* __restrict__
   const int WP = W + 4;                                                      // padded row length
   float* map = reinterpret_cast<float*>(smem_raw);                           // [H][WP][33]
   const int map_floats = (H * WP * kRowLd + 3) & ~3;
-  float* tiles = map + map_floats;                                           // [kRowStages][TILE]
-  SepRec* recs = reinterpret_cast<SepRec*>(tiles + kRowStages * TILE);       // [kRowStages]
+  float* tiles = map + map_floats;                                           // [kRowStages][2][TILE]
+  SepRec* recs = reinterpret_cast<SepRec*>(tiles + kRowStages * 2 * TILE);   // [kRowStages][2]
   __shared__ uint64_t full_bar[kRowStages], empty_bar[kRowStages];
 
   const int b = blockIdx.y, c0 = blockIdx.x * CC;
@@ -648,135 +672,11 @@ roi_crop_bwd_rows_kernel(const float* __restrict__ dout, const int* __restrict__
   __syncthreads();
 
   const int beg = seg[b], end = seg[b + 1];
-  const uint32_t tile_bytes = (uint32_t)(cvalid * kPP * sizeof(float));
-
-  if (wid == kRowWarps) {
-    // ---------------- producer warp ----------------
-    for (int r0 = beg, k = 0; r0 < end; r0 += 32) {
-      const int mine = r0 + lane;
-      const int nl = (mine < end) ? __ldg(&sep[mine].n) : 0;
-      {   // L2 prefetch of the group after this one (and of the first group itself)
-        const int ahead = mine + (r0 == beg ? 0 : 32);
-        for (int a = ahead; a < end && a <= mine + 32; a += 32)
-          bulk_prefetch_l2(dout + ((size_t)__ldg(&sep[a].n) * g.C + c0) * kPP, tile_bytes);
-      }
-      const int cnt = min(32, end - r0);
-      for (int j = 0; j < cnt; ++j, ++k) {
-        const int n = __shfl_sync(0xffffffffu, nl, j);
-        if (lane == 0) {
-          const int s = k % kRowStages;
-          if (k >= kRowStages) mbar_wait(&empty_bar[s], ((k / kRowStages) - 1) & 1);
-          mbar_arrive_expect_tx(&full_bar[s], tile_bytes + (uint32_t)sizeof(SepRec));
-          bulk_g2s(recs + s, sep + r0 + j, (uint32_t)sizeof(SepRec), &full_bar[s]);
-          bulk_g2s(tiles + (size_t)s * TILE, dout + ((size_t)n * g.C + c0) * kPP, tile_bytes, &full_bar[s]);
-        }
-      }
-    }
-  } else {
-    // ---------------- consumers: warp = rows, lane = channel ----------------
-    const int cl = lane < cvalid ? lane : 0;          // idle lanes shadow channel 0 into their own column
-    float* mlane = map + 2 * kRowLd + lane;           // (row 0, col 0, my channel); lanes >= cvalid never unstaged
-    for (int ri = beg, k = 0; ri < end; ++ri, ++k) {
-      const int s = k % kRowStages;
-      mbar_wait(&full_bar[s], (k / kRowStages) & 1);
-      const SepRec* rec = recs + s;
-      // lanes 0..13 test the 14 (sample row i, upper/lower map row) pairs of the ROI against this warp's rows
-      int yrow = -1;
-      if (lane < 14) yrow = (int)rec->y0[lane >> 1] + (lane & 1);
-      const bool hit = (unsigned)yrow < (unsigned)H && (yrow % kRowWarps) == wid;
-      unsigned hits = __ballot_sync(0xffffffffu, hit);
-      if (hits) {
-        int xoff[7];
-        float wa[7], wb[7];
-#pragma unroll
-        for (int j = 0; j < 7; ++j) {
-          xoff[j] = (int)rec->x0[j] * kRowLd;
-          wb[j] = rec->lx[j];
-          wa[j] = 1.f - wb[j];
-        }
-        const float* tcol = tiles + (size_t)s * TILE + (size_t)cl * kPP;
-        while (hits) {
-          const int bsel = __ffs(hits) - 1;
-          hits &= hits - 1;
-          const int i = bsel >> 1;
-          const int yy = __shfl_sync(0xffffffffu, yrow, bsel);
-          const float ly = rec->ly[i];
-          const float wy = (bsel & 1) ? ly : 1.f - ly;
-          float* mrow = mlane + (size_t)yy * WP * kRowLd;
-          const float* trow = tcol + i * 7;
-#pragma unroll
-          for (int j = 0; j < 7; ++j) {
-            const float v = trow[j] * wy;
-            float* m = mrow + xoff[j];
-            m[0] = fmaf(wa[j], v, m[0]);
-            m[kRowLd] = fmaf(wb[j], v, m[kRowLd]);
-          }
-        }
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty_bar[s]);
-    }
-  }
-  __syncthreads();
-  // read-out: warp = (channel, 32 consecutive pixels of a row)
-  float* dst = dbottom + ((size_t)b * g.C + c0) * HW;
-  const int nw = blockDim.x >> 5;
-  const int xblocks = (W + 31) >> 5;
-  for (int it = wid; it < cvalid * H * xblocks; it += nw) {
-    const int c = it % cvalid, rest = it / cvalid;
-    const int y = rest / xblocks, x = (rest % xblocks) * 32 + lane;
-    if (x < W) dst[(size_t)c * HW + y * W + x] = map[((size_t)y * WP + x + 2) * kRowLd + c];
-  }
-}
-
-// ------------------------------------------------------------------ backward, row-owner variant 2
-// Same ownership (lane = channel, warp w owns map rows y = w mod 31) with the per-ROI critical path shortened --
-// the first version spent ~1160 clk per ROI although a warp's own work is ~130 clk, because (i) the 14
-// read-modify-writes of a row item were one dependent chain (the compiler must assume that the 14 addresses alias),
-// (ii) a flat box sends all 7 sample rows to the same two warps, (iii) every warp pays the barrier / hit-test overhead
-// for every ROI.  Here:
-//   * a stage carries TWO ROIs (one mbarrier round trip, one ballot for the 2 x 14 (sample row, map row) pairs);
-//   * sample rows of a ROI that fall into the same map row are first combined in registers
-//     (v_j = sum_i wy_i g_ij : the column geometry does not depend on i), then written with ONE set of 14 RMWs;
-//   * the geometry record says whether the 14 corner columns are pairwise distinct (one batch of 14 independent
-//     loads / FMAs / stores), or x0 is strictly increasing (two batches: left corners, right corners), or neither
-//     (the serial chain, narrow boxes only).
-constexpr int kRow2Stages = 6;
-
-__global__ void __launch_bounds__((kRowWarps + 1) * 32, 1)
-roi_crop_bwd_rows2_kernel(const float* __restrict__ dout, const int* __restrict__ seg,
-                          const SepRec* __restrict__ sep, float* __restrict__ dbottom, CropGeom g) {
-  constexpr int CC = 32;
-  constexpr int TILE = CC * kPP;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int HW = g.H * g.W, W = g.W, H = g.H;
-  const int WP = W + 4;                                                      // padded row length
-  float* map = reinterpret_cast<float*>(smem_raw);                           // [H][WP][33]
-  const int map_floats = (H * WP * kRowLd + 3) & ~3;
-  float* tiles = map + map_floats;                                           // [kRow2Stages][2][TILE]
-  SepRec* recs = reinterpret_cast<SepRec*>(tiles + kRow2Stages * 2 * TILE);  // [kRow2Stages][2]
-  __shared__ uint64_t full_bar[kRow2Stages], empty_bar[kRow2Stages];
-
-  const int b = blockIdx.y, c0 = blockIdx.x * CC;
-  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
-  const int cvalid = min(CC, g.C - c0);
-
-  for (int i = t; i < map_floats; i += blockDim.x) map[i] = 0.f;
-  if (t == 0) {
-    for (int s = 0; s < kRow2Stages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], kRowWarps);
-    }
-    mbar_fence_init();
-  }
-  __syncthreads();
-
-  const int beg = seg[b], end = seg[b + 1];
   const int nst = (end - beg + 1) >> 1;                 // stages: pairs of ROIs
   const uint32_t tile_bytes = (uint32_t)(cvalid * kPP * sizeof(float));
 
   if (wid == kRowWarps) {
-    // ---------------- producer warp: lane l of a group fetches the ROI ids of stage group l/2 ----------------
+    // ---------------- producer warp (ROI ids fetched 32 at a time) ----------------
     for (int r0 = beg, k = 0; r0 < end; r0 += 32) {
       const int mine = r0 + lane;
       const int nl = (mine < end) ? __ldg(&sep[mine].n) : 0;
@@ -791,8 +691,8 @@ roi_crop_bwd_rows2_kernel(const float* __restrict__ dout, const int* __restrict_
         const int n1 = __shfl_sync(0xffffffffu, nl, (j + 1) & 31);
         const int two = (j + 1 < cnt) ? 2 : 1;
         if (lane == 0) {
-          const int s = k % kRow2Stages;
-          if (k >= kRow2Stages) mbar_wait(&empty_bar[s], ((k / kRow2Stages) - 1) & 1);
+          const int s = k % kRowStages;
+          if (k >= kRowStages) mbar_wait(&empty_bar[s], ((k / kRowStages) - 1) & 1);
           mbar_arrive_expect_tx(&full_bar[s], (uint32_t)two * (tile_bytes + (uint32_t)sizeof(SepRec)));
           bulk_g2s(recs + 2 * s, sep + r0 + j, (uint32_t)(two * sizeof(SepRec)), &full_bar[s]);
           bulk_g2s(tiles + (size_t)(2 * s) * TILE, dout + ((size_t)n0 * g.C + c0) * kPP, tile_bytes, &full_bar[s]);
@@ -805,81 +705,81 @@ roi_crop_bwd_rows2_kernel(const float* __restrict__ dout, const int* __restrict_
     // ---------------- consumers: warp = rows, lane = channel ----------------
     const int cl = lane < cvalid ? lane : 0;          // idle lanes shadow channel 0 into their own column
     float* mlane = map + 2 * kRowLd + lane;           // (row 0, col 0, my channel); lanes >= cvalid never unstaged
-    const int hroi = lane >> 4, hidx = lane & 15;     // hit-test role: (ROI of the stage, (sample row, upper/lower))
+    const int row_stride = WP * kRowLd;
     for (int k = 0; k < nst; ++k) {
-      const int s = k % kRow2Stages;
-      mbar_wait(&full_bar[s], (k / kRow2Stages) & 1);
+      const int s = k % kRowStages;
+      mbar_wait(&full_bar[s], (k / kRowStages) & 1);
       const int cnt = min(2, end - beg - 2 * k);
-      const SepRec* rec2 = recs + 2 * s;
-      int yrow = -1;
-      if (hidx < 14 && hroi < cnt) yrow = (int)rec2[hroi].y0[hidx >> 1] + (hidx & 1);
-      const bool hit = (unsigned)yrow < (unsigned)H && (yrow % kRowWarps) == wid;
-      unsigned hits = __ballot_sync(0xffffffffu, hit);
-      int cur = -1, mode = 0;
-      int xoff[7];
-      float wa[7], wb[7];
-      while (hits) {
-        const int bsel = __ffs(hits) - 1;
-        const int roi = bsel >> 4;
-        const int yy = __shfl_sync(0xffffffffu, yrow, bsel);
-        // every (sample row, upper/lower) pair of this ROI that lands in map row yy
-        unsigned same = __ballot_sync(0xffffffffu, hit && yrow == yy && hroi == roi);
-        hits &= ~same;
-        const SepRec* rec = rec2 + roi;
-        if (roi != cur) {
-          cur = roi;
-          mode = rec->mode;
+#pragma unroll 1
+      for (int roi = 0; roi < cnt; ++roi) {
+        const SepRec* rec = recs + 2 * s + roi;
+        unsigned hits = rec->wmask[wid];              // same word for every lane: all control flow below is uniform
+        if (hits == 0) continue;
+        int xoff[7];
+        float wa[7], wb[7];
+        {
+          const int4 xa = *reinterpret_cast<const int4*>(rec->xoff), xb = *reinterpret_cast<const int4*>(rec->xoff + 4);
+          const float4 la = *reinterpret_cast<const float4*>(rec->lx), lb = *reinterpret_cast<const float4*>(rec->lx + 4);
+          xoff[0] = xa.x; xoff[1] = xa.y; xoff[2] = xa.z; xoff[3] = xa.w; xoff[4] = xb.x; xoff[5] = xb.y; xoff[6] = xb.z;
+          wb[0] = la.x; wb[1] = la.y; wb[2] = la.z; wb[3] = la.w; wb[4] = lb.x; wb[5] = lb.y; wb[6] = lb.z;
 #pragma unroll
-          for (int j = 0; j < 7; ++j) {
-            xoff[j] = (int)rec->x0[j] * kRowLd;
-            wb[j] = rec->lx[j];
-            wa[j] = 1.f - wb[j];
-          }
+          for (int j = 0; j < 7; ++j) wa[j] = 1.f - wb[j];
         }
+        const int mode = rec->mode;
         const float* tcol = tiles + (size_t)(2 * s + roi) * TILE + (size_t)cl * kPP;
-        float v[7];
+        while (hits) {
+          const int bsel = __ffs(hits) - 1;
+          hits &= hits - 1;
+          const int yy = (int)rec->y0[bsel >> 1] + (bsel & 1);
+          float v[7];
+          {
+            const float ly = rec->ly[bsel >> 1];
+            const float wy = (bsel & 1) ? ly : 1.f - ly;
+            const float* trow = tcol + (bsel >> 1) * 7;
 #pragma unroll
-        for (int j = 0; j < 7; ++j) v[j] = 0.f;
-        while (same) {
-          const int bb = (__ffs(same) - 1) & 15;
-          same &= same - 1;
-          const int i = bb >> 1;
-          const float ly = rec->ly[i];
-          const float wy = (bb & 1) ? ly : 1.f - ly;
-          const float* trow = tcol + i * 7;
+            for (int j = 0; j < 7; ++j) v[j] = wy * trow[j];
+          }
+          // further sample rows of this ROI in the same map row (adjacent bits: the rows are monotone in i)
+          while (hits) {
+            const int b2 = __ffs(hits) - 1;
+            if ((int)rec->y0[b2 >> 1] + (b2 & 1) != yy) break;
+            hits &= hits - 1;
+            const float ly = rec->ly[b2 >> 1];
+            const float wy = (b2 & 1) ? ly : 1.f - ly;
+            const float* trow = tcol + (b2 >> 1) * 7;
 #pragma unroll
-          for (int j = 0; j < 7; ++j) v[j] = fmaf(wy, trow[j], v[j]);
-        }
-        float* mrow = mlane + (size_t)yy * WP * kRowLd;
-        if (mode == 2) {
-          float m0[7], m1[7];
+            for (int j = 0; j < 7; ++j) v[j] = fmaf(wy, trow[j], v[j]);
+          }
+          float* mrow = mlane + yy * row_stride;
+          if (mode == 2) {
+            float m0[7], m1[7];
 #pragma unroll
-          for (int j = 0; j < 7; ++j) { m0[j] = mrow[xoff[j]]; m1[j] = mrow[xoff[j] + kRowLd]; }
+            for (int j = 0; j < 7; ++j) { m0[j] = mrow[xoff[j]]; m1[j] = mrow[xoff[j] + kRowLd]; }
 #pragma unroll
-          for (int j = 0; j < 7; ++j) { m0[j] = fmaf(wa[j], v[j], m0[j]); m1[j] = fmaf(wb[j], v[j], m1[j]); }
+            for (int j = 0; j < 7; ++j) { m0[j] = fmaf(wa[j], v[j], m0[j]); m1[j] = fmaf(wb[j], v[j], m1[j]); }
 #pragma unroll
-          for (int j = 0; j < 7; ++j) { mrow[xoff[j]] = m0[j]; mrow[xoff[j] + kRowLd] = m1[j]; }
-        } else if (mode == 1) {
-          float m0[7];
+            for (int j = 0; j < 7; ++j) { mrow[xoff[j]] = m0[j]; mrow[xoff[j] + kRowLd] = m1[j]; }
+          } else if (mode == 1) {
+            float m0[7];
 #pragma unroll
-          for (int j = 0; j < 7; ++j) m0[j] = mrow[xoff[j]];
+            for (int j = 0; j < 7; ++j) m0[j] = mrow[xoff[j]];
 #pragma unroll
-          for (int j = 0; j < 7; ++j) m0[j] = fmaf(wa[j], v[j], m0[j]);
+            for (int j = 0; j < 7; ++j) m0[j] = fmaf(wa[j], v[j], m0[j]);
 #pragma unroll
-          for (int j = 0; j < 7; ++j) mrow[xoff[j]] = m0[j];
-          __syncwarp();
+            for (int j = 0; j < 7; ++j) mrow[xoff[j]] = m0[j];
 #pragma unroll
-          for (int j = 0; j < 7; ++j) m0[j] = mrow[xoff[j] + kRowLd];
+            for (int j = 0; j < 7; ++j) m0[j] = mrow[xoff[j] + kRowLd];
 #pragma unroll
-          for (int j = 0; j < 7; ++j) m0[j] = fmaf(wb[j], v[j], m0[j]);
+            for (int j = 0; j < 7; ++j) m0[j] = fmaf(wb[j], v[j], m0[j]);
 #pragma unroll
-          for (int j = 0; j < 7; ++j) mrow[xoff[j] + kRowLd] = m0[j];
-        } else {
+            for (int j = 0; j < 7; ++j) mrow[xoff[j] + kRowLd] = m0[j];
+          } else {
 #pragma unroll
-          for (int j = 0; j < 7; ++j) {
-            float* m = mrow + xoff[j];
-            m[0] = fmaf(wa[j], v[j], m[0]);
-            m[kRowLd] = fmaf(wb[j], v[j], m[kRowLd]);
+            for (int j = 0; j < 7; ++j) {
+              float* m = mrow + xoff[j];
+              m[0] = fmaf(wa[j], v[j], m[0]);
+              m[kRowLd] = fmaf(wb[j], v[j], m[kRowLd]);
+            }
           }
         }
       }
@@ -1075,30 +975,17 @@ extern "C" int l2s_roi_crop_bwd(const float* dout, const float* rois, const uint
   SepRec* sep;
   rc = prepare(rois, g, pl.cc / 4, workspace, st, &seg, &table, &sep);
   if (rc) return rc;
-  // row-owner kernels: need the whole 32-channel accumulator with guard columns + the tile ring in shared memory
-  const size_t map_bytes = (((size_t)H * (W + 4) * kRowLd + 3) & ~(size_t)3) * 4;
-  const size_t smem_rows2 = map_bytes + kRow2Stages * 2 * ((size_t)32 * kPP * 4 + sizeof(SepRec)) + 128;
-  pl.smem_rows = map_bytes + kRowStages * ((size_t)32 * kPP * 4 + sizeof(SepRec)) + 128;
-  const size_t cap = (size_t)max_smem_optin() - 1024;
-  if (!g.maxpool && pl.cc == 32 && !(flags & L2S_CROP_BWD_RANKED)) {
-    const char* v1 = getenv("L2S_CROP_BWD_ROWS_V1");      // diagnostics: the first row-owner kernel
+  // row-owner kernel: needs the whole 32-channel accumulator with guard columns + the tile ring in shared memory
+  pl.smem_rows = (((size_t)H * (W + 4) * kRowLd + 3) & ~(size_t)3) * 4 +
+                 kRowStages * 2 * ((size_t)32 * kPP * 4 + sizeof(SepRec)) + 128;
+  if (!g.maxpool && pl.cc == 32 && pl.smem_rows <= (size_t)max_smem_optin() - 1024 && !(flags & L2S_CROP_BWD_RANKED)) {
+    auto kern = roi_crop_bwd_rows_kernel;
+    L2S_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_rows));
     dim3 grid((g.C + 31) / 32, g.B);
-    if (smem_rows2 <= cap && !(v1 && v1[0] == '1')) {
-      auto kern = roi_crop_bwd_rows2_kernel;
-      L2S_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rows2));
-      kern<<<grid, (kRowWarps + 1) * 32, smem_rows2, st>>>(dout, seg, sep, dbottom, g);
-      L2S_LAUNCH_OK("roi_crop_bwd_rows2_kernel");
-      count_launch();
-      return L2S_OK;
-    }
-    if (pl.smem_rows <= cap) {
-      auto kern = roi_crop_bwd_rows_kernel;
-      L2S_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_rows));
-      kern<<<grid, (kRowWarps + 1) * 32, pl.smem_rows, st>>>(dout, seg, sep, dbottom, g);
-      L2S_LAUNCH_OK("roi_crop_bwd_rows_kernel");
-      count_launch();
-      return L2S_OK;
-    }
+    kern<<<grid, (kRowWarps + 1) * 32, pl.smem_rows, st>>>(dout, seg, sep, dbottom, g);
+    L2S_LAUNCH_OK("roi_crop_bwd_rows_kernel");
+    count_launch();
+    return L2S_OK;
   }
   L2S_CROP_DISPATCH(launch_bwd, dout, seg, table, argmax, dbottom, g, pl.smem_bwd, st);
 }
