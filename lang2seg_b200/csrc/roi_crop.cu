@@ -137,8 +137,7 @@ struct __align__(16) SepRec {
   uint16_t wmask[32];   // per consumer warp: bit 2i+d set <=> map row y0_i + d is inside the map and owned by the warp
   int n;                // ROI index
   int mode;             // column pattern: 2 = all 14 corner columns distinct, 1 = x0 strictly increasing, 0 = general
-  int nwork;            // number of consumer warps with a non-zero wmask
-  int pad;
+  int pad[2];
 };
 static_assert(sizeof(SepRec) == 192, "SepRec layout");
 
@@ -220,7 +219,6 @@ roi_geom_kernel(const float* __restrict__ rois, const int* __restrict__ order, u
       }
     if (p >= kRowWarps) m = 0;
     sr->wmask[p] = (uint16_t)m;
-    const int nwork = __popc(__ballot_sync(0xffffffffu, m != 0));      // threads 0..31 are one full warp
     if (p < 8) {
       const Corner c = sample_at(box, min(p, 6), min(p, 6), inv);
       sr->xoff[p] = min(max(c.x0, -2), g.W) * kRowLd;
@@ -241,8 +239,7 @@ roi_geom_kernel(const float* __restrict__ rois, const int* __restrict__ order, u
       }
       sr->n = n;
       sr->mode = mode;
-      sr->nwork = nwork;
-      sr->pad = 0;
+      sr->pad[0] = sr->pad[1] = 0;
     }
   }
 }
@@ -634,24 +631,22 @@ roi_crop_bwd_kernel(const float* __restrict__ dout, const int* __restrict__ seg,
 // on each side absorb the corners that fall outside the map (x0 is clamped to [-2, W] in the record), so the inner
 // loop has no bounds checks.
 //
-// The kernel is ISSUE bound (ncu: ~80 % of the issue slots; of ~4000 warp instructions per ROI in the first version
-// only ~1000 were the read-modify-writes, the rest was the 31 warps' per-ROI bookkeeping -- mbarrier spin, 14 row
-// tests with a modulo, ballots, shuffles -- paid by every warp for every ROI although a ROI touches the rows of only
-// ~11 warps).  So the bookkeeping is done ONCE per ROI by roi_geom_kernel and shipped in the record:
-//   * wmask[w]: the (sample row, upper/lower) pairs that land in warp w's rows.  A warp fetches its word for 32 ROIs
-//     with one load per lane, ballots, and then visits ONLY the ROIs in which it has work;
-//   * nwork: how many warps do.  The producer arrives on the stage's `empty` barrier on behalf of the 31 - nwork
-//     idle warps when it fills the stage, so an idle warp executes no instruction at all for that ROI;
+// What bounds it (ncu + scripts/probes/tma_bulk_probe.cu, profiles/r01_tma_bulk_probe.txt): not bandwidth but the
+// serial mbarrier round trips.  One wait -> arrive hand-off costs ~400 clk on the thread that does it, so a ring that
+// moves ONE 6272-byte tile per barrier tops out at ~15 B/clk/SM even with nothing else to do, and the first versions
+// spent ~950 clk per ROI.  Hence:
+//   * a stage of the ring carries FOUR ROIs (25 KB: 4 tiles + their 4 records, 5 bulk copies, one barrier round
+//     trip) -- the probe sustains 25.6 B/clk/SM at that size, above the HBM share of an SM;
+//   * the per-ROI bookkeeping is done ONCE by roi_geom_kernel and shipped in the record: wmask[w] says which
+//     (sample row, upper/lower) pairs land in warp w's rows (a warp reads one 16-bit word per ROI and skips the ROI
+//     when it is zero -- no row tests, modulos, ballots or shuffles in the loop);
 //   * sample rows that fall into the same map row are first combined in registers (v_j = sum_i wy_i g_ij: the column
 //     geometry does not depend on i) and written with ONE set of 14 read-modify-writes;
 //   * mode: whether the 14 corner columns are pairwise distinct (one batch of 14 independent loads / FMAs / stores),
 //     or x0 is strictly increasing (two batches: left corners, right corners), or neither (serial chain).
 // Bit-reproducible (fixed order, no atomics).
-constexpr int kRowStages = 12;
-
-__device__ __forceinline__ void mbar_arrive_n(uint64_t* bar, uint32_t n) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(n) : "memory");
-}
+constexpr int kRowStages = 3;
+constexpr int kRowGroup = 4;        // ROIs per stage
 
 __global__ void __launch_bounds__((kRowWarps + 1) * 32, 1)
 roi_crop_bwd_rows_kernel(const float* __restrict__ dout, const int* __restrict__ seg,
@@ -663,13 +658,9 @@ roi_crop_bwd_rows_kernel(const float* __restrict__ dout, const int* __restrict__
   const int WP = W + 4;                                                      // padded row length
   float* map = reinterpret_cast<float*>(smem_raw);                           // [H][WP][33]
   const int map_floats = (H * WP * kRowLd + 3) & ~3;
-  float* tiles = map + map_floats;                                           // [kRowStages][TILE]
-  SepRec* recs = reinterpret_cast<SepRec*>(tiles + kRowStages * TILE);       // [kRowStages]
+  float* tiles = map + map_floats;                                           // [kRowStages][kRowGroup][TILE]
+  SepRec* recs = reinterpret_cast<SepRec*>(tiles + kRowStages * kRowGroup * TILE);   // [kRowStages][kRowGroup]
   __shared__ uint64_t full_bar[kRowStages], empty_bar[kRowStages];
-  // Number of ROIs the producer has armed so far.  A warp that skips ROIs may be more than one lap of the ring ahead
-  // of the producer, where the parity of a `full` barrier is ambiguous (an old phase of the same parity has completed):
-  // it first waits until the producer has reached its ROI, then on the barrier.
-  __shared__ volatile int armed;
 
   const int b = blockIdx.y, c0 = blockIdx.x * CC;
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
@@ -681,47 +672,42 @@ roi_crop_bwd_rows_kernel(const float* __restrict__ dout, const int* __restrict__
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], kRowWarps);
     }
-    armed = 0;
     mbar_fence_init();
   }
   __syncthreads();
 
   const int beg = seg[b], end = seg[b + 1];
+  const int nst = (end - beg + kRowGroup - 1) / kRowGroup;
   const uint32_t tile_bytes = (uint32_t)(cvalid * kPP * sizeof(float));
 
   if (wid == kRowWarps) {
-    // ---------------- producer warp (ROI ids and worker counts fetched 32 at a time) ----------------
-    for (int r0 = beg, k = 0; r0 < end; r0 += 32) {
+    // ---------------- producer warp (ROI ids fetched 32 at a time = 8 stages) ----------------
+    int sidx = 0, lap = 0;
+    for (int r0 = beg; r0 < end; r0 += 32) {
       const int mine = r0 + lane;
-      int nl = 0, nwk = 0;
-      if (mine < end) {
-        nl = __ldg(&sep[mine].n);
-        nwk = __ldg(&sep[mine].nwork);
-      }
+      const int nl = (mine < end) ? __ldg(&sep[mine].n) : 0;
       {   // L2 prefetch of the group after this one (and of the first group itself)
         const int ahead = mine + (r0 == beg ? 0 : 32);
         for (int a = ahead; a < end && a <= mine + 32; a += 32)
           bulk_prefetch_l2(dout + ((size_t)__ldg(&sep[a].n) * g.C + c0) * kPP, tile_bytes);
       }
       const int cnt = min(32, end - r0);
-      for (int j = 0; j < cnt; ++j, ++k) {
-        const int n = __shfl_sync(0xffffffffu, nl, j);
-        const int nw = __shfl_sync(0xffffffffu, nwk, j);
+      for (int j = 0; j < cnt; j += kRowGroup) {
+        const int gc = min(kRowGroup, cnt - j);               // ROIs in this stage
+        int n[kRowGroup];
+#pragma unroll
+        for (int q = 0; q < kRowGroup; ++q) n[q] = __shfl_sync(0xffffffffu, nl, (j + q) & 31);
         if (lane == 0) {
-          const int s = k % kRowStages;
-          if (k >= kRowStages) mbar_wait(&empty_bar[s], ((k / kRowStages) - 1) & 1);
-          // the warps without work in this ROI never look at the stage: arrive for them
-          if (nw < kRowWarps) mbar_arrive_n(&empty_bar[s], (uint32_t)(kRowWarps - nw));
-          if (nw > 0) {
-            mbar_arrive_expect_tx(&full_bar[s], tile_bytes + (uint32_t)sizeof(SepRec));
-            bulk_g2s(recs + s, sep + r0 + j, (uint32_t)sizeof(SepRec), &full_bar[s]);
-            bulk_g2s(tiles + (size_t)s * TILE, dout + ((size_t)n * g.C + c0) * kPP, tile_bytes, &full_bar[s]);
-          } else {
-            mbar_arrive(&full_bar[s]);      // nobody reads this ROI (all samples outside the map): keep the phase moving
-          }
-          __threadfence_block();
-          armed = k + 1;
+          if (lap > 0) mbar_wait(&empty_bar[sidx], (lap - 1) & 1);
+          mbar_arrive_expect_tx(&full_bar[sidx], (uint32_t)gc * (tile_bytes + (uint32_t)sizeof(SepRec)));
+          bulk_g2s(recs + sidx * kRowGroup, sep + r0 + j, (uint32_t)(gc * sizeof(SepRec)), &full_bar[sidx]);
+#pragma unroll
+          for (int q = 0; q < kRowGroup; ++q)
+            if (q < gc)
+              bulk_g2s(tiles + (size_t)(sidx * kRowGroup + q) * TILE, dout + ((size_t)n[q] * g.C + c0) * kPP, tile_bytes,
+                       &full_bar[sidx]);
         }
+        if (++sidx == kRowStages) { sidx = 0; ++lap; }
       }
     }
   } else {
@@ -729,20 +715,15 @@ roi_crop_bwd_rows_kernel(const float* __restrict__ dout, const int* __restrict__
     const int cl = lane < cvalid ? lane : 0;          // idle lanes shadow channel 0 into their own column
     float* mlane = map + 2 * kRowLd + lane;           // (row 0, col 0, my channel); lanes >= cvalid never unstaged
     const int row_stride = WP * kRowLd;
-    for (int r0 = beg; r0 < end; r0 += 32) {
-      // which of the next 32 ROIs touch this warp's rows
-      const int mine = r0 + lane;
-      const unsigned mymask = (mine < end) ? (unsigned)__ldg(&sep[mine].wmask[wid]) : 0u;
-      unsigned work = __ballot_sync(0xffffffffu, mymask != 0u);
-      while (work) {
-        const int jj = __ffs(work) - 1;
-        work &= work - 1;
-        const int k = r0 - beg + jj;
-        const int s = k % kRowStages;
-        while (armed <= k) __nanosleep(64);           // ahead of the producer (see `armed`)
-        mbar_wait(&full_bar[s], (k / kRowStages) & 1);
-        const SepRec* rec = recs + s;
-        unsigned hits = __shfl_sync(0xffffffffu, mymask, jj);     // == rec->wmask[wid]; uniform control flow below
+    int sidx = 0, lap = 0;
+    for (int k = 0; k < nst; ++k) {
+      mbar_wait(&full_bar[sidx], lap & 1);
+      const int gc = min(kRowGroup, end - beg - k * kRowGroup);
+#pragma unroll 1
+      for (int q = 0; q < gc; ++q) {
+        const SepRec* rec = recs + sidx * kRowGroup + q;
+        unsigned hits = rec->wmask[wid];              // same word for every lane: all control flow below is uniform
+        if (hits == 0) continue;
         int xoff[7];
         float wa[7], wb[7];
         {
@@ -754,7 +735,7 @@ roi_crop_bwd_rows_kernel(const float* __restrict__ dout, const int* __restrict__
           for (int j = 0; j < 7; ++j) wa[j] = 1.f - wb[j];
         }
         const int mode = rec->mode;
-        const float* tcol = tiles + (size_t)s * TILE + (size_t)cl * kPP;
+        const float* tcol = tiles + (size_t)(sidx * kRowGroup + q) * TILE + (size_t)cl * kPP;
         while (hits) {
           const int bsel = __ffs(hits) - 1;
           hits &= hits - 1;
@@ -810,9 +791,10 @@ roi_crop_bwd_rows_kernel(const float* __restrict__ dout, const int* __restrict__
             }
           }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[s]);
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[sidx]);
+      if (++sidx == kRowStages) { sidx = 0; ++lap; }
     }
   }
   __syncthreads();
@@ -1005,7 +987,7 @@ extern "C" int l2s_roi_crop_bwd(const float* dout, const float* rois, const uint
   if (rc) return rc;
   // row-owner kernel: needs the whole 32-channel accumulator with guard columns + the tile ring in shared memory
   pl.smem_rows = (((size_t)H * (W + 4) * kRowLd + 3) & ~(size_t)3) * 4 +
-                 kRowStages * ((size_t)32 * kPP * 4 + sizeof(SepRec)) + 128;
+                 kRowStages * kRowGroup * ((size_t)32 * kPP * 4 + sizeof(SepRec)) + 128;
   if (!g.maxpool && pl.cc == 32 && pl.smem_rows <= (size_t)max_smem_optin() - 1024 && !(flags & L2S_CROP_BWD_RANKED)) {
     auto kern = roi_crop_bwd_rows_kernel;
     L2S_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_rows));
