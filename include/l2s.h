@@ -132,8 +132,10 @@ int l2s_roi_maxpool_bwd(int pooled_height, int pooled_width, float spatial_scale
  *     a_layout/b_layout 0: operand stored K-major  (A: [M][K], B: [N][K])
  *                       1: operand stored MN-major (A: [K][M], B: [K][N])
  *     epilogue  0: D = acc ; 1: D += acc ; 2: D = relu(acc + bias[col/bias_div]) ; 4: D = acc + bias[col/bias_div]
- *     split_k >= 1 (with split_k > 1 the epilogue accumulates atomically; D must be zeroed
- *     or hold the value to accumulate into).
+ *     split_k >= 1 as given, 0 = the library picks the factor that fills the machine (epilogues 0/1 only);
+ *     with split_k != 1 the epilogue accumulates atomically (epilogue 0 zeroes D first).
+ *     The CTA shape (128- or 256-row tile, 4 or 8 epilogue warps) is chosen per problem; the environment
+ *     variable L2S_GEMM_SHAPE=0|1|2 pins it (parity tests, profiling).
  *     Any M, N, K (tails use TMA out-of-bounds zero fill); operand row strides and pointers must be
  *     16-byte aligned (K % 8 == 0 for K-major operands, rows % 8 == 0 for MN-major ones).
  * ------------------------------------------------------------------------------------- */

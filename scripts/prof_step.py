@@ -35,7 +35,7 @@ def main():
     t1.record()
     torch.cuda.synchronize()
     print("# un-profiled: %.3f ms/step" % (t0.elapsed_time(t1) / a.steps))
-    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+    with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU], record_shapes=True) as prof:
         for _ in range(a.steps):
             step(d)
         torch.cuda.synchronize()
@@ -49,6 +49,19 @@ def main():
     print("%-110s %8s %12s %7s" % ("kernel", "n/step", "us/step", "share"))
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:70]:
         print("%-110s %8.1f %12.1f %6.2f%%" % (k, v[0] / a.steps, v[1] / a.steps, 100 * v[1] / tot))
+
+
+    # framework-side operators (not library kernels) by device time, with their input shapes
+    print("\n# aten operators by device time (per step)")
+    rows = []
+    for e in prof.key_averages(group_by_input_shape=True):
+        dt = getattr(e, "self_device_time_total", None)
+        if dt is None:
+            dt = getattr(e, "self_cuda_time_total", 0.0)
+        if dt > 0:
+            rows.append((dt / a.steps, e.count / a.steps, e.key, str(e.input_shapes)[:110]))
+    for dt, n, key, shp in sorted(rows, reverse=True)[:45]:
+        print("%9.1f us %6.1f x  %-42s %s" % (dt, n, key[:42], shp))
 
 
 if __name__ == "__main__":
