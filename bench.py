@@ -147,7 +147,7 @@ class HotPathStep:
         self.wl, self.device = wl, device
         self.net = HotPathNet(dict(seq_length=wl["L"], vocab_size=wl["V"])).to(device).eval()   # eval: dropout off (D8)
         self.params = [p for p in self.net.parameters() if p.requires_grad]
-        self.opt = torch.optim.SGD(self.params, lr=1e-5, momentum=0.9, foreach=True)
+        self.opt = torch.optim.SGD(self.params, lr=1e-5, momentum=0.9, fused=True)
         self.reducer = GradientAllReducer(self.net.gradient_groups()) if world > 1 else None
         E = wl["I"] * wl["EPI"]
         g = torch.Generator().manual_seed(99)
@@ -166,7 +166,7 @@ class HotPathStep:
         gated = net._dynamic_filter(X, d["labels"], expr2img=d["e2i"], resp_target=d["resp_tgt"],
                                     lengths=meta.get("lens"))
         pool5 = net._crop_pool_layer(gated, d["rois"], max_pool=False)
-        net._mask_prediction(fc7)
+        net._mask_prediction(fc7, d["mlab"], d["mtgt"])       # prediction + mask loss as one node (fused backward)
         loss = (net._losses["loss_response_per_expr"].sum() + net._mask_loss(d["mlab"], d["mtgt"])
                 + net._cap_loss_weight * net._caption_loss(d["fc"], att, d["cap"], d["msk"], steps=meta.get("steps")))
         torch.autograd.backward([loss, pool5], [self.one, self.g_pool])

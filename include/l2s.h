@@ -168,6 +168,17 @@ int l2s_mask_head_bwd(const float* dscore, const float* up_w, const float* pred_
                       float* dx, float* d_up_w, float* d_up_b, float* d_pred_w, float* d_pred_b, int n,
                       int Cin, int Cmid, int ncls, void* workspace, size_t workspace_bytes,
                       l2s_stream_t stream);
+/* Backward of the mask head when the ONLY gradient on the scores is the mask loss below (the reference's training
+ * step: network_cycle_response.py:404-413 reads nothing but channel label_i of mask_score).  dscore is then one
+ * non-zero channel per ROI, so dU = g (x) pred_w[label_i] needs no GEMM: one streaming kernel builds the dU planes,
+ * d_up_b, d_pred_w and d_pred_b straight from (score, labels, target) -- dscore is never materialised -- and the two
+ * big GEMMs (dx, d_up_w) follow as in l2s_mask_head_bwd.  gscale (1): upstream gradient of the scalar loss.
+ * Requires Cmid = 8*d with d a divisor of 256 (returns L2S_ERR_SHAPE otherwise: use l2s_mask_bce_bwd +
+ * l2s_mask_head_bwd). */
+int l2s_mask_head_bce_bwd(const float* score, const int64_t* labels, const float* target, const float* gscale,
+                          const float* up_w, const float* pred_w, const void* saved, float* dx, float* d_up_w,
+                          float* d_up_b, float* d_pred_w, float* d_pred_b, int n, int Cin, int Cmid, int ncls,
+                          void* workspace, size_t workspace_bytes, l2s_stream_t stream);
 /* loss = mean_{i,y,x} BCEWithLogits(score[i,label_i,y,x], target[i,y,x]) ; labels int64 (n).
  * bwd writes dscore (n,ncls,hw) = gscale * dloss/dscore (zero outside the label channel). */
 int l2s_mask_bce_fwd(const float* score, const int64_t* labels, const float* target, float* loss, int n,

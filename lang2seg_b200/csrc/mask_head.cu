@@ -473,6 +473,95 @@ repack_dscore_kernel(const float* __restrict__ ds, uint16_t* __restrict__ hi, ui
   }
 }
 
+// ---- mask BCE gradient fused into the dU planes ---------------------------------------------------
+// One CTA per ROI i.  g[r] = gscale * (sigmoid(score[i,lab,pos(r)]) - target[i,pos(r)]) / (n*196) for the 196 rows
+// r = (yx, q) of the ROI; dU[r][o] = g[r] * pred_w[lab][o] * [U[r][o] > 0].  Thread = (row group, 8 columns):
+// 16-byte loads of the saved U planes, 16-byte stores of the dU planes.
+__global__ void __launch_bounds__(256)
+mask_bce_du_kernel(const float* __restrict__ score, const int64_t* __restrict__ labels, const float* __restrict__ target,
+                   const float* __restrict__ gscale, const float* __restrict__ pred_w,
+                   const uint16_t* __restrict__ u_hi, const uint16_t* __restrict__ u_lo, uint16_t* __restrict__ du_hi,
+                   uint16_t* __restrict__ du_lo, float* __restrict__ d_up_b, float* __restrict__ d_pred_w,
+                   float* __restrict__ d_pred_b, int n, int ncls, int Cmid) {
+  __shared__ float g[196];
+  __shared__ float red[2048];        // [rows per iteration][Cmid] = 256 * 8 floats
+  const int i = blockIdx.x, t = threadIdx.x;
+  const int64_t lab = labels[i];
+  const bool valid = lab >= 0 && lab < ncls;
+  const float gs = __ldg(gscale) / ((float)n * 196.f);
+  if (t < 196) {
+    const int yx = t >> 2, q = t & 3;
+    const int y = yx / 7, x = yx - y * 7;
+    const int pos = (2 * y + (q >> 1)) * 14 + 2 * x + (q & 1);
+    float v = 0.f;
+    if (valid) v = gs * (sigmoidf_acc(__ldg(score + ((size_t)i * ncls + lab) * 196 + pos)) - __ldg(target + (size_t)i * 196 + pos));
+    g[t] = v;
+  }
+  __syncthreads();
+  const int tpr = Cmid >> 3;               // threads per row
+  const int rpi = 256 / tpr;               // rows per iteration
+  const int rg = t / tpr, col0 = (t - rg * tpr) << 3;
+  float wp[8], sb[8], sw[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    wp[k] = valid ? __ldg(pred_w + (size_t)lab * Cmid + col0 + k) : 0.f;
+    sb[k] = 0.f;
+    sw[k] = 0.f;
+  }
+  for (int r = rg; r < 196; r += rpi) {
+    const size_t o = ((size_t)i * 196 + r) * Cmid + col0;
+    const uint4 uh = __ldg(reinterpret_cast<const uint4*>(u_hi + o));
+    const uint4 ul = __ldg(reinterpret_cast<const uint4*>(u_lo + o));
+    const uint32_t hs[4] = {uh.x, uh.y, uh.z, uh.w}, ls[4] = {ul.x, ul.y, ul.z, ul.w};
+    const float gr = g[r];
+    uint32_t ph[4], pl[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      uint16_t oh[2], ol[2];
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const uint32_t h16 = (hs[e] >> (16 * b)) & 0xffffu, l16 = (ls[e] >> (16 * b)) & 0xffffu;
+        const float u = __uint_as_float(h16 << 16) + __uint_as_float(l16 << 16);
+        const bool on = h16 != 0 && h16 < 0x8000u;          // U > 0 (bf16: sign clear, magnitude non-zero)
+        const float d = on ? gr * wp[2 * e + b] : 0.f;
+        sb[2 * e + b] += d;
+        sw[2 * e + b] = fmaf(gr, u, sw[2 * e + b]);
+        split2(d, &oh[b], &ol[b]);
+      }
+      ph[e] = (uint32_t)oh[0] | ((uint32_t)oh[1] << 16);
+      pl[e] = (uint32_t)ol[0] | ((uint32_t)ol[1] << 16);
+    }
+    *reinterpret_cast<uint4*>(du_hi + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+    *reinterpret_cast<uint4*>(du_lo + o) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+  }
+  // column sums over the row groups: d_up_b[o] += sum_r dU[r][o] ; d_pred_w[lab][o] += sum_r g[r] U[r][o]
+#pragma unroll
+  for (int k = 0; k < 8; ++k) red[rg * Cmid + col0 + k] = sb[k];
+  __syncthreads();
+  for (int c = t; c < Cmid; c += 256) {
+    float a = 0.f;
+    for (int q = 0; q < rpi; ++q) a += red[q * Cmid + c];
+    atomicAdd(d_up_b + c, a);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 8; ++k) red[rg * Cmid + col0 + k] = sw[k];
+  __syncthreads();
+  if (valid) {
+    for (int c = t; c < Cmid; c += 256) {
+      float a = 0.f;
+      for (int q = 0; q < rpi; ++q) a += red[q * Cmid + c];
+      atomicAdd(d_pred_w + (size_t)lab * Cmid + c, a);
+    }
+    if (t < 32) {
+      float a = 0.f;
+      for (int r = t; r < 196; r += 32) a += g[r];
+      a = warp_sum(a);
+      if (t == 0) atomicAdd(d_pred_b + lab, a);
+    }
+  }
+}
+
 // ---- exact fp32 GEMM (FFMA) for small / ragged shapes -------------------------------------------
 __global__ void __launch_bounds__(256)
 gemm_f32_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D, int M, int N, int K,
@@ -697,6 +786,31 @@ extern "C" int l2s_mask_head_fwd(const float* x, const float* up_w, const float*
   return tc::launch_gemm<128, false, false>(sv.u_hi, sv.u_lo, Cmid, w.b2h, w.b2l, Cmid, 4 * M, ncls, Cmid, 1, e2, st, tc::kShape128E2);
 }
 
+namespace {
+// dF[M x Cin] = dU[M x 4Cmid] * Wd[Cin x 4Cmid]^T -> dx NCHW ;  dWd[Cin x 4Cmid] = F^T * dU  (both MN-major, K = M)
+int mask_head_bwd_tail(const float* up_w, const Saved& sv, const Work& w, float* dx, float* d_up_w, int n, int Cin,
+                       int Cmid, cudaStream_t st) {
+  const int M = n * 49;
+  repack_upw_kernel<<<std::min(1024, (Cin * Cmid * 4 + 255) / 256), 256, 0, st>>>(up_w, nullptr, nullptr, w.b3h, w.b3l, Cin, Cmid);
+  L2S_LAUNCH_OK("repack_upw_kernel");
+  count_launch();
+  EpiDx e5{dx, Cin};
+  int rc = tc::launch_gemm<256, false, false>(w.duh, w.dul, 4 * Cmid, w.b3h, w.b3l, 4 * Cmid, M, Cin, 4 * Cmid, 1, e5, st, tc::kShape256);
+  if (rc) return rc;
+  EpiDWd e6{d_up_w, Cmid};
+  return tc::launch_gemm<256, true, true>(sv.a_hi, sv.a_lo, Cin, w.duh, w.dul, 4 * Cmid, Cin, 4 * Cmid, M, 0, e6, st, tc::kShape256);
+}
+
+int mask_head_bwd_zero(float* d_up_w, float* d_up_b, float* d_pred_w, float* d_pred_b, int Cin, int Cmid, int ncls,
+                       cudaStream_t st) {
+  L2S_CUDA_OK(cudaMemsetAsync(d_up_w, 0, sizeof(float) * (size_t)Cin * Cmid * 4, st));
+  L2S_CUDA_OK(cudaMemsetAsync(d_up_b, 0, sizeof(float) * Cmid, st));
+  L2S_CUDA_OK(cudaMemsetAsync(d_pred_w, 0, sizeof(float) * (size_t)ncls * Cmid, st));
+  L2S_CUDA_OK(cudaMemsetAsync(d_pred_b, 0, sizeof(float) * ncls, st));
+  return L2S_OK;
+}
+}  // namespace
+
 extern "C" int l2s_mask_head_bwd(const float* dscore, const float* up_w, const float* pred_w, const void* saved,
                                  float* dx, float* d_up_w, float* d_up_b, float* d_pred_w, float* d_pred_b, int n,
                                  int Cin, int Cmid, int ncls, void* workspace, size_t workspace_bytes,
@@ -705,10 +819,8 @@ extern "C" int l2s_mask_head_bwd(const float* dscore, const float* up_w, const f
   if (rc) return rc;
   L2S_REQUIRE(up_w && pred_w && d_up_w && d_up_b && d_pred_w && d_pred_b, L2S_ERR_ARG, "mask_head_bwd: null pointer");
   cudaStream_t st = (cudaStream_t)stream;
-  L2S_CUDA_OK(cudaMemsetAsync(d_up_w, 0, sizeof(float) * (size_t)Cin * Cmid * 4, st));
-  L2S_CUDA_OK(cudaMemsetAsync(d_up_b, 0, sizeof(float) * Cmid, st));
-  L2S_CUDA_OK(cudaMemsetAsync(d_pred_w, 0, sizeof(float) * (size_t)ncls * Cmid, st));
-  L2S_CUDA_OK(cudaMemsetAsync(d_pred_b, 0, sizeof(float) * ncls, st));
+  rc = mask_head_bwd_zero(d_up_w, d_up_b, d_pred_w, d_pred_b, Cin, Cmid, ncls, st);
+  if (rc) return rc;
   if (n == 0) return L2S_OK;
   L2S_REQUIRE(dscore && saved && dx, L2S_ERR_ARG, "mask_head_bwd: null pointer");
   L2S_REQUIRE(workspace && workspace_bytes >= l2s_mask_head_workspace_bytes(n, Cin, Cmid, ncls), L2S_ERR_WORKSPACE,
@@ -721,11 +833,9 @@ extern "C" int l2s_mask_head_bwd(const float* dscore, const float* up_w, const f
   L2S_CUDA_OK(cudaFuncSetAttribute(repack_dscore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   repack_dscore_kernel<<<n, 256, smem, st>>>(dscore, w.dsh, w.dsl, d_pred_b, ncls, KP);
   L2S_LAUNCH_OK("repack_dscore_kernel");
-  repack_upw_kernel<<<std::min(1024, (Cin * Cmid * 4 + 255) / 256), 256, 0, st>>>(up_w, nullptr, nullptr, w.b3h, w.b3l, Cin, Cmid);
-  L2S_LAUNCH_OK("repack_upw_kernel");
   repack_predw_kernel<<<std::min(256, (Cmid * KP + 255) / 256), 256, 0, st>>>(pred_w, nullptr, nullptr, w.b4h, w.b4l, ncls, Cmid, KP);
   L2S_LAUNCH_OK("repack_predw_kernel");
-  count_launch(3);
+  count_launch(2);
   // dU[4M x Cmid] = dS[4M x KP] * Wp^T[Cmid x KP]^T, masked by U > 0
   EpiDU e3{w.duh, w.dul, sv.u_hi, d_up_b, Cmid};
   rc = tc::launch_gemm<256, false, false>(w.dsh, w.dsl, KP, w.b4h, w.b4l, KP, 4 * M, Cmid, KP, 1, e3, st, tc::kShape256);
@@ -734,13 +844,32 @@ extern "C" int l2s_mask_head_bwd(const float* dscore, const float* up_w, const f
   EpiDWp e4{d_pred_w, ncls, Cmid};
   rc = tc::launch_gemm<256, true, true>(w.dsh, w.dsl, KP, sv.u_hi, sv.u_lo, Cmid, KP, Cmid, 4 * M, 0, e4, st, tc::kShape128);
   if (rc) return rc;
-  // dF[M x Cin] = dU[M x 4Cmid] * Wd[Cin x 4Cmid]^T -> dx NCHW
-  EpiDx e5{dx, Cin};
-  rc = tc::launch_gemm<256, false, false>(w.duh, w.dul, 4 * Cmid, w.b3h, w.b3l, 4 * Cmid, M, Cin, 4 * Cmid, 1, e5, st, tc::kShape256);
+  return mask_head_bwd_tail(up_w, sv, w, dx, d_up_w, n, Cin, Cmid, st);
+}
+
+extern "C" int l2s_mask_head_bce_bwd(const float* score, const int64_t* labels, const float* target, const float* gscale,
+                                     const float* up_w, const float* pred_w, const void* saved, float* dx,
+                                     float* d_up_w, float* d_up_b, float* d_pred_w, float* d_pred_b, int n, int Cin,
+                                     int Cmid, int ncls, void* workspace, size_t workspace_bytes, l2s_stream_t stream) {
+  int rc = check_head(n, Cin, Cmid, ncls);
   if (rc) return rc;
-  // dWd[Cin x 4Cmid] = F^T * dU   (both MN-major, K = M)
-  EpiDWd e6{d_up_w, Cmid};
-  return tc::launch_gemm<256, true, true>(sv.a_hi, sv.a_lo, Cin, w.duh, w.dul, 4 * Cmid, Cin, 4 * Cmid, M, 0, e6, st, tc::kShape256);
+  L2S_REQUIRE(Cmid % 8 == 0 && Cmid / 8 <= 256 && 256 % (Cmid / 8) == 0, L2S_ERR_SHAPE,
+              "mask_head_bce_bwd: Cmid must be 8*d with d a divisor of 256, got %d", Cmid);
+  L2S_REQUIRE(up_w && pred_w && d_up_w && d_up_b && d_pred_w && d_pred_b, L2S_ERR_ARG, "mask_head_bce_bwd: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  rc = mask_head_bwd_zero(d_up_w, d_up_b, d_pred_w, d_pred_b, Cin, Cmid, ncls, st);
+  if (rc) return rc;
+  if (n == 0) return L2S_OK;
+  L2S_REQUIRE(score && labels && target && gscale && saved && dx, L2S_ERR_ARG, "mask_head_bce_bwd: null pointer");
+  L2S_REQUIRE(workspace && workspace_bytes >= l2s_mask_head_workspace_bytes(n, Cin, Cmid, ncls), L2S_ERR_WORKSPACE,
+              "mask_head_bce_bwd: workspace too small");
+  const Saved sv = saved_layout(const_cast<void*>(saved), n, Cin, Cmid);
+  const Work w = work_layout(workspace, n, Cin, Cmid, ncls);
+  mask_bce_du_kernel<<<n, 256, 0, st>>>(score, labels, target, gscale, pred_w, sv.u_hi, sv.u_lo, w.duh, w.dul, d_up_b,
+                                        d_pred_w, d_pred_b, n, ncls, Cmid);
+  L2S_LAUNCH_OK("mask_bce_du_kernel");
+  count_launch();
+  return mask_head_bwd_tail(up_w, sv, w, dx, d_up_w, n, Cin, Cmid, st);
 }
 
 extern "C" int l2s_mask_bce_fwd(const float* score, const int64_t* labels, const float* target, float* loss, int n,

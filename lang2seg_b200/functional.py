@@ -40,6 +40,7 @@ class _DynamicFilter(torch.autograd.Function):
              ptr(tgt), ptr(loss), I, E, C, H, W, gate, stream())
         ctx.save_for_backward(X, filt, fuse, e2i, response, rk, tgt)
         ctx.gate = gate
+        ctx.set_materialize_grads(False)       # unused outputs arrive as None in backward (handled there)
         if loss is None:
             loss = X.new_zeros(E)
         return response, Y, loss
@@ -178,6 +179,9 @@ class _MaskHead(torch.autograd.Function):
              ptr(saved), n, Cin, Cmid, ncls, ptr(ws), nbytes, stream())
         ctx.save_for_backward(up_w, pred_w, saved, prob)
         ctx.meta = (n, Cin, Cmid, ncls)
+        # an unused output (the reference's loss only reads mask_score) must arrive as None in backward, not as a
+        # materialised (n,ncls,14,14) tensor of zeros that is then pushed through the sigmoid chain rule
+        ctx.set_materialize_grads(False)
         return score, prob
 
     @staticmethod
@@ -227,6 +231,74 @@ class _MaskBCE(torch.autograd.Function):
         gs = f32c(g).reshape(1)
         call("l2s_mask_bce_bwd", ptr(score), ptr(labels), ptr(target), ptr(gs), ptr(dscore), n, ncls, hw, stream())
         return dscore, None, None
+
+
+def _bce_du_supported(Cmid):
+    return Cmid % 8 == 0 and Cmid // 8 <= 256 and 256 % (Cmid // 8) == 0
+
+
+class _MaskHeadLoss(torch.autograd.Function):
+    """Mask head + mask loss as ONE autograd node.  When the loss is the only consumer of the scores (the reference's
+    training step) the backward never materialises dscore: l2s_mask_head_bce_bwd builds the dU planes and the
+    prediction-layer gradients straight from (score, labels, target).  Any other upstream gradient on score / prob
+    falls back to the general path (l2s_mask_bce_bwd + l2s_mask_head_bwd)."""
+
+    @staticmethod
+    def forward(ctx, x, up_w, up_b, pred_w, pred_b, labels, target):
+        x, up_w, up_b, pred_w, pred_b, target = (f32c(t) for t in (x, up_w, up_b, pred_w, pred_b, target))
+        labels = labels.to(torch.int64).contiguous()
+        n, Cin = x.shape[0], x.shape[1]
+        assert x.shape[2:] == (7, 7), "mask head expects (n,Cin,7,7) res5 features"
+        Cmid, ncls = up_w.shape[1], pred_w.shape[0]
+        assert up_w.shape == (Cin, Cmid, 2, 2) and pred_w.shape[:2] == (ncls, Cmid)
+        score = torch.empty(n, ncls, 14, 14, device=x.device, dtype=torch.float32)
+        prob = torch.empty_like(score)
+        saved = _ws(_lib.size("l2s_mask_head_saved_bytes", n, Cin, Cmid, ncls), x.device)
+        nbytes = _lib.size("l2s_mask_head_workspace_bytes", n, Cin, Cmid, ncls)
+        ws = _ws(nbytes, x.device)
+        call("l2s_mask_head_fwd", ptr(x), ptr(up_w), ptr(up_b), ptr(pred_w), ptr(pred_b), ptr(score), ptr(prob),
+             ptr(saved), n, Cin, Cmid, ncls, ptr(ws), nbytes, stream())
+        loss = torch.empty(1, device=x.device, dtype=torch.float32)
+        call("l2s_mask_bce_fwd", ptr(score), ptr(labels), ptr(target), ptr(loss), n, ncls, 196, stream())
+        ctx.save_for_backward(up_w, pred_w, saved, prob, score, labels, target)
+        ctx.meta = (n, Cin, Cmid, ncls)
+        ctx.set_materialize_grads(False)
+        return score, prob, loss[0]
+
+    @staticmethod
+    def backward(ctx, dscore, dprob, dloss):
+        up_w, pred_w, saved, prob, score, labels, target = ctx.saved_tensors
+        n, Cin, Cmid, ncls = ctx.meta
+        dev = score.device
+        dx = torch.empty(n, Cin, 7, 7, device=dev, dtype=torch.float32)
+        d_up_w = torch.empty_like(up_w)
+        d_up_b = torch.empty(Cmid, device=dev, dtype=torch.float32)
+        d_pred_w = torch.empty(ncls, Cmid, device=dev, dtype=torch.float32)
+        d_pred_b = torch.empty(ncls, device=dev, dtype=torch.float32)
+        nbytes = _lib.size("l2s_mask_head_workspace_bytes", n, Cin, Cmid, ncls)
+        ws = _ws(nbytes, dev)
+        if dscore is None and dprob is None and _bce_du_supported(Cmid):
+            gs = f32c(dloss).reshape(1) if dloss is not None else torch.zeros(1, device=dev)
+            call("l2s_mask_head_bce_bwd", ptr(score), ptr(labels), ptr(target), ptr(gs), ptr(up_w), ptr(pred_w),
+                 ptr(saved), ptr(dx), ptr(d_up_w), ptr(d_up_b), ptr(d_pred_w), ptr(d_pred_b), n, Cin, Cmid, ncls,
+                 ptr(ws), nbytes, stream())
+        else:
+            ds = torch.empty_like(score)
+            gs = f32c(dloss).reshape(1) if dloss is not None else torch.zeros(1, device=dev)
+            call("l2s_mask_bce_bwd", ptr(score), ptr(labels), ptr(target), ptr(gs), ptr(ds), n, ncls, 196, stream())
+            if dscore is not None:
+                ds = ds + f32c(dscore)
+            if dprob is not None:
+                ds = ds + dprob * prob * (1 - prob)
+            call("l2s_mask_head_bwd", ptr(ds), ptr(up_w), ptr(pred_w), ptr(saved), ptr(dx), ptr(d_up_w), ptr(d_up_b),
+                 ptr(d_pred_w), ptr(d_pred_b), n, Cin, Cmid, ncls, ptr(ws), nbytes, stream())
+        return dx, d_up_w, d_up_b, d_pred_w.view_as(pred_w), d_pred_b, None, None
+
+
+def mask_head_with_loss(x, up_w, up_b, pred_w, pred_b, labels, mask_targets):
+    """_mask_prediction (network_cycle_response.py:292-307) and the mask loss (:404-413) in one node ->
+    (mask_score, mask_prob, loss).  Same values as mask_head(...) followed by mask_bce_loss(...)."""
+    return _MaskHeadLoss.apply(x, up_w, up_b, pred_w, pred_b, labels, mask_targets)
 
 
 def mask_bce_loss(mask_score, labels, mask_targets):
@@ -434,6 +506,7 @@ class _BiLSTM(torch.autograd.Function):
         call("l2s_bilstm_fwd", ptr(G), ptr(w_hh), ptr(lens), ptr(c_all), ptr(h_all), ptr(out), ptr(hidden), L, B, H,
              ptr(ws), nbytes, stream())
         ctx.save_for_backward(G, w_hh, lens, c_all, h_all)
+        ctx.set_materialize_grads(False)       # `out` is usually unused: its gradient arrives as None (NULL dout)
         return out, hidden
 
     @staticmethod
@@ -444,6 +517,8 @@ class _BiLSTM(torch.autograd.Function):
         dev = G.device
         dout = f32c(dout) if dout is not None else None
         dhidden = f32c(dhidden) if dhidden is not None else None
+        if dout is None and dhidden is None:
+            return torch.zeros_like(G), torch.zeros_like(w_hh[0]), torch.zeros_like(w_hh[1]), None
         w_hh_t = w_hh.transpose(1, 2).contiguous()
         dG = torch.empty_like(G)
         nbytes = _lib.size("l2s_bilstm_workspace_bytes", L, B, H)

@@ -64,9 +64,17 @@ class Network(nn.Module):
         self._predictions["bbox_pred"] = bbox_pred
         return cls_prob, bbox_pred
 
-    def _mask_prediction(self, spatial_fc7):
-        mask_score, mask_prob = L2F.mask_head(spatial_fc7, self.mask_up_sampling.weight, self.mask_up_sampling.bias,
-                                              self.mask_pred_net.weight, self.mask_pred_net.bias)
+    def _mask_prediction(self, spatial_fc7, labels=None, mask_targets=None):
+        """:292-307.  In training the reference already holds the mask targets when it predicts (they come from the
+        proposal target layer, :586-590): passing them here makes prediction + mask loss (:404-413) one autograd node
+        whose backward never materialises the (n,81,14,14) score gradient; `_mask_loss` then returns that loss."""
+        ws = (self.mask_up_sampling.weight, self.mask_up_sampling.bias, self.mask_pred_net.weight, self.mask_pred_net.bias)
+        if labels is not None and mask_targets is not None:
+            mask_score, mask_prob, loss = L2F.mask_head_with_loss(spatial_fc7, *ws, labels, mask_targets)
+            self._losses["mask_loss"] = loss
+        else:
+            mask_score, mask_prob = L2F.mask_head(spatial_fc7, *ws)
+            self._losses.pop("mask_loss", None)
         self._predictions["mask_score"] = mask_score
         self._predictions["mask_prob"] = mask_prob
         return mask_prob
@@ -87,6 +95,8 @@ class Network(nn.Module):
 
     # ---- losses on the path ----------------------------------------------------------------------
     def _mask_loss(self, labels, mask_targets):
+        if "mask_loss" in self._losses:          # computed together with the prediction
+            return self._losses["mask_loss"]
         return L2F.mask_bce_loss(self._predictions["mask_score"], labels, mask_targets)
 
     def _caption_loss(self, fc_feats, att_feats, cap_labels, cap_masks, steps=None):

@@ -51,17 +51,20 @@ def main():
         print("%-110s %8.1f %12.1f %6.2f%%" % (k, v[0] / a.steps, v[1] / a.steps, 100 * v[1] / tot))
 
 
-    # framework-side operators (not library kernels) by device time, with their input shapes
-    print("\n# aten operators by device time (per step)")
+    # framework-side operators by (inclusive) device time, with their input shapes
+    print("\n# aten operators by device time (per step, inclusive of children)")
     rows = []
     for e in prof.key_averages(group_by_input_shape=True):
-        dt = getattr(e, "self_device_time_total", None)
-        if dt is None:
-            dt = getattr(e, "self_cuda_time_total", 0.0)
-        if dt > 0:
-            rows.append((dt / a.steps, e.count / a.steps, e.key, str(e.input_shapes)[:110]))
-    for dt, n, key, shp in sorted(rows, reverse=True)[:45]:
-        print("%9.1f us %6.1f x  %-42s %s" % (dt, n, key[:42], shp))
+        dt = 0.0
+        for attr in ("device_time_total", "cuda_time_total", "self_device_time_total", "self_cuda_time_total"):
+            v = getattr(e, attr, None)
+            if v:
+                dt = float(v)
+                break
+        if dt > 0 and e.key.startswith(("aten::", "Optimizer", "autograd::")):
+            rows.append((dt / a.steps, e.count / a.steps, e.key, str(e.input_shapes)[:120]))
+    for dt, n, key, shp in sorted(rows, reverse=True)[:60]:
+        print("%9.1f us %6.1f x  %-40s %s" % (dt, n, key[:40], shp))
 
 
 if __name__ == "__main__":

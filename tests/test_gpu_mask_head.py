@@ -128,6 +128,37 @@ def test_mask_head_full_size_vs_oracle(n, gemm_shape):
         assert relerr(a, b) < TOL, name
 
 
+@pytest.mark.parametrize("n,Cin,Cmid,ncls", [(8, 2048, 256, 81), (5, 128, 32, 9), (3, 64, 24, 5)])
+@pytest.mark.parametrize("extra", [False, True])
+def test_mask_head_with_loss_fused_backward(n, Cin, Cmid, ncls, extra):
+    """prediction + mask loss as one node: the backward that never builds dscore (l2s_mask_head_bce_bwd) against the
+    oracle, and its fallback when the scores have another consumer (`extra`) or Cmid is not supported (24)."""
+    import lang2seg_b200.functional as F
+    g = torch.Generator().manual_seed(100 + n)
+    x = torch.relu(torch.randn(n, Cin, 7, 7, generator=g))
+    up_w, up_b = torch.randn(Cin, Cmid, 2, 2, generator=g) * 0.02, torch.randn(Cmid, generator=g) * 0.02
+    pw, pb = torch.randn(ncls, Cmid, 1, 1, generator=g) * 0.05, torch.randn(ncls, generator=g) * 0.05
+    labels = torch.randint(1, ncls, (n,), generator=g)
+    tgt = (torch.rand(n, 14, 14, generator=g) < 0.5).float()
+    Gs = torch.randn(n, ncls, 14, 14, generator=g) * 1e-3
+
+    def run(dev):
+        ts = [t.to(dev).clone().requires_grad_(True) for t in (x, up_w, up_b, pw, pb)]
+        if dev == "cpu":
+            s, p = R.mask_head(*ts)
+            loss = R.mask_loss(s, labels, tgt)
+        else:
+            s, p, loss = F.mask_head_with_loss(*ts, labels.to(dev), tgt.to(dev))
+        tot = 3.0 * loss
+        if extra:
+            tot = tot + (s * Gs.to(dev)).sum() + (p * Gs.to(dev)).sum()
+        return [s, p, loss] + list(torch.autograd.grad(tot, ts))
+
+    ref, out = run("cpu"), run("cuda")
+    for name, a, b in zip(["score", "prob", "loss", "dx", "d_up_w", "d_up_b", "d_pred_w", "d_pred_b"], out, ref):
+        assert relerr(a, b) < TOL, name
+
+
 @pytest.mark.parametrize("gemm_shape", [None, 1, 2], indirect=True)
 def test_linear_tc_vs_fp64(gemm_shape):
     import lang2seg_b200.functional as F
