@@ -187,6 +187,19 @@ int l2s_mask_bce_bwd(const float* score, const int64_t* labels, const float* tar
                      float* dscore, int n, int ncls, int hw, l2s_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Targets on the device: crop a uint8 {0,1} ground-truth mask to a box and resize it
+ * to (outH,outW) with scipy.misc.imresize(..., interp='nearest') semantics.  Replaces the host loop of
+ * MFR/layer_utils/proposal_target_layer.py:193-201 (mask targets: masks[assign[i], int(y1):int(y2)+1,
+ * int(x1):int(x2)+1] -> 14x14) and, with rois == NULL, the response target of
+ * MFR/nets/network_cycle_response.py:418 (whole mask -> response size).
+ *   masks (G,imH,imW) uint8 ; rois (n,roi_stride) fp32 rows [batch,x1,y1,x2,y2,...] in image pixels or NULL ;
+ *   assign (n) int32 index of each output's mask, or NULL (output i uses mask i) ; out (n,outH,outW) fp32.
+ *   Bit exact: destination index i reads source index floor((i+0.5)*src/dst).  Empty crops give zeros.
+ * ------------------------------------------------------------------------------------- */
+int l2s_mask_crop_resize(const uint8_t* masks, const float* rois, int roi_stride, const int32_t* assign, float* out,
+                         int G, int imH, int imW, int n, int outH, int outW, l2s_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
  * (3) att2in2 attention step.  Replaces Attention.forward
  * (lib/caption_models/AttModel.py:406-423) after the h2att Linear:
  *   e_a = alpha_w . tanh(p_att[b,a,:] + att_h[b,:]) + alpha_b ; weight = softmax_a(e) ;

@@ -233,6 +233,33 @@ class _MaskBCE(torch.autograd.Function):
         return dscore, None, None
 
 
+def mask_targets(gt_masks, rois, gt_assignment, size=14):
+    """Mask targets of the proposal target layer (proposal_target_layer.py:193-201) on the device.
+
+    gt_masks (G,imH,imW) uint8 {0,1} ; rois (n,5) [batch,x1,y1,x2,y2] image pixels ; gt_assignment (n) ->
+    (n,size,size) float {0,1}: masks[assign[i], int(y1):int(y2)+1, int(x1):int(x2)+1] resized 'nearest'."""
+    assert gt_masks.is_cuda and gt_masks.dtype == torch.uint8 and gt_masks.dim() == 3
+    m = gt_masks.contiguous()
+    r = f32c(rois)
+    a = gt_assignment.to(device=m.device, dtype=torch.int32).contiguous()
+    n = r.shape[0]
+    out = torch.empty(n, size, size, device=m.device, dtype=torch.float32)
+    call("l2s_mask_crop_resize", ptr(m), ptr(r), r.shape[1], ptr(a), ptr(out), m.shape[0], m.shape[1], m.shape[2], n,
+         size, size, stream())
+    return out
+
+
+def resize_masks_nearest(gt_masks, H, W):
+    """imresize(mask, (H,W), interp='nearest') of network_cycle_response.py:418 for a stack of uint8 {0,1} masks
+    (G,imH,imW) -> (G,H,W) float: the response target, built on the device."""
+    assert gt_masks.is_cuda and gt_masks.dtype == torch.uint8 and gt_masks.dim() == 3
+    m = gt_masks.contiguous()
+    out = torch.empty(m.shape[0], H, W, device=m.device, dtype=torch.float32)
+    call("l2s_mask_crop_resize", ptr(m), None, 0, None, ptr(out), m.shape[0], m.shape[1], m.shape[2], m.shape[0], H, W,
+         stream())
+    return out
+
+
 def _bce_du_supported(Cmid):
     return Cmid % 8 == 0 and Cmid // 8 <= 256 and 256 % (Cmid // 8) == 0
 

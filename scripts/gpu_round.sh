@@ -9,8 +9,8 @@ echo "bench cfg2 exit=$?" | tee -a gpurun_out/summary.txt; tail -c 800 gpurun_ou
 cat gpurun_out/bench_cfg2_$TAG.json
 bash scripts/gpu_launches.sh $TAG
 timeout 900 ncu --set full --clock-control none --import-source on \
-    -k regex:'roi_crop_(fwd|bwd)|dynfilter_(fwd|bwd)|att_step|gemm_bf16x3|linear_small|att_accum' -c 36 -f -o gpurun_out/prof_$TAG \
-    python scripts/prof_ops.py --reps 1 --only dyn,crop,mask,att,lin > gpurun_out/prof_$TAG.log 2>&1
+    -k regex:'roi_crop_(fwd|bwd)|dynfilter_(fwd|bwd)|att_step|gemm_bf16x3|mask_bce_du|repack_x|att_accum' -c 24 -f -o gpurun_out/prof_$TAG \
+    python scripts/prof_ops.py --reps 1 --only dyn,crop,maskloss,att > gpurun_out/prof_$TAG.log 2>&1
 echo "ncu full exit=$?" | tee -a gpurun_out/summary.txt
 ncu -i gpurun_out/prof_$TAG.ncu-rep --page raw --csv > gpurun_out/prof_${TAG}_raw.csv 2>/dev/null
 ls -la gpurun_out/

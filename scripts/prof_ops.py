@@ -60,6 +60,16 @@ def main():
             loss = F.mask_bce_loss(s, d["mlab"], d["mtgt"])
             torch.autograd.grad(loss, [fc7, up_w, up_b, pw, pb])
             del s, fc7
+        if "maskloss" in only:
+            # prediction + mask loss as one node: the fused backward of the training step
+            up_w = (torch.randn(2048, 256, 2, 2, device=dev) * 0.01).requires_grad_(True)
+            up_b = torch.zeros(256, device=dev, requires_grad=True)
+            pw = (torch.randn(81, 256, 1, 1, device=dev) * 0.01).requires_grad_(True)
+            pb = torch.zeros(81, device=dev, requires_grad=True)
+            fc7 = d["fc7"].detach().requires_grad_(True)
+            s, _, loss = F.mask_head_with_loss(fc7, up_w, up_b, pw, pb, d["mlab"], d["mtgt"])
+            torch.autograd.grad(loss, [fc7, up_w, up_b, pw, pb])
+            del s, fc7
         if "att" in only:
             A, D = 196, 512
             att_h = torch.randn(E, D, device=dev, requires_grad=True)
