@@ -200,6 +200,21 @@ int l2s_mask_crop_resize(const uint8_t* masks, const float* rois, int roi_stride
                          int G, int imH, int imW, int n, int outH, int outW, l2s_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
+ * Greedy NMS on the device.  Replaces
+ *   int gpu_nms(THLongTensor* keep, THLongTensor* num_out, THCudaTensor* boxes, float nms_overlap_thresh)
+ * (MFR/nms/src/nms_cuda.c:17-67; bit-mask kernel MFR/nms/src/cuda/nms_kernel.cu:26-83, IoU with the +1 pixel
+ * convention :15-24), whose greedy scan runs on the HOST after copying the N x N/64 mask back.
+ *   boxes_sorted (n,5) [x1,y1,x2,y2,score], sorted by descending score (as pth_nms.py:36 does) ;
+ *   keep (n) int64 and num_out (1) int64 are DEVICE buffers (the reference's are host tensors): keep[0..num_out)
+ *   are the indices (into boxes_sorted) of the surviving boxes in score order ;
+ *   max_out > 0 stops after that many survivors (RPN_POST_NMS_TOP_N), 0 keeps all ;
+ *   workspace: l2s_nms_workspace_bytes(n) (the bit mask), 16-byte aligned.
+ * ------------------------------------------------------------------------------------- */
+size_t l2s_nms_workspace_bytes(int n);
+int l2s_nms(const float* boxes_sorted, int n, float thresh, int max_out, int64_t* keep, int64_t* num_out,
+            void* workspace, size_t workspace_bytes, l2s_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
  * (3) att2in2 attention step.  Replaces Attention.forward
  * (lib/caption_models/AttModel.py:406-423) after the h2att Linear:
  *   e_a = alpha_w . tanh(p_att[b,a,:] + att_h[b,:]) + alpha_b ; weight = softmax_a(e) ;

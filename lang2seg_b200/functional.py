@@ -260,6 +260,20 @@ def resize_masks_nearest(gt_masks, H, W):
     return out
 
 
+def nms_sorted(boxes_sorted, thresh, max_out=0):
+    """gpu_nms (nms_cuda.c:17-67) on score-sorted boxes (N,5), scan included, on the device ->
+    (keep (N,) int64: positions of the survivors in score order, valid up to num ; num (1,) int64)."""
+    b = f32c(boxes_sorted)
+    assert b.dim() == 2 and b.shape[1] == 5
+    n = b.shape[0]
+    keep = torch.zeros(max(n, 1), device=b.device, dtype=torch.int64)
+    num = torch.zeros(1, device=b.device, dtype=torch.int64)
+    nbytes = _lib.size("l2s_nms_workspace_bytes", n)
+    ws = _ws(nbytes, b.device)
+    call("l2s_nms", ptr(b), n, float(thresh), int(max_out), ptr(keep), ptr(num), ptr(ws), nbytes, stream())
+    return keep[:n], num
+
+
 def _bce_du_supported(Cmid):
     return Cmid % 8 == 0 and Cmid // 8 <= 256 and 256 % (Cmid // 8) == 0
 

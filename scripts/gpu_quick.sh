@@ -1,7 +1,7 @@
 #!/bin/bash
 # quick GPU visit: the parity suites named in $1 (default all), then the bench without the CPU baseline
 mkdir -p gpurun_out
-for t in ${1:-roi dynfilter att mask_head targets net}; do
+for t in ${1:-roi dynfilter att mask_head targets nms net}; do
   timeout 420 python -m pytest tests/test_gpu_$t.py -x -q -m gpu -p no:cacheprovider > gpurun_out/test_$t.log 2>&1
   echo "test_gpu_$t exit=$?" | tee -a gpurun_out/summary_quick.txt
   tail -n 3 gpurun_out/test_$t.log
