@@ -56,6 +56,8 @@ att_step_fwd_kernel(const float* __restrict__ att_h, const float* __restrict__ a
   int a0, a1;
   slice(g.A, rank, &a0, &a1);
   const int na = a1 - a0;
+  pdl_launch_dependents();
+  pdl_wait();                          // att_h / datt_res come from the previous kernel of the decode chain
   for (int d = t; d < g.Dh; d += kAttThreads) {
     s_ah[d] = __ldg(att_h + (size_t)b * g.ldh + d);
     s_aw[d] = __ldg(alpha_w + d);
@@ -172,6 +174,8 @@ att_step_bwd_kernel(const float* __restrict__ datt_res, const float* __restrict_
   int a0, a1;
   slice(g.A, rank, &a0, &a1);
   const int na = a1 - a0;
+  pdl_launch_dependents();
+  pdl_wait();                          // att_h / datt_res come from the previous kernel of the decode chain
   for (int d = t; d < g.Dh; d += kAttThreads) {
     s_ah[d] = __ldg(att_h + (size_t)b * g.ldh + d);
     s_aw[d] = __ldg(alpha_w + d);
@@ -289,6 +293,8 @@ att_step_bwd_kernel(const float* __restrict__ datt_res, const float* __restrict_
 __global__ void gates_fwd_kernel(const float* __restrict__ sums, int lds, const float* __restrict__ a2c,
                                  const float* __restrict__ c_prev, float* __restrict__ h, float* __restrict__ c,
                                  int B, int D) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * D) return;
   const int b = idx / D, d = idx - b * D;
@@ -308,6 +314,8 @@ __global__ void gates_bwd_kernel(const float* __restrict__ sums, int lds, const 
                                  const float* __restrict__ dh_a, const float* __restrict__ dh_b,
                                  const float* __restrict__ dc, float* __restrict__ dsums, int ld_ds,
                                  float* __restrict__ da2c, float* __restrict__ dc_prev, int B, int D) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * D) return;
   const int b = idx / D, d = idx - b * D;
@@ -481,8 +489,11 @@ int launch_cluster(const void* kern, dim3 grid, size_t smem, cudaStream_t st, vo
   cfg.blockDim = dim3(kAttThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cfg.attrs = nullptr;      // cluster dims are compiled in (__cluster_dims__)
-  cfg.numAttrs = 0;
+  cudaLaunchAttribute attr[1];      // cluster dims are compiled in (__cluster_dims__)
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
   L2S_CUDA_OK(cudaLaunchKernelExC(&cfg, kern, args));
   count_launch();
   return L2S_OK;
@@ -538,7 +549,7 @@ int launch_gates_fwd(const float* sums, int lds, const float* a2c_out, const flo
                      int D, cudaStream_t st) {
   L2S_REQUIRE(sums && a2c_out && h && c, L2S_ERR_ARG, "gates_fwd: null pointer");
   L2S_REQUIRE(B > 0 && D > 0 && lds >= 5 * D, L2S_ERR_SHAPE, "gates_fwd: bad shape");
-  gates_fwd_kernel<<<(B * D + 255) / 256, 256, 0, st>>>(sums, lds, a2c_out, c_prev, h, c, B, D);
+  L2S_CUDA_OK(launch_chain(gates_fwd_kernel, dim3((B * D + 255) / 256), dim3(256), 0, st, sums, lds, a2c_out, c_prev, h, c, B, D));
   L2S_LAUNCH_OK("gates_fwd_kernel");
   count_launch();
   return L2S_OK;
@@ -549,8 +560,8 @@ int launch_gates_bwd(const float* sums, int lds, const float* a2c_out, const flo
                      float* dc_prev, int B, int D, cudaStream_t st) {
   L2S_REQUIRE(sums && a2c_out && c && (dh_a || dh_b) && dsums && da2c && dc_prev, L2S_ERR_ARG, "gates_bwd: null pointer");
   L2S_REQUIRE(B > 0 && D > 0 && lds >= 5 * D && ld_ds >= 5 * D, L2S_ERR_SHAPE, "gates_bwd: bad shape");
-  gates_bwd_kernel<<<(B * D + 255) / 256, 256, 0, st>>>(sums, lds, a2c_out, c_prev, c, dh_a, dh_b, dc, dsums, ld_ds,
-                                                        da2c, dc_prev, B, D);
+  L2S_CUDA_OK(launch_chain(gates_bwd_kernel, dim3((B * D + 255) / 256), dim3(256), 0, st, sums, lds, a2c_out, c_prev, c, dh_a,
+                           dh_b, dc, dsums, ld_ds, da2c, dc_prev, B, D));
   L2S_LAUNCH_OK("gates_bwd_kernel");
   count_launch();
   return L2S_OK;

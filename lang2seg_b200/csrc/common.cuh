@@ -37,6 +37,11 @@ static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t
 
 int  sm_count();
 int  max_smem_optin();
+// Programmatic dependent launch for the chains of short kernels (decode loop, LSTM recurrence): the next kernel of
+// the chain is scheduled while the current one runs and blocks in griddepcontrol.wait until that one has completed
+// and flushed.  Opt-in (L2S_PDL=1): inside the whole-step CUDA graph, where kernel-to-kernel gaps are already
+// sub-microsecond, it made the step SLOWER on B200 (11.05 vs 10.57 ms); it only pays for eager launches.
+bool pdl_enabled();
 void count_launch(int n = 1);          // feeds l2s_launch_count()
 
 // ---- internal launchers shared between translation units (att.cu <-> decode.cu) -----------
@@ -82,6 +87,13 @@ __device__ __forceinline__ float tanhf_fast_acc(float x) {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
+
+// ---- programmatic dependent launch ----
+// Every kernel launched through launch_chain() starts with pdl_launch_dependents() and executes pdl_wait() before its
+// first access to memory that the previous kernel of the stream may write (and before its own first global write).
+// Both are no-ops for a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ---- mbarrier ----
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -141,6 +153,22 @@ __device__ __forceinline__ void bulk_wait_read() {
 template <int N>
 __device__ __forceinline__ void bulk_wait() {
   asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <class... KArgs, class... Args>
+inline cudaError_t launch_chain(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
 #endif  // __CUDACC__

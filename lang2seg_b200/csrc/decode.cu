@@ -99,6 +99,23 @@ linear_small_kernel(const float* __restrict__ A, const float* __restrict__ W, co
   const int k0 = s * kLinKC;
   const int kc = min(kLinKC, g.K - k0);            // valid k in this chunk (multiple of 4)
 
+  // ---- this warp's weight rows: lane holds float4 #(lane + 32 j), j = 0..3 of the chunk.  The weights do not depend
+  // on the previous kernel of the chain, so they are requested BEFORE the dependency wait (programmatic dependent
+  // launch): their L2 latency overlaps the tail of that kernel.
+  pdl_launch_dependents();
+  const int n0 = (cb * (kLinThreads / 32) + wid) * CPW;
+  float4 w[CPW][4];
+#pragma unroll
+  for (int c = 0; c < CPW; ++c)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int q = lane + 32 * j;
+      w[c][j] = (n0 + c < g.N && 4 * q < kc)
+                    ? __ldg(reinterpret_cast<const float4*>(W + (size_t)(n0 + c) * g.ldw + k0) + q)
+                    : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  pdl_wait();
+
   // ---- stage the A chunk (zero fill outside M / K)
   {
     const int nf4 = g.rows_pad * (kLinKC / 4);
@@ -111,18 +128,6 @@ linear_small_kernel(const float* __restrict__ A, const float* __restrict__ W, co
       As4[i] = v;
     }
   }
-  // ---- this warp's weight rows: lane holds float4 #(lane + 32 j), j = 0..3 of the chunk
-  const int n0 = (cb * (kLinThreads / 32) + wid) * CPW;
-  float4 w[CPW][4];
-#pragma unroll
-  for (int c = 0; c < CPW; ++c)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int q = lane + 32 * j;
-      w[c][j] = (n0 + c < g.N && 4 * q < kc)
-                    ? __ldg(reinterpret_cast<const float4*>(W + (size_t)(n0 + c) * g.ldw + k0) + q)
-                    : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
   __syncthreads();
 
   const float4* As4 = reinterpret_cast<const float4*>(As);
@@ -219,7 +224,7 @@ int launch_linear_small(const float* A, int lda, const float* W, int ldw, const 
   do {                                                                                                   \
     auto kern = linear_small_kernel<CPW>;                                                                \
     L2S_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
-    kern<<<grid, kLinThreads, smem, st>>>(A, W, bias, D, partials, counters, g);                         \
+    L2S_CUDA_OK(launch_chain(kern, grid, dim3(kLinThreads), smem, st, A, W, bias, D, partials, counters, g)); \
   } while (0)
   if (cpw == 3) L2S_LIN_LAUNCH(3);
   else if (cpw == 2) L2S_LIN_LAUNCH(2);
@@ -253,6 +258,8 @@ att_accum_kernel(const float* __restrict__ p_att, const float* __restrict__ cat_
   float* s_da = s_pi + T * kAccLoc;          // [Dh] alpha-gradient partial (phase 1 adds onto phase 0)
   const int b = blockIdx.y, a0 = blockIdx.x * kAccLoc, na = min(kAccLoc, A - a0);
   const int t = threadIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();
   for (int i = t; i < T * Dh; i += kAccThreads) {
     const int tt = i / Dh, d = i - tt * Dh;
     s_ah[i] = __ldg(cat_all + ((size_t)tt * B + b) * ldc + d);
@@ -321,6 +328,8 @@ att_accum_kernel(const float* __restrict__ p_att, const float* __restrict__ cat_
 // out[c] = sum_r in[r][c]   (fixed order)
 __global__ void colsum_kernel(const float* __restrict__ in, float* __restrict__ out, int R, int C) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();
   if (c >= C) return;
   float s = 0.f;
   for (int r = 0; r < R; ++r) s += in[(size_t)r * C + c];
@@ -469,11 +478,10 @@ extern "C" int l2s_att2in2_decode_bwd(const float* dh_all, const float* cat_all,
   const size_t smem = ((size_t)T * (Dh + D) + (size_t)2 * T * kAccLoc + Dh) * sizeof(float);
   L2S_REQUIRE(smem <= (size_t)max_smem_optin(), L2S_ERR_SHAPE, "att2in2_decode_bwd: T=%d too long for one pass", T);
   L2S_CUDA_OK(cudaFuncSetAttribute(att_accum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  att_accum_kernel<<<dim3(nchunk, B), kAccThreads, smem, st>>>(p_att, cat_all, LC, dres_all, de_all, pi_all, alpha_w,
-                                                              dp_att, datt_feats, w.dalpha_part, T, B, A, D, Dh);
-  L2S_LAUNCH_OK("att_accum_kernel");
-  colsum_kernel<<<(Dh + 127) / 128, 128, 0, st>>>(w.dalpha_part, dalpha_w, nchunk * B, Dh);
-  L2S_LAUNCH_OK("colsum_kernel");
+  L2S_CUDA_OK(launch_chain(att_accum_kernel, dim3(nchunk, B), dim3(kAccThreads), smem, st, p_att, cat_all, LC, dres_all,
+                           de_all, pi_all, alpha_w, dp_att, datt_feats, w.dalpha_part, T, B, A, D, Dh));
+  L2S_CUDA_OK(launch_chain(colsum_kernel, dim3((Dh + 127) / 128), dim3(128), 0, st, (const float*)w.dalpha_part, dalpha_w,
+                           nchunk * B, Dh));
   count_launch(2);
   return L2S_OK;
 }

@@ -22,6 +22,8 @@ struct LstmGeom {
 // step s: direction 0 works on t = s, direction 1 on t = L-1-s.
 __global__ void lstm_cell_fwd_kernel(const float* __restrict__ G, const int* __restrict__ lens, float* __restrict__ c_all,
                                      float* __restrict__ h_all, float* __restrict__ out, int s, LstmGeom g) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int H = g.H, B = g.B, L = g.L;
   if (idx >= 2 * B * H) return;
@@ -53,6 +55,8 @@ __global__ void lstm_cell_bwd_kernel(const float* __restrict__ G, const int* __r
                                      const float* __restrict__ dh_pass /* (2,B,H) gradient passed through masked steps */,
                                      const float* __restrict__ dc_in, float* __restrict__ dG,
                                      float* __restrict__ dh_pass_out, float* __restrict__ dc_out, int s, LstmGeom g) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int H = g.H, B = g.B, L = g.L;
   if (idx >= 2 * B * H) return;
@@ -88,6 +92,8 @@ __global__ void lstm_cell_bwd_kernel(const float* __restrict__ G, const int* __r
 
 // hidden (B,2H) = [h_fwd after t = L-1 | h_bwd after t = 0]
 __global__ void lstm_final_kernel(const float* __restrict__ h_all, float* __restrict__ hidden, LstmGeom g) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int H = g.H, B = g.B, L = g.L;
   if (idx >= 2 * B * H) return;
@@ -97,6 +103,8 @@ __global__ void lstm_final_kernel(const float* __restrict__ h_all, float* __rest
 }
 
 __global__ void lstm_seed_kernel(const float* __restrict__ dhidden, float* __restrict__ dh_pass, LstmGeom g) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   const int H = g.H, B = g.B;
   if (idx >= 2 * B * H) return;
@@ -150,11 +158,11 @@ extern "C" int l2s_bilstm_fwd(float* G, const float* w_hh, const int32_t* lens, 
         if (rc) return rc;
       }
     }
-    lstm_cell_fwd_kernel<<<blocks, threads, 0, st>>>(G, lens, c_all, h_all, out, s, g);
+    L2S_CUDA_OK(launch_chain(lstm_cell_fwd_kernel, dim3(blocks), dim3(threads), 0, st, (const float*)G, lens, c_all, h_all, out, s, g));
     L2S_LAUNCH_OK("lstm_cell_fwd_kernel");
     count_launch();
   }
-  lstm_final_kernel<<<blocks, threads, 0, st>>>(h_all, hidden, g);
+  L2S_CUDA_OK(launch_chain(lstm_final_kernel, dim3(blocks), dim3(threads), 0, st, (const float*)h_all, hidden, g));
   L2S_LAUNCH_OK("lstm_final_kernel");
   count_launch();
   return L2S_OK;
@@ -180,14 +188,14 @@ extern "C" int l2s_bilstm_bwd(const float* dout, const float* dhidden, const flo
   float* dc[2] = {fb + 3 * n, fb + 4 * n};
   const int threads = 256, blocks = (int)((n + threads - 1) / threads);
   const int ldg = L * 8 * H;
-  lstm_seed_kernel<<<blocks, threads, 0, st>>>(dhidden, dh_pass[0], g);
+  L2S_CUDA_OK(launch_chain(lstm_seed_kernel, dim3(blocks), dim3(threads), 0, st, dhidden, dh_pass[0], g));
   L2S_LAUNCH_OK("lstm_seed_kernel");
   count_launch();
   for (int s = L - 1, k = 0; s >= 0; --s, ++k) {
     const bool last = (s == L - 1);
-    lstm_cell_bwd_kernel<<<blocks, threads, 0, st>>>(G, lens, c_all, dout, last ? nullptr : dh_rec, dh_pass[k & 1],
-                                                     last ? nullptr : dc[k & 1], dG, dh_pass[(k & 1) ^ 1],
-                                                     dc[(k & 1) ^ 1], s, g);
+    L2S_CUDA_OK(launch_chain(lstm_cell_bwd_kernel, dim3(blocks), dim3(threads), 0, st, G, lens, c_all, dout,
+                             (const float*)(last ? nullptr : dh_rec), (const float*)dh_pass[k & 1],
+                             (const float*)(last ? nullptr : dc[k & 1]), dG, dh_pass[(k & 1) ^ 1], dc[(k & 1) ^ 1], s, g));
     L2S_LAUNCH_OK("lstm_cell_bwd_kernel");
     count_launch();
     if (s > 0) {   // gradient on the previous state: dG_t . W_hh   (w_hh_t = W_hh^T stored (2, H, 4H))
