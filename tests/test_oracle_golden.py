@@ -159,3 +159,47 @@ def test_c_oracle_matches_numpy_oracle(golden):
     assert relerr(clib.crop_resize_fwd(b, r, 14, True), d["p14max.out"]) < 3e-5
     assert relerr(clib.crop_resize_fwd(b, r, 7, False, imhw), d["align7.out"]) < 3e-5
     assert relerr(clib.crop_resize_fwd(b, r, 14, True, imhw), d["align14max.out"]) < 3e-5
+
+
+def test_nms_oracle_vs_brute_force():
+    """The vectorised fp32 restatement of gpu_nms (nms_cuda.c:44-56 + devIoU nms_kernel.cu:15-24) against a scalar loop."""
+    rs = np.random.RandomState(0)
+    n = 300
+    x1, y1 = rs.uniform(0, 100, n), rs.uniform(0, 100, n)
+    b = np.stack([x1, y1, x1 + rs.uniform(5, 60, n), y1 + rs.uniform(5, 60, n), np.linspace(1, 0, n)], 1).astype(np.float32)
+    one, zero = np.float32(1), np.float32(0)
+
+    def iou(a, c):
+        w = max(np.float32(min(a[2], c[2]) - max(a[0], c[0]) + one), zero)
+        h = max(np.float32(min(a[3], c[3]) - max(a[1], c[1]) + one), zero)
+        inter = np.float32(w * h)
+        sa = np.float32((a[2] - a[0] + one) * (a[3] - a[1] + one))
+        sb = np.float32((c[2] - c[0] + one) * (c[3] - c[1] + one))
+        return np.float32(inter / np.float32(np.float32(sa + sb) - inter))
+
+    for thresh in (0.3, 0.7):
+        removed, keep = [False] * n, []
+        for i in range(n):
+            if removed[i]:
+                continue
+            keep.append(i)
+            for j in range(i + 1, n):
+                if iou(b[i], b[j]) > np.float32(thresh):
+                    removed[j] = True
+        assert list(R.nms_sorted(b, thresh)) == keep
+
+
+def test_mask_targets_oracle(golden):
+    """proposal_target_layer.py:193-201: python slicing + imresize 'nearest' (pinned by the imresize golden)."""
+    d = golden("imresize.npz")
+    m = d["mask"].numpy().astype(np.uint8)[None]
+    H, W = m.shape[1:]
+    rois = np.array([[0, 0, 0, W - 1, H - 1], [0, 3.7, 2.2, 20.9, 30.1], [0, 5.5, 5.5, 5.6, 5.6]], np.float32)
+    t = R.mask_targets(m, rois, [0, 0, 0], 14)
+    assert np.array_equal(t[0], R.nearest_resize_mask(m[0], 14, 14))
+    assert np.array_equal(t[1], R.nearest_resize_mask(m[0, 2:31, 3:21], 14, 14))
+    assert np.array_equal(t[2], np.full((14, 14), float(m[0, 5, 5]), np.float32))
+    # the integer form used by the kernel equals the float form of the oracle
+    for src in range(1, 70):
+        for dst in (7, 14, 32):
+            assert R.nearest_resize_index(dst, src) == [min(((2 * i + 1) * src) // (2 * dst), src - 1) for i in range(dst)]
