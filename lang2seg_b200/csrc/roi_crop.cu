@@ -22,6 +22,8 @@
 //     lanes are samples, the four corners are four phases, and equal-cell samples are serialised by their
 //     precomputed rank (fixed order => bit-reproducible sums).  No floating-point atomics anywhere
 //     (shared fp32 atomicAdd costs 2 cycles per lane on sm_100).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace l2s {
@@ -442,6 +444,90 @@ roi_crop_fwd_kernel(const float* __restrict__ bottom, const int* __restrict__ se
     }
   }
   if (t == 0) bulk_wait<0>();
+}
+
+// ------------------------------------------------------------------ forward, warp-per-ROI variant (CC = 32, 7x7)
+// The block-synchronous kernel above spends 20 % of its issue slots waiting at the per-iteration barrier and keeps the
+// shared-memory pipe only ~50 % busy (ncu).  Here nothing is block wide after the map has been staged: every warp owns
+// whole ROIs (ROI r = beg + wid, beg + wid + NW, ...), reads the 49 geometry entries of its ROI straight from L2 into
+// registers one ROI ahead (13 independent 16-byte loads per lane), gathers into its OWN [32 ch][49] tile and sends the
+// tile off with its own TMA bulk store; the only wait is the warp's own previous store having been read out of the
+// tile.  Up to kFwdWarps stores are in flight per SM, and warps drift apart so that gathers, tile writes and TMA
+// reads of different ROIs overlap in the shared-memory pipe.
+constexpr int kFwdWarps = 14;
+
+__global__ void __launch_bounds__(kFwdWarps * 32, 1)
+roi_crop_fwd_warp_kernel(const float* __restrict__ bottom, const int* __restrict__ seg,
+                         const unsigned char* __restrict__ table, float* __restrict__ out, CropGeom g) {
+  constexpr int CC = 32;
+  constexpr int CGN = CC / 4;
+  constexpr int TILE = CC * kPP;           // floats per ROI tile
+  constexpr int NPASS = (kPP * CGN + 31) / 32;      // 13 passes of (4 samples x 8 channel quads)
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int HW = g.H * g.W;
+  float* map = reinterpret_cast<float*>(smem_raw);
+  float* tiles = map + (size_t)(HW + 1) * CC;        // [kFwdWarps][TILE]
+
+  const int b = blockIdx.y, c0 = blockIdx.x * CC;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int cvalid = min(CC, g.C - c0);
+  const int beg = seg[b], end = seg[b + 1];
+
+  stage_map<CC>(map, bottom + (size_t)b * g.C * HW, c0, g.C, HW);
+  __syncthreads();
+
+  const float4* map4 = reinterpret_cast<const float4*>(map);
+  float* tile = tiles + (size_t)wid * TILE;
+  const int cg = lane & (CGN - 1), ps = lane >> 3;   // channel quad, sample slot of a pass
+  const int cb = cg * 4;
+  const uint32_t tile_bytes = (uint32_t)(cvalid * kPP * sizeof(float));
+
+  auto load_entries = [&](int r, uint4 (&e)[NPASS], int* n) {
+    const unsigned char* rec = table + (size_t)r * g.rec;
+    const uint4* ent = reinterpret_cast<const uint4*>(rec);
+#pragma unroll
+    for (int k = 0; k < NPASS; ++k) {
+      const int p = 4 * k + ps;
+      e[k] = (p < kPP) ? __ldg(ent + p) : make_uint4(0, 0, 0, 0);
+    }
+    *n = __ldg(reinterpret_cast<const int*>(rec + (size_t)kPP * 16 + 56));
+  };
+
+  uint4 cur[NPASS];
+  int ncur = 0;
+  int r = beg + wid;
+  if (r < end) load_entries(r, cur, &ncur);
+  for (; r < end; r += kFwdWarps) {
+    uint4 nxt[NPASS];
+    int nnxt = 0;
+    const bool more = r + kFwdWarps < end;
+    if (more) load_entries(r + kFwdWarps, nxt, &nnxt);       // in flight during this ROI's gathers
+    if (lane == 0) bulk_wait_read<0>();                      // my previous store has left the tile
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < NPASS; ++k) {
+      const int p = 4 * k + ps;
+      if (p < kPP) {
+        const float4 o = bilerp4(map4, cur[k], cg);
+        tile[(cb + 0) * kPP + p] = o.x;
+        tile[(cb + 1) * kPP + p] = o.y;
+        tile[(cb + 2) * kPP + p] = o.z;
+        tile[(cb + 3) * kPP + p] = o.w;
+      }
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      bulk_s2g(out + ((size_t)ncur * g.C + c0) * kPP, tile, tile_bytes);
+      bulk_commit();
+    }
+    if (more) {
+#pragma unroll
+      for (int k = 0; k < NPASS; ++k) cur[k] = nxt[k];
+      ncur = nnxt;
+    }
+  }
+  if (lane == 0) bulk_wait<0>();
 }
 
 // ------------------------------------------------------------------ backward
@@ -958,6 +1044,18 @@ extern "C" int l2s_roi_crop_fwd(const float* bottom, const float* rois, float* o
   SepRec* sep;
   rc = prepare(rois, g, pl.cc / 4, workspace, st, &seg, &table, &sep);
   if (rc) return rc;
+  // warp-per-ROI kernel: 7x7 crops of maps whose 32-channel slice + one tile per warp fit in shared memory
+  const size_t smem_warp = (size_t)(H * W + 1) * 32 * 4 + (size_t)kFwdWarps * 32 * kPP * 4 + 128;
+  const char* blk = getenv("L2S_CROP_FWD_BLOCK");          // diagnostics: force the block-synchronous kernel
+  if (!g.maxpool && pl.cc == 32 && smem_warp <= (size_t)max_smem_optin() - 1024 && !(blk && blk[0] == '1')) {
+    auto kern = roi_crop_fwd_warp_kernel;
+    L2S_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_warp));
+    dim3 grid((g.C + 31) / 32, g.B);
+    kern<<<grid, kFwdWarps * 32, smem_warp, st>>>(bottom, seg, table, out, g);
+    L2S_LAUNCH_OK("roi_crop_fwd_warp_kernel");
+    count_launch();
+    return L2S_OK;
+  }
   L2S_CROP_DISPATCH(launch_fwd, bottom, seg, table, out, argmax, g, pl.smem_fwd, st);
 }
 
