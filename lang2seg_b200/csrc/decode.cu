@@ -53,7 +53,8 @@ struct LinGeom {
   int lda, ldw, ldd;
   int ks;          // number of K splits (gridDim.y)
   int accumulate;  // D += result
-  int rows_pad;    // rows of A staged per CTA (32 or 64)
+  int rows_pad;    // rows of A staged per CTA, padded to a multiple of 16 (<= 64)
+  int rows_blk;    // rows of A per CTA (blockIdx.z selects the row block)
 };
 
 // NR rows of the staged A chunk against this warp's CPW weight rows; lane (l % NR) ends with row mg + l % NR
@@ -94,8 +95,9 @@ linear_small_kernel(const float* __restrict__ A, const float* __restrict__ W, co
   __shared__ int s_last;
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
   const int cb = blockIdx.x, s = blockIdx.y, mb = blockIdx.z;
-  const int m0 = mb * kLinMaxRows;
-  const int rows = min(g.rows_pad, g.M - m0);      // valid rows in this block
+  const int m0 = mb * g.rows_blk;
+  const int rows = min(g.rows_blk, g.M - m0);      // valid rows in this block
+  const int rp = min(g.rows_pad, (rows + 15) & ~15);   // rows this block stages and multiplies (the last block may be short)
   const int k0 = s * kLinKC;
   const int kc = min(kLinKC, g.K - k0);            // valid k in this chunk (multiple of 4)
 
@@ -118,7 +120,7 @@ linear_small_kernel(const float* __restrict__ A, const float* __restrict__ W, co
 
   // ---- stage the A chunk (zero fill outside M / K)
   {
-    const int nf4 = g.rows_pad * (kLinKC / 4);
+    const int nf4 = rp * (kLinKC / 4);
     float4* As4 = reinterpret_cast<float4*>(As);
 #pragma unroll 4
     for (int i = t; i < nf4; i += kLinThreads) {
@@ -145,8 +147,8 @@ linear_small_kernel(const float* __restrict__ A, const float* __restrict__ W, co
     }
   };
   int mg = 0;
-  for (; mg + 32 <= g.rows_pad; mg += 32) row_group<CPW, 32>(As4, w, mg, lane, n0, store);
-  if (mg < g.rows_pad) row_group<CPW, 16>(As4, w, mg, lane, n0, store);
+  for (; mg + 32 <= rp; mg += 32) row_group<CPW, 32>(As4, w, mg, lane, n0, store);
+  if (mg < rp) row_group<CPW, 16>(As4, w, mg, lane, n0, store);
   if (g.ks == 1) return;
 
   // ---- split-K: the last CTA of this (column block, row block) sums the partials in split order
@@ -162,7 +164,7 @@ linear_small_kernel(const float* __restrict__ A, const float* __restrict__ W, co
   __threadfence();
   const int nb0 = cb * (kLinThreads / 32) * CPW;
   const int ncols = min((kLinThreads / 32) * CPW, g.N - nb0);
-  const int mrows = min(kLinMaxRows, g.M - m0);
+  const int mrows = rows;
   for (int i = t; i < mrows * ncols; i += kLinThreads) {
     const int m = m0 + i / ncols, n = nb0 + i % ncols;
     float v = bias ? __ldg(bias + n) : 0.f;
@@ -207,11 +209,12 @@ int launch_linear_small(const float* A, int lda, const float* W, int ldw, const 
   g.M = M; g.N = N; g.K = K; g.lda = lda; g.ldw = ldw; g.ldd = ldd;
   g.ks = (K + kLinKC - 1) / kLinKC;
   g.accumulate = accumulate;
-  const int mblocks = (M + kLinMaxRows - 1) / kLinMaxRows;
-  {
-    const int mrows = M < kLinMaxRows ? M : kLinMaxRows;
-    g.rows_pad = (mrows + 15) & ~15;      // staged rows per CTA: 16..64 (two CTAs per SM fit up to 48)
-  }
+  // Row blocks of 32: at M = 48 (expressions per GPU) one 48-row CTA per SM leaves 8 warps per SM, too few to hide the
+  // smem / FFMA latencies of the inner loop; a 32-row and a 16-row CTA (64 + 32 KB of shared memory) co-reside and
+  // double the warps in flight for the same staging traffic.
+  g.rows_blk = M > 32 ? 32 : M;
+  const int mblocks = (M + g.rows_blk - 1) / g.rows_blk;
+  g.rows_pad = (g.rows_blk + 15) & ~15;   // staged rows per CTA: 16 or 32
   const int cpw = pick_cpw(N, g.ks, mblocks);
   const int cbs = (N + 8 * cpw - 1) / (8 * cpw);
   L2S_REQUIRE((size_t)cbs * mblocks * sizeof(unsigned int) <= kLinCounterBytes, L2S_ERR_SHAPE,
