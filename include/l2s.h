@@ -304,6 +304,11 @@ int l2s_bilstm_bwd(const float* dout, const float* dhidden, const float* G, cons
 
 /* Skinny exact-fp32 linear layer used inside the decode loop (nn.Linear on a batch of <= a few hundred
  * rows): D[M,N] (+)= A[M,K] . W[N,K]^T + bias[N].  K, lda, ldw multiples of 4; deterministic split-K. */
+/* out[c] = sum_r in[r*ld + c] (bias gradients of the projections: torch's dim-0 reduction of a tall matrix takes
+ * ~20 us per call, this two-stage fixed-order sum ~5 us).  workspace: l2s_colsum_workspace_bytes(R, C). */
+size_t l2s_colsum_workspace_bytes(int R, int C);
+int l2s_colsum(const float* in, int64_t ld, float* out, int R, int C, void* workspace, size_t workspace_bytes,
+               l2s_stream_t stream);
 size_t l2s_linear_small_workspace_bytes(int M, int N, int K);
 int l2s_linear_small(const float* A, const float* W, const float* bias, float* D, int M, int N, int K, int lda,
                      int ldw, int ldd, int accumulate, void* workspace, size_t workspace_bytes,

@@ -33,6 +33,8 @@ SIGNATURES = {
     "l2s_mask_head_fwd": (_i, [_vp] * 8 + [_i] * 4 + [_vp, _sz, _vp]),
     "l2s_mask_head_bwd": (_i, [_vp] * 9 + [_i] * 4 + [_vp, _sz, _vp]),
     "l2s_mask_head_bce_bwd": (_i, [_vp] * 12 + [_i] * 4 + [_vp, _sz, _vp]),
+    "l2s_colsum_workspace_bytes": (_sz, [_i, _i]),
+    "l2s_colsum": (_i, [_vp, _i64, _vp, _i, _i, _vp, _sz, _vp]),
     "l2s_nms_workspace_bytes": (_sz, [_i]),
     "l2s_nms": (_i, [_vp, _i, _f, _i, _vp, _vp, _vp, _sz, _vp]),
     "l2s_mask_crop_resize": (_i, [_vp, _vp, _i, _vp, _vp] + [_i] * 6 + [_vp]),

@@ -339,6 +339,25 @@ __global__ void colsum_kernel(const float* __restrict__ in, float* __restrict__ 
   out[c] = s;
 }
 
+// partial[chunk][c] = sum of rows [chunk*RPC, (chunk+1)*RPC) of in (R x C, row stride ld): thread = column, coalesced rows
+constexpr int kColsumRows = 128;
+__global__ void __launch_bounds__(128)
+colsum_partial_kernel(const float* __restrict__ in, int64_t ld, float* __restrict__ partial, int R, int C) {
+  const int c = blockIdx.x * 128 + threadIdx.x;
+  const int r0 = blockIdx.y * kColsumRows, r1 = min(R, r0 + kColsumRows);
+  if (c >= C) return;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int r = r0;
+  for (; r + 4 <= r1; r += 4) {
+    s0 += __ldg(in + (size_t)r * ld + c);
+    s1 += __ldg(in + (size_t)(r + 1) * ld + c);
+    s2 += __ldg(in + (size_t)(r + 2) * ld + c);
+    s3 += __ldg(in + (size_t)(r + 3) * ld + c);
+  }
+  for (; r < r1; ++r) s0 += __ldg(in + (size_t)r * ld + c);
+  partial[(size_t)blockIdx.y * C + c] = (s0 + s1) + (s2 + s3);
+}
+
 struct DecodeWs {
   char* lin;          // linear_small workspace (shared by every GEMM of the loop: they are stream ordered)
   size_t lin_bytes;
@@ -385,6 +404,32 @@ extern "C" int l2s_linear_small(const float* A, const float* W, const float* bia
   cudaStream_t st = (cudaStream_t)stream;
   L2S_CUDA_OK(cudaMemsetAsync(workspace, 0, kLinCounterBytes, st));
   return launch_linear_small(A, lda, W, ldw, bias, D, ldd, M, N, K, accumulate, workspace, workspace_bytes, st);
+}
+
+extern "C" size_t l2s_colsum_workspace_bytes(int R, int C) {
+  const size_t chunks = (size_t)((R > 0 ? R : 0) + kColsumRows - 1) / kColsumRows;
+  return chunks * (size_t)(C > 0 ? C : 0) * sizeof(float) + 256;
+}
+
+extern "C" int l2s_colsum(const float* in, int64_t ld, float* out, int R, int C, void* workspace, size_t workspace_bytes,
+                          l2s_stream_t stream) {
+  L2S_REQUIRE(R >= 0 && C > 0 && ld >= C, L2S_ERR_SHAPE, "colsum: bad shape R=%d C=%d ld=%lld", R, C, (long long)ld);
+  L2S_REQUIRE(out, L2S_ERR_ARG, "colsum: null output");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (R == 0) {
+    L2S_CUDA_OK(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)C, st));
+    return L2S_OK;
+  }
+  L2S_REQUIRE(in, L2S_ERR_ARG, "colsum: null input");
+  L2S_REQUIRE(workspace && workspace_bytes >= l2s_colsum_workspace_bytes(R, C), L2S_ERR_WORKSPACE, "colsum: workspace too small");
+  const int chunks = (R + kColsumRows - 1) / kColsumRows;
+  float* partial = reinterpret_cast<float*>(workspace);
+  colsum_partial_kernel<<<dim3((C + 127) / 128, chunks), 128, 0, st>>>(in, ld, partial, R, C);
+  L2S_LAUNCH_OK("colsum_partial_kernel");
+  colsum_kernel<<<(C + 127) / 128, 128, 0, st>>>(partial, out, chunks, C);
+  L2S_LAUNCH_OK("colsum_kernel");
+  count_launch(2);
+  return L2S_OK;
 }
 
 extern "C" size_t l2s_att2in2_decode_workspace_bytes(int T, int B, int A, int D, int Dh) {

@@ -260,6 +260,22 @@ def resize_masks_nearest(gt_masks, H, W):
     return out
 
 
+def colsum(x):
+    """Sum over every dimension but the last (bias gradients) of an fp32 CUDA tensor, fixed summation order.
+    Accepts a row-strided 2-D view (stride(1) == 1) without copying; anything else is made contiguous first."""
+    if x.dim() == 2 and x.stride(1) == 1 and x.dtype == torch.float32:
+        R, C, ld = x.shape[0], x.shape[1], x.stride(0)
+    else:
+        x = f32c(x)
+        C = x.shape[-1]
+        R, ld = x.numel() // C, C
+    out = torch.empty(C, device=x.device, dtype=torch.float32)
+    nbytes = _lib.size("l2s_colsum_workspace_bytes", R, C)
+    ws = _ws(nbytes, x.device)
+    call("l2s_colsum", ptr(x), ld, ptr(out), R, C, ptr(ws), nbytes, stream())
+    return out
+
+
 def nms_sorted(boxes_sorted, thresh, max_out=0):
     """gpu_nms (nms_cuda.c:17-67) on score-sorted boxes (N,5), scan included, on the device ->
     (keep (N,) int64: positions of the survivors in score order, valid up to num ; num (1,) int64)."""
@@ -472,8 +488,8 @@ class _Att2in2Decode(torch.autograd.Function):
         # weight gradients: one GEMM each over the stacked rows (h_{-1} = 0 contributes nothing)
         dw_cat = dcat_all[1:].reshape(-1, LC).t() @ h_all[:-1].reshape(-1, D)
         dw_a2c = da2c_all.reshape(-1, 2 * D).t() @ res_all.reshape(-1, D)
-        return (dcat_all[:, :, Dh:], datt, dp_att, dw_cat[:Dh], dcat_all[:, :, :Dh].sum((0, 1)), dw_cat[Dh:], dw_a2c,
-                da2c_all.sum((0, 1)), dalpha.view(aw_shape), de_all.sum().reshape(ab_shape))
+        return (dcat_all[:, :, Dh:], datt, dp_att, dw_cat[:Dh], colsum(dcat_all.view(T * B, LC)[:, :Dh]), dw_cat[Dh:], dw_a2c,
+                colsum(da2c_all), dalpha.view(aw_shape), de_all.sum().reshape(ab_shape))
 
 
 def att2in2_decode(i2h_all, att_feats, p_att, w_h2att, b_h2att, w_h2h, w_a2c, b_a2c, alpha_w, alpha_b):
@@ -504,7 +520,7 @@ class _LinearSmallFn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             dw = dy.t() @ x
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = dy.sum(0)
+            db = colsum(dy)
         return dx, dw, db
 
 
@@ -706,7 +722,7 @@ class _LinearTC(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             dw = gemm_bf16x3(dyh, dyl, xh, xl, N, K, M, a_mn=True, b_mn=True, split_k=0)  # dY^T [N,M] . X [M,K]; split chosen by the library
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = dy.sum(0)
+            db = colsum(dy)
         return dx, dw, db
 
 

@@ -249,3 +249,14 @@ def test_lang_encoder_masked_bilstm_vs_oracle(B, L, H):
     assert relerr(out, oo) < TOL and relerr(hid, ho) < TOL and relerr(emb, eo) < TOL
     for k, v in enc.named_parameters():
         assert relerr(v.grad, p[k].grad) < TOL, k
+
+
+@pytest.mark.parametrize("R,C", [(9408, 512), (528, 2000), (1, 7), (130, 129)])
+def test_colsum_vs_fp64(R, C):
+    import lang2seg_b200.functional as F
+    g = torch.Generator().manual_seed(R + C)
+    x = torch.randn(R, C + 5, generator=g).cuda()
+    ref = x.double().cpu()
+    assert relerr(F.colsum(x[:, :C]), ref[:, :C].sum(0)) < 1e-6          # row-strided view, no copy
+    assert relerr(F.colsum(x.reshape(R, 1, C + 5)), ref.sum(0)) < 1e-6   # any leading dimensions
+    assert torch.equal(F.colsum(x[:, :C]), F.colsum(x[:, :C]))           # fixed order
