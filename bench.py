@@ -72,7 +72,7 @@ TRAFFIC_KEY = {"dynfilter_fwd": "dynfilter_fwd", "roi_crop_fwd": "roi_crop_fwd",
 
 def make_inputs(wl, seed, device, pinned=False):
     """Seeded synthetic inputs of SURVEY 8d on the host; moved to `device` unless pinned host copies are wanted."""
-    from oracle import restate as R   # generators only (allowed: bench synthetic inputs share the oracle's helpers)
+    from lang2seg_b200 import synth as R      # seeded generators (plain torch; the B200 arm never imports oracle/)
     g = torch.Generator().manual_seed(seed)
     I, EPI, C, H, W, Rn, NFG, L, V = (wl[k] for k in ("I", "EPI", "C", "H", "W", "R", "NFG", "L", "V"))
     E = I * EPI
