@@ -85,3 +85,17 @@ def reference_roi_pool_cuda():
     lib.ROIPoolForwardLaucher.argtypes = [vp, f, i, i, i, i, i, i, vp, vp, vp, vp]
     lib.ROIPoolBackwardLaucher.argtypes = [vp, f, i, i, i, i, i, i, i, vp, vp, vp, vp]
     return lib
+
+
+REF_NMS_LIB = os.path.join(HERE, "_ref", "libnms_ref.so")
+
+
+def reference_nms_cuda():
+    """The reference's `_nms(boxes_num, boxes_dev, mask_dev, thresh)` launcher (nms/src/cuda/nms_kernel.cu:72-83,
+    default stream) or None when oracle/_ref/libnms_ref.so has not been built."""
+    if not os.path.exists(REF_NMS_LIB):
+        return None
+    lib = ctypes.CDLL(REF_NMS_LIB)
+    lib._nms.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_float]
+    lib._nms.restype = None
+    return lib

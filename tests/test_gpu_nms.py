@@ -57,3 +57,33 @@ def test_nms_max_out_and_empty():
     assert int(cnt) == 100 and np.array_equal(idx.cpu().numpy(), order[ref[:100]])
     keep, num = F.nms_sorted(torch.zeros(0, 5, device="cuda"), 0.7)
     assert int(num) == 0 and keep.numel() == 0
+
+
+def test_nms_vs_reference_cuda_kernel():
+    """Keep list against the REFERENCE's own bit-mask kernel (nms_kernel.cu, compiled for sm_100a by oracle/Makefile into
+    oracle/_ref) followed by the host scan of nms_cuda.c:44-56 restated in numpy."""
+    import lang2seg_b200.functional as F
+    from oracle import clib
+    lib = clib.reference_nms_cuda()
+    if lib is None:
+        pytest.skip("oracle/_ref/libnms_ref.so not built")
+    for n, thresh in ((777, 0.7), (4000, 0.5)):
+        rs = np.random.RandomState(n)
+        dets = _boxes(rs, n, clustered=True)
+        order = np.argsort(-dets[:, 4], kind="stable")
+        boxes = torch.from_numpy(dets[order]).cuda().contiguous()
+        cb = (n + 63) // 64
+        mask = torch.zeros(n, cb, dtype=torch.int64, device="cuda")
+        torch.cuda.synchronize()
+        lib._nms(n, boxes.data_ptr(), mask.data_ptr(), thresh)          # launches on the default stream
+        torch.cuda.synchronize()
+        m = mask.cpu().numpy().view(np.uint64)
+        remv = np.zeros(cb, np.uint64)
+        keep_ref = []
+        for i in range(n):                                               # nms_cuda.c:44-56
+            nb, ib = divmod(i, 64)
+            if not (int(remv[nb]) >> ib) & 1:
+                keep_ref.append(i)
+                remv[nb:] |= m[i, nb:]
+        keep, num = F.nms_sorted(boxes, thresh)
+        assert np.array_equal(keep[:int(num)].cpu().numpy(), np.asarray(keep_ref, dtype=np.int64))
