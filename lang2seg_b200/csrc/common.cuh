@@ -125,6 +125,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// try_wait with a suspend-time hint (ns): the waiting warp is parked by the hardware until the phase completes or the
+// hint expires, instead of burning issue slots in a tight retry loop next to the warps that do the work
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(2000u)
+        : "memory");
+  } while (!ok);
+}
+
 // ---- bulk async copies (TMA engine, 1-D) ----
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

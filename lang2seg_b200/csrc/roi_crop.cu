@@ -803,13 +803,16 @@ roi_crop_bwd_rows_kernel(const float* __restrict__ dout, const int* __restrict__
     const int row_stride = WP * kRowLd;
     int sidx = 0, lap = 0;
     for (int k = 0; k < nst; ++k) {
-      mbar_wait(&full_bar[sidx], lap & 1);
+      mbar_wait_parked(&full_bar[sidx], lap & 1);
       const int gc = min(kRowGroup, end - beg - k * kRowGroup);
-#pragma unroll 1
-      for (int q = 0; q < gc; ++q) {
+      // lane q < gc fetches this warp's hit word of ROI q of the stage; only the ROIs with work are visited
+      const unsigned mymask = (lane < gc) ? (unsigned)recs[sidx * kRowGroup + lane].wmask[wid] : 0u;
+      unsigned act = __ballot_sync(0xffffffffu, mymask != 0u);
+      while (act) {
+        const int q = __ffs(act) - 1;
+        act &= act - 1;
         const SepRec* rec = recs + sidx * kRowGroup + q;
-        unsigned hits = rec->wmask[wid];              // same word for every lane: all control flow below is uniform
-        if (hits == 0) continue;
+        unsigned hits = __shfl_sync(0xffffffffu, mymask, q);      // same word for every lane: uniform control flow below
         int xoff[7];
         float wa[7], wb[7];
         {
