@@ -508,7 +508,7 @@ def main():
     if rank == 0 and not args.no_components:
         comps = component_rooflines(wl, d, step, pk)
     cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:      # the CPU leg is timed at N = 1 only
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
         v, dt, e = cpu_sample(wl, repeats=max(1, int(12.0 / max(1.0, 0.7 * wl["EPI"]))))
