@@ -61,3 +61,16 @@ def test_cpu_tensors_are_rejected():
     import lang2seg_b200.functional as F
     with pytest.raises(AssertionError):
         F.roi_max_pool(torch.zeros(1, 4, 8, 8), torch.zeros(1, 5))
+
+
+def test_header_is_plain_c99(tmp_path):
+    """include/l2s.h is the C ABI: it must compile as C (no C++ or torch types in any signature)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "abi.c"
+    src.write_text('#include "l2s.h"\nint main(void) { return l2s_version() > 0 ? 0 : 1; }\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only",
+                        "-I", os.path.join(ROOT, "include"), str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
