@@ -35,13 +35,33 @@ METRIC = "expressions/sec fwd+bwd (dynfilter+ROIAlign+mask head+att2in2)"
 UNIT = "expressions/s"
 
 WORKLOADS = {
+    # BASELINE.json configs[0] / SURVEY 8d config 1 -- the reference's own CPU-runnable case, forward only
+    "cfg1": dict(name="cfg1: 1 image x 1 expression, C4 1024x32x32, 100 ROIs (mask head on all 100), L=10 (T=11), "
+                      "forward only",
+                 I=1, EPI=1, C=1024, H=32, W=32, R=100, NFG=100, L=10, V=1999,
+                 parts=("resp", "crop7", "mask", "caption"), fwd_only=True),
     # BASELINE.json configs[1] / SURVEY 8d config 2 -- the configuration the metric is quoted on (fits one GPU)
     "cfg2": dict(name="cfg2: 16 images x 3 expressions, C4 1024x32x32, 256 ROIs + 64 fg per expression, "
                       "L=10 (T=11), V=1999, 7x7 crop, response+mask+caption losses",
-                 I=16, EPI=3, C=1024, H=32, W=32, R=256, NFG=64, L=10, V=1999),
-    "cfg4": dict(name="cfg4 shard: 16 images x 1 expression, L=20 (T=21)", I=16, EPI=1, C=1024, H=32, W=32, R=256,
-                 NFG=64, L=20, V=1999),
-    "tiny": dict(name="tiny smoke workload", I=2, EPI=2, C=1024, H=32, W=32, R=16, NFG=4, L=10, V=1999),
+                 I=16, EPI=3, C=1024, H=32, W=32, R=256, NFG=64, L=10, V=1999,
+                 parts=("resp", "crop7", "mask", "caption")),
+    # configs[2]: 64 images over 8 GPUs = 8 images x 3 expressions per GPU; the 14x14-sample + 2x2-max crop
+    # (network_cycle_response.py:140-144) AND the default 7x7 crop both run on the gated map; mask head; no caption
+    "cfg3": dict(name="cfg3 (per-GPU shard of 64 images / 8): 8 images x 3 expressions, C4 1024x32x32, 256 ROIs, "
+                      "crop 14x14+2x2max and 7x7, response BCE, mask head 14x14 on 64 fg",
+                 I=8, EPI=3, C=1024, H=32, W=32, R=256, NFG=64, L=10, V=1999,
+                 parts=("resp", "crop_max", "crop7", "mask")),
+    # configs[3]: 128 image/expression pairs over 8 GPUs = 16 per GPU; dynamic filter + att2in2 only (L=20, T=21)
+    "cfg4": dict(name="cfg4 (per-GPU shard of 128 / 8): 16 images x 1 expression, C4 1024x32x32, spatial filters + "
+                      "att2in2 caption loss, L=20 (T=21), V=1999; no crop, no mask head",
+                 I=16, EPI=1, C=1024, H=32, W=32, R=0, NFG=0, L=20, V=1999, parts=("caption", "dY")),
+    # configs[4]: VGG16 variant -- conv5_3 512x37x62 (600x1000 image), 300 ROIs, crop with max_pool=True
+    # (network_vgg.py:137-141), response loss, no mask head, no caption; --batch sweeps I = E
+    "cfg5": dict(name="cfg5 (VGG16): I=E images x 1 expression, conv5_3 512x37x62, 300 ROIs, crop 14x14+2x2max, "
+                      "response BCE; no mask head",
+                 I=32, EPI=1, C=512, H=37, W=62, R=300, NFG=0, L=10, V=1999, parts=("resp", "crop_max")),
+    "tiny": dict(name="tiny smoke workload", I=2, EPI=2, C=1024, H=32, W=32, R=16, NFG=4, L=10, V=1999,
+                 parts=("resp", "crop7", "mask", "caption")),
 }
 
 
@@ -67,29 +87,35 @@ def ncu_traffic():
 
 # bench component -> kernel name in profiles/r01_traffic.json
 TRAFFIC_KEY = {"dynfilter_fwd": "dynfilter_fwd", "roi_crop_fwd": "roi_crop_fwd", "roi_crop_bwd": "roi_crop_bwd_rows",
-               "gemm_bf16x3_kernel<256,K,K> (mask head GEMM1 shape)": "EpiUp", "att_step_fwd": "att_step_fwd"}
+               "gemm_bf16x3_kernel<EpiUp> (mask head GEMM1, in-step epilogue)": "EpiUp", "att_step_fwd": "att_step_fwd"}
 
 
 def make_inputs(wl, seed, device, pinned=False):
-    """Seeded synthetic inputs of SURVEY 8d on the host; moved to `device` unless pinned host copies are wanted."""
+    """Seeded synthetic inputs of SURVEY 8d on the host (only those the workload's parts consume); moved to `device`
+    unless pinned host copies are wanted."""
     from lang2seg_b200 import synth as R      # seeded generators (plain torch; the B200 arm never imports oracle/)
     g = torch.Generator().manual_seed(seed)
     I, EPI, C, H, W, Rn, NFG, L, V = (wl[k] for k in ("I", "EPI", "C", "H", "W", "R", "NFG", "L", "V"))
+    parts = wl["parts"]
     E = I * EPI
     d = {}
     d["X"] = torch.relu(torch.randn(I, C, H, W, generator=g))
     labels, lens = R.synth_labels(g, E, L, V)
     d["labels"] = labels
     host_meta = {"lens": lens.clone(), "steps": int(lens.max()) + 1}    # host-side facts about the batch (never copied)
-    d["cap"], d["msk"] = R.caption_targets(labels, lens, L)
     d["e2i"] = torch.arange(I).repeat_interleave(EPI).int()
-    d["rois"] = torch.cat([R.synth_rois(g, Rn, H * 16, W * 16, e) for e in range(E)])
-    d["resp_tgt"] = (torch.rand(E, H, W, generator=g) < 0.3).float()
-    d["fc7"] = torch.relu(torch.randn(E * NFG, 2048, 7, 7, generator=g))
-    d["mlab"] = torch.randint(1, 81, (E * NFG,), generator=g)
-    d["mtgt"] = (torch.rand(E * NFG, 14, 14, generator=g) < 0.5).float()
-    d["fc"] = torch.randn(E, 4096, generator=g)
-    d["att"] = torch.relu(torch.randn(E, 14, 14, 4096, generator=g))
+    if "resp" in parts:
+        d["resp_tgt"] = (torch.rand(E, H, W, generator=g) < 0.3).float()
+    if "crop7" in parts or "crop_max" in parts:
+        d["rois"] = torch.cat([R.synth_rois(g, Rn, H * 16, W * 16, e) for e in range(E)])
+    if "mask" in parts:
+        d["fc7"] = torch.relu(torch.randn(E * NFG, 2048, 7, 7, generator=g))
+        d["mlab"] = torch.randint(1, 81, (E * NFG,), generator=g)
+        d["mtgt"] = (torch.rand(E * NFG, 14, 14, generator=g) < 0.5).float()
+    if "caption" in parts:
+        d["cap"], d["msk"] = R.caption_targets(labels, lens, L)
+        d["fc"] = torch.randn(E, 4096, generator=g)
+        d["att"] = torch.relu(torch.randn(E, 14, 14, 4096, generator=g))
     if pinned:
         out = {k: v.pin_memory() for k, v in d.items()}
     else:
@@ -140,37 +166,88 @@ class ClockSampler:
 # the B200 arm
 # --------------------------------------------------------------------------------------------------
 class HotPathStep:
+    """The chained hot-path step of one workload: which of {response BCE, 7x7 crop, 14x14+max crop, mask head,
+    att2in2} run is the workload's `parts`."""
+
     def __init__(self, wl, device, world):
         from lang2seg_b200.nets.network import HotPathNet
         from lang2seg_b200.parallel import GradientAllReducer
         torch.manual_seed(1234)
         self.wl, self.device = wl, device
-        self.net = HotPathNet(dict(seq_length=wl["L"], vocab_size=wl["V"])).to(device).eval()   # eval: dropout off (D8)
+        self.parts = wl["parts"]
+        self.fwd_only = bool(wl.get("fwd_only"))
+        self.net = HotPathNet(dict(seq_length=wl["L"], vocab_size=wl["V"], C4_feat_dim=wl["C"])).to(device).eval()   # eval: dropout off (D8)
         self.params = [p for p in self.net.parameters() if p.requires_grad]
         self.opt = torch.optim.SGD(self.params, lr=1e-5, momentum=0.9, fused=True)
         self.reducer = GradientAllReducer(self.net.gradient_groups()) if world > 1 else None
         E = wl["I"] * wl["EPI"]
         g = torch.Generator().manual_seed(99)
-        # upstream gradient of pool5: stands in for res5's backward (device resident, not an input)
-        self.g_pool = (torch.randn(E * wl["R"], wl["C"], 7, 7, generator=g) * 1e-4).to(device)
+        # upstream gradients of pool5 (stand in for res5's backward) and, where nothing else consumes the gated map,
+        # of the gated map itself (stands in for layer4 <- caption features): device resident, not inputs
+        self.g_pool = self.g_pool_max = self.g_Y = None
+        if not self.fwd_only:
+            if "crop7" in self.parts:
+                self.g_pool = (torch.randn(E * wl["R"], wl["C"], 7, 7, generator=g) * 1e-4).to(device)
+            if "crop_max" in self.parts:
+                self.g_pool_max = (torch.randn(E * wl["R"], wl["C"], 7, 7, generator=g) * 1e-4).to(device)
+            if "dY" in self.parts:
+                self.g_Y = (torch.randn(E, wl["C"], wl["H"], wl["W"], generator=g) * 1e-4).to(device)
         self.one = torch.ones((), device=device)
+
+    def forward_only(self, d, meta):
+        """cfg-1: the inference-side forward (network_cycle_response.py:576-596 without res5) -> a scalar checksum"""
+        net = self.net
+        with torch.no_grad():
+            gated = net._dynamic_filter(d["X"], d["labels"], expr2img=d["e2i"], resp_target=d.get("resp_tgt"),
+                                        lengths=meta.get("lens"))
+            acc = net._predictions["response"].sum()
+            if "crop7" in self.parts:
+                acc = acc + net._crop_pool_layer(gated, d["rois"], max_pool=False).sum()
+            if "crop_max" in self.parts:
+                acc = acc + net._crop_pool_layer(gated, d["rois"], max_pool=True).sum()
+            if "mask" in self.parts:
+                acc = acc + net._mask_prediction(d["fc7"]).sum()
+            if "caption" in self.parts:
+                acc = acc + net.caption_model(d["fc"], d["att"], d["cap"], steps=meta.get("steps")).sum()
+        net._predictions.clear()
+        net._losses.clear()
+        return acc
 
     def fwd_bwd(self, d, meta=None):
         """forward + backward of the chained hot path; leaves the gradients in p.grad"""
-        net = self.net
+        net, parts = self.net, self.parts
         meta = meta if meta is not None else d.get("_meta", {})
+        if self.fwd_only:
+            return self.forward_only(d, meta)
         self.opt.zero_grad(set_to_none=True)
         X = d["X"].requires_grad_(True)
-        fc7 = d["fc7"].requires_grad_(True)
-        att = d["att"].requires_grad_(True)
-        gated = net._dynamic_filter(X, d["labels"], expr2img=d["e2i"], resp_target=d["resp_tgt"],
+        gated = net._dynamic_filter(X, d["labels"], expr2img=d["e2i"], resp_target=d.get("resp_tgt"),
                                     lengths=meta.get("lens"))
-        pool5 = net._crop_pool_layer(gated, d["rois"], max_pool=False)
-        net._mask_prediction(fc7, d["mlab"], d["mtgt"])       # prediction + mask loss as one node (fused backward)
-        loss = (net._losses["loss_response_per_expr"].sum() + net._mask_loss(d["mlab"], d["mtgt"])
-                + net._cap_loss_weight * net._caption_loss(d["fc"], att, d["cap"], d["msk"], steps=meta.get("steps")))
-        torch.autograd.backward([loss, pool5], [self.one, self.g_pool])
-        X.grad = fc7.grad = att.grad = None
+        loss = 0
+        outs, grads = [], []
+        if "resp" in parts:
+            loss = loss + net._losses["loss_response_per_expr"].sum()
+        if "crop_max" in parts:
+            outs.append(net._crop_pool_layer(gated, d["rois"], max_pool=True)); grads.append(self.g_pool_max)
+        if "crop7" in parts:
+            outs.append(net._crop_pool_layer(gated, d["rois"], max_pool=False)); grads.append(self.g_pool)
+        if "dY" in parts:
+            outs.append(gated); grads.append(self.g_Y)
+        fc7 = att = None
+        if "mask" in parts:
+            fc7 = d["fc7"].requires_grad_(True)
+            net._mask_prediction(fc7, d["mlab"], d["mtgt"])   # prediction + mask loss as one node (fused backward)
+            loss = loss + net._mask_loss(d["mlab"], d["mtgt"])
+        if "caption" in parts:
+            att = d["att"].requires_grad_(True)
+            loss = loss + net._cap_loss_weight * net._caption_loss(d["fc"], att, d["cap"], d["msk"],
+                                                                   steps=meta.get("steps"))
+        torch.autograd.backward([loss] + outs, [self.one] + grads)
+        X.grad = None
+        if fc7 is not None:
+            fc7.grad = None
+        if att is not None:
+            att.grad = None
         # drop the references into this step's autograd graph (the reference keeps them in _predictions/_losses for its
         # tensorboard summaries): a graph kept alive across steps pins AccumulateGrad nodes to the stream they were
         # created on, which breaks CUDA-graph capture on another stream
@@ -180,6 +257,8 @@ class HotPathStep:
 
     def update(self):
         """gradient all-reduce of the three parameter groups (N > 1) and the SGD update"""
+        if self.fwd_only:
+            return
         if self.reducer is not None:
             self.reducer.all_reduce()
         self.opt.step()
@@ -230,80 +309,90 @@ def component_rooflines(wl, d, step, pk):
     from lang2seg_b200 import _lib
     from lang2seg_b200._lib import call, ptr, stream
     I, EPI, C, H, W, Rn, NFG = (wl[k] for k in ("I", "EPI", "C", "H", "W", "R", "NFG"))
+    parts = wl["parts"]
     E, HW = I * EPI, H * W
     dev = d["X"].device
     out = []
     filt = torch.tanh(torch.randn(E, 7, C, device=dev) * 0.1)
     fuse = torch.tanh(torch.randn(E, 7, device=dev))
+    tgt = d.get("resp_tgt")
     # --- dynamic filter
-    resp, Y, rl = F.dynamic_filter(d["X"], filt, fuse, d["e2i"], "sigmoid", d["resp_tgt"])
+    resp, Y, rl = F.dynamic_filter(d["X"], filt, fuse, d["e2i"], "sigmoid", tgt)
     rk = torch.empty(E, 7, H, W, device=dev)
     lossb = torch.empty(E, device=dev)
     t = ev_time(lambda: call("l2s_dynfilter_fwd", ptr(d["X"]), ptr(filt), ptr(fuse), ptr(d["e2i"]), ptr(resp), ptr(rk),
-                             ptr(Y), ptr(d["resp_tgt"]), ptr(lossb), I, E, C, H, W, 0, stream()))
+                             ptr(Y), ptr(tgt), ptr(lossb if tgt is not None else None), I, E, C, H, W, 0, stream()))
     out.append(dict(kernel="dynfilter_fwd", ms=t, bound="hbm", work=4.0 * C * HW * (I + E)))
-    dY = torch.randn_like(Y) * 1e-3
-    dX, dfilt, dfuse = torch.empty_like(d["X"]), torch.empty_like(filt), torch.empty_like(fuse)
-    gs = torch.ones(E, device=dev)
-    nb = _lib.size("l2s_dynfilter_bwd_workspace_bytes", I, E, C, H, W)
-    ws = torch.empty(nb, dtype=torch.uint8, device=dev)
-    t = ev_time(lambda: call("l2s_dynfilter_bwd", ptr(d["X"]), ptr(filt), ptr(fuse), ptr(d["e2i"]), ptr(resp), ptr(rk),
-                             ptr(dY), None, ptr(d["resp_tgt"]), ptr(gs), ptr(dX), ptr(dfilt), ptr(dfuse), I, E, C, H, W,
-                             0, ptr(ws), nb, stream()))
-    out.append(dict(kernel="dynfilter_bwd", ms=t, bound="hbm", work=4.0 * C * HW * (E + 2 * I)))
-    del dY, dX
-    # --- ROI crop
+    if not step.fwd_only:
+        dY = torch.randn_like(Y) * 1e-3
+        dX, dfilt, dfuse = torch.empty_like(d["X"]), torch.empty_like(filt), torch.empty_like(fuse)
+        gs = torch.ones(E, device=dev)
+        nb = _lib.size("l2s_dynfilter_bwd_workspace_bytes", I, E, C, H, W)
+        ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+        t = ev_time(lambda: call("l2s_dynfilter_bwd", ptr(d["X"]), ptr(filt), ptr(fuse), ptr(d["e2i"]), ptr(resp), ptr(rk),
+                                 ptr(dY), None, ptr(tgt), ptr(gs if tgt is not None else None), ptr(dX), ptr(dfilt),
+                                 ptr(dfuse), I, E, C, H, W, 0, ptr(ws), nb, stream()))
+        out.append(dict(kernel="dynfilter_bwd", ms=t, bound="hbm", work=4.0 * C * HW * (E + 2 * I)))
+        del dY, dX
+    # --- ROI crop (7x7 and / or 14x14 samples + 2x2 max): 4*C*(49R+HW) B per expression and direction (+1 B/elt argmax)
     N = E * Rn
-    pool = torch.empty(N, C, 7, 7, device=dev)
-    nb2 = _lib.size("l2s_roi_crop_workspace_bytes", E, N, 0)
-    ws2 = torch.empty(nb2, dtype=torch.uint8, device=dev)
-    t = ev_time(lambda: call("l2s_roi_crop_fwd", ptr(Y), ptr(d["rois"]), ptr(pool), None, E, C, H, W, N, 7, 0, 0.0, 0.0,
-                             ptr(ws2), nb2, stream()))
-    out.append(dict(kernel="roi_crop_fwd", ms=t, bound="hbm", work=4.0 * C * (49 * Rn + HW) * E))
-    dYb = torch.empty_like(Y)
-    t = ev_time(lambda: call("l2s_roi_crop_bwd", ptr(step.g_pool), ptr(d["rois"]), None, ptr(dYb), E, C, H, W, N, 7, 0,
-                             0.0, 0.0, ptr(ws2), nb2, stream()))
-    out.append(dict(kernel="roi_crop_bwd", ms=t, bound="hbm", work=4.0 * C * (49 * Rn + HW) * E))
-    t = ev_time(lambda: call("l2s_roi_crop_bwd", ptr(step.g_pool), ptr(d["rois"]), None, ptr(dYb), E, C, H, W, N, 7, 4,
-                             0.0, 0.0, ptr(ws2), nb2, stream()))
-    out.append(dict(kernel="roi_crop_bwd (sample-per-lane variant, not used by the step)", ms=t, bound="hbm",
-                    work=4.0 * C * (49 * Rn + HW) * E))
-    del pool, dYb
+    for part, flags, tag in (("crop7", 0, "roi_crop"), ("crop_max", 1, "roi_crop_max")):
+        if part not in parts:
+            continue
+        pool = torch.empty(N, C, 7, 7, device=dev)
+        arg = torch.empty(N, C, 7, 7, device=dev, dtype=torch.uint8) if flags else None
+        nb2 = _lib.size("l2s_roi_crop_workspace_bytes", E, N, flags)
+        ws2 = torch.empty(nb2, dtype=torch.uint8, device=dev)
+        work = (4.0 + (1.0 if flags else 0.0)) * C * 49 * Rn * E + 4.0 * C * HW * E
+        t = ev_time(lambda: call("l2s_roi_crop_fwd", ptr(Y), ptr(d["rois"]), ptr(pool), ptr(arg), E, C, H, W, N, 7, flags,
+                                 0.0, 0.0, ptr(ws2), nb2, stream()))
+        out.append(dict(kernel=tag + "_fwd", ms=t, bound="hbm", work=work))
+        if not step.fwd_only:
+            gp = step.g_pool_max if flags else step.g_pool
+            dYb = torch.empty_like(Y)
+            t = ev_time(lambda: call("l2s_roi_crop_bwd", ptr(gp), ptr(d["rois"]), ptr(arg), ptr(dYb), E, C, H, W, N, 7,
+                                     flags, 0.0, 0.0, ptr(ws2), nb2, stream()))
+            out.append(dict(kernel=tag + "_bwd", ms=t, bound="hbm", work=work))
+            del dYb
+        del pool, arg
     # --- mask head (tensor bound): fwd 2*n*49*2048*1024 + 2*n*196*256*81 ; bwd = 2x
-    n = E * NFG
-    net = step.net
-    with torch.no_grad():
-        t = ev_time(lambda: F.mask_head(d["fc7"], net.mask_up_sampling.weight, net.mask_up_sampling.bias,
-                                        net.mask_pred_net.weight, net.mask_pred_net.bias), iters=3, warm=1)
-    flops_f = 2.0 * n * 49 * 2048 * 1024 + 2.0 * n * 196 * 256 * 81
-    out.append(dict(kernel="mask_head_fwd (2 GEMM + repack)", ms=t, bound="tensor", work=flops_f))
-    fc7 = d["fc7"].detach().requires_grad_(True)
-    s, p = F.mask_head(fc7, net.mask_up_sampling.weight, net.mask_up_sampling.bias, net.mask_pred_net.weight,
-                       net.mask_pred_net.bias)
-    gsc = torch.randn_like(s) * 1e-4
-    t = ev_time(lambda: torch.autograd.grad(s, [fc7, net.mask_up_sampling.weight, net.mask_pred_net.weight], gsc,
-                                            retain_graph=True), iters=3, warm=1)
-    out.append(dict(kernel="mask_head_bwd (4 GEMM + repack)", ms=t, bound="tensor", work=2 * flops_f))
-    del s, p, gsc
-    # --- the dominant GEMM alone: GEMM1 of the mask head  [49n x 2048] x [1024 x 2048]^T
-    M, Nn, K = n * 49, 1024, 2048
-    a_hi = torch.randn(M, K, device=dev).bfloat16(); a_lo = (torch.randn(M, K, device=dev) * 1e-3).bfloat16()
-    b_hi = torch.randn(Nn, K, device=dev).bfloat16(); b_lo = (torch.randn(Nn, K, device=dev) * 1e-3).bfloat16()
-    D = torch.empty(M, Nn, device=dev)
-    t = ev_time(lambda: F.gemm_bf16x3(a_hi, a_lo, b_hi, b_lo, M, Nn, K, out=D), iters=5, warm=2)
-    out.append(dict(kernel="gemm_bf16x3_kernel<256,K,K> (mask head GEMM1 shape)", ms=t, bound="tensor",
-                    work=2.0 * M * Nn * K))
-    del a_hi, a_lo, b_hi, b_lo, D
-    # --- attention step (L2/HBM bound): one step fwd + bwd
-    A, Dd = 196, 512
-    att_h = torch.randn(E, Dd, device=dev)
-    feats = torch.randn(E, A, Dd, device=dev)
-    p_att = torch.randn(E, A, Dd, device=dev)
-    aw, ab = torch.randn(Dd, device=dev) * 0.04, torch.zeros(1, device=dev)
-    wgt, res = torch.empty(E, A, device=dev), torch.empty(E, Dd, device=dev)
-    t = ev_time(lambda: call("l2s_att_step_fwd", ptr(att_h), ptr(feats), ptr(p_att), ptr(aw), ptr(ab), ptr(wgt), ptr(res),
-                             E, A, Dd, Dd, stream()), iters=20)
-    out.append(dict(kernel="att_step_fwd", ms=t, bound="hbm", work=2.0 * A * Dd * 4 * E))
+    if "mask" in parts:
+        n = E * NFG
+        net = step.net
+        with torch.no_grad():
+            t = ev_time(lambda: F.mask_head(d["fc7"], net.mask_up_sampling.weight, net.mask_up_sampling.bias,
+                                            net.mask_pred_net.weight, net.mask_pred_net.bias), iters=3, warm=1)
+        flops_f = 2.0 * n * 49 * 2048 * 1024 + 2.0 * n * 196 * 256 * 81
+        out.append(dict(kernel="mask_head_fwd (2 GEMM + repack)", ms=t, bound="tensor", work=flops_f))
+        if not step.fwd_only:
+            fc7 = d["fc7"].detach().requires_grad_(True)
+            sc, p, ml = F.mask_head_with_loss(fc7, net.mask_up_sampling.weight, net.mask_up_sampling.bias,
+                                              net.mask_pred_net.weight, net.mask_pred_net.bias, d["mlab"], d["mtgt"])
+            t = ev_time(lambda: torch.autograd.grad(ml, [fc7, net.mask_up_sampling.weight, net.mask_pred_net.weight],
+                                                    retain_graph=True), iters=3, warm=1)
+            out.append(dict(kernel="mask_head_bwd (in-step: fused loss backward, dF + dWd GEMMs)", ms=t, bound="tensor",
+                            work=2 * flops_f))
+            del sc, p, ml
+        # --- the dominant GEMM as the step runs it: GEMM1 of the mask head [49n x 2048] x [1024 x 2048]^T with the
+        # bias + ReLU -> bf16-plane epilogue (EpiUp), timed through l2s_mask_head_gemm1 on the step's own operands
+        M, Nn, K = n * 49, 1024, 2048
+        g1 = F.mask_head_stage_runner(d["fc7"], net.mask_up_sampling.weight, net.mask_up_sampling.bias,
+                                      net.mask_pred_net.weight, net.mask_pred_net.bias, stages=2)
+        t = ev_time(g1, iters=5, warm=2)
+        del g1
+        out.append(dict(kernel="gemm_bf16x3_kernel<EpiUp> (mask head GEMM1, in-step epilogue)", ms=t, bound="tensor",
+                        work=2.0 * M * Nn * K))
+    # --- attention step (L2/HBM bound): one step fwd
+    if "caption" in parts:
+        A, Dd = 196, 512
+        att_h = torch.randn(E, Dd, device=dev)
+        feats = torch.randn(E, A, Dd, device=dev)
+        p_att = torch.randn(E, A, Dd, device=dev)
+        aw, ab = torch.randn(Dd, device=dev) * 0.04, torch.zeros(1, device=dev)
+        wgt, res = torch.empty(E, A, device=dev), torch.empty(E, Dd, device=dev)
+        t = ev_time(lambda: call("l2s_att_step_fwd", ptr(att_h), ptr(feats), ptr(p_att), ptr(aw), ptr(ab), ptr(wgt), ptr(res),
+                                 E, A, Dd, Dd, stream()), iters=20)
+        out.append(dict(kernel="att_step_fwd", ms=t, bound="hbm", work=2.0 * A * Dd * 4 * E))
     traffic = ncu_traffic() if wl is WORKLOADS["cfg2"] else {}
     for o in out:
         o["traffic"] = traffic.get(TRAFFIC_KEY.get(o["kernel"], ""))
@@ -320,12 +409,14 @@ def component_rooflines(wl, d, step, pk):
 
 def cpu_sample(wl, repeats=1, threads=None):
     """The oracle's torch-CPU port of the reference modules on ONE image and its expressions (the reference's
-    native batching), fwd+bwd, timed on the host cores."""
+    native batching), the workload's parts, fwd+bwd (fwd only for cfg-1), timed on the host
+    cores."""
     from oracle import restate as R
-    from lang2seg_b200.layers.lang_encoder import RNNEncoder    # pure torch (cuDNN/CPU LSTM), as the reference's
+    from lang2seg_b200.layers.lang_encoder import RNNEncoder    # pure torch (CPU LSTM), as the reference's
     if threads:
         torch.set_num_threads(threads)
     w1 = dict(wl, I=1)
+    parts, fwd_only = wl["parts"], bool(wl.get("fwd_only"))
     d = make_inputs(w1, 4321, "cpu")
     E, C, V, L = w1["EPI"], w1["C"], w1["V"], w1["L"]
     torch.manual_seed(7)
@@ -342,23 +433,36 @@ def cpu_sample(wl, repeats=1, threads=None):
           "core.attention.h2att.weight": P(D, D), "core.attention.h2att.bias": P(D),
           "core.attention.alpha_net.weight": P(1, D), "core.attention.alpha_net.bias": P(1)}
     g_pool = torch.randn(E * w1["R"], C, 7, 7) * 1e-4
+    g_Y = torch.randn(E, C, w1["H"], w1["W"]) * 1e-4
     params = list(enc.parameters()) + dyn_w + dyn_b + [rw, rb, up_w, up_b, pw, pb] + list(cp.values())
 
     def one():
         for p in params:
             p.grad = None
-        X = d["X"].clone().requires_grad_(True)
-        fc7 = d["fc7"].clone().requires_grad_(True)
-        att = d["att"].clone().requires_grad_(True)
-        _, hidden, _ = enc(d["labels"])
-        filt, fuse = R.filter_generator(hidden, dyn_w, dyn_b, rw, rb)
-        r, Y = R.dynamic_filter(X, filt, fuse, d["e2i"].tolist())
-        rl = R.response_loss(r, d["resp_tgt"]).sum()
-        pool5 = R.crop_pool(Y, d["rois"])
-        s, _ = R.mask_head(fc7, up_w, up_b, pw, pb)
-        ml = R.mask_loss(s, d["mlab"], d["mtgt"])
-        cl = R.caption_loss(d["fc"], att, d["cap"], d["msk"], cp)
-        torch.autograd.backward([rl + ml + cl, pool5], [torch.ones(()), g_pool])
+        with torch.set_grad_enabled(not fwd_only):
+            X = d["X"].clone().requires_grad_(not fwd_only)
+            _, hidden, _ = enc(d["labels"])
+            filt, fuse = R.filter_generator(hidden, dyn_w, dyn_b, rw, rb)
+            r, Y = R.dynamic_filter(X, filt, fuse, d["e2i"].tolist())
+            loss = torch.zeros(())
+            outs, grads = [], []
+            if "resp" in parts:
+                loss = loss + R.response_loss(r, d["resp_tgt"]).sum()
+            if "crop_max" in parts:
+                outs.append(R.crop_pool(Y, d["rois"], max_pool=True)); grads.append(g_pool)
+            if "crop7" in parts:
+                outs.append(R.crop_pool(Y, d["rois"])); grads.append(g_pool)
+            if "dY" in parts:
+                outs.append(Y); grads.append(g_Y)
+            if "mask" in parts:
+                fc7 = d["fc7"].clone().requires_grad_(not fwd_only)
+                s, _ = R.mask_head(fc7, up_w, up_b, pw, pb)
+                loss = loss + R.mask_loss(s, d["mlab"], d["mtgt"])
+            if "caption" in parts:
+                att = d["att"].clone().requires_grad_(not fwd_only)
+                loss = loss + R.caption_loss(d["fc"], att, d["cap"], d["msk"], cp)
+            if not fwd_only:
+                torch.autograd.backward([loss] + outs, [torch.ones(())] + grads)
 
     one()   # warm-up
     t0 = time.perf_counter()
@@ -403,11 +507,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="images per GPU (overrides the workload's I; cfg5 sweeps 8..256 total)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-components", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a captured CUDA graph")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
+    if args.batch > 0:
+        wl = dict(wl, I=args.batch, name=wl["name"] + " [--batch %d images per GPU]" % args.batch)
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
     if args.impl == "reference":
@@ -518,9 +625,10 @@ def main():
     if rank == 0:
         roof = None
         if comps:
+            gemms = [c for c in comps if c["kernel"].startswith("gemm_")]
             dom = max((c for c in comps if not c["kernel"].startswith("gemm_")), key=lambda c: c["ms"])
-            if dom["bound"] == "tensor":
-                dom = next(c for c in comps if c["kernel"].startswith("gemm_"))
+            if dom["bound"] == "tensor" and gemms:
+                dom = gemms[0]
             roof = {"kernel": dom["kernel"], "bound": dom["bound"], "achieved": dom["achieved"], "peak": dom["peak"],
                     "unit": dom["unit"], "frac": dom["frac"], "traffic": dom.get("traffic"), "peak_source": pk["source"],
                     "ms_per_launch": dom["ms"]}
@@ -531,12 +639,18 @@ def main():
                 roof["frac_of_fp32_exact_ceiling"] = 3.0 * dom["frac"]
                 roof["traffic_note"] = ("DRAM bytes per launch of the in-step GEMM of this shape (EpiUp: bf16 plane "
                                         "output) from the ncu --set full capture, profiles/r01_traffic.json")
+        part_names = {"resp": "response BCE", "crop7": "7x7 crop", "crop_max": "14x14+2x2max crop", "mask": "mask head",
+                      "caption": "att2in2", "dY": "synthetic upstream gradient on the gated map"}
+        includes = "lang encoder, filter generator, dynamic filter, " + ", ".join(part_names[p] for p in wl["parts"]) + \
+                   (" -- forward only" if wl.get("fwd_only") else " -- fwd+bwd, grad all-reduce, SGD")
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
                 "config": {"workload": wl["name"], "per_gpu_expressions": E, "parallelism": "dp%d" % world,
-                           "l2": "inputs larger than L2 (>= 1.2 GB streamed per step); no flush needed",
-                           "includes": "lang encoder, filter generator, 4 hot components fwd+bwd, grad all-reduce, SGD",
+                           "l2": "working set per step (feature maps, ROI crops, res5 features) far larger than the 126 MB L2; no flush needed"
+                           if "caption" not in wl["parts"] or wl["I"] * wl["EPI"] >= 32 else
+                           "inputs + activations per step exceed the 126 MB L2 (att/fc features alone: %d MB)" % (wl["I"] * wl["EPI"] * 196 * 4096 * 4 // 2**20),
+                           "includes": includes,
                            "launch": ("one CUDA graph replay per step" + ("" if world == 1 else " (fwd+bwd) + eager all-reduce/SGD"))
                            if graphed else "eager launches"},
                 "clocks": clocks, "gpu_launches": launches,

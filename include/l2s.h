@@ -164,6 +164,13 @@ size_t l2s_mask_head_workspace_bytes(int n, int Cin, int Cmid, int ncls);
 int l2s_mask_head_fwd(const float* x, const float* up_w, const float* up_b, const float* pred_w,
                       const float* pred_b, float* score, float* prob, void* saved, int n, int Cin,
                       int Cmid, int ncls, void* workspace, size_t workspace_bytes, l2s_stream_t stream);
+/* The forward by stage: stages is a subset of 1 (operand repacks -> bf16 planes) | 2 (deconv GEMM + bias + ReLU ->
+ * U planes in `saved`) | 4 (1x1 GEMM + bias -> score/prob).  l2s_mask_head_fwd == stages 7; a single stage may be
+ * re-run on the buffers a full call left behind (profiling / bench.py's in-step roofline kernel). */
+int l2s_mask_head_fwd_stages(const float* x, const float* up_w, const float* up_b, const float* pred_w,
+                             const float* pred_b, float* score, float* prob, void* saved, int n, int Cin,
+                             int Cmid, int ncls, void* workspace, size_t workspace_bytes, int stages,
+                             l2s_stream_t stream);
 int l2s_mask_head_bwd(const float* dscore, const float* up_w, const float* pred_w, const void* saved,
                       float* dx, float* d_up_w, float* d_up_b, float* d_pred_w, float* d_pred_b, int n,
                       int Cin, int Cmid, int ncls, void* workspace, size_t workspace_bytes,

@@ -31,6 +31,7 @@ SIGNATURES = {
     "l2s_mask_head_saved_bytes": (_sz, [_i] * 4),
     "l2s_mask_head_workspace_bytes": (_sz, [_i] * 4),
     "l2s_mask_head_fwd": (_i, [_vp] * 8 + [_i] * 4 + [_vp, _sz, _vp]),
+    "l2s_mask_head_fwd_stages": (_i, [_vp] * 8 + [_i] * 4 + [_vp, _sz, _i, _vp]),
     "l2s_mask_head_bwd": (_i, [_vp] * 9 + [_i] * 4 + [_vp, _sz, _vp]),
     "l2s_mask_head_bce_bwd": (_i, [_vp] * 12 + [_i] * 4 + [_vp, _sz, _vp]),
     "l2s_colsum_workspace_bytes": (_sz, [_i, _i]),

@@ -755,9 +755,13 @@ Work work_layout(void* base, int n, int Cin, int Cmid, int ncls) {
 }
 }  // namespace
 
-extern "C" int l2s_mask_head_fwd(const float* x, const float* up_w, const float* up_b, const float* pred_w,
-                                 const float* pred_b, float* score, float* prob, void* saved, int n, int Cin, int Cmid,
-                                 int ncls, void* workspace, size_t workspace_bytes, l2s_stream_t stream) {
+// stages: 1 = operand repacks (x and the two weights -> bf16 planes), 2 = GEMM1 (+bias, ReLU -> U planes),
+// 4 = GEMM2 (+bias -> score / prob).  The forward is all three; a single stage can be re-run on the buffers a full
+// call left behind (bench.py times the in-step GEMM1 that way).
+extern "C" int l2s_mask_head_fwd_stages(const float* x, const float* up_w, const float* up_b, const float* pred_w,
+                                        const float* pred_b, float* score, float* prob, void* saved, int n, int Cin,
+                                        int Cmid, int ncls, void* workspace, size_t workspace_bytes, int stages,
+                                        l2s_stream_t stream) {
   int rc = check_head(n, Cin, Cmid, ncls);
   if (rc) return rc;
   if (n == 0) return L2S_OK;
@@ -765,25 +769,41 @@ extern "C" int l2s_mask_head_fwd(const float* x, const float* up_w, const float*
   L2S_REQUIRE(workspace && workspace_bytes >= l2s_mask_head_workspace_bytes(n, Cin, Cmid, ncls), L2S_ERR_WORKSPACE,
               "mask_head_fwd: workspace too small");
   L2S_REQUIRE(aligned16(saved) && aligned16(workspace), L2S_ERR_ALIGN, "mask_head_fwd: saved / workspace must be 16-byte aligned");
+  L2S_REQUIRE(stages > 0 && stages < 8, L2S_ERR_ARG, "mask_head_fwd: stages must be a non-empty subset of 1|2|4");
   cudaStream_t st = (cudaStream_t)stream;
   const int M = n * 49;
   const Saved sv = saved_layout(saved, n, Cin, Cmid);
   const Work w = work_layout(workspace, n, Cin, Cmid, ncls);
-  repack_x_kernel<<<dim3((Cin + 63) / 64, n), 256, 0, st>>>(x, sv.a_hi, sv.a_lo, Cin);
-  L2S_LAUNCH_OK("repack_x_kernel");
-  repack_upw_kernel<<<std::min(1024, (Cin * Cmid * 4 + 255) / 256), 256, 0, st>>>(up_w, w.b1h, w.b1l, nullptr, nullptr, Cin, Cmid);
-  L2S_LAUNCH_OK("repack_upw_kernel");
-  repack_predw_kernel<<<std::min(256, (Cmid * kpad(ncls) + 255) / 256), 256, 0, st>>>(pred_w, w.b2h, w.b2l, nullptr, nullptr,
-                                                                                     ncls, Cmid, kpad(ncls));
-  L2S_LAUNCH_OK("repack_predw_kernel");
-  count_launch(3);
-  // GEMM1: [M x Cin] * [4Cmid x Cin]^T -> U planes
-  EpiUp e1{sv.u_hi, sv.u_lo, up_b, Cmid, 4 * Cmid};
-  rc = tc::launch_gemm<256, false, false>(sv.a_hi, sv.a_lo, Cin, w.b1h, w.b1l, Cin, M, 4 * Cmid, Cin, 1, e1, st, tc::kShape128E2);
-  if (rc) return rc;
-  // GEMM2: [4M x Cmid] * [ncls x Cmid]^T -> score / prob
-  EpiScore e2{score, prob, pred_b, ncls};
-  return tc::launch_gemm<128, false, false>(sv.u_hi, sv.u_lo, Cmid, w.b2h, w.b2l, Cmid, 4 * M, ncls, Cmid, 1, e2, st, tc::kShape128E2);
+  if (stages & 1) {
+    repack_x_kernel<<<dim3((Cin + 63) / 64, n), 256, 0, st>>>(x, sv.a_hi, sv.a_lo, Cin);
+    L2S_LAUNCH_OK("repack_x_kernel");
+    repack_upw_kernel<<<std::min(1024, (Cin * Cmid * 4 + 255) / 256), 256, 0, st>>>(up_w, w.b1h, w.b1l, nullptr, nullptr, Cin, Cmid);
+    L2S_LAUNCH_OK("repack_upw_kernel");
+    repack_predw_kernel<<<std::min(256, (Cmid * kpad(ncls) + 255) / 256), 256, 0, st>>>(pred_w, w.b2h, w.b2l, nullptr, nullptr,
+                                                                                       ncls, Cmid, kpad(ncls));
+    L2S_LAUNCH_OK("repack_predw_kernel");
+    count_launch(3);
+  }
+  if (stages & 2) {
+    // GEMM1: [M x Cin] * [4Cmid x Cin]^T -> U planes
+    EpiUp e1{sv.u_hi, sv.u_lo, up_b, Cmid, 4 * Cmid};
+    rc = tc::launch_gemm<256, false, false>(sv.a_hi, sv.a_lo, Cin, w.b1h, w.b1l, Cin, M, 4 * Cmid, Cin, 1, e1, st, tc::kShape128E2);
+    if (rc) return rc;
+  }
+  if (stages & 4) {
+    // GEMM2: [4M x Cmid] * [ncls x Cmid]^T -> score / prob
+    EpiScore e2{score, prob, pred_b, ncls};
+    rc = tc::launch_gemm<128, false, false>(sv.u_hi, sv.u_lo, Cmid, w.b2h, w.b2l, Cmid, 4 * M, ncls, Cmid, 1, e2, st, tc::kShape128E2);
+    if (rc) return rc;
+  }
+  return L2S_OK;
+}
+
+extern "C" int l2s_mask_head_fwd(const float* x, const float* up_w, const float* up_b, const float* pred_w,
+                                 const float* pred_b, float* score, float* prob, void* saved, int n, int Cin, int Cmid,
+                                 int ncls, void* workspace, size_t workspace_bytes, l2s_stream_t stream) {
+  return l2s_mask_head_fwd_stages(x, up_w, up_b, pred_w, pred_b, score, prob, saved, n, Cin, Cmid, ncls, workspace,
+                                  workspace_bytes, 7, stream);
 }
 
 namespace {

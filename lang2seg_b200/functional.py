@@ -210,6 +210,28 @@ def mask_head(x, up_w, up_b, pred_w, pred_b):
     return _MaskHead.apply(x, up_w, up_b, pred_w, pred_b)
 
 
+def mask_head_stage_runner(x, up_w, up_b, pred_w, pred_b, stages=2):
+    """Runs the full mask-head forward once and returns a closure that re-launches only `stages` of it (1 repacks,
+    2 GEMM1 with the bias+ReLU -> bf16-plane epilogue, 4 GEMM2) on the same buffers -- the kernels exactly as the step
+    runs them, for timing / profiling."""
+    x, up_w, up_b, pred_w, pred_b = (f32c(t.detach()) for t in (x, up_w, up_b, pred_w, pred_b))
+    n, Cin = x.shape[0], x.shape[1]
+    Cmid, ncls = up_w.shape[1], pred_w.shape[0]
+    score = torch.empty(n, ncls, 14, 14, device=x.device, dtype=torch.float32)
+    prob = torch.empty_like(score)
+    saved = _ws(_lib.size("l2s_mask_head_saved_bytes", n, Cin, Cmid, ncls), x.device)
+    nbytes = _lib.size("l2s_mask_head_workspace_bytes", n, Cin, Cmid, ncls)
+    ws = _ws(nbytes, x.device)
+
+    def run(st=stages):
+        call("l2s_mask_head_fwd_stages", ptr(x), ptr(up_w), ptr(up_b), ptr(pred_w), ptr(pred_b), ptr(score), ptr(prob),
+             ptr(saved), n, Cin, Cmid, ncls, ptr(ws), nbytes, st, stream())
+
+    run(7)
+    run.keep = (x, up_w, up_b, pred_w, pred_b, score, prob, saved, ws)
+    return run
+
+
 class _MaskBCE(torch.autograd.Function):
     @staticmethod
     def forward(ctx, score, labels, target):

@@ -176,3 +176,79 @@ def test_roi_maxpool_vs_reference_cuda_kernel():
     (gb,) = torch.autograd.grad((o2 * top).sum(), fr)
     torch.cuda.synchronize()
     assert relerr(gb, gb_ref) < 1e-6
+
+
+def _maxpool_tie_mask(bottom, rois, ref_shape):
+    """1 where the two best samples of a 2x2 window differ by more than the coordinate rounding noise"""
+    with torch.no_grad():
+        s14 = R.crop_pool(bottom, rois, max_pool=False, pool=14)
+        win = s14.unfold(2, 2, 2).unfold(3, 2, 2).reshape(*ref_shape, 4)
+        top2 = win.topk(2, dim=-1).values
+        return ((top2[..., 0] - top2[..., 1]) > 1e-3)
+
+
+# the benchmark's own shapes (BASELINE.json configs 2/3 and 5): one expression = all its ROIs on its own map
+FULL = {"cfg2_7x7": dict(B=2, C=1024, H=32, W=32, N=256, max_pool=False),
+        "cfg3_14max": dict(B=2, C=1024, H=32, W=32, N=256, max_pool=True),
+        "cfg5_vgg_14max": dict(B=2, C=512, H=37, W=62, N=300, max_pool=True),
+        "cfg5_vgg_7x7": dict(B=1, C=512, H=37, W=62, N=300, max_pool=False)}
+
+
+@pytest.mark.parametrize("tag", list(FULL))
+def test_crop_full_size_vs_oracle(tag):
+    """ROI crop at the real channel / ROI / map sizes of the bench workloads against oracle.restate.crop_pool."""
+    k = FULL[tag]
+    B, C, H, W, N, max_pool = (k[x] for x in ("B", "C", "H", "W", "N", "max_pool"))
+    g = torch.Generator().manual_seed(len(tag) * 7 + C)
+    bottom = torch.relu(torch.randn(B, C, H, W, generator=g))
+    rois = torch.cat([R.synth_rois(g, N, H * 16, W * 16, b) for b in range(B)])
+    bo = bottom.clone().requires_grad_(True)
+    ref = R.crop_pool(bo, rois, max_pool=max_pool)
+    G = torch.randn(ref.shape, generator=g)
+    if max_pool:
+        G = G * _maxpool_tie_mask(bottom, rois, ref.shape)
+    (gref,) = torch.autograd.grad((ref * G).sum(), bo)
+    bc = bottom.cuda().requires_grad_(True)
+    out = _f().roi_crop(bc, rois.cuda(), max_pool=max_pool)
+    assert relerr(out, ref) < TOL
+    (gb,) = torch.autograd.grad((out * G.cuda()).sum(), bc)
+    assert relerr(gb, gref) < TOL
+
+
+@pytest.mark.parametrize("max_pool", [False, True])
+def test_crop_bench_scale_properties(max_pool):
+    """cfg-2 at full size (48 expressions x 256 ROIs, C = 1024): size-independent properties of the 32-chunk grid --
+    expressions are independent (a random pair of them equals the oracle on those two alone), the backward is
+    bit-reproducible, and forward/backward are adjoint: <crop(Y), G> == <Y, crop^T(G)>."""
+    E, C, H, W, N = 48, 1024, 32, 32, 256
+    g = torch.Generator().manual_seed(77)
+    Y = torch.relu(torch.randn(E, C, H, W, generator=g)).cuda().requires_grad_(True)
+    rois = torch.cat([R.synth_rois(g, N, H * 16, W * 16, e) for e in range(E)]).cuda()
+    out = _f().roi_crop(Y, rois, max_pool=max_pool)
+    G = torch.randn(out.shape, generator=torch.Generator(device="cuda").manual_seed(3), device="cuda")
+    (gY,) = torch.autograd.grad((out * G).sum(), Y, retain_graph=True)
+    (gY2,) = torch.autograd.grad((out * G).sum(), Y)
+    assert torch.equal(gY, gY2)
+    lhs = float((out.double() * G.double()).sum())
+    rhs = float((Y.detach().double() * gY.double()).sum())
+    assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), 1.0) + 1e-3      # piecewise linear in Y (max-pool: same winners)
+    for e in (5, 41):
+        sl = slice(e * N, (e + 1) * N)
+        r1 = rois[sl].cpu().clone()
+        r1[:, 0] = 0
+        ye = Y[e:e + 1].detach().cpu().requires_grad_(True)
+        ref = R.crop_pool(ye, r1, max_pool=max_pool)
+        assert relerr(out[sl], ref) < TOL
+        Ge = G[sl].cpu()
+        if max_pool:
+            keep = _maxpool_tie_mask(ye.detach(), r1, ref.shape)
+            # compare the gradient only through windows without near-ties: re-run both sides with the masked G
+            Ge = Ge * keep
+            Gm = torch.zeros_like(G)
+            Gm[sl] = Ge.cuda()
+            (gsel,) = torch.autograd.grad((_f().roi_crop(Y, rois, max_pool=True) * Gm).sum(), Y)
+            got = gsel[e:e + 1]
+        else:
+            got = gY[e:e + 1]
+        (gref,) = torch.autograd.grad((ref * Ge).sum(), ye)
+        assert relerr(got, gref) < TOL
