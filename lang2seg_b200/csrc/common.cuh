@@ -42,6 +42,7 @@ int  max_smem_optin();
 // and flushed.  Opt-in (L2S_PDL=1): inside the whole-step CUDA graph, where kernel-to-kernel gaps are already
 // sub-microsecond, it made the step SLOWER on B200 (11.05 vs 10.57 ms); it only pays for eager launches.
 bool pdl_enabled();
+bool env_flag(const char* name);   // getenv(name) starts with '1'; callers cache the result in a function-local static
 void count_launch(int n = 1);          // feeds l2s_launch_count()
 
 // ---- internal launchers shared between translation units (att.cu <-> decode.cu) -----------

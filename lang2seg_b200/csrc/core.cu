@@ -29,30 +29,39 @@ int fail(int code, const char* fmt, ...) {
 
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
-static int query_attr(cudaDeviceAttr a, int fallback) {
-  int dev = 0, v = 0;
+// device attributes are cached per device id (a process may drive several GPUs from one thread)
+static int cached_attr(cudaDeviceAttr a, int which, int fallback) {
+  constexpr int kMaxDev = 64;
+  static std::atomic<int> cache[2][kMaxDev];          // zero-initialised; 0 = not queried yet
+  int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return fallback;
-  if (cudaDeviceGetAttribute(&v, a, dev) != cudaSuccess) return fallback;
+  if (dev < 0 || dev >= kMaxDev) {
+    int v = 0;
+    return cudaDeviceGetAttribute(&v, a, dev) == cudaSuccess ? v : fallback;
+  }
+  int v = cache[which][dev].load(std::memory_order_relaxed);
+  if (v == 0) {
+    if (cudaDeviceGetAttribute(&v, a, dev) != cudaSuccess || v <= 0) return fallback;
+    cache[which][dev].store(v, std::memory_order_relaxed);
+  }
   return v;
 }
 
+// environment switches are read ONCE (first use): no getenv on the launch path, no race with setenv afterwards
+bool env_flag(const char* name) {
+  const char* e = getenv(name);
+  return e && e[0] == '1';
+}
+
 bool pdl_enabled() {
-  const char* e = getenv("L2S_PDL");
-  if (e && (e[0] == '0' || e[0] == '1')) return e[0] == '1';
-  return false;     // measured on B200 inside the whole-step CUDA graph: 11.05 ms with, 10.57 ms without -> opt-in only
+  // measured on B200 inside the whole-step CUDA graph: 11.05 ms with, 10.57 ms without -> opt-in only
+  static const bool on = env_flag("L2S_PDL");
+  return on;
 }
 
-int sm_count() {
-  static thread_local int cached = 0;
-  if (!cached) cached = query_attr(cudaDevAttrMultiProcessorCount, 148);
-  return cached;
-}
+int sm_count() { return cached_attr(cudaDevAttrMultiProcessorCount, 0, 148); }
 
-int max_smem_optin() {
-  static thread_local int cached = 0;
-  if (!cached) cached = query_attr(cudaDevAttrMaxSharedMemoryPerBlockOptin, 232448);
-  return cached;
-}
+int max_smem_optin() { return cached_attr(cudaDevAttrMaxSharedMemoryPerBlockOptin, 1, 232448); }
 
 }  // namespace l2s
 

@@ -23,6 +23,7 @@
 //     precomputed rank (fixed order => bit-reproducible sums).  No floating-point atomics anywhere
 //     (shared fp32 atomicAdd costs 2 cycles per lane on sm_100).
 #include <cstdlib>
+#include <initializer_list>
 
 #include "common.cuh"
 
@@ -144,9 +145,10 @@ struct __align__(16) SepRec {
 static_assert(sizeof(SepRec) == 192, "SepRec layout");
 
 __global__ void __launch_bounds__(256)
-roi_geom_kernel(const float* __restrict__ rois, const int* __restrict__ order, unsigned char* __restrict__ table,
-                SepRec* __restrict__ sep, CropGeom g, int CGN) {
+roi_geom_kernel(const float* __restrict__ rois, const int* __restrict__ order, const int* __restrict__ seg,
+                unsigned char* __restrict__ table, SepRec* __restrict__ sep, CropGeom g, int CGN) {
   const int r = blockIdx.x, p = threadIdx.x;
+  if (r >= seg[g.B]) return;     // ROIs with a batch index outside [0,B) are not listed in `order` (block uniform)
   const int n = __ldg(order + r);
   const int SS = g.S * g.S;
   __shared__ int s_key[64];
@@ -898,6 +900,278 @@ roi_crop_bwd_rows_kernel(const float* __restrict__ dout, const int* __restrict__
   }
 }
 
+// ------------------------------------------------------------------ backward, generic row-owner variant
+// The same ownership idea for the cases the kernel above does not take: the 14x14-sample + 2x2-max crop
+// (network_cycle_response.py:140-144; cfg-3 and the VGG path of cfg-5) and 7x7 crops of maps too large for a
+// 32-channel accumulator.  The max-pool backward becomes channel independent again by EXPANDING the pooled gradient
+// to the 2S x 2S sample grid on the fly: gs[c][i][j] = (winner[c][i/2][j/2] == (i%2, j%2)) ? g[c][i/2][j/2] : 0 -- the
+// geometry of sample (i, j) does not depend on the channel, only the VALUE does, so lane = channel keeps control flow
+// uniform and the per-lane winner is a select, not a branch.  (The previous kernel -- lanes = samples, four scalar
+// channel streams, match.any ranking of colliding corners -- ran at 1 % of the HBM roofline: 17.8 ms at cfg-3.)
+//   * CC = 32 or 16 channels per CTA (the accumulator [H][W+4][CC+1] must fit in shared memory: 32x32 maps take 32,
+//     37x62 / 38x63 maps take 16); with CC = 16 a warp holds two row owners (half-warps), so the owner count doubles;
+//   * per owned map row the contributions of all sample rows that land in it are combined in registers
+//     (v_j = sum_i wy_i gs_ij), then adjacent sample columns that share a map column are merged in registers as well
+//     (x0_j is non-decreasing in j: a sliding two-column window), so one (ROI, map row) costs one read-modify-write
+//     per DISTINCT map column (box width + 1), software pipelined two deep;
+//   * a stage of the TMA ring carries kRowGroup ROIs: gradient tiles, winner tiles and records.
+// Bit-reproducible (fixed order, no atomics).
+struct __align__(16) SepRecX {
+  int16_t xoff[16];     // (clamped x0_j) * (CC+1): float offset of the left corner inside a padded accumulator row
+  float lx[16];
+  float ly[16];
+  int16_t y0[16];       // clamped to [-2, 30000]
+  uint32_t wmask[64];   // per row owner: bit 2i+d set <=> map row y0_i + d is inside the map and owned by it
+  int n;                // ROI index
+  int pad[3];
+};
+static_assert(sizeof(SepRecX) == 464, "SepRecX layout");
+
+__global__ void __launch_bounds__(64)
+roi_sepx_kernel(const float* __restrict__ rois, const int* __restrict__ order, const int* __restrict__ seg,
+                SepRecX* __restrict__ sep, CropGeom g, int LD, int owners) {
+  const int r = blockIdx.x, p = threadIdx.x;
+  if (r >= seg[g.B]) return;                 // ROIs whose batch index is outside [0,B) are not in `order`
+  const int n = __ldg(order + r);
+  const float* rp = rois + 5 * (size_t)n;
+  float4 box;
+  box.x = __ldg(rp + 1) * g.sx;
+  box.y = __ldg(rp + 2) * g.sy;
+  box.z = __ldg(rp + 3) * g.sx;
+  box.w = __ldg(rp + 4) * g.sy;
+  const float inv = 1.0f / (float)(g.S - 1);
+  __shared__ int s_y0[16];
+  SepRecX* sr = sep + r;
+  if (p < 16) {
+    const Corner c = sample_at(box, min(p, g.S - 1), min(p, g.S - 1), inv);
+    const int y0 = min(max(c.y0, -2), 30000);
+    s_y0[p] = y0;
+    sr->xoff[p] = (int16_t)(min(max(c.x0, -2), g.W) * LD);
+    sr->lx[p] = c.lx;
+    sr->ly[p] = c.ly;
+    sr->y0[p] = (int16_t)y0;
+  }
+  __syncthreads();
+  unsigned m = 0;
+  if (p < owners) {
+    for (int i = 0; i < g.S; ++i)
+#pragma unroll
+      for (int d = 0; d < 2; ++d) {
+        const int row = s_y0[i] + d;
+        if (row >= 0 && row < g.H && (row % owners) == p) m |= 1u << (2 * i + d);
+      }
+  }
+  sr->wmask[p] = m;
+  if (p == 0) {
+    sr->n = n;
+    sr->pad[0] = sr->pad[1] = sr->pad[2] = 0;
+  }
+}
+
+constexpr int kRowXMaxStages = 4;
+
+template <int CC, int S, bool MAXPOOL>
+__global__ void __launch_bounds__((kRowWarps + 1) * 32, 1)
+roi_crop_bwd_rowsx_kernel(const float* __restrict__ dout, const int* __restrict__ seg, const SepRecX* __restrict__ sep,
+                          const uint8_t* __restrict__ argmax, float* __restrict__ dbottom, CropGeom g, int nstages) {
+  constexpr int LD = CC + 1;
+  constexpr int SUB = 32 / CC;                 // row owners per warp
+  constexpr int OWNERS = kRowWarps * SUB;
+  constexpr int TILE = CC * kPP;               // floats (gradients) / bytes (winners) per ROI tile
+  constexpr int ATILE = (TILE + 15) & ~15;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int HW = g.H * g.W, W = g.W, H = g.H;
+  const int WP = W + 4;                                                      // padded row length
+  float* map = reinterpret_cast<float*>(smem_raw);                           // [H][WP][LD]
+  const int map_floats = (H * WP * LD + 3) & ~3;
+  float* tiles = map + map_floats;                                           // [nstages][kRowGroup][TILE]
+  SepRecX* recs = reinterpret_cast<SepRecX*>(tiles + (size_t)nstages * kRowGroup * TILE);   // [nstages][kRowGroup]
+  uint8_t* atiles = reinterpret_cast<uint8_t*>(recs + (size_t)nstages * kRowGroup);         // [nstages][kRowGroup][ATILE]
+  __shared__ uint64_t full_bar[kRowXMaxStages], empty_bar[kRowXMaxStages];
+
+  const int b = blockIdx.y, c0 = blockIdx.x * CC;
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  const int cvalid = min(CC, g.C - c0);
+
+  for (int i = t; i < map_floats; i += blockDim.x) map[i] = 0.f;
+  if (t == 0) {
+    for (int s = 0; s < nstages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], kRowWarps);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  const int beg = seg[b], end = seg[b + 1];
+  const int nst = (end - beg + kRowGroup - 1) / kRowGroup;
+  const uint32_t tile_bytes = (uint32_t)(cvalid * kPP * sizeof(float));
+  const uint32_t arg_bytes = (uint32_t)(cvalid * kPP);
+  // winners travel by TMA only when their rows are 16-byte sized / aligned; otherwise they are read in place
+  const bool arg_smem = MAXPOOL && (g.C % 16 == 0) && (cvalid % 16 == 0);
+
+  if (wid == kRowWarps) {
+    // ---------------- producer warp (ROI ids fetched 32 at a time) ----------------
+    int sidx = 0, lap = 0;
+    for (int r0 = beg; r0 < end; r0 += 32) {
+      const int mine = r0 + lane;
+      const int nl = (mine < end) ? __ldg(&sep[mine].n) : 0;
+      {   // L2 prefetch of the group after this one (and of the first group itself)
+        const int ahead = mine + (r0 == beg ? 0 : 32);
+        for (int a = ahead; a < end && a <= mine + 32; a += 32)
+          bulk_prefetch_l2(dout + ((size_t)__ldg(&sep[a].n) * g.C + c0) * kPP, tile_bytes);
+      }
+      const int cnt = min(32, end - r0);
+      for (int j = 0; j < cnt; j += kRowGroup) {
+        const int gc = min(kRowGroup, cnt - j);               // ROIs in this stage
+        int n[kRowGroup];
+#pragma unroll
+        for (int q = 0; q < kRowGroup; ++q) n[q] = __shfl_sync(0xffffffffu, nl, (j + q) & 31);
+        if (lane == 0) {
+          if (lap > 0) mbar_wait(&empty_bar[sidx], (lap - 1) & 1);
+          mbar_arrive_expect_tx(&full_bar[sidx],
+                                (uint32_t)gc * (tile_bytes + (uint32_t)sizeof(SepRecX) + (arg_smem ? arg_bytes : 0u)));
+          bulk_g2s(recs + sidx * kRowGroup, sep + r0 + j, (uint32_t)(gc * sizeof(SepRecX)), &full_bar[sidx]);
+#pragma unroll
+          for (int q = 0; q < kRowGroup; ++q)
+            if (q < gc) {
+              bulk_g2s(tiles + (size_t)(sidx * kRowGroup + q) * TILE, dout + ((size_t)n[q] * g.C + c0) * kPP, tile_bytes,
+                       &full_bar[sidx]);
+              if (arg_smem)
+                bulk_g2s(atiles + (size_t)(sidx * kRowGroup + q) * ATILE, argmax + ((size_t)n[q] * g.C + c0) * kPP,
+                         arg_bytes, &full_bar[sidx]);
+            }
+        }
+        if (++sidx == nstages) { sidx = 0; ++lap; }
+      }
+    }
+  } else {
+    // ---------------- consumers: (half-)warp = rows, lane = channel ----------------
+    const int ch = lane % CC, sub = lane / CC;
+    const int owner = wid * SUB + sub;
+    const int cl = ch < cvalid ? ch : 0;              // idle lanes shadow channel 0 into their own column
+    float* mlane = map + 2 * LD + ch;                 // (row 0, col 0, my channel); channels >= cvalid never unstaged
+    const int row_stride = WP * LD;
+    int sidx = 0, lap = 0;
+    for (int k = 0; k < nst; ++k) {
+      mbar_wait_parked(&full_bar[sidx], lap & 1);
+      const int gc = min(kRowGroup, end - beg - k * kRowGroup);
+      for (int q = 0; q < gc; ++q) {
+        const SepRecX* rec = recs + sidx * kRowGroup + q;
+        unsigned hits = rec->wmask[owner];
+        if (__ballot_sync(0xffffffffu, hits != 0u) == 0u) continue;        // warp uniform
+        // column geometry of the ROI (the same for every lane)
+        int xoff[S];
+        float wa[S], wb[S];
+#pragma unroll
+        for (int j = 0; j < S; ++j) {
+          xoff[j] = (int)rec->xoff[j];
+          wb[j] = rec->lx[j];
+          wa[j] = 1.f - wb[j];
+        }
+        const float* tcol = tiles + (size_t)(sidx * kRowGroup + q) * TILE + (size_t)cl * kPP;
+        const uint8_t* acol = nullptr;
+        if (MAXPOOL)
+          acol = arg_smem ? atiles + (size_t)(sidx * kRowGroup + q) * ATILE + (size_t)cl * kPP
+                          : argmax + ((size_t)rec->n * g.C + c0 + cl) * kPP;
+        while (hits) {
+          const int bsel = __ffs(hits) - 1;
+          const int yy = (int)rec->y0[bsel >> 1] + (bsel & 1);
+          float v[S];
+#pragma unroll
+          for (int j = 0; j < S; ++j) v[j] = 0.f;
+          // every sample row of this ROI that lands in map row yy (adjacent bits of this owner's mask)
+          while (hits) {
+            const int b2 = __ffs(hits) - 1;
+            const int i = b2 >> 1;
+            if ((int)rec->y0[i] + (b2 & 1) != yy) break;
+            hits &= hits - 1;
+            const float ly = rec->ly[i];
+            const float wy = (b2 & 1) ? ly : 1.f - ly;
+            if (MAXPOOL) {
+              const float* trow = tcol + (i >> 1) * 7;
+              const uint8_t* arow = acol + (i >> 1) * 7;
+              const int code = (i & 1) << 1;
+#pragma unroll
+              for (int pj = 0; pj < 7; ++pj) {
+                const float gq = wy * trow[pj];
+                const int a = (int)arow[pj] & 3;
+                v[2 * pj] += (a == code) ? gq : 0.f;
+                v[2 * pj + 1] += (a == code + 1) ? gq : 0.f;
+              }
+            } else {
+              const float* trow = tcol + i * 7;
+#pragma unroll
+              for (int j = 0; j < S; ++j) v[j] = fmaf(wy, trow[j], v[j]);
+            }
+          }
+          // scatter with column merging: window (a0 @ column cx, a1 @ cx + 1); flushes are pipelined two deep
+          float* mrow = mlane + yy * row_stride;
+          float* pp = nullptr;
+          float pv = 0.f, pm = 0.f;
+          auto flush = [&](int off, float val) {
+            float* addr = mrow + off;
+            const float m = *addr;                  // the new column's load is in flight ...
+            if (pp) *pp = pm + pv;                  // ... while the previous (different) column completes
+            pp = addr; pv = val; pm = m;
+          };
+          auto drain = [&]() {
+            if (pp) *pp = pm + pv;
+            pp = nullptr;
+          };
+          int cx = xoff[0];
+          float a0 = wa[0] * v[0], a1 = wb[0] * v[0];
+#pragma unroll
+          for (int j = 1; j < S; ++j) {
+            const int dx = xoff[j] - cx;              // warp uniform
+            if (dx == 0) {
+              a0 = fmaf(wa[j], v[j], a0);
+              a1 = fmaf(wb[j], v[j], a1);
+            } else if (dx == LD) {
+              flush(cx, a0);
+              a0 = fmaf(wa[j], v[j], a1);
+              a1 = wb[j] * v[j];
+              cx = xoff[j];
+            } else {
+              flush(cx, a0);
+              flush(cx + LD, a1);
+              if (dx < 0) drain();                    // degenerate box (x2 < x1): columns are no longer increasing
+              a0 = wa[j] * v[j];
+              a1 = wb[j] * v[j];
+              cx = xoff[j];
+            }
+          }
+          flush(cx, a0);
+          flush(cx + LD, a1);
+          drain();
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[sidx]);
+      if (++sidx == nstages) { sidx = 0; ++lap; }
+    }
+    (void)owner;
+  }
+  __syncthreads();
+  // read-out: warp = (channel, 32 consecutive pixels of a row)
+  float* dst = dbottom + ((size_t)b * g.C + c0) * HW;
+  const int nw = blockDim.x >> 5;
+  const int xblocks = (W + 31) >> 5;
+  for (int it = wid; it < cvalid * H * xblocks; it += nw) {
+    const int c = it % cvalid, rest = it / cvalid;
+    const int y = rest / xblocks, x = (rest % xblocks) * 32 + lane;
+    if (x < W) dst[(size_t)c * HW + y * W + x] = map[((size_t)y * WP + x + 2) * LD + c];
+  }
+}
+
+// shared memory of the generic row-owner backward for `cc` channels and `nstages` ring stages
+size_t rowsx_smem(int H, int W, int cc, bool maxpool, int nstages) {
+  const size_t map = (((size_t)H * (W + 4) * (cc + 1) + 3) & ~(size_t)3) * 4;
+  const size_t tile = (size_t)cc * kPP;
+  const size_t per_roi = tile * 4 + sizeof(SepRecX) + (maxpool ? ((tile + 15) & ~(size_t)15) : 0);
+  return map + (size_t)nstages * kRowGroup * per_roi + 128;
+}
+
 // ------------------------------------------------------------------ host side
 struct Plan {
   int cc;
@@ -961,21 +1235,48 @@ CropGeom make_geom(int B, int C, int H, int W, int N, int pool, int flags, float
   return g;
 }
 
-// bins the ROIs by batch index and writes the geometry records (3 small launches)
-int prepare(const float* rois, const CropGeom& g, int cgn, void* ws, cudaStream_t st, int** seg,
-            unsigned char** table, SepRec** sep) {
+// ROIs whose batch index is outside [0,B) belong to no map: they are skipped by every kernel and their output rows
+// are zero (the reference never has them: proposal_layer.py:65 writes batch index 0)
+__global__ void roi_invalid_zero_kernel(const float* __restrict__ rois, float* __restrict__ out, int B, int row_floats) {
+  const int n = blockIdx.x;
+  const float bf = __ldg(rois + 5 * (size_t)n);
+  const int b = (int)bf;
+  if (bf == bf && b >= 0 && b < B && (float)b <= bf) return;       // a valid index (NaN, negative, >= B fall through)
+  float4* o = reinterpret_cast<float4*>(out + (size_t)n * row_floats);
+  for (int i = threadIdx.x; i < row_floats / 4; i += blockDim.x) o[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+struct Prep {
+  int* seg;
+  int* order;
+  unsigned char* table;
+  SepRec* sep;
+  SepRecX* sepx;
+};
+
+// bins the ROIs by batch index (2 small launches)
+int prepare_order(const float* rois, const CropGeom& g, void* ws, cudaStream_t st, Prep* p) {
   int* counts = reinterpret_cast<int*>(ws);
-  *seg = counts + g.B;
-  int* order = counts + 2 * g.B + 1;
-  *table = reinterpret_cast<unsigned char*>(ws) + table_offset(g.B, g.N);
+  p->seg = counts + g.B;
+  p->order = counts + 2 * g.B + 1;
+  p->table = reinterpret_cast<unsigned char*>(ws) + table_offset(g.B, g.N);
+  p->sep = reinterpret_cast<SepRec*>(p->table + (size_t)g.N * g.rec);
+  p->sepx = reinterpret_cast<SepRecX*>(p->table + (size_t)g.N * g.rec + (g.S == 7 ? (size_t)g.N * sizeof(SepRec) : 0));
   roi_count_kernel<<<g.B, 256, 0, st>>>(rois, g.N, counts);
   L2S_LAUNCH_OK("roi_count_kernel");
-  roi_order_kernel<<<g.B, 256, 0, st>>>(rois, g.N, counts, *seg, order);
+  roi_order_kernel<<<g.B, 256, 0, st>>>(rois, g.N, counts, p->seg, p->order);
   L2S_LAUNCH_OK("roi_order_kernel");
-  *sep = g.maxpool ? nullptr : reinterpret_cast<SepRec*>(*table + (size_t)g.N * g.rec);
-  roi_geom_kernel<<<g.N, g.S == 7 ? 64 : 256, 0, st>>>(rois, order, *table, *sep, g, cgn);
+  count_launch(2);
+  return L2S_OK;
+}
+
+// ... and writes the per-sample geometry records (forward, ranked backward, 7x7 row-owner backward)
+int prepare(const float* rois, const CropGeom& g, int cgn, void* ws, cudaStream_t st, Prep* p) {
+  int rc = prepare_order(rois, g, ws, st, p);
+  if (rc) return rc;
+  roi_geom_kernel<<<g.N, g.S == 7 ? 64 : 256, 0, st>>>(rois, p->order, p->seg, p->table, g.S == 7 ? p->sep : nullptr, g, cgn);
   L2S_LAUNCH_OK("roi_geom_kernel");
-  count_launch(3);
+  count_launch();
   return L2S_OK;
 }
 
@@ -1010,7 +1311,8 @@ using namespace l2s;
 
 extern "C" size_t l2s_roi_crop_workspace_bytes(int B, int N, int flags) {
   const int S = (flags & L2S_CROP_MAX_POOL) ? 14 : 7;
-  return table_offset(B, N) + (size_t)(N > 0 ? N : 0) * (S * S * 16 + kRecTail + (S == 7 ? sizeof(SepRec) : 0)) + 256;
+  return table_offset(B, N) +
+         (size_t)(N > 0 ? N : 0) * (S * S * 16 + kRecTail + (S == 7 ? sizeof(SepRec) : 0) + sizeof(SepRecX)) + 256;
 }
 
 #define L2S_CROP_DISPATCH(FN, ...)                                                      \
@@ -1042,15 +1344,18 @@ extern "C" int l2s_roi_crop_fwd(const float* bottom, const float* rois, float* o
   Plan pl;
   L2S_REQUIRE(make_plan(H * W, g.maxpool, g.rec, &pl), L2S_ERR_SHAPE,
               "roi_crop: feature map %dx%d does not fit the shared-memory staging", H, W);
-  int* seg;
-  unsigned char* table;
-  SepRec* sep;
-  rc = prepare(rois, g, pl.cc / 4, workspace, st, &seg, &table, &sep);
+  Prep pr;
+  rc = prepare(rois, g, pl.cc / 4, workspace, st, &pr);
   if (rc) return rc;
+  const int* seg = pr.seg;
+  const unsigned char* table = pr.table;
+  roi_invalid_zero_kernel<<<N, 128, 0, st>>>(rois, out, B, C * kPP);
+  L2S_LAUNCH_OK("roi_invalid_zero_kernel");
+  count_launch();
   // warp-per-ROI kernel: 7x7 crops of maps whose 32-channel slice + one tile per warp fit in shared memory
   const size_t smem_warp = (size_t)(H * W + 1) * 32 * 4 + (size_t)kFwdWarps * 32 * kPP * 4 + 128;
-  const char* blk = getenv("L2S_CROP_FWD_BLOCK");          // diagnostics: force the block-synchronous kernel
-  if (!g.maxpool && pl.cc == 32 && smem_warp <= (size_t)max_smem_optin() - 1024 && !(blk && blk[0] == '1')) {
+  static const bool force_block = env_flag("L2S_CROP_FWD_BLOCK");     // diagnostics: force the block-synchronous kernel
+  if (!g.maxpool && pl.cc == 32 && smem_warp <= (size_t)max_smem_optin() - 1024 && !force_block) {
     auto kern = roi_crop_fwd_warp_kernel;
     L2S_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_warp));
     dim3 grid((g.C + 31) / 32, g.B);
@@ -1081,22 +1386,54 @@ extern "C" int l2s_roi_crop_bwd(const float* dout, const float* rois, const uint
   Plan pl;
   L2S_REQUIRE(make_plan(H * W, g.maxpool, g.rec, &pl), L2S_ERR_SHAPE,
               "roi_crop: feature map %dx%d does not fit the shared-memory staging", H, W);
-  int* seg;
-  unsigned char* table;
-  SepRec* sep;
-  rc = prepare(rois, g, pl.cc / 4, workspace, st, &seg, &table, &sep);
-  if (rc) return rc;
-  // row-owner kernel: needs the whole 32-channel accumulator with guard columns + the tile ring in shared memory
+  const size_t cap = (size_t)max_smem_optin() - 1024;
+  const bool ranked = (flags & L2S_CROP_BWD_RANKED) != 0;
+  Prep pr;
+  // 7x7 row-owner kernel: needs the whole 32-channel accumulator with guard columns + the tile ring in shared memory
   pl.smem_rows = (((size_t)H * (W + 4) * kRowLd + 3) & ~(size_t)3) * 4 +
                  kRowStages * kRowGroup * ((size_t)32 * kPP * 4 + sizeof(SepRec)) + 128;
-  if (!g.maxpool && pl.cc == 32 && pl.smem_rows <= (size_t)max_smem_optin() - 1024 && !(flags & L2S_CROP_BWD_RANKED)) {
+  if (!g.maxpool && pl.cc == 32 && pl.smem_rows <= cap && !ranked) {
+    rc = prepare(rois, g, pl.cc / 4, workspace, st, &pr);
+    if (rc) return rc;
     auto kern = roi_crop_bwd_rows_kernel;
     L2S_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_rows));
     dim3 grid((g.C + 31) / 32, g.B);
-    kern<<<grid, (kRowWarps + 1) * 32, pl.smem_rows, st>>>(dout, seg, sep, dbottom, g);
+    kern<<<grid, (kRowWarps + 1) * 32, pl.smem_rows, st>>>(dout, pr.seg, pr.sep, dbottom, g);
     L2S_LAUNCH_OK("roi_crop_bwd_rows_kernel");
     count_launch();
     return L2S_OK;
   }
+  // generic row-owner kernel: 14x14 + 2x2 max, and 7x7 on maps that only fit a 16-channel accumulator
+  if (!ranked) {
+    int cc = 0, nst = 0;
+    for (int c : {32, 16})
+      if (rowsx_smem(H, W, c, g.maxpool, 2) <= cap) { cc = c; break; }
+    if (cc) {
+      for (nst = 2; nst < kRowXMaxStages && rowsx_smem(H, W, cc, g.maxpool, nst + 1) <= cap; ++nst) {}
+      rc = prepare_order(rois, g, workspace, st, &pr);
+      if (rc) return rc;
+      roi_sepx_kernel<<<g.N, 64, 0, st>>>(rois, pr.order, pr.seg, pr.sepx, g, cc + 1, kRowWarps * (32 / cc));
+      L2S_LAUNCH_OK("roi_sepx_kernel");
+      count_launch();
+      const size_t smem = rowsx_smem(H, W, cc, g.maxpool, nst);
+      dim3 grid((g.C + cc - 1) / cc, g.B);
+#define L2S_ROWSX(CCV, SV, MPV)                                                                               \
+  do {                                                                                                        \
+    auto kern = roi_crop_bwd_rowsx_kernel<CCV, SV, MPV>;                                                      \
+    L2S_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
+    kern<<<grid, (kRowWarps + 1) * 32, smem, st>>>(dout, pr.seg, pr.sepx, argmax, dbottom, g, nst);           \
+  } while (0)
+      if (g.maxpool) { if (cc == 32) L2S_ROWSX(32, 14, true); else L2S_ROWSX(16, 14, true); }
+      else           { if (cc == 32) L2S_ROWSX(32, 7, false); else L2S_ROWSX(16, 7, false); }
+#undef L2S_ROWSX
+      L2S_LAUNCH_OK("roi_crop_bwd_rowsx_kernel");
+      count_launch();
+      return L2S_OK;
+    }
+  }
+  rc = prepare(rois, g, pl.cc / 4, workspace, st, &pr);
+  if (rc) return rc;
+  const int* seg = pr.seg;
+  const unsigned char* table = pr.table;
   L2S_CROP_DISPATCH(launch_bwd, dout, seg, table, argmax, dbottom, g, pl.smem_bwd, st);
 }
