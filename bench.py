@@ -412,7 +412,7 @@ def cpu_sample(wl, repeats=1, threads=None):
     native batching), the workload's parts, fwd+bwd (fwd only for cfg-1), timed on the host
     cores."""
     from oracle import restate as R
-    from lang2seg_b200.layers.lang_encoder import RNNEncoder    # pure torch (CPU LSTM), as the reference's
+    from lang2seg_b200.layers.lang_encoder import RNNEncoder    # only as the container of default-initialised weights
     if threads:
         torch.set_num_threads(threads)
     w1 = dict(wl, I=1)
@@ -420,7 +420,8 @@ def cpu_sample(wl, repeats=1, threads=None):
     d = make_inputs(w1, 4321, "cpu")
     E, C, V, L = w1["EPI"], w1["C"], w1["V"], w1["L"]
     torch.manual_seed(7)
-    enc = RNNEncoder(V, 512, 512, 512, bidirectional=True, n_layers=1).eval()
+    enc = {k: v.detach().clone().requires_grad_(v.is_floating_point())
+           for k, v in RNNEncoder(V, 512, 512, 512, bidirectional=True, n_layers=1).state_dict().items()}
     P = lambda *s: (torch.randn(*s) * 0.01).requires_grad_(True)      # noqa: E731
     dyn_w, dyn_b = [P(C, 1024) for _ in range(7)], [P(C) for _ in range(7)]
     rw, rb = P(7, 1024), P(7)
@@ -434,14 +435,14 @@ def cpu_sample(wl, repeats=1, threads=None):
           "core.attention.alpha_net.weight": P(1, D), "core.attention.alpha_net.bias": P(1)}
     g_pool = torch.randn(E * w1["R"], C, 7, 7) * 1e-4
     g_Y = torch.randn(E, C, w1["H"], w1["W"]) * 1e-4
-    params = list(enc.parameters()) + dyn_w + dyn_b + [rw, rb, up_w, up_b, pw, pb] + list(cp.values())
+    params = [v for v in enc.values() if v.requires_grad] + dyn_w + dyn_b + [rw, rb, up_w, up_b, pw, pb] + list(cp.values())
 
     def one():
         for p in params:
             p.grad = None
         with torch.set_grad_enabled(not fwd_only):
             X = d["X"].clone().requires_grad_(not fwd_only)
-            _, hidden, _ = enc(d["labels"])
+            _, hidden, _ = R.rnn_encoder_packed(d["labels"], enc)   # the reference's pack -> nn.LSTM -> unpack calls
             filt, fuse = R.filter_generator(hidden, dyn_w, dyn_b, rw, rb)
             r, Y = R.dynamic_filter(X, filt, fuse, d["e2i"].tolist())
             loss = torch.zeros(())

@@ -48,6 +48,10 @@ int l2s_version(void);
 const char* l2s_last_error_string(void);
 /* number of kernels this library launched since load (process wide) */
 uint64_t l2s_launch_count(void);
+/* Diagnostics: hand the library a device buffer of >= 8192 bytes (or NULL to stop); CTA 0 of the persistent decode
+ * kernels then writes %globaltimer at its phase boundaries (slot 0: forward, slot 1: backward; [64 steps][8 marks] u64
+ * each).  Not for production use: the pointer is process-global. */
+int l2s_set_debug_buffer(void* device_buffer, size_t bytes);
 
 /* ---------------------------------------------------------------------------------------
  * (1) Spatial dynamic filter response + fusion + gate.
@@ -192,6 +196,21 @@ int l2s_mask_bce_fwd(const float* score, const int64_t* labels, const float* tar
                      int ncls, int hw, l2s_stream_t stream);
 int l2s_mask_bce_bwd(const float* score, const int64_t* labels, const float* target, const float* gscale,
                      float* dscore, int n, int ncls, int hw, l2s_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Box head glue.  Replaces the pieces of Network._region_classification
+ * (MFR/nets/network_cycle_response.py:277-290) around its two Linears: `spatial_fc7.mean(3).mean(2)` and
+ * `F.softmax(cls_score, 1)` / `torch.max(cls_score, 1)[1]`.  (The two Linears run stacked as one GEMM on
+ * l2s_gemm_bf16x3 / l2s_linear_small.)
+ *   x (rows, P) fp32 with rows = N*C and P = 7*7 -> out (rows) ; the square case takes the mean over W then over H
+ *   like the reference.  bwd: dx[r, p] = dout[r] / P.
+ *   softmax_argmax: score (R, ncls) with row stride ld -> prob (R, ncls) dense and / or pred (R) int64 = index of the
+ *   first maximum.  Either output may be NULL.
+ * ------------------------------------------------------------------------------------- */
+int l2s_spatial_mean_fwd(const float* x, float* out, int64_t rows, int P, l2s_stream_t stream);
+int l2s_spatial_mean_bwd(const float* dout, float* dx, int64_t rows, int P, l2s_stream_t stream);
+int l2s_softmax_argmax(const float* score, int64_t ld, float* prob, int64_t* pred, int R, int ncls,
+                       l2s_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * Targets on the device: crop a uint8 {0,1} ground-truth mask to a box and resize it

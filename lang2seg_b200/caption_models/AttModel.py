@@ -5,8 +5,8 @@ Classes, constructor options, parameter names and call signatures follow the ref
 `caption_model.core.attention.h2att.weight` etc. load from its checkpoints.  What changes is where
 the arithmetic runs:
 
-  Attention.forward    h2att Linear (cuBLAS) + ONE fused kernel: score, softmax, weighted sum
-  Att2in2Core.forward  i2h/h2h/a2c Linears (cuBLAS) + one gate kernel (sigmoid/maxout/tanh/cell)
+  Attention.forward    h2att Linear (skinny exact-fp32 GEMM) + ONE fused kernel: score, softmax, weighted sum
+  Att2in2Core.forward  i2h/h2h/a2c Linears (skinny exact-fp32 GEMM) + one gate kernel (sigmoid/maxout/tanh/cell)
   AttModel.forward     same T-step loop with the reference's early break; `forward_loss` fuses
                        logit -> log-softmax -> masked NLL (LanguageModelCriterion) per step
 """
@@ -28,7 +28,7 @@ class Attention(nn.Module):
     def forward(self, h, att_feats, p_att_feats):
         B = att_feats.size(0)
         att_size = att_feats.numel() // B // self.rnn_size
-        att_h = self.h2att(h)
+        att_h = L2F.dense(h, self.h2att.weight, self.h2att.bias)
         res, _ = L2F.attention_step(att_h, att_feats.reshape(B, att_size, self.rnn_size),
                                     p_att_feats.reshape(B, att_size, self.att_hid_size),
                                     self.alpha_net.weight, self.alpha_net.bias)
@@ -53,8 +53,8 @@ class Att2in2Core(nn.Module):
     def forward(self, xt, fc_feats, att_feats, p_att_feats, state):
         h_prev, c_prev = state[0][-1], state[1][-1]
         att_res = self.attention(h_prev, att_feats, p_att_feats)
-        sums = self.i2h(xt) + self.h2h(h_prev)
-        next_h, next_c = L2F.att2in2_gates(sums, self.a2c(att_res), c_prev)
+        sums = L2F.dense(xt, self.i2h.weight, self.i2h.bias) + L2F.dense(h_prev, self.h2h.weight, self.h2h.bias)
+        next_h, next_c = L2F.att2in2_gates(sums, L2F.dense(att_res, self.a2c.weight, self.a2c.bias), c_prev)
         output = self.dropout(next_h)
         return output, (next_h.unsqueeze(0), next_c.unsqueeze(0))
 
@@ -95,12 +95,9 @@ class AttModel(nn.Module):
 
     @staticmethod
     def _big_linear(lin, x):
-        """The two (B*196)-row projections dominate the caption model's flops (822 MFLOP/sample): run them on
-        the tcgen05 bf16x3 GEMM; small / unaligned cases stay on cuBLAS."""
-        M, K = x.shape
-        if x.is_cuda and M >= 512 and K % 8 == 0 and lin.out_features % 8 == 0:
-            return L2F.linear(x, lin.weight, lin.bias)
-        return lin(x)
+        """The (B*196)-row projections dominate the caption model's flops (822 MFLOP/sample): L2F.dense runs them on
+        the tcgen05 bf16x3 GEMM; small batches take the skinny exact-fp32 GEMM.  No cuBLAS behind either."""
+        return L2F.dense(x, lin.weight, lin.bias)
 
     def _prepare(self, fc_feats, att_feats):
         fc_feats = self.fc_embed(fc_feats)
@@ -113,7 +110,9 @@ class AttModel(nn.Module):
 
     def _fast_decode_ok(self, att):
         core = self.core
-        return (att.is_cuda and isinstance(core, Att2in2Core) and self.num_layers == 1
+        if not att.is_cuda:
+            raise L2F._lib.L2SError("AttModel: CUDA tensors only (there is no CPU path; the CPU baseline is oracle/)")
+        return (isinstance(core, Att2in2Core) and self.num_layers == 1
                 and self.rnn_size == self.att_hid_size and self.rnn_size % 4 == 0 and self.rnn_size <= 1024)
 
     def _decode(self, att, p_att, seq, T):
@@ -123,11 +122,7 @@ class AttModel(nn.Module):
         B = att.size(0)
         xt = self.embed(seq[:, :T].t())                                   # (T,B,E): Embedding+ReLU+Dropout (:95)
         bias = core.i2h.bias + core.h2h.bias
-        x2 = xt.reshape(T * B, -1)
-        if x2.shape[0] >= 512 and x2.shape[1] % 8 == 0:
-            i2h_all = L2F.linear(x2, core.i2h.weight, bias)
-        else:
-            i2h_all = F.linear(x2, core.i2h.weight, bias)
+        i2h_all = L2F.dense(xt.reshape(T * B, -1), core.i2h.weight, bias)
         att3 = att.reshape(B, -1, self.rnn_size)
         h_all = L2F.att2in2_decode(i2h_all.view(T, B, -1), att3, p_att.reshape(B, -1, self.att_hid_size),
                                    core.attention.h2att.weight, core.attention.h2att.bias, core.h2h.weight,
@@ -151,8 +146,8 @@ class AttModel(nn.Module):
         for i in range(T):
             xt = self.embed(seq[:, i])
             output, state = self.core(xt, fc_feats, att, p_att, state)
-            outputs.append(L2F.log_softmax(self.logit(output)) if not torch.is_grad_enabled()
-                           else F.log_softmax(self.logit(output), dim=1))
+            logits = self._big_linear(self.logit, output)
+            outputs.append(L2F.log_softmax(logits) if not torch.is_grad_enabled() else F.log_softmax(logits, dim=1))
         return torch.stack(outputs, 1)
 
     def forward_loss(self, fc_feats, att_feats, seq, masks, steps=None):
@@ -172,14 +167,14 @@ class AttModel(nn.Module):
         for i in range(T):
             xt = self.embed(seq[:, i])
             output, state = self.core(xt, fc_feats, att, p_att, state)
-            nll, _ = L2F.logsoftmax_nll(self.logit(output), seq[:, i + 1], masks[:, i + 1])
+            nll, _ = L2F.logsoftmax_nll(self._big_linear(self.logit, output), seq[:, i + 1], masks[:, i + 1])
             total = total + nll
         return total / masks[:, 1:T + 1].sum()
 
     def get_logprobs_state(self, it, tmp_fc_feats, tmp_att_feats, tmp_p_att_feats, state):
         xt = self.embed(it)
         output, state = self.core(xt, tmp_fc_feats, tmp_att_feats, tmp_p_att_feats, state)
-        return L2F.log_softmax(self.logit(output)), state
+        return L2F.log_softmax(self._big_linear(self.logit, output)), state
 
 
 class Att2in2Model(AttModel):

@@ -44,6 +44,7 @@ int  max_smem_optin();
 bool pdl_enabled();
 bool env_flag(const char* name);   // getenv(name) starts with '1'; callers cache the result in a function-local static
 void count_launch(int n = 1);          // feeds l2s_launch_count()
+unsigned long long* debug_buffer(int slot);   // l2s_set_debug_buffer: phase timestamps of the persistent kernels, or null
 
 // ---- internal launchers shared between translation units (att.cu <-> decode.cu) -----------
 int launch_att_step_fwd(const float* att_h, int ldh, const float* att_feats, const float* p_att, const float* alpha_w,
@@ -58,8 +59,31 @@ int launch_gates_bwd(const float* sums, int lds, const float* a2c_out, const flo
                      const float* dh_a, const float* dh_b, const float* dc, float* dsums, int ld_ds, float* da2c,
                      float* dc_prev, int B, int D, cudaStream_t st);
 
+// persistent decode kernels (decode_persist.cu): cluster size to launch with, 0 = shape / device not eligible
+int decode_persist_cluster(int B, int A, int D, int Dh);
+int launch_decode_fwd_persist(int cs, float* cat_all, const float* att, const float* p_att, const float* w_cat,
+                              const float* w_a2c, const float* b_a2c, const float* alpha_w, const float* alpha_b,
+                              float* h_all, float* c_all, float* a2c_all, float* pi_all, float* res_all, int T, int B,
+                              int A, unsigned* bar, cudaStream_t st);
+
+bool decode_bwd_persist_ok(int B, int A, int D, int Dh);
+int launch_decode_bwd_persist(const float* dh_all, const float* cat_all, const float* att, const float* p_att,
+                              const float* w_cat_t, const float* w_a2c_t, const float* alpha_w, const float* c_all,
+                              const float* a2c_all, const float* pi_all, float* dcat_all, float* da2c_all,
+                              float* dres_all, float* de_all, float* dh_carry, int T, int B, int A, unsigned* bar,
+                              cudaStream_t st);
+
+// persistent bi-LSTM kernels (lstm_persist.cu)
+bool bilstm_persist_ok(int L, int B, int H);
+int launch_bilstm_fwd_persist(float* G, const float* w_hh, const int* lens, float* c_all, float* h_all, float* out,
+                              float* hidden, int L, int B, unsigned* bar, cudaStream_t st);
+int launch_bilstm_bwd_persist(const float* dout, const float* dhidden, const float* G, const float* w_hh_t,
+                              const int* lens, const float* c_all, float* dG, int L, int B, unsigned* bar,
+                              cudaStream_t st);
+
 size_t linear_small_workspace_bytes(int M, int N, int K);
-// D[M,N] (+)= A[M,K] . W[N,K]^T + bias ; workspace = [4096 B of zeroed counters | split-K partials]
+size_t linear_small_counter_bytes(int M, int N);
+// D[M,N] (+)= A[M,K] . W[N,K]^T + bias ; workspace = [linear_small_counter_bytes(M,N) of zeroed counters | split-K partials]
 int launch_linear_small(const float* A, int lda, const float* W, int ldw, const float* bias, float* D, int ldd, int M,
                         int N, int K, int accumulate, void* workspace, size_t ws_bytes, cudaStream_t st);
 

@@ -63,7 +63,22 @@ int sm_count() { return cached_attr(cudaDevAttrMultiProcessorCount, 0, 148); }
 
 int max_smem_optin() { return cached_attr(cudaDevAttrMaxSharedMemoryPerBlockOptin, 1, 232448); }
 
+// diagnostics: a caller-owned device buffer the persistent kernels write phase timestamps into (slot 0: decode
+// forward, slot 1: decode backward; 64 steps x 8 marks x 8 bytes each)
+static std::atomic<unsigned long long*> g_debug{nullptr};
+unsigned long long* debug_buffer(int slot) {
+  unsigned long long* b = g_debug.load(std::memory_order_relaxed);
+  return b ? b + (size_t)slot * 64 * 8 : nullptr;
+}
+
 }  // namespace l2s
+
+extern "C" int l2s_set_debug_buffer(void* device_buffer, size_t bytes) {
+  if (device_buffer != nullptr && bytes < 2 * 64 * 8 * sizeof(unsigned long long))
+    return l2s::fail(L2S_ERR_ARG, "set_debug_buffer: need at least %zu bytes", 2 * 64 * 8 * sizeof(unsigned long long));
+  l2s::g_debug.store(reinterpret_cast<unsigned long long*>(device_buffer), std::memory_order_relaxed);
+  return L2S_OK;
+}
 
 extern "C" int l2s_version(void) { return 100; }
 extern "C" const char* l2s_last_error_string(void) { return l2s::g_err; }

@@ -176,7 +176,11 @@ linear_small_kernel(const float* __restrict__ A, const float* __restrict__ W, co
   if (t == 0) counters[slot] = 0u;   // ready for the next launch on this stream
 }
 
-constexpr size_t kLinCounterBytes = 4096;   // 1024 (column block, row block) slots
+// split-K arrival counters: one per (column block, row block); sized for the narrowest column blocks (8 columns)
+size_t lin_counter_bytes(int M, int N) {
+  const int mblocks = M > 32 ? (M + 31) / 32 : 1;
+  return (((size_t)((N + 7) / 8) * mblocks * sizeof(unsigned int)) + 255) & ~(size_t)255;
+}
 
 int pick_cpw(int N, int ks, int mblocks) {
   // largest column count per warp that still gives every SM a CTA; more columns per warp reuse the
@@ -191,12 +195,14 @@ int pick_cpw(int N, int ks, int mblocks) {
 
 }  // namespace
 
+size_t linear_small_counter_bytes(int M, int N) { return lin_counter_bytes(M > 0 ? M : 1, N > 0 ? N : 1); }
+
 size_t linear_small_workspace_bytes(int M, int N, int K) {
   const int ks = (K + kLinKC - 1) / kLinKC;
-  return kLinCounterBytes + (ks > 1 ? (size_t)ks * M * N * sizeof(float) : 0) + 256;
+  return linear_small_counter_bytes(M, N) + (ks > 1 ? (size_t)ks * M * N * sizeof(float) : 0) + 256;
 }
 
-// workspace: [counters (zero before first use; the kernel leaves them zero) | partials]
+// workspace: [linear_small_counter_bytes(M,N) of counters (zero before first use; the kernel leaves them zero) | partials]
 int launch_linear_small(const float* A, int lda, const float* W, int ldw, const float* bias, float* D, int ldd, int M,
                         int N, int K, int accumulate, void* workspace, size_t ws_bytes, cudaStream_t st) {
   L2S_REQUIRE(A && W && D, L2S_ERR_ARG, "linear_small: null pointer");
@@ -217,10 +223,11 @@ int launch_linear_small(const float* A, int lda, const float* W, int ldw, const 
   g.rows_pad = (g.rows_blk + 15) & ~15;   // staged rows per CTA: 16 or 32
   const int cpw = pick_cpw(N, g.ks, mblocks);
   const int cbs = (N + 8 * cpw - 1) / (8 * cpw);
-  L2S_REQUIRE((size_t)cbs * mblocks * sizeof(unsigned int) <= kLinCounterBytes, L2S_ERR_SHAPE,
-              "linear_small: N=%d too large", N);
+  const size_t cbytes = linear_small_counter_bytes(M, N);
+  L2S_REQUIRE((size_t)cbs * mblocks * sizeof(unsigned int) <= cbytes, L2S_ERR_SHAPE,
+              "linear_small: counter area too small for M=%d N=%d", M, N);
   unsigned int* counters = reinterpret_cast<unsigned int*>(workspace);
-  float* partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + kLinCounterBytes);
+  float* partials = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + cbytes);
   const size_t smem = (size_t)g.rows_pad * kLinKC * sizeof(float);
   dim3 grid(cbs, g.ks, mblocks);
 #define L2S_LIN_LAUNCH(CPW)                                                                              \
@@ -359,6 +366,7 @@ colsum_partial_kernel(const float* __restrict__ in, int64_t ld, float* __restric
 }
 
 struct DecodeWs {
+  unsigned* bar;      // grid-barrier counter of the persistent kernels (256 B)
   char* lin;          // linear_small workspace (shared by every GEMM of the loop: they are stream ordered)
   size_t lin_bytes;
   float* dalpha_part; // [B * ceil(A/kAccLoc)][Dh]
@@ -374,6 +382,8 @@ size_t decode_ws_layout(int B, int A, int D, int Dh, DecodeWs* w, char* base) {
   lin = (lin + 255) & ~(size_t)255;
   const size_t nchunk = (size_t)B * ((A + kAccLoc - 1) / kAccLoc);
   size_t off = 0;
+  if (w) w->bar = reinterpret_cast<unsigned*>(base + off);
+  off += 256;
   if (w) { w->lin = base + off; w->lin_bytes = lin; }
   off += lin;
   if (w) w->dalpha_part = reinterpret_cast<float*>(base + off);
@@ -402,7 +412,9 @@ extern "C" int l2s_linear_small(const float* A, const float* W, const float* bia
                                 l2s_stream_t stream) {
   L2S_REQUIRE(workspace, L2S_ERR_WORKSPACE, "linear_small: workspace missing");
   cudaStream_t st = (cudaStream_t)stream;
-  L2S_CUDA_OK(cudaMemsetAsync(workspace, 0, kLinCounterBytes, st));
+  L2S_REQUIRE(M > 0 && N > 0, L2S_ERR_SHAPE, "linear_small: bad shape M=%d N=%d", M, N);
+  L2S_REQUIRE(workspace_bytes >= linear_small_workspace_bytes(M, N, K), L2S_ERR_WORKSPACE, "linear_small: workspace too small");
+  L2S_CUDA_OK(cudaMemsetAsync(workspace, 0, linear_small_counter_bytes(M, N), st));
   return launch_linear_small(A, lda, W, ldw, bias, D, ldd, M, N, K, accumulate, workspace, workspace_bytes, st);
 }
 
@@ -451,7 +463,11 @@ extern "C" int l2s_att2in2_decode_fwd(float* cat_all, const float* att_feats, co
   cudaStream_t st = (cudaStream_t)stream;
   DecodeWs w;
   decode_ws_layout(B, A, D, Dh, &w, reinterpret_cast<char*>(workspace));
-  L2S_CUDA_OK(cudaMemsetAsync(w.lin, 0, 4096, st));
+  // one persistent weight-stationary kernel for all T steps where the shape allows it (decode_persist.cu)
+  if (const int cs = decode_persist_cluster(B, A, D, Dh))
+    return launch_decode_fwd_persist(cs, cat_all, att_feats, p_att, w_cat, w_a2c, b_a2c, alpha_w, alpha_b, h_all, c_all,
+                                     a2c_all, pi_all, att_res_all, T, B, A, w.bar, st);
+  L2S_CUDA_OK(cudaMemsetAsync(w.lin, 0, linear_small_counter_bytes(B, Dh + 5 * D), st));   // the widest GEMM of the loop
   const int LC = Dh + 5 * D;
   for (int t = 0; t < T; ++t) {
     float* cat_t = cat_all + (size_t)t * B * LC;
@@ -493,11 +509,17 @@ extern "C" int l2s_att2in2_decode_bwd(const float* dh_all, const float* cat_all,
   cudaStream_t st = (cudaStream_t)stream;
   DecodeWs w;
   decode_ws_layout(B, A, D, Dh, &w, reinterpret_cast<char*>(workspace));
-  L2S_CUDA_OK(cudaMemsetAsync(w.lin, 0, 4096, st));
+  L2S_CUDA_OK(cudaMemsetAsync(w.lin, 0, linear_small_counter_bytes(B, Dh + 5 * D), st));
   const int LC = Dh + 5 * D;
   float* dh_carry = w.carry;
   float* dc_buf[2] = {w.carry + (size_t)B * D, w.carry + (size_t)2 * B * D};
-  for (int t = T - 1; t >= 0; --t) {
+  const bool persistent = decode_bwd_persist_ok(B, A, D, Dh);
+  if (persistent) {      // the whole reverse loop as one persistent weight-stationary kernel (decode_persist.cu)
+    rc = launch_decode_bwd_persist(dh_all, cat_all, att_feats, p_att, w_cat_t, w_a2c_t, alpha_w, c_all, a2c_all, pi_all,
+                                   dcat_all, da2c_all, dres_all, de_all, dh_carry, T, B, A, w.bar, st);
+    if (rc) return rc;
+  }
+  for (int t = persistent ? -1 : T - 1; t >= 0; --t) {
     const float* cat_t = cat_all + (size_t)t * B * LC;
     const float* c_t = c_all + (size_t)t * B * D;
     const float* a2c_t = a2c_all + (size_t)t * B * 2 * D;

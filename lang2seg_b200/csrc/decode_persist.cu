@@ -30,107 +30,10 @@
 // Restrictions: rnn_size == att_hid_size == 512, B <= 64, A <= 1024; anything else takes the launch chain of decode.cu.
 #include <cooperative_groups.h>
 
-#include "common.cuh"
-
-namespace cg = cooperative_groups;
+#include "persist.cuh"
 
 namespace l2s {
 namespace {
-
-constexpr int PD = 512;           // rnn_size == att_hid_size
-constexpr int PG = 128;           // CTAs of the persistent grid
-constexpr int PT = 256;           // threads per CTA
-constexpr int PMAXB = 64;         // samples
-constexpr int PQ = PD / 4;        // float4 per 512-float row
-constexpr int PMAXLOC = 256;      // attention locations per CTA slice
-
-__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void red_release_gpu(unsigned* p) {
-  asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p) : "memory");
-}
-
-// Grid barrier on one monotonically increasing counter (zeroed by the host before the launch).  arrive() and wait()
-// are separate so that work which does not depend on the other CTAs can run in between.
-struct GridBar {
-  unsigned* ctr;
-  unsigned epoch;
-  __device__ __forceinline__ void arrive() {
-    __syncthreads();                     // every thread's global writes of this phase are ordered before the release
-    if (threadIdx.x == 0) {
-      __threadfence();
-      red_release_gpu(ctr);
-    }
-    ++epoch;
-  }
-  __device__ __forceinline__ void wait() const {
-    if (threadIdx.x == 0) {
-      const unsigned target = epoch * (unsigned)PG;
-      while (ld_acquire_gpu(ctr) < target) {
-      }
-      __threadfence();
-    }
-    __syncthreads();
-  }
-};
-
-// transpose-reduce: lane l ends with the sum over all lanes of v[l]
-__device__ __forceinline__ float transpose_reduce32(float (&v)[32], int lane) {
-#pragma unroll
-  for (int s = 16; s >= 1; s >>= 1) {
-    const bool up = (lane & s) != 0;
-#pragma unroll
-    for (int i = 0; i < s; ++i) {
-      const float a = v[i], b = v[i + s];
-      const float keep = up ? b : a, send = up ? a : b;
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-    }
-  }
-  return v[0];
-}
-
-__device__ __forceinline__ float dot4(const float4& a, const float4& w, float acc) {
-  acc = fmaf(a.x, w.x, acc);
-  acc = fmaf(a.y, w.y, acc);
-  acc = fmaf(a.z, w.z, acc);
-  return fmaf(a.w, w.w, acc);
-}
-
-// One register-blocked tile of a skinny GEMM: out[r*NC + c] = sum_k A[row_r][k] * W[col_c][k] for R rows and NC columns
-// held in shared memory (row stride lda4 / ldw4 float4), K = 128 * KS (lane l owns float4 l + 32 ks of every row).
-// On return lane (r*NC + c) holds the total of output (r, c).
-template <int R, int NC, int KS>
-__device__ __forceinline__ float gemv_tile(const float4* __restrict__ sA4, int lda4, const int (&arow)[R],
-                                           const float4* __restrict__ sW4, int ldw4, int wrow0, int lane) {
-  static_assert(R * NC <= 32, "tile too large for one transpose-reduce");
-  float acc[32];
-#pragma unroll
-  for (int i = 0; i < 32; ++i) acc[i] = 0.f;
-#pragma unroll
-  for (int ks = 0; ks < KS; ++ks) {
-    float4 a[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) a[r] = sA4[arow[r] * lda4 + ks * 32 + lane];
-#pragma unroll
-    for (int c = 0; c < NC; ++c) {
-      const float4 w = sW4[(wrow0 + c) * ldw4 + ks * 32 + lane];
-#pragma unroll
-      for (int r = 0; r < R; ++r) acc[r * NC + c] = dot4(a[r], w, acc[r * NC + c]);
-    }
-  }
-  return transpose_reduce32(acc, lane);
-}
-
-// rows [0,B) x 512 floats from global (produced by other CTAs of this launch: L2 loads, never L1) into shared memory
-__device__ __forceinline__ void stage_rows(float4* __restrict__ sA4, const float* __restrict__ src, int B, int ld) {
-  for (int i = threadIdx.x; i < B * PQ; i += PT) {
-    const int b = i / PQ, q = i - b * PQ;
-    sA4[i] = __ldcg(reinterpret_cast<const float4*>(src + (size_t)b * ld) + q);
-  }
-}
 
 struct DecFwdArgs {
   float* cat_all;          // (T,B,LC) in: [b_h2att | i2h(x_t) + b_i2h + b_h2h]  out: [att_h_t | sums_t]
@@ -147,6 +50,7 @@ struct DecFwdArgs {
   float* pi_all;           // (T,B,A)
   float* res_all;          // (T,B,D)
   unsigned* bar;
+  unsigned long long* prof;   // diagnostics or null
   int T, B, A;
 };
 
@@ -307,12 +211,14 @@ __global__ void __launch_bounds__(PT, 1) decode_fwd_persist_kernel(const DecFwdA
   const float alpha_b = __ldg(p.alpha_b);
   __syncthreads();
 
-  GridBar gb{p.bar, 0u};
+  GridBar gb{p.bar, 0u, (unsigned)PG};
+  const PhaseProf prof{p.prof};
   const float4* sA4 = reinterpret_cast<const float4*>(sA);
   const float4* sW4 = reinterpret_cast<const float4*>(sW);
 
   for (int step = 0; step < T; ++step) {
     float* cat_t = p.cat_all + (size_t)step * B * LC;
+    prof.mark(step, 0);
     if (step > 0) {
       stage_rows(reinterpret_cast<float4*>(sA), p.h_all + (size_t)(step - 1) * B * PD, B, PD);
       __syncthreads();
@@ -330,6 +236,7 @@ __global__ void __launch_bounds__(PT, 1) decode_fwd_persist_kernel(const DecFwdA
           }
         }
       }
+      prof.mark(step, 1);
       gb.arrive();
       // ---- A2: the five gate columns of unit u = wid & 3 for rows b = rg + 2 i (runs while barrier 1 completes)
       {
@@ -344,15 +251,19 @@ __global__ void __launch_bounds__(PT, 1) decode_fwd_persist_kernel(const DecFwdA
           if (lane < 30 && b < B) s_sums[b * 20 + 5 * u + g] = tot;
         }
       }
+      prof.mark(step, 2);
       gb.wait();
     }
+    prof.mark(step, 3);
     // ---- B: attention, one sample per cluster round
     for (int b = cid; b < B; b += NCL)
       attention_fwd_item<CS>(cluster, rank, b, cat_t + (size_t)b * LC, p.att, p.p_att, alpha_b,
                              p.pi_all + ((size_t)step * B + b) * A, p.res_all + ((size_t)step * B + b) * PD, A, s_ah, s_aw,
                              s_acc, s_e, s_ml, s_red);
+    prof.mark(step, 4);
     gb.arrive();
     gb.wait();
+    prof.mark(step, 5);
     // ---- C: a2c columns + gates
     stage_rows(reinterpret_cast<float4*>(sA), p.res_all + (size_t)step * B * PD, B, PD);
     __syncthreads();
@@ -388,63 +299,292 @@ __global__ void __launch_bounds__(PT, 1) decode_fwd_persist_kernel(const DecFwdA
       p.c_all[((size_t)step * B + b) * PD + d] = cn;
       p.h_all[((size_t)step * B + b) * PD + d] = og * tanhf(cn);
     }
+    prof.mark(step, 6);
     if (step + 1 < T) {
+      gb.arrive();
+      gb.wait();
+    }
+    prof.mark(step, 7);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ backward
+constexpr int BCS = 4;            // cluster size of the backward kernel: 32 clusters x 16 output columns, rank = K quarter
+constexpr int BMAXB = 48;         // samples (the staged (B x 640) operand block must fit next to the weights)
+constexpr int BNC = PD / (PG / BCS);   // 16 output columns per cluster
+
+struct DecBwdArgs {
+  const float* dh_all;     // (T,B,D) upstream gradient on h_t
+  const float* cat_all;    // (T,B,LC) [att_h | sums] kept by the forward
+  const float* att;
+  const float* p_att;
+  const float* w_cat_t;    // (D, LC) = [W_h2att ; W_h2h]^T
+  const float* w_a2c_t;    // (D, 2D) = W_a2c^T
+  const float* alpha_w;
+  const float* c_all;      // (T,B,D)
+  const float* a2c_all;    // (T,B,2D)
+  const float* pi_all;     // (T,B,A)
+  float* dcat_all;         // (T,B,LC) [datt_h | dsums]
+  float* da2c_all;         // (T,B,2D)
+  float* dres_all;         // (T,B,D)
+  float* de_all;           // (T,B,A)
+  float* dh_carry;         // (B,D) scratch
+  unsigned* bar;
+  unsigned long long* prof;   // diagnostics or null
+  int T, B, A;
+};
+
+// out[b][4 cg + c] (partial over this CTA's K slice) for rows b = rg + 2 i : warp = (column group cg, row group rg)
+template <int KS>
+__device__ __forceinline__ void partial_gemm16(const float4* sA4, int lda4, const float4* sW4, int B, float* s_part,
+                                               bool accumulate, int lane, int wid) {
+  const int cgp = wid & 3, rg = wid >> 2;
+  for (int i0 = 0; rg + 2 * i0 < B; i0 += 8) {
+    int arow[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) arow[r] = (rg + 2 * (i0 + r) < B) ? rg + 2 * (i0 + r) : 0;
+    const float tot = gemv_tile<8, 4, KS>(sA4, lda4, arow, sW4, lda4, 4 * cgp, lane);
+    const int b = rg + 2 * (i0 + (lane >> 2)), c = 4 * cgp + (lane & 3);
+    if (b < B) s_part[b * BNC + c] = accumulate ? s_part[b * BNC + c] + tot : tot;
+  }
+}
+
+// sum of the four ranks' partials for this rank's quarter of the cluster's 16 columns -> dst[b][col0 + ...]
+__device__ __forceinline__ void cluster_reduce16(cg::cluster_group& cluster, int rank, const float* s_part, int B,
+                                                 float* __restrict__ dst, int ld, int col0) {
+  const int t = threadIdx.x;
+  if (t < 4 * B) {
+    const int b = t >> 2, c = 4 * rank + (t & 3);
+    float v = 0.f;
+#pragma unroll
+    for (int q = 0; q < BCS; ++q) v += cluster.map_shared_rank(s_part, q)[b * BNC + c];
+    dst[(size_t)b * ld + col0 + c] = v;
+  }
+}
+
+// light attention backward of one sample by a cluster of BCS CTAs: datt_h (-> dcat row) and de (AttModel.py:411-421)
+__device__ __forceinline__ void attention_bwd_item(cg::cluster_group& cluster, int rank, int b, const float* __restrict__ dres_row,
+                                                   const float* __restrict__ att_h_row, const float* __restrict__ att,
+                                                   const float* __restrict__ p_att, const float* __restrict__ pi_row,
+                                                   float* __restrict__ datt_h_row, float* __restrict__ de_row, int A,
+                                                   float* s_ah, const float* s_aw, float* s_dah /*[2][PD]*/, float* s_do,
+                                                   float* s_w, float* s_dpi, float* s_part, float* s_red) {
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  const int per = (A + BCS - 1) / BCS;
+  const int a0 = min(A, rank * per), a1 = min(A, a0 + per);
+  const int na = a1 - a0;
+  for (int q = t; q < PQ; q += PT) {
+    reinterpret_cast<float4*>(s_ah)[q] = __ldg(reinterpret_cast<const float4*>(att_h_row) + q);
+    reinterpret_cast<float4*>(s_do)[q] = __ldcg(reinterpret_cast<const float4*>(dres_row) + q);
+  }
+  for (int a = t; a < na; a += PT) s_w[a] = __ldg(pi_row + a0 + a);
+  __syncthreads();
+  // d pi_a = <datt_res, att_feats[a]>
+  for (int a = wid; a < na; a += PT / 32) {
+    const float4* row = reinterpret_cast<const float4*>(att + ((size_t)b * A + a0 + a) * PD);
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < PQ / 32; ++k) {
+      const int q = lane + 32 * k;
+      const float4 v = __ldg(row + q);
+      const float4 d = reinterpret_cast<const float4*>(s_do)[q];
+      s = dot4(v, d, s);
+    }
+    s = warp_sum(s);
+    if (lane == 0) s_dpi[a] = s;
+  }
+  __syncthreads();
+  float part = 0.f;
+  for (int a = t; a < na; a += PT) part = fmaf(s_w[a], s_dpi[a], part);
+  part = warp_sum(part);
+  if (lane == 0) s_red[wid] = part;
+  __syncthreads();
+  if (t == 0) {
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < PT / 32; ++w) tot += s_red[w];
+    s_part[0] = tot;
+  }
+  cluster.sync();
+  float S = 0.f;
+#pragma unroll
+  for (int r = 0; r < BCS; ++r) S += cluster.map_shared_rank(s_part, r)[0];
+  for (int a = t; a < na; a += PT) {
+    const float de = s_w[a] * (s_dpi[a] - S);
+    s_dpi[a] = de;
+    de_row[a0 + a] = de;
+  }
+  __syncthreads();
+  // datt_h[d] = alpha_d sum_a de_a (1 - tanh^2(p_att[a,d] + att_h[d])): thread = (float4 column group, location phase)
+  {
+    const int q = t & (PQ - 1), ph = t / PQ;
+    const float4 h = reinterpret_cast<const float4*>(s_ah)[q];
+    const float4 w = reinterpret_cast<const float4*>(s_aw)[q];
+    float4 dah = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
+    for (int a = ph; a < na; a += PT / PQ) {
+      const float4 p = __ldg(reinterpret_cast<const float4*>(p_att + ((size_t)b * A + a0 + a) * PD) + q);
+      const float de = s_dpi[a];
+      const float tx = tanhf_fast_acc(p.x + h.x), ty = tanhf_fast_acc(p.y + h.y);
+      const float tz = tanhf_fast_acc(p.z + h.z), tw = tanhf_fast_acc(p.w + h.w);
+      dah.x += de * w.x * (1.f - tx * tx); dah.y += de * w.y * (1.f - ty * ty);
+      dah.z += de * w.z * (1.f - tz * tz); dah.w += de * w.w * (1.f - tw * tw);
+    }
+    reinterpret_cast<float4*>(s_dah + ph * PD)[q] = dah;
+  }
+  cluster.sync();
+  constexpr int DPER = PD / BCS;
+  for (int d = rank * DPER + t; d < (rank + 1) * DPER; d += PT) {
+    float v = 0.f;
+#pragma unroll
+    for (int r = 0; r < BCS; ++r) {
+      const float* ra = cluster.map_shared_rank(s_dah, r);
+      v += ra[d] + ra[PD + d];
+    }
+    datt_h_row[d] = v;
+  }
+  cluster.sync();
+}
+
+struct DecBwdSmem {
+  static constexpr int W2 = 0;                        // [16][256]  W_a2c^T rows of the cluster, this rank's K quarter
+  static constexpr int W4A = W2 + BNC * 256;          // [16][640]  W_cat^T, dsums part of K
+  static constexpr int W4B = W4A + BNC * 640;         // [16][128]  W_cat^T, datt_h part of K
+  static constexpr int A_OFF = W4B + BNC * 128;       // [BMAXB][640] staged operand block
+  static constexpr int MISC = A_OFF + BMAXB * 640;
+  static constexpr int TOTAL = MISC + 2 * BMAXB * BNC + BMAXB * 4 + 5 * PD + 2 * PMAXLOC + 16;
+};
+
+__global__ void __launch_bounds__(PT, 1) decode_bwd_persist_kernel(const DecBwdArgs p) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int j = blockIdx.x;
+  const int cid = j / BCS;
+  constexpr int NCL = PG / BCS;
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  const int B = p.B, A = p.A, T = p.T;
+  constexpr int LC = 6 * PD;
+
+  extern __shared__ __align__(16) float smem[];
+  float* sW2 = smem + DecBwdSmem::W2;
+  float* sW4a = smem + DecBwdSmem::W4A;
+  float* sW4b = smem + DecBwdSmem::W4B;
+  float* sA = smem + DecBwdSmem::A_OFF;
+  float* s_part2 = smem + DecBwdSmem::MISC;       // [BMAXB][16]
+  float* s_part4 = s_part2 + BMAXB * BNC;         // [BMAXB][16]
+  float* s_dc = s_part4 + BMAXB * BNC;            // [BMAXB][4]  dc carry of the CTA's units
+  float* s_ah = s_dc + BMAXB * 4;                 // [PD]
+  float* s_aw = s_ah + PD;                        // [PD]
+  float* s_dah = s_aw + PD;                       // [2][PD]
+  float* s_do = s_dah + 2 * PD;                   // [PD]
+  float* s_w = s_do + PD;                         // [PMAXLOC]
+  float* s_dpi = s_w + PMAXLOC;                   // [PMAXLOC]
+  float* s_ps = s_dpi + PMAXLOC;                  // [4]
+  float* s_red = s_ps + 4;                        // [8]
+
+  // ---- stationary weights: rows n = 16 cid + i of the transposed matrices, this rank's K slices
+  for (int i = t; i < BNC * 64; i += PT) {
+    const int r = i >> 6, q = i & 63;
+    reinterpret_cast<float4*>(sW2)[i] =
+        __ldg(reinterpret_cast<const float4*>(p.w_a2c_t + (size_t)(BNC * cid + r) * 2 * PD + 256 * rank) + q);
+  }
+  for (int i = t; i < BNC * 160; i += PT) {
+    const int r = i / 160, q = i - r * 160;
+    reinterpret_cast<float4*>(sW4a)[i] =
+        __ldg(reinterpret_cast<const float4*>(p.w_cat_t + (size_t)(BNC * cid + r) * LC + PD + 640 * rank) + q);
+  }
+  for (int i = t; i < BNC * 32; i += PT) {
+    const int r = i >> 5, q = i & 31;
+    reinterpret_cast<float4*>(sW4b)[i] =
+        __ldg(reinterpret_cast<const float4*>(p.w_cat_t + (size_t)(BNC * cid + r) * LC + 128 * rank) + q);
+  }
+  for (int i = t; i < PD; i += PT) s_aw[i] = __ldg(p.alpha_w + i);
+  for (int i = t; i < BMAXB * 4; i += PT) s_dc[i] = 0.f;
+  __syncthreads();
+
+  GridBar gb{p.bar, 0u, (unsigned)PG};
+  const PhaseProf prof{p.prof};
+  const float4* sA4 = reinterpret_cast<const float4*>(sA);
+
+  for (int step = T - 1; step >= 0; --step) {
+    prof.mark(step, 0);
+    const float* cat_t = p.cat_all + (size_t)step * B * LC;
+    float* dcat_t = p.dcat_all + (size_t)step * B * LC;
+    float* da2c_t = p.da2c_all + (size_t)step * B * 2 * PD;
+    float* dres_t = p.dres_all + (size_t)step * B * PD;
+    const bool last = (step == T - 1);
+    // ---- S1: gates backward for (b, unit 4j + u)
+    if (t < 4 * B) {
+      const int b = t >> 2, u = t & 3, d = 4 * j + u;
+      const float* srow = cat_t + (size_t)b * LC + PD;
+      const float* a2c = p.a2c_all + ((size_t)step * B + b) * 2 * PD;
+      const size_t idx = ((size_t)step * B + b) * PD + d;
+      const float ig = sigmoidf_acc(__ldg(srow + d)), fg = sigmoidf_acc(__ldg(srow + PD + d));
+      const float og = sigmoidf_acc(__ldg(srow + 2 * PD + d));
+      const float g1 = __ldg(srow + 3 * PD + d) + __ldg(a2c + d), g2 = __ldg(srow + 4 * PD + d) + __ldg(a2c + PD + d);
+      const bool first = g1 >= g2;
+      const float gg = first ? g1 : g2;
+      const float tc = tanhf(__ldg(p.c_all + idx));
+      const float cp = step > 0 ? __ldg(p.c_all + idx - (size_t)B * PD) : 0.f;
+      const float gh = __ldg(p.dh_all + idx) + (last ? 0.f : __ldcg(p.dh_carry + (size_t)b * PD + d));
+      const float dct = (last ? 0.f : s_dc[b * 4 + u]) + gh * og * (1.f - tc * tc);
+      float* ds = dcat_t + (size_t)b * LC + PD;
+      ds[d] = dct * gg * ig * (1.f - ig);
+      ds[PD + d] = dct * cp * fg * (1.f - fg);
+      ds[2 * PD + d] = gh * tc * og * (1.f - og);
+      const float dg = dct * ig;
+      ds[3 * PD + d] = first ? dg : 0.f;
+      ds[4 * PD + d] = first ? 0.f : dg;
+      da2c_t[(size_t)b * 2 * PD + d] = first ? dg : 0.f;
+      da2c_t[(size_t)b * 2 * PD + PD + d] = first ? 0.f : dg;
+      s_dc[b * 4 + u] = dct * fg;
+    }
+    prof.mark(step, 1);
+    gb.arrive();
+    gb.wait();
+    prof.mark(step, 2);
+    // ---- S2: datt_res_t[:, 16 cid ..] = da2c_t W_a2c  (K quarter per rank, summed through DSMEM)
+    stage_slice(reinterpret_cast<float4*>(sA), da2c_t + 256 * rank, B, 2 * PD, 64);
+    __syncthreads();
+    partial_gemm16<2>(sA4, 64, reinterpret_cast<const float4*>(sW2), B, s_part2, false, lane, wid);
+    cluster.sync();
+    cluster_reduce16(cluster, rank, s_part2, B, dres_t, PD, BNC * cid);
+    prof.mark(step, 3);
+    gb.arrive();
+    // ---- S4a (runs while barrier 2 completes): dh_{t-1} partial over the dsums part of K
+    if (step > 0) {
+      stage_slice(reinterpret_cast<float4*>(sA), dcat_t + PD + 640 * rank, B, LC, 160);
+      __syncthreads();
+      partial_gemm16<5>(sA4, 160, reinterpret_cast<const float4*>(sW4a), B, s_part4, false, lane, wid);
+    }
+    prof.mark(step, 4);
+    gb.wait();
+    prof.mark(step, 5);
+    // ---- S3: attention backward, one sample per cluster round
+    for (int b = cid; b < B; b += NCL)
+      attention_bwd_item(cluster, rank, b, dres_t + (size_t)b * PD, cat_t + (size_t)b * LC, p.att, p.p_att,
+                         p.pi_all + ((size_t)step * B + b) * A, dcat_t + (size_t)b * LC,
+                         p.de_all + ((size_t)step * B + b) * A, A, s_ah, s_aw, s_dah, s_do, s_w, s_dpi, s_ps, s_red);
+    prof.mark(step, 6);
+    if (step > 0) {
+      gb.arrive();
+      gb.wait();
+      prof.mark(step, 7);
+      // ---- S4b: + datt_h part of K, cluster sum -> dh carry
+      stage_slice(reinterpret_cast<float4*>(sA), dcat_t + 128 * rank, B, LC, 32);
+      __syncthreads();
+      partial_gemm16<1>(sA4, 32, reinterpret_cast<const float4*>(sW4b), B, s_part4, true, lane, wid);
+      cluster.sync();
+      cluster_reduce16(cluster, rank, s_part4, B, p.dh_carry, PD, BNC * cid);
       gb.arrive();
       gb.wait();
     }
   }
 }
 
+size_t dec_bwd_smem() { return (size_t)DecBwdSmem::TOTAL * sizeof(float) + 64; }
+
 size_t dec_fwd_smem() { return (size_t)(DecSmem::MISC_OFF + PMAXB * 32 + 4 * PD + PMAXLOC + 4 + 8) * sizeof(float) + 64; }
-
-template <class Kern, class Args>
-int launch_persistent(Kern kern, int cs, size_t smem, cudaStream_t st, const Args& args, bool coop) {
-  L2S_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (cs > 8) L2S_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(PG);
-  cfg.blockDim = dim3(PT);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[2];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = cs;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  attr[1].id = cudaLaunchAttributeCooperative;
-  attr[1].val.cooperative = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = coop ? 2 : 1;
-  L2S_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, args));
-  count_launch();
-  return L2S_OK;
-}
-
-// how many clusters of `cs` CTAs of this kernel can be resident at once (0 on error)
-template <class Kern>
-int max_clusters(Kern kern, int cs, size_t smem) {
-  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-    cudaGetLastError();
-    return 0;
-  }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(PG);
-  cfg.blockDim = dim3(PT);
-  cfg.dynamicSmemBytes = smem;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = cs;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) {
-    cudaGetLastError();
-    return 0;
-  }
-  return n;
-}
 
 }  // namespace
 
@@ -476,10 +616,42 @@ int launch_decode_fwd_persist(int cs, float* cat_all, const float* att, const fl
   L2S_REQUIRE(aligned16(cat_all) && aligned16(att) && aligned16(p_att) && aligned16(w_cat) && aligned16(w_a2c) &&
                   aligned16(h_all) && aligned16(res_all), L2S_ERR_ALIGN, "att2in2_decode_fwd: pointers must be 16-byte aligned");
   L2S_CUDA_OK(cudaMemsetAsync(bar, 0, 64, st));
-  DecFwdArgs a{cat_all, att, p_att, w_cat, w_a2c, b_a2c, alpha_w, alpha_b, h_all, c_all, a2c_all, pi_all, res_all, bar, T, B, A};
+  DecFwdArgs a{cat_all, att, p_att, w_cat, w_a2c, b_a2c, alpha_w, alpha_b, h_all, c_all, a2c_all, pi_all, res_all, bar,
+               T <= 64 ? debug_buffer(0) : nullptr, T, B, A};
   static const bool coop = !env_flag("L2S_DECODE_NOCOOP");
   if (cs == 8) return launch_persistent(decode_fwd_persist_kernel<8>, 8, dec_fwd_smem(), st, a, coop);
   return launch_persistent(decode_fwd_persist_kernel<4>, 4, dec_fwd_smem(), st, a, coop);
+}
+
+
+// backward eligibility: forward eligibility + B <= 48 + the 4-CTA-cluster grid must be co-resident
+bool decode_bwd_persist_ok(int B, int A, int D, int Dh) {
+  if (!decode_persist_cluster(B, A, D, Dh) || B > BMAXB || (A + BCS - 1) / BCS > PMAXLOC) return false;
+  static thread_local int cached_dev = -1;
+  static thread_local bool cached_ok = false;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  if (dev != cached_dev) {
+    cached_dev = dev;
+    cached_ok = (size_t)max_smem_optin() >= dec_bwd_smem() &&
+                max_clusters(decode_bwd_persist_kernel, BCS, dec_bwd_smem()) >= PG / BCS;
+  }
+  return cached_ok;
+}
+
+int launch_decode_bwd_persist(const float* dh_all, const float* cat_all, const float* att, const float* p_att,
+                              const float* w_cat_t, const float* w_a2c_t, const float* alpha_w, const float* c_all,
+                              const float* a2c_all, const float* pi_all, float* dcat_all, float* da2c_all,
+                              float* dres_all, float* de_all, float* dh_carry, int T, int B, int A, unsigned* bar,
+                              cudaStream_t st) {
+  L2S_REQUIRE(aligned16(dh_all) && aligned16(cat_all) && aligned16(att) && aligned16(p_att) && aligned16(w_cat_t) &&
+                  aligned16(w_a2c_t) && aligned16(dcat_all) && aligned16(da2c_all) && aligned16(dres_all) &&
+                  aligned16(dh_carry), L2S_ERR_ALIGN, "att2in2_decode_bwd: pointers must be 16-byte aligned");
+  L2S_CUDA_OK(cudaMemsetAsync(bar, 0, 64, st));
+  DecBwdArgs a{dh_all, cat_all, att, p_att, w_cat_t, w_a2c_t, alpha_w, c_all, a2c_all, pi_all, dcat_all, da2c_all,
+               dres_all, de_all, dh_carry, bar, T <= 64 ? debug_buffer(1) : nullptr, T, B, A};
+  static const bool coop = !env_flag("L2S_DECODE_NOCOOP");
+  return launch_persistent(decode_bwd_persist_kernel, BCS, dec_bwd_smem(), st, a, coop);
 }
 
 }  // namespace l2s

@@ -121,7 +121,8 @@ size_t lstm_ws_bytes(int B, int H) {
   size_t lin = linear_small_workspace_bytes(B, 4 * H, H);
   const size_t lin2 = linear_small_workspace_bytes(B, H, 4 * H);
   lin = ((lin > lin2 ? lin : lin2) + 255) & ~(size_t)255;
-  return 2 * lin + (size_t)6 * 2 * B * H * sizeof(float) + 256;     // two GEMM workspaces + dh_rec, 2x dh_pass, 2x dc, spare
+  // two GEMM workspaces + dh_rec, 2x dh_pass, 2x dc, spare + 256 B of grid-barrier counters (persistent kernels)
+  return 2 * lin + (size_t)6 * 2 * B * H * sizeof(float) + 256 + 256;
 }
 
 }  // namespace
@@ -144,9 +145,12 @@ extern "C" int l2s_bilstm_fwd(float* G, const float* w_hh, const int32_t* lens, 
   cudaStream_t st = (cudaStream_t)stream;
   const LstmGeom g{L, B, H};
   char* ws = reinterpret_cast<char*>(workspace);
-  const size_t lin = (lstm_ws_bytes(B, H) - 256 - (size_t)6 * 2 * B * H * sizeof(float)) / 2;
-  L2S_CUDA_OK(cudaMemsetAsync(ws, 0, 4096, st));
-  L2S_CUDA_OK(cudaMemsetAsync(ws + lin, 0, 4096, st));
+  if (bilstm_persist_ok(L, B, H))      // one persistent weight-stationary kernel for all L steps (lstm_persist.cu)
+    return launch_bilstm_fwd_persist(G, w_hh, lens, c_all, h_all, out, hidden, L, B,
+                                     reinterpret_cast<unsigned*>(ws + ((lstm_ws_bytes(B, H) - 256) & ~(size_t)255)), st);
+  const size_t lin = (lstm_ws_bytes(B, H) - 512 - (size_t)6 * 2 * B * H * sizeof(float)) / 2;
+  L2S_CUDA_OK(cudaMemsetAsync(ws, 0, linear_small_counter_bytes(B, 4 * H), st));
+  L2S_CUDA_OK(cudaMemsetAsync(ws + lin, 0, linear_small_counter_bytes(B, 4 * H), st));
   const int threads = 256, blocks = (2 * B * H + threads - 1) / threads;
   const int ldg = L * 8 * H;
   for (int s = 0; s < L; ++s) {
@@ -178,9 +182,12 @@ extern "C" int l2s_bilstm_bwd(const float* dout, const float* dhidden, const flo
   cudaStream_t st = (cudaStream_t)stream;
   const LstmGeom g{L, B, H};
   char* ws = reinterpret_cast<char*>(workspace);
-  const size_t lin = (lstm_ws_bytes(B, H) - 256 - (size_t)6 * 2 * B * H * sizeof(float)) / 2;
-  L2S_CUDA_OK(cudaMemsetAsync(ws, 0, 4096, st));
-  L2S_CUDA_OK(cudaMemsetAsync(ws + lin, 0, 4096, st));
+  if (bilstm_persist_ok(L, B, H))
+    return launch_bilstm_bwd_persist(dout, dhidden, G, w_hh_t, lens, c_all, dG, L, B,
+                                     reinterpret_cast<unsigned*>(ws + ((lstm_ws_bytes(B, H) - 256) & ~(size_t)255)), st);
+  const size_t lin = (lstm_ws_bytes(B, H) - 512 - (size_t)6 * 2 * B * H * sizeof(float)) / 2;
+  L2S_CUDA_OK(cudaMemsetAsync(ws, 0, linear_small_counter_bytes(B, 4 * H), st));
+  L2S_CUDA_OK(cudaMemsetAsync(ws + lin, 0, linear_small_counter_bytes(B, 4 * H), st));
   const size_t n = (size_t)2 * B * H;
   float* fb = reinterpret_cast<float*>(ws + 2 * lin);
   float* dh_rec = fb;

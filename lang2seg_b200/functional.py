@@ -386,6 +386,60 @@ def mask_bce_loss(mask_score, labels, mask_targets):
 
 
 # ------------------------------------------------------------------------------------------------
+# box head glue (row a9)
+# ------------------------------------------------------------------------------------------------
+class _SpatialMean(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = f32c(x)
+        N, C = x.shape[0], x.shape[1]
+        P = x.numel() // max(N * C, 1)
+        out = torch.empty(N, C, device=x.device, dtype=torch.float32)
+        call("l2s_spatial_mean_fwd", ptr(x), ptr(out), N * C, P, stream())
+        ctx.shape = tuple(x.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        dout = f32c(dout)
+        dx = torch.empty(ctx.shape, device=dout.device, dtype=torch.float32)
+        N, C = ctx.shape[0], ctx.shape[1]
+        call("l2s_spatial_mean_bwd", ptr(dout), ptr(dx), N * C, dx.numel() // max(N * C, 1), stream())
+        return dx
+
+
+def spatial_mean(x):
+    """spatial_fc7.mean(3).mean(2) (network_cycle_response.py:278): (N,C,h,w) -> (N,C)."""
+    return _SpatialMean.apply(x)
+
+
+def softmax_argmax(score):
+    """(F.softmax(score, 1), torch.max(score, 1)[1]) of network_cycle_response.py:280-281 in one kernel (no gradient:
+    the reference's losses read cls_score, not cls_prob).  `score` may be a column slice of a wider matrix."""
+    assert score.dim() == 2 and score.stride(1) == 1 and score.dtype == torch.float32
+    R, ncls = score.shape
+    prob = torch.empty(R, ncls, device=score.device, dtype=torch.float32)
+    pred = torch.empty(R, device=score.device, dtype=torch.int64)
+    call("l2s_softmax_argmax", ptr(score), score.stride(0) if R > 1 else ncls, ptr(prob), ptr(pred), R, ncls, stream())
+    return prob, pred
+
+
+def region_classification(spatial_fc7, cls_w, cls_b, bbox_w, bbox_b):
+    """Network._region_classification (network_cycle_response.py:277-290): 7x7 mean -> cls_score_net and bbox_pred_net
+    as ONE stacked GEMM (tcgen05 bf16x3 for >= 512 ROIs, the skinny exact-fp32 GEMM below that) -> softmax / argmax.
+    Returns (cls_score, cls_pred, cls_prob, bbox_pred)."""
+    fc7 = spatial_mean(spatial_fc7)
+    ncls, nbox = cls_w.shape[0], bbox_w.shape[0]
+    pad = (-(ncls + nbox)) % 8                       # operand rows of the tensor-core GEMM must be 16-byte multiples
+    W = torch.cat([cls_w, bbox_w] + ([cls_w.new_zeros(pad, cls_w.shape[1])] if pad else []), 0)
+    b = torch.cat([cls_b, bbox_b] + ([cls_b.new_zeros(pad)] if pad else []), 0)
+    y = linear(fc7, W, b) if fc7.shape[0] >= 512 and fc7.shape[1] % 8 == 0 else linear_small_fn(fc7, W, b)
+    cls_score, bbox_pred = y[:, :ncls], y[:, ncls:ncls + nbox]
+    cls_prob, cls_pred = softmax_argmax(cls_score.detach())
+    return cls_score, cls_pred, cls_prob, bbox_pred
+
+
+# ------------------------------------------------------------------------------------------------
 # (3) attention step and the att2in2 epilogues
 # ------------------------------------------------------------------------------------------------
 class _AttStep(torch.autograd.Function):
@@ -522,15 +576,19 @@ def att2in2_decode(i2h_all, att_feats, p_att, w_h2att, b_h2att, w_h2h, w_a2c, b_
 
 
 class _LinearSmallFn(torch.autograd.Function):
-    """nn.Linear on a small batch (rows <= a few hundred) in exact fp32 through l2s_linear_small, fwd and dX;
-    the weight gradient is one rank-`rows` update (cuBLAS)."""
+    """nn.Linear on a small batch (rows <= a few hundred) in exact fp32 through l2s_linear_small, fwd and dX (the
+    strided FFMA GEMM l2s_gemm_f32 where a reduction length is not a multiple of 4); the weight gradient is one
+    rank-`rows` update (cuBLAS)."""
 
     @staticmethod
     def forward(ctx, x, w, b):
         x, w = f32c(x), f32c(w)
         ctx.save_for_backward(x, w)
         ctx.has_bias = b is not None
-        return linear_small(x, w, b)
+        if x.shape[1] % 4 == 0:
+            return linear_small(x, w, b)
+        y = gemm_f32(x, w)
+        return y + f32c(b) if b is not None else y
 
     @staticmethod
     def backward(ctx, dy):
@@ -538,7 +596,13 @@ class _LinearSmallFn(torch.autograd.Function):
         dy = f32c(dy)
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = linear_small(dy, w.t().contiguous())
+            M, N = dy.shape
+            K = w.shape[1]
+            if N % 4 == 0:
+                dx = linear_small(dy, w.t().contiguous())
+            else:       # dx[m,k] = sum_n dy[m,n] w[n,k]: w read in place with strides (1, K)
+                dx = torch.empty(M, K, device=dy.device, dtype=torch.float32)
+                call("l2s_gemm_f32", ptr(dy), ptr(w), ptr(dx), M, K, N, N, 1, 1, K, K, 0, stream())
         if ctx.needs_input_grad[1]:
             dw = dy.t() @ x
         if ctx.has_bias and ctx.needs_input_grad[2]:
@@ -751,6 +815,23 @@ class _LinearTC(torch.autograd.Function):
 def linear(x, weight, bias=None):
     """nn.Linear forward/backward for large row counts on the tensor pipe at fp32 accuracy (bf16x3)."""
     return _LinearTC.apply(x, weight, bias)
+
+
+def dense(x, weight, bias=None):
+    """nn.Linear on the library's own kernels, chosen by shape: the tcgen05 bf16x3 GEMM (fp32 accuracy, ~1e-5) when
+    there are enough rows to fill 128-row MMA tiles and the operands meet TMA's 16-byte row alignment, the skinny
+    exact-fp32 GEMM otherwise.  There is no cuBLAS / CPU path behind it: CPU tensors raise."""
+    if not x.is_cuda:
+        raise _lib.L2SError("lang2seg_b200.dense: CUDA tensors only (there is no CPU path)")
+    lead = x.shape[:-1]
+    x2 = x.reshape(-1, x.shape[-1])
+    M, K = x2.shape
+    N = weight.shape[0]
+    if M >= 256 and K % 8 == 0 and N % 8 == 0:
+        y = linear(x2, weight, bias)
+    else:
+        y = linear_small_fn(x2, weight, bias)
+    return y.view(*lead, N)
 
 
 def gemm_f32(A, B, accumulate=False, out=None):

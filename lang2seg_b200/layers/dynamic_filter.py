@@ -12,18 +12,19 @@ from .. import functional as L2F
 def generate_filters(hidden, dynamic_fcs, response_fc):
     """f_k = tanh(dynamic_fc_k(hidden)) stacked to (E,7,C) ; w = tanh(response_fc(hidden)) (E,7).  (:510-532)
 
-    The reference issues 8 separate Linears per expression; on the GPU the seven (C x Dh) projections run as ONE
-    skinny exact-fp32 GEMM over the stacked weights (l2s_linear_small), forward and backward."""
+    The reference issues 8 separate Linears per expression; here the seven (C x Dh) projections AND response_fc run as
+    ONE GEMM over the stacked weights (7C + 7 rows, padded to a multiple of 8), forward and backward, on the library's
+    kernels (L2F.dense: skinny exact-fp32 GEMM for small batches of expressions, tcgen05 above 256)."""
     E, Dh = hidden.shape
+    nf = len(dynamic_fcs)
     C = dynamic_fcs[0].out_features
-    if hidden.is_cuda and Dh % 4 == 0 and (len(dynamic_fcs) * C) % 4 == 0 and E <= 512:
-        W = torch.cat([fc.weight for fc in dynamic_fcs], 0)
-        b = torch.cat([fc.bias for fc in dynamic_fcs], 0)
-        filt = torch.tanh(L2F.linear_small_fn(hidden, W, b)).view(E, len(dynamic_fcs), C)
-    else:
-        filt = torch.tanh(torch.stack([fc(hidden) for fc in dynamic_fcs], 1))
-    fuse = torch.tanh(response_fc(hidden))
-    return filt, fuse
+    nr = response_fc.out_features
+    pad = (-(nf * C + nr)) % 8
+    W = torch.cat([fc.weight for fc in dynamic_fcs] + [response_fc.weight] +
+                  ([hidden.new_zeros(pad, Dh)] if pad else []), 0)
+    b = torch.cat([fc.bias for fc in dynamic_fcs] + [response_fc.bias] + ([hidden.new_zeros(pad)] if pad else []), 0)
+    y = torch.tanh(L2F.dense(hidden, W, b))
+    return y[:, :nf * C].reshape(E, nf, C), y[:, nf * C:nf * C + nr]
 
 
 class DynamicFilterResponse(nn.Module):

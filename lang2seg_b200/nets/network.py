@@ -9,7 +9,7 @@ argument orders, so that a reference Network subclass can inherit them (INTEGRAT
     _region_classification(spatial_fc7)                            :277-290
     _mask_prediction(spatial_fc7)                                  :292-307
     _dynamic_filter(net_conv, labels | hidden)                     :503-570
-    _add_hot_path_losses(...)                                      :404-422, :443 (mask, response, caption)
+    _add_hot_path_losses(...)                                      :375-453 (cls, box, mask, response, caption; weights :449)
 
 `HotPathNet` is the concrete module (parameter names of resnet_v1_cycle_response.py:238-335) used by
 bench.py and the tests; backbone, RPN and res5 are outside this repository's scope and are supplied
@@ -53,11 +53,10 @@ class Network(nn.Module):
 
     # ---- heads ---------------------------------------------------------------------------------
     def _region_classification(self, spatial_fc7):
-        fc7 = spatial_fc7.mean(3).mean(2)
-        cls_score = self.cls_score_net(fc7)
-        cls_pred = torch.max(cls_score, 1)[1]
-        cls_prob = F.softmax(cls_score, 1)
-        bbox_pred = self.bbox_pred_net(fc7)
+        """:277-290 -- 7x7 mean, the two Linears as one stacked GEMM, softmax / argmax (L2F.region_classification)."""
+        cls_score, cls_pred, cls_prob, bbox_pred = L2F.region_classification(
+            spatial_fc7, self.cls_score_net.weight, self.cls_score_net.bias, self.bbox_pred_net.weight,
+            self.bbox_pred_net.bias)
         self._predictions["cls_score"] = cls_score
         self._predictions["cls_pred"] = cls_pred
         self._predictions["cls_prob"] = cls_prob
@@ -90,7 +89,9 @@ class Network(nn.Module):
         filt, fuse = generate_filters(hidden, [getattr(self, "dynamic_fc_%d" % k) for k in range(7)], self.response_fc)
         response, gated, resp_loss = L2F.dynamic_filter(net_conv, filt, fuse, expr2img, self._gate, resp_target)
         self._predictions["response"] = response
+        self._predictions["net_conv"] = gated
         self._losses["loss_response_per_expr"] = resp_loss
+        self._expr2img = expr2img.long() if torch.is_tensor(expr2img) else None
         return gated
 
     # ---- losses on the path ----------------------------------------------------------------------
@@ -102,6 +103,68 @@ class Network(nn.Module):
     def _caption_loss(self, fc_feats, att_feats, cap_labels, cap_masks, steps=None):
         """`steps`: host-known number of decode steps (max caption length + 1); None reads it from the labels."""
         return self.caption_model.forward_loss(fc_feats, att_feats, cap_labels, cap_masks, steps=steps)
+
+    def _smooth_l1_loss(self, bbox_pred, bbox_targets, bbox_inside_weights, bbox_outside_weights, sigma=1.0, dim=(1,)):
+        """:360-373, unchanged arithmetic (elementwise on (N, 4*classes): framework ops)."""
+        sigma_2 = sigma ** 2
+        in_box_diff = bbox_inside_weights * (bbox_pred - bbox_targets)
+        abs_in_box_diff = torch.abs(in_box_diff)
+        sign = (abs_in_box_diff < 1. / sigma_2).detach().float()
+        in_loss_box = torch.pow(in_box_diff, 2) * (sigma_2 / 2.) * sign + (abs_in_box_diff - (0.5 / sigma_2)) * (1. - sign)
+        loss_box = bbox_outside_weights * in_loss_box
+        for i in sorted(dim, reverse=True):
+            loss_box = loss_box.sum(i)
+        return loss_box.mean()
+
+    def _add_hot_path_losses(self, cap_labels=None, cap_masks=None, fc_feats=None, att_feats=None, steps=None,
+                             rpn_cross_entropy=0., rpn_loss_box=0., num_expressions=1):
+        """The hot-path terms of Network._add_losses (:375-453) from what the forward methods left in
+        `_predictions` / `_proposal_targets` / `_losses`, under the reference's keys, and their weighted sum (:449):
+
+            cross_entropy + loss_box + rpn_cross_entropy + rpn_loss_box + loss_mask + loss_response
+                + cap_loss_weight * loss_caption
+
+        The RPN terms belong to the caller (RPN is outside this repository's scope) and are passed in.  A term whose
+        inputs are absent is skipped.  Batched extension: the reference runs one expression per step, so with
+        `num_expressions` = E expressions in the batch (same number of ROIs each) every ROI-mean term is multiplied by
+        E and the per-expression response losses are summed -- the total then equals the sum of the reference's E
+        per-step losses (E = 1 reproduces :449 exactly).
+        fc_feats / att_feats default to the caption features of `net_conv_before` / `net_conv` through
+        `_head_to_tail` (:424-438) when a head was supplied."""
+        E = float(num_expressions)
+        L, P, T = self._losses, self._predictions, self._proposal_targets
+        total = 0.
+        if "cls_score" in P and "labels" in T:
+            label = T["labels"].view(-1)
+            score = P["cls_score"].reshape(-1, P["cls_score"].shape[-1])
+            nll, _ = L2F.logsoftmax_nll(score, label, torch.ones_like(label, dtype=torch.float32))
+            L["cross_entropy"] = E * nll / label.numel()
+            total = total + L["cross_entropy"]
+        if "bbox_pred" in P and "bbox_targets" in T:
+            L["loss_box"] = E * self._smooth_l1_loss(P["bbox_pred"], T["bbox_targets"], T["bbox_inside_weights"],
+                                                     T["bbox_outside_weights"])
+            total = total + L["loss_box"]
+        L["rpn_cross_entropy"], L["rpn_loss_box"] = rpn_cross_entropy, rpn_loss_box
+        total = total + rpn_cross_entropy + rpn_loss_box
+        if "mask_targets" in T and ("mask_loss" in L or "mask_score" in P):
+            n_fg = T["mask_targets"].shape[0]
+            L["loss_mask"] = E * self._mask_loss(T["labels"].view(-1)[:n_fg], T["mask_targets"])
+            total = total + L["loss_mask"]
+        if "loss_response_per_expr" in L:
+            L["loss_response"] = L["loss_response_per_expr"].sum()
+            total = total + L["loss_response"]
+        if cap_labels is not None:
+            if att_feats is None:
+                before = self._head_to_tail(P["net_conv_before"] if P["net_conv_before"].shape[0] == P["net_conv"].shape[0]
+                                            else P["net_conv_before"][self._expr2img])
+                after = self._head_to_tail(P["net_conv"])
+                fc_feats, att_feats = L2F.caption_features(before, after, 14)
+            # LanguageModelCriterion normalises by the number of caption tokens of the batch: for E > 1 the sum of the
+            # per-expression losses is not a multiple of the batched mean, so the batched mean is used as is
+            L["loss_caption"] = self._caption_loss(fc_feats, att_feats, cap_labels, cap_masks, steps=steps)
+            total = total + self._cap_loss_weight * L["loss_caption"]
+        L["total_loss"] = total
+        return total
 
 
 DEFAULT_OPT = dict(

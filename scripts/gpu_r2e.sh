@@ -1,0 +1,7 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_att.py -x -q -m gpu -p no:cacheprovider > gpurun_out/test_att.log 2>&1
+echo "test_gpu_att exit=$?" | tee -a gpurun_out/summary_r2e.txt
+tail -n 12 gpurun_out/test_att.log
+timeout 300 python scripts/prof_decode_phases.py --B 48 --L 10 > gpurun_out/decode_phases_B48.txt 2>&1; cat gpurun_out/decode_phases_B48.txt
+timeout 300 python scripts/prof_decode_phases.py --B 16 --L 20 > gpurun_out/decode_phases_B16.txt 2>&1; cat gpurun_out/decode_phases_B16.txt

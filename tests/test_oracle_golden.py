@@ -21,6 +21,21 @@ def test_lang_encoder(golden):
     assert relerr(emb, d["embedded"]) < TOL
 
 
+def test_lang_encoder_packed_equals_loops(golden):
+    """bench.py's CPU baseline runs the encoder through torch's packed nn.LSTM (the reference's own calls): same
+    outputs and gradients as the per-token restatement, and as the reference's golden output."""
+    import torch
+    d = golden("lang_encoder.npz")
+    p = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in _params(d).items()}
+    out, hid, emb = R.rnn_encoder_packed(d["labels"], p)
+    assert relerr(out, d["output"]) < TOL and relerr(hid, d["hidden"]) < TOL and relerr(emb, d["embedded"]) < TOL
+    g1 = torch.autograd.grad(hid.pow(2).sum() + out.sum(), [p["rnn.weight_hh_l0"], p["rnn.weight_ih_l0_reverse"]])
+    out2, hid2, _ = R.rnn_encoder(d["labels"], p)
+    g2 = torch.autograd.grad(hid2.pow(2).sum() + out2.sum(), [p["rnn.weight_hh_l0"], p["rnn.weight_ih_l0_reverse"]])
+    for a, b in zip(g1, g2):
+        assert relerr(a, b) < 1e-5
+
+
 def test_partition_bounds():
     # SURVEY T4: int() of true division
     assert R.partition_bounds(38, 63) == (19, 9, 28, 31, 15, 47)
