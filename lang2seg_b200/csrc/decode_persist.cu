@@ -12,6 +12,9 @@
 //     boundaries;
 //   * the attention phase keeps the design of att_step_{fwd,bwd}_kernel: a thread-block cluster shares one sample,
 //     flash-style partial (max, sum, weighted accumulator) per CTA, merged through distributed shared memory;
+//   * operand row blocks reach shared memory through the TMA engine (1-D bulk copies on an mbarrier), not LDG loops;
+//   * the attention phase processes ALL samples of a cluster as one batch (every load of the batch in flight
+//     together, one pair of cluster barriers per step) -- a per-sample loop was a chain of exposed L2 latencies;
 //   * skinny GEMM tiles: lanes split K (one float4 per k-step), R rows x NC columns register blocked against shared
 //     memory (4 (R + NC) LDS.128 per 16 R NC FMA), one 31-shuffle transpose-reduce per 32 outputs; exact fp32 FFMA
 //     with a fixed summation order (deterministic; same arithmetic class as linear_small_kernel).
@@ -27,13 +30,17 @@
 //                                                                                    | grid barrier 2
 //     S3  attention backward (light: datt_h_t, de_t)  (cluster per sample)            | grid barrier 3
 //     S4b dh_{t-1} += datt_h_t W_h2att  -> cluster reduce -> dh carry                 | grid barrier 4
-// Restrictions: rnn_size == att_hid_size == 512, B <= 64, A <= 1024; anything else takes the launch chain of decode.cu.
+// Restrictions: rnn_size == att_hid_size == 512, B <= 64 (backward: 48), A <= 1024; anything else takes the launch
+// chain of decode.cu.
 #include <cooperative_groups.h>
 
 #include "persist.cuh"
 
 namespace l2s {
 namespace {
+
+constexpr int NIMAX = 2;          // samples a cluster handles per step: ceil(PMAXB / clusters) with >= 32 clusters
+constexpr int LC = 6 * PD;        // [att_h | 5 gate pre-activations]
 
 struct DecFwdArgs {
   float* cat_all;          // (T,B,LC) in: [b_h2att | i2h(x_t) + b_i2h + b_h2h]  out: [att_h_t | sums_t]
@@ -54,118 +61,174 @@ struct DecFwdArgs {
   int T, B, A;
 };
 
-// attention of one sample by a cluster of CS CTAs (Attention.forward, AttModel.py:411-421): scores, softmax, weighted sum
+// attention scratch (floats), aliased onto the operand staging area (never live at the same time)
+struct AttScratch {
+  static constexpr int AH = 0;                          // [NIMAX][PD]       att_h rows
+  static constexpr int DO = AH + NIMAX * PD;            // [NIMAX][PD]       (bwd) datt_res rows
+  static constexpr int ACC = DO + NIMAX * PD;           // [NIMAX][4][PD]    per-phase partial column sums
+  static constexpr int ACCF = ACC + NIMAX * 4 * PD;     // [NIMAX][PD]       their sum (read remotely)
+  static constexpr int E = ACCF + NIMAX * PD;           // [NIMAX][PMAXLOC]  scores / exp / de
+  static constexpr int W = E + NIMAX * PMAXLOC;         // [NIMAX][PMAXLOC]  (bwd) pi
+  static constexpr int ML = W + NIMAX * PMAXLOC;        // [NIMAX][2]        partial (max, sum) | (bwd) partial S
+  static constexpr int TOTAL = ML + NIMAX * 2 + 4;
+};
+
+// Attention.forward (AttModel.py:411-421) for the `ni` samples b = b0 + i * bstride of this cluster, as one batch
 template <int CS>
-__device__ __forceinline__ void attention_fwd_item(cg::cluster_group& cluster, int rank, int b, const float* __restrict__ att_h_row,
-                                                   const float* __restrict__ att, const float* __restrict__ p_att,
-                                                   float alpha_b, float* __restrict__ pi_out, float* __restrict__ res_out,
-                                                   int A, float* s_ah, const float* s_aw, float* s_acc /*[2][PD]*/,
-                                                   float* s_e, float* s_ml, float* s_red) {
+__device__ __forceinline__ void attention_fwd_batch(cg::cluster_group& cluster, int rank, int b0, int bstride, int ni,
+                                                    const float* __restrict__ cat_t, const float* __restrict__ att,
+                                                    const float* __restrict__ p_att, float alpha_b,
+                                                    float* __restrict__ pi_t, float* __restrict__ res_t, int A,
+                                                    float* sc_, const float* s_aw) {
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  float* s_ah = sc_ + AttScratch::AH;
+  float* s_acc = sc_ + AttScratch::ACC;
+  float* s_accf = sc_ + AttScratch::ACCF;
+  float* s_e = sc_ + AttScratch::E;
+  float* s_ml = sc_ + AttScratch::ML;
   const int per = (A + CS - 1) / CS;
   const int a0 = min(A, rank * per), a1 = min(A, a0 + per);
   const int na = a1 - a0;
-  for (int q = t; q < PQ; q += PT) reinterpret_cast<float4*>(s_ah)[q] = __ldcg(reinterpret_cast<const float4*>(att_h_row) + q);
+  for (int i = t; i < ni * PQ; i += PT) {
+    const int it = i / PQ, q = i - it * PQ;
+    reinterpret_cast<float4*>(s_ah)[i] = __ldcg(reinterpret_cast<const float4*>(cat_t + (size_t)(b0 + it * bstride) * LC) + q);
+  }
   __syncthreads();
-  // scores: one warp per location, lanes over the hidden dimension
-  for (int a = wid; a < na; a += PT / 32) {
-    const float4* row = reinterpret_cast<const float4*>(p_att + ((size_t)b * A + a0 + a) * PD);
-    float s = 0.f;
+  // ---- scores: one warp per (sample, location), two pairs per batch: 8 row loads per lane, 128 per SM in flight
+  const int npairs = ni * na;
+  for (int p0 = wid; p0 < npairs; p0 += 2 * (PT / 32)) {
+    float4 pr[2][4];
 #pragma unroll
-    for (int k = 0; k < PQ / 32; ++k) {
-      const int q = lane + 32 * k;
-      const float4 p = __ldg(row + q);
-      const float4 h = reinterpret_cast<const float4*>(s_ah)[q];
-      const float4 w = reinterpret_cast<const float4*>(s_aw)[q];
-      s = fmaf(w.x, tanhf_fast_acc(p.x + h.x), s);
-      s = fmaf(w.y, tanhf_fast_acc(p.y + h.y), s);
-      s = fmaf(w.z, tanhf_fast_acc(p.z + h.z), s);
-      s = fmaf(w.w, tanhf_fast_acc(p.w + h.w), s);
+    for (int k = 0; k < 2; ++k) {
+      const int p = p0 + k * (PT / 32);
+      if (p < npairs) {
+        const int it = p / na, a = p - it * na;
+        const float4* row = reinterpret_cast<const float4*>(p_att + ((size_t)(b0 + it * bstride) * A + a0 + a) * PD);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pr[k][j] = __ldg(row + lane + 32 * j);
+      }
     }
-    s = warp_sum(s);
-    if (lane == 0) s_e[a] = s + alpha_b;
-  }
-  __syncthreads();
-  float m = -INFINITY;
-  for (int a = t; a < na; a += PT) m = fmaxf(m, s_e[a]);
-  m = warp_max(m);
-  if (lane == 0) s_red[wid] = m;
-  __syncthreads();
-  m = s_red[0];
 #pragma unroll
-  for (int w = 1; w < PT / 32; ++w) m = fmaxf(m, s_red[w]);
-  __syncthreads();
-  float l = 0.f;
-  for (int a = t; a < na; a += PT) {
-    const float ex = expf(s_e[a] - m);
-    s_e[a] = ex;
-    l += ex;
-  }
-  l = warp_sum(l);
-  if (lane == 0) s_red[wid] = l;
-  __syncthreads();
-  if (t == 0) {
-    float tot = 0.f;
+    for (int k = 0; k < 2; ++k) {
+      const int p = p0 + k * (PT / 32);
+      if (p < npairs) {                          // warp uniform
+        const int it = p / na, a = p - it * na;
+        float s = 0.f;
 #pragma unroll
-    for (int w = 0; w < PT / 32; ++w) tot += s_red[w];
-    s_ml[0] = m;
-    s_ml[1] = tot;
+        for (int j = 0; j < 4; ++j) {
+          const int q = lane + 32 * j;
+          const float4 h = reinterpret_cast<const float4*>(s_ah + it * PD)[q];
+          const float4 w = reinterpret_cast<const float4*>(s_aw)[q];
+          s = fmaf(w.x, tanhf_fast_acc(pr[k][j].x + h.x), s);
+          s = fmaf(w.y, tanhf_fast_acc(pr[k][j].y + h.y), s);
+          s = fmaf(w.z, tanhf_fast_acc(pr[k][j].z + h.z), s);
+          s = fmaf(w.w, tanhf_fast_acc(pr[k][j].w + h.w), s);
+        }
+        s = warp_sum(s);
+        if (lane == 0) s_e[it * PMAXLOC + a] = s + alpha_b;
+      }
+    }
   }
-  // partial weighted sum over this slice: thread = (float4 column group, location phase)
+  __syncthreads();
+  // ---- partial softmax statistics of this slice: warp `it` takes sample `it`
+  if (wid < ni) {
+    float* e = s_e + wid * PMAXLOC;
+    float m = -INFINITY;
+    for (int a = lane; a < na; a += 32) m = fmaxf(m, e[a]);
+    m = warp_max(m);
+    float l = 0.f;
+    for (int a = lane; a < na; a += 32) {
+      const float ex = expf(e[a] - m);
+      e[a] = ex;
+      l += ex;
+    }
+    l = warp_sum(l);
+    if (lane == 0) {
+      s_ml[wid * 2] = m;
+      s_ml[wid * 2 + 1] = l;
+    }
+  }
+  __syncthreads();
+  // ---- partial weighted sums: thread = (float4 column group q, location phase ph), 6 row loads in flight
   {
-    const int q = t & (PQ - 1), ph = t / PQ;      // PT / PQ == 2 phases
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4* col = reinterpret_cast<const float4*>(att + ((size_t)b * A + a0) * PD) + q;
-#pragma unroll 4
-    for (int a = ph; a < na; a += PT / PQ) {
-      const float4 v = __ldg(col + (size_t)a * PQ);
-      const float w = s_e[a];
-      acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y);
-      acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+    const int q = t & (PQ - 1), ph = t / PQ;        // PT / PQ == 4 phases
+    for (int it = 0; it < ni; ++it) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4* col = reinterpret_cast<const float4*>(att + ((size_t)(b0 + it * bstride) * A + a0) * PD) + q;
+      const float* e = s_e + it * PMAXLOC;
+      for (int ab = ph; ab < na; ab += 6 * (PT / PQ)) {
+        float4 v[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          const int a = ab + k * (PT / PQ);
+          if (a < na) v[k] = __ldg(col + (size_t)a * PQ);
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          const int a = ab + k * (PT / PQ);
+          if (a < na) {
+            const float w = e[a];
+            acc.x = fmaf(w, v[k].x, acc.x); acc.y = fmaf(w, v[k].y, acc.y);
+            acc.z = fmaf(w, v[k].z, acc.z); acc.w = fmaf(w, v[k].w, acc.w);
+          }
+        }
+      }
+      reinterpret_cast<float4*>(s_acc + (it * 4 + ph) * PD)[q] = acc;
     }
-    reinterpret_cast<float4*>(s_acc + ph * PD)[q] = acc;
+  }
+  __syncthreads();
+  for (int i = t; i < ni * PQ; i += PT) {
+    const int it = i / PQ, q = i - it * PQ;
+    const float4* src = reinterpret_cast<const float4*>(s_acc + it * 4 * PD) + q;
+    const float4 x0 = src[0], x1 = src[PQ], x2 = src[2 * PQ], x3 = src[3 * PQ];
+    reinterpret_cast<float4*>(s_accf)[i] = make_float4((x0.x + x1.x) + (x2.x + x3.x), (x0.y + x1.y) + (x2.y + x3.y),
+                                                       (x0.z + x1.z) + (x2.z + x3.z), (x0.w + x1.w) + (x2.w + x3.w));
   }
   cluster.sync();
-  // merge the CS partial states
-  float ms[CS], ls[CS], M = -INFINITY;
-#pragma unroll
-  for (int r = 0; r < CS; ++r) {
-    const float* rm = cluster.map_shared_rank(s_ml, r);
-    ms[r] = rm[0];
-    ls[r] = rm[1];
-    M = fmaxf(M, ms[r]);
-  }
-  float L = 0.f, sc[CS];
-#pragma unroll
-  for (int r = 0; r < CS; ++r) {
-    sc[r] = (ls[r] > 0.f) ? expf(ms[r] - M) : 0.f;
-    L = fmaf(sc[r], ls[r], L);
-  }
-  const float invL = 1.f / L;
-  constexpr int DPER = PD / CS;                  // this CTA finalises columns [rank*DPER, ...) of att_res
-  for (int d = rank * DPER + t; d < (rank + 1) * DPER; d += PT) {
-    float v = 0.f;
+  // ---- merge the CS partial states; this CTA finalises columns [rank*DPER, ...) of att_res and its slice of pi
+  constexpr int DPER = PD / CS;
+  for (int it = 0; it < ni; ++it) {
+    float ms[CS], ls[CS], M = -INFINITY;
 #pragma unroll
     for (int r = 0; r < CS; ++r) {
-      const float* ra = cluster.map_shared_rank(s_acc, r);
-      v = fmaf(sc[r], ra[d] + ra[PD + d], v);
+      const float* rm = cluster.map_shared_rank(s_ml, r);
+      ms[r] = rm[it * 2];
+      ls[r] = rm[it * 2 + 1];
+      M = fmaxf(M, ms[r]);
     }
-    res_out[d] = v * invL;
-  }
-  float myscale = 0.f;
+    float L = 0.f, scl[CS], mine = 0.f;
 #pragma unroll
-  for (int r = 0; r < CS; ++r)
-    if (r == rank) myscale = sc[r] * invL;
-  for (int a = t; a < na; a += PT) pi_out[a0 + a] = s_e[a] * myscale;
+    for (int r = 0; r < CS; ++r) {
+      scl[r] = (ls[r] > 0.f) ? expf(ms[r] - M) : 0.f;
+      L = fmaf(scl[r], ls[r], L);
+      if (r == rank) mine = scl[r];
+    }
+    const float invL = 1.f / L;
+    const int b = b0 + it * bstride;
+    for (int d = rank * DPER + t; d < (rank + 1) * DPER; d += PT) {
+      float v = 0.f;
+#pragma unroll
+      for (int r = 0; r < CS; ++r) v = fmaf(scl[r], cluster.map_shared_rank(s_accf, r)[it * PD + d], v);
+      res_t[(size_t)b * PD + d] = v * invL;
+    }
+    const float myscale = mine * invL;
+    for (int a = t; a < na; a += PT) pi_t[(size_t)b * A + a0 + a] = s_e[it * PMAXLOC + a] * myscale;
+  }
   cluster.sync();   // nobody moves on while its shared memory may still be read remotely
 }
 
-// shared-memory plan of both kernels (floats)
+// shared-memory plan of the forward kernel (floats)
 struct DecSmem {
-  static constexpr int W = 32 * PD;                 // stationary weight rows
-  static constexpr int A_OFF = W;                   // [PMAXB][PD] staged operand rows
-  static constexpr int MISC_OFF = A_OFF + PMAXB * PD;
+  static constexpr int W = 0;                        // [32][PD] stationary weight rows
+  static constexpr int A_OFF = W + 32 * PD;          // [PMAXB][PD] staged operand rows | attention scratch
+  static constexpr int SUMS = A_OFF + PMAXB * PD;    // [PMAXB][20]
+  static constexpr int A2C = SUMS + PMAXB * 20;      // [PMAXB][8]
+  static constexpr int C = A2C + PMAXB * 8;          // [PMAXB][4]
+  static constexpr int AW = C + PMAXB * 4;           // [PD]
+  static constexpr int BAR = AW + PD;                // mbarrier (2 floats)
+  static constexpr int TOTAL = BAR + 4;
 };
+static_assert(AttScratch::TOTAL <= PMAXB * PD, "attention scratch must fit the staging area");
 
 template <int CS>
 __global__ void __launch_bounds__(PT, 1) decode_fwd_persist_kernel(const DecFwdArgs p) {
@@ -176,22 +239,17 @@ __global__ void __launch_bounds__(PT, 1) decode_fwd_persist_kernel(const DecFwdA
   constexpr int NCL = PG / CS;
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
   const int B = p.B, A = p.A, T = p.T;
-  constexpr int LC = 6 * PD;
 
   extern __shared__ __align__(16) float smem[];
-  float* sW = smem;                               // [32][PD]: 0-3 h2att | 4 + 5u + g: h2h gate g of unit u | 24 + 4h + u: a2c
-  float* sA = smem + DecSmem::A_OFF;              // [B][PD]
-  float* s_sums = smem + DecSmem::MISC_OFF;       // [PMAXB][20]  h_{t-1} W_h2h^T for the CTA's units (col = 5u + g)
-  float* s_a2c = s_sums + PMAXB * 20;             // [PMAXB][8]   col = 4 half + u
-  float* s_c = s_a2c + PMAXB * 8;                 // [PMAXB][4]   cell state of the CTA's units
-  float* s_ah = s_c + PMAXB * 4;                  // [PD]
-  float* s_aw = s_ah + PD;                        // [PD]
-  float* s_acc = s_aw + PD;                       // [2][PD]
-  float* s_e = s_acc + 2 * PD;                    // [PMAXLOC]
-  float* s_ml = s_e + PMAXLOC;                    // [2] (+2 pad)
-  float* s_red = s_ml + 4;                        // [8]
+  float* sW = smem + DecSmem::W;                  // row 0-3 h2att | 4 + 5u + g: h2h gate g of unit u | 24 + 4h + u: a2c
+  float* sA = smem + DecSmem::A_OFF;
+  float* s_sums = smem + DecSmem::SUMS;           // h_{t-1} W_h2h^T for the CTA's units (col = 5u + g)
+  float* s_a2c = smem + DecSmem::A2C;             // col = 4 half + u
+  float* s_c = smem + DecSmem::C;                 // cell state of the CTA's units
+  float* s_aw = smem + DecSmem::AW;
+  Stager stg{reinterpret_cast<uint64_t*>(smem + DecSmem::BAR), 0u};
+  stg.init();
 
-  // ---- stationary weights
   for (int i = t; i < 32 * PQ; i += PT) {
     const int r = i / PQ, q = i - r * PQ;
     const float* src;
@@ -215,39 +273,38 @@ __global__ void __launch_bounds__(PT, 1) decode_fwd_persist_kernel(const DecFwdA
   const PhaseProf prof{p.prof};
   const float4* sA4 = reinterpret_cast<const float4*>(sA);
   const float4* sW4 = reinterpret_cast<const float4*>(sW);
+  const int ni = cid < B ? (B - cid + NCL - 1) / NCL : 0;     // samples of this cluster: cid, cid + NCL, ...
 
   for (int step = 0; step < T; ++step) {
     float* cat_t = p.cat_all + (size_t)step * B * LC;
     prof.mark(step, 0);
     if (step > 0) {
-      stage_rows(reinterpret_cast<float4*>(sA), p.h_all + (size_t)(step - 1) * B * PD, B, PD);
-      __syncthreads();
-      // ---- A1: att_h columns 4j..4j+3 for rows b = wid + 8 r
-      {
-        int arow[8];
+      stg.load_contig(sA, p.h_all + (size_t)(step - 1) * B * PD, (uint32_t)B * PD * 4u);
+      stg.wait();
+      // ---- A1: att_h columns 4j..4j+3 for rows b = wid + 16 r
+      if (wid < B) {                        // warp uniform
+        int arow[4];
 #pragma unroll
-        for (int r = 0; r < 8; ++r) arow[r] = (wid + 8 * r < B) ? wid + 8 * r : 0;
-        if (wid < B) {                      // warp uniform
-          const float tot = gemv_tile<8, 4, 4>(sA4, PQ, arow, sW4, PQ, 0, lane);
-          const int b = wid + 8 * (lane >> 2), c = lane & 3;
-          if (b < B) {
-            float* dp = cat_t + (size_t)b * LC + 4 * j + c;
-            *dp = __ldcg(dp) + tot;
-          }
+        for (int r = 0; r < 4; ++r) arow[r] = (wid + 16 * r < B) ? wid + 16 * r : 0;
+        const float tot = gemv_tile<4, 4, 4>(sA4, PQ, arow, sW4, PQ, 0, lane);
+        const int b = wid + 16 * (lane >> 2), c = lane & 3;
+        if (lane < 16 && b < B) {
+          float* dp = cat_t + (size_t)b * LC + 4 * j + c;
+          *dp = __ldcg(dp) + tot;
         }
       }
       prof.mark(step, 1);
       gb.arrive();
-      // ---- A2: the five gate columns of unit u = wid & 3 for rows b = rg + 2 i (runs while barrier 1 completes)
+      // ---- A2: the five gate columns of unit u = wid & 3 for rows b = rg + 4 i (runs while barrier 1 completes)
       {
         const int u = wid & 3, rg = wid >> 2;
-        for (int i0 = 0; rg + 2 * i0 < B; i0 += 6) {
+        for (int i0 = 0; rg + 4 * i0 < B; i0 += 6) {
           int arow[6];
 #pragma unroll
-          for (int r = 0; r < 6; ++r) arow[r] = (rg + 2 * (i0 + r) < B) ? rg + 2 * (i0 + r) : 0;
+          for (int r = 0; r < 6; ++r) arow[r] = (rg + 4 * (i0 + r) < B) ? rg + 4 * (i0 + r) : 0;
           const float tot = gemv_tile<6, 5, 4>(sA4, PQ, arow, sW4, PQ, 4 + 5 * u, lane);
           const int r = lane / 5, g = lane - 5 * r;
-          const int b = rg + 2 * (i0 + r);
+          const int b = rg + 4 * (i0 + r);
           if (lane < 30 && b < B) s_sums[b * 20 + 5 * u + g] = tot;
         }
       }
@@ -255,26 +312,25 @@ __global__ void __launch_bounds__(PT, 1) decode_fwd_persist_kernel(const DecFwdA
       gb.wait();
     }
     prof.mark(step, 3);
-    // ---- B: attention, one sample per cluster round
-    for (int b = cid; b < B; b += NCL)
-      attention_fwd_item<CS>(cluster, rank, b, cat_t + (size_t)b * LC, p.att, p.p_att, alpha_b,
-                             p.pi_all + ((size_t)step * B + b) * A, p.res_all + ((size_t)step * B + b) * PD, A, s_ah, s_aw,
-                             s_acc, s_e, s_ml, s_red);
+    // ---- B: attention, all samples of this cluster in one batch
+    if (ni > 0)
+      attention_fwd_batch<CS>(cluster, rank, cid, NCL, ni, cat_t, p.att, p.p_att, alpha_b, p.pi_all + (size_t)step * B * A,
+                              p.res_all + (size_t)step * B * PD, A, sA, s_aw);
     prof.mark(step, 4);
     gb.arrive();
     gb.wait();
     prof.mark(step, 5);
     // ---- C: a2c columns + gates
-    stage_rows(reinterpret_cast<float4*>(sA), p.res_all + (size_t)step * B * PD, B, PD);
-    __syncthreads();
+    stg.load_contig(sA, p.res_all + (size_t)step * B * PD, (uint32_t)B * PD * 4u);
+    stg.wait();
     {
       const int half = wid & 1, rg = wid >> 1;
-      for (int i0 = 0; rg + 4 * i0 < B; i0 += 8) {
+      if (rg < B) {
         int arow[8];
 #pragma unroll
-        for (int r = 0; r < 8; ++r) arow[r] = (rg + 4 * (i0 + r) < B) ? rg + 4 * (i0 + r) : 0;
+        for (int r = 0; r < 8; ++r) arow[r] = (rg + 8 * r < B) ? rg + 8 * r : 0;
         const float tot = gemv_tile<8, 4, 4>(sA4, PQ, arow, sW4, PQ, 24 + 4 * half, lane);
-        const int b = rg + 4 * (i0 + (lane >> 2)), u = lane & 3;
+        const int b = rg + 8 * (lane >> 2), u = lane & 3;
         if (b < B) s_a2c[b * 8 + 4 * half + u] = tot;
       }
     }
@@ -334,17 +390,17 @@ struct DecBwdArgs {
   int T, B, A;
 };
 
-// out[b][4 cg + c] (partial over this CTA's K slice) for rows b = rg + 2 i : warp = (column group cg, row group rg)
+// out[b][4 cg + c] (partial over this CTA's K slice) for rows b = rg + 4 i : warp = (column group cg, row group rg)
 template <int KS>
 __device__ __forceinline__ void partial_gemm16(const float4* sA4, int lda4, const float4* sW4, int B, float* s_part,
                                                bool accumulate, int lane, int wid) {
   const int cgp = wid & 3, rg = wid >> 2;
-  for (int i0 = 0; rg + 2 * i0 < B; i0 += 8) {
+  for (int i0 = 0; rg + 4 * i0 < B; i0 += 8) {
     int arow[8];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) arow[r] = (rg + 2 * (i0 + r) < B) ? rg + 2 * (i0 + r) : 0;
+    for (int r = 0; r < 8; ++r) arow[r] = (rg + 4 * (i0 + r) < B) ? rg + 4 * (i0 + r) : 0;
     const float tot = gemv_tile<8, 4, KS>(sA4, lda4, arow, sW4, lda4, 4 * cgp, lane);
-    const int b = rg + 2 * (i0 + (lane >> 2)), c = 4 * cgp + (lane & 3);
+    const int b = rg + 4 * (i0 + (lane >> 2)), c = 4 * cgp + (lane & 3);
     if (b < B) s_part[b * BNC + c] = accumulate ? s_part[b * BNC + c] + tot : tot;
   }
 }
@@ -362,86 +418,126 @@ __device__ __forceinline__ void cluster_reduce16(cg::cluster_group& cluster, int
   }
 }
 
-// light attention backward of one sample by a cluster of BCS CTAs: datt_h (-> dcat row) and de (AttModel.py:411-421)
-__device__ __forceinline__ void attention_bwd_item(cg::cluster_group& cluster, int rank, int b, const float* __restrict__ dres_row,
-                                                   const float* __restrict__ att_h_row, const float* __restrict__ att,
-                                                   const float* __restrict__ p_att, const float* __restrict__ pi_row,
-                                                   float* __restrict__ datt_h_row, float* __restrict__ de_row, int A,
-                                                   float* s_ah, const float* s_aw, float* s_dah /*[2][PD]*/, float* s_do,
-                                                   float* s_w, float* s_dpi, float* s_part, float* s_red) {
+// light attention backward (datt_h -> dcat rows, de) for the `ni` samples of this cluster as one batch
+__device__ __forceinline__ void attention_bwd_batch(cg::cluster_group& cluster, int rank, int b0, int bstride, int ni,
+                                                    const float* __restrict__ dres_t, const float* __restrict__ cat_t,
+                                                    const float* __restrict__ att, const float* __restrict__ p_att,
+                                                    const float* __restrict__ pi_t, float* __restrict__ dcat_t,
+                                                    float* __restrict__ de_t, int A, float* sc_, const float* s_aw) {
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  float* s_ah = sc_ + AttScratch::AH;
+  float* s_do = sc_ + AttScratch::DO;
+  float* s_dah = sc_ + AttScratch::ACC;
+  float* s_dahf = sc_ + AttScratch::ACCF;
+  float* s_dpi = sc_ + AttScratch::E;
+  float* s_w = sc_ + AttScratch::W;
+  float* s_ps = sc_ + AttScratch::ML;
   const int per = (A + BCS - 1) / BCS;
   const int a0 = min(A, rank * per), a1 = min(A, a0 + per);
   const int na = a1 - a0;
-  for (int q = t; q < PQ; q += PT) {
-    reinterpret_cast<float4*>(s_ah)[q] = __ldg(reinterpret_cast<const float4*>(att_h_row) + q);
-    reinterpret_cast<float4*>(s_do)[q] = __ldcg(reinterpret_cast<const float4*>(dres_row) + q);
+  for (int i = t; i < ni * PQ; i += PT) {
+    const int it = i / PQ, q = i - it * PQ;
+    const int b = b0 + it * bstride;
+    reinterpret_cast<float4*>(s_ah)[i] = __ldg(reinterpret_cast<const float4*>(cat_t + (size_t)b * LC) + q);
+    reinterpret_cast<float4*>(s_do)[i] = __ldcg(reinterpret_cast<const float4*>(dres_t + (size_t)b * PD) + q);
   }
-  for (int a = t; a < na; a += PT) s_w[a] = __ldg(pi_row + a0 + a);
+  for (int i = t; i < ni * na; i += PT) {
+    const int it = i / na, a = i - it * na;
+    s_w[it * PMAXLOC + a] = __ldg(pi_t + (size_t)(b0 + it * bstride) * A + a0 + a);
+  }
   __syncthreads();
-  // d pi_a = <datt_res, att_feats[a]>
-  for (int a = wid; a < na; a += PT / 32) {
-    const float4* row = reinterpret_cast<const float4*>(att + ((size_t)b * A + a0 + a) * PD);
-    float s = 0.f;
+  // ---- d pi_a = <datt_res, att_feats[a]>: warp per (sample, location), two pairs per batch
+  const int npairs = ni * na;
+  for (int p0 = wid; p0 < npairs; p0 += 2 * (PT / 32)) {
+    float4 pr[2][4];
 #pragma unroll
-    for (int k = 0; k < PQ / 32; ++k) {
-      const int q = lane + 32 * k;
-      const float4 v = __ldg(row + q);
-      const float4 d = reinterpret_cast<const float4*>(s_do)[q];
-      s = dot4(v, d, s);
+    for (int k = 0; k < 2; ++k) {
+      const int p = p0 + k * (PT / 32);
+      if (p < npairs) {
+        const int it = p / na, a = p - it * na;
+        const float4* row = reinterpret_cast<const float4*>(att + ((size_t)(b0 + it * bstride) * A + a0 + a) * PD);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pr[k][j] = __ldg(row + lane + 32 * j);
+      }
     }
-    s = warp_sum(s);
-    if (lane == 0) s_dpi[a] = s;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int p = p0 + k * (PT / 32);
+      if (p < npairs) {
+        const int it = p / na, a = p - it * na;
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s = dot4(pr[k][j], reinterpret_cast<const float4*>(s_do + it * PD)[lane + 32 * j], s);
+        s = warp_sum(s);
+        if (lane == 0) s_dpi[it * PMAXLOC + a] = s;
+      }
+    }
   }
   __syncthreads();
-  float part = 0.f;
-  for (int a = t; a < na; a += PT) part = fmaf(s_w[a], s_dpi[a], part);
-  part = warp_sum(part);
-  if (lane == 0) s_red[wid] = part;
-  __syncthreads();
-  if (t == 0) {
-    float tot = 0.f;
-#pragma unroll
-    for (int w = 0; w < PT / 32; ++w) tot += s_red[w];
-    s_part[0] = tot;
+  if (wid < ni) {
+    float part = 0.f;
+    for (int a = lane; a < na; a += 32) part = fmaf(s_w[wid * PMAXLOC + a], s_dpi[wid * PMAXLOC + a], part);
+    part = warp_sum(part);
+    if (lane == 0) s_ps[wid] = part;
   }
   cluster.sync();
-  float S = 0.f;
+  for (int i = t; i < ni * na; i += PT) {
+    const int it = i / na, a = i - it * na;
+    float S = 0.f;
 #pragma unroll
-  for (int r = 0; r < BCS; ++r) S += cluster.map_shared_rank(s_part, r)[0];
-  for (int a = t; a < na; a += PT) {
-    const float de = s_w[a] * (s_dpi[a] - S);
-    s_dpi[a] = de;
-    de_row[a0 + a] = de;
+    for (int r = 0; r < BCS; ++r) S += cluster.map_shared_rank(s_ps, r)[it];
+    const float de = s_w[it * PMAXLOC + a] * (s_dpi[it * PMAXLOC + a] - S);
+    s_dpi[it * PMAXLOC + a] = de;
+    de_t[(size_t)(b0 + it * bstride) * A + a0 + a] = de;
   }
   __syncthreads();
-  // datt_h[d] = alpha_d sum_a de_a (1 - tanh^2(p_att[a,d] + att_h[d])): thread = (float4 column group, location phase)
+  // ---- datt_h[d] = alpha_d sum_a de_a (1 - tanh^2(p_att[a,d] + att_h[d])): thread = (float4 column group, phase)
   {
     const int q = t & (PQ - 1), ph = t / PQ;
-    const float4 h = reinterpret_cast<const float4*>(s_ah)[q];
     const float4 w = reinterpret_cast<const float4*>(s_aw)[q];
-    float4 dah = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 2
-    for (int a = ph; a < na; a += PT / PQ) {
-      const float4 p = __ldg(reinterpret_cast<const float4*>(p_att + ((size_t)b * A + a0 + a) * PD) + q);
-      const float de = s_dpi[a];
-      const float tx = tanhf_fast_acc(p.x + h.x), ty = tanhf_fast_acc(p.y + h.y);
-      const float tz = tanhf_fast_acc(p.z + h.z), tw = tanhf_fast_acc(p.w + h.w);
-      dah.x += de * w.x * (1.f - tx * tx); dah.y += de * w.y * (1.f - ty * ty);
-      dah.z += de * w.z * (1.f - tz * tz); dah.w += de * w.w * (1.f - tw * tw);
+    for (int it = 0; it < ni; ++it) {
+      const float4 h = reinterpret_cast<const float4*>(s_ah + it * PD)[q];
+      const float4* col = reinterpret_cast<const float4*>(p_att + ((size_t)(b0 + it * bstride) * A + a0) * PD) + q;
+      const float* de = s_dpi + it * PMAXLOC;
+      float4 dah = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int ab = ph; ab < na; ab += 6 * (PT / PQ)) {
+        float4 v[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          const int a = ab + k * (PT / PQ);
+          if (a < na) v[k] = __ldg(col + (size_t)a * PQ);
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          const int a = ab + k * (PT / PQ);
+          if (a < na) {
+            const float d = de[a];
+            const float tx = tanhf_fast_acc(v[k].x + h.x), ty = tanhf_fast_acc(v[k].y + h.y);
+            const float tz = tanhf_fast_acc(v[k].z + h.z), tw = tanhf_fast_acc(v[k].w + h.w);
+            dah.x += d * w.x * (1.f - tx * tx); dah.y += d * w.y * (1.f - ty * ty);
+            dah.z += d * w.z * (1.f - tz * tz); dah.w += d * w.w * (1.f - tw * tw);
+          }
+        }
+      }
+      reinterpret_cast<float4*>(s_dah + (it * 4 + ph) * PD)[q] = dah;
     }
-    reinterpret_cast<float4*>(s_dah + ph * PD)[q] = dah;
+  }
+  __syncthreads();
+  for (int i = t; i < ni * PQ; i += PT) {
+    const int it = i / PQ, q = i - it * PQ;
+    const float4* src = reinterpret_cast<const float4*>(s_dah + it * 4 * PD) + q;
+    const float4 x0 = src[0], x1 = src[PQ], x2 = src[2 * PQ], x3 = src[3 * PQ];
+    reinterpret_cast<float4*>(s_dahf)[i] = make_float4((x0.x + x1.x) + (x2.x + x3.x), (x0.y + x1.y) + (x2.y + x3.y),
+                                                       (x0.z + x1.z) + (x2.z + x3.z), (x0.w + x1.w) + (x2.w + x3.w));
   }
   cluster.sync();
   constexpr int DPER = PD / BCS;
-  for (int d = rank * DPER + t; d < (rank + 1) * DPER; d += PT) {
+  for (int i = t; i < ni * DPER; i += PT) {
+    const int it = i / DPER, d = rank * DPER + (i - it * DPER);
     float v = 0.f;
 #pragma unroll
-    for (int r = 0; r < BCS; ++r) {
-      const float* ra = cluster.map_shared_rank(s_dah, r);
-      v += ra[d] + ra[PD + d];
-    }
-    datt_h_row[d] = v;
+    for (int r = 0; r < BCS; ++r) v += cluster.map_shared_rank(s_dahf, r)[it * PD + d];
+    dcat_t[(size_t)(b0 + it * bstride) * LC + d] = v;
   }
   cluster.sync();
 }
@@ -450,10 +546,15 @@ struct DecBwdSmem {
   static constexpr int W2 = 0;                        // [16][256]  W_a2c^T rows of the cluster, this rank's K quarter
   static constexpr int W4A = W2 + BNC * 256;          // [16][640]  W_cat^T, dsums part of K
   static constexpr int W4B = W4A + BNC * 640;         // [16][128]  W_cat^T, datt_h part of K
-  static constexpr int A_OFF = W4B + BNC * 128;       // [BMAXB][640] staged operand block
-  static constexpr int MISC = A_OFF + BMAXB * 640;
-  static constexpr int TOTAL = MISC + 2 * BMAXB * BNC + BMAXB * 4 + 5 * PD + 2 * PMAXLOC + 16;
+  static constexpr int A_OFF = W4B + BNC * 128;       // [BMAXB][640] staged operand block | attention scratch
+  static constexpr int PART2 = A_OFF + BMAXB * 640;   // [BMAXB][16]
+  static constexpr int PART4 = PART2 + BMAXB * BNC;   // [BMAXB][16]
+  static constexpr int DC = PART4 + BMAXB * BNC;      // [BMAXB][4]
+  static constexpr int AW = DC + BMAXB * 4;           // [PD]
+  static constexpr int BAR = AW + PD;
+  static constexpr int TOTAL = BAR + 4;
 };
+static_assert(AttScratch::TOTAL <= BMAXB * 640, "attention scratch must fit the staging area");
 
 __global__ void __launch_bounds__(PT, 1) decode_bwd_persist_kernel(const DecBwdArgs p) {
   cg::cluster_group cluster = cg::this_cluster();
@@ -463,24 +564,18 @@ __global__ void __launch_bounds__(PT, 1) decode_bwd_persist_kernel(const DecBwdA
   constexpr int NCL = PG / BCS;
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
   const int B = p.B, A = p.A, T = p.T;
-  constexpr int LC = 6 * PD;
 
   extern __shared__ __align__(16) float smem[];
   float* sW2 = smem + DecBwdSmem::W2;
   float* sW4a = smem + DecBwdSmem::W4A;
   float* sW4b = smem + DecBwdSmem::W4B;
   float* sA = smem + DecBwdSmem::A_OFF;
-  float* s_part2 = smem + DecBwdSmem::MISC;       // [BMAXB][16]
-  float* s_part4 = s_part2 + BMAXB * BNC;         // [BMAXB][16]
-  float* s_dc = s_part4 + BMAXB * BNC;            // [BMAXB][4]  dc carry of the CTA's units
-  float* s_ah = s_dc + BMAXB * 4;                 // [PD]
-  float* s_aw = s_ah + PD;                        // [PD]
-  float* s_dah = s_aw + PD;                       // [2][PD]
-  float* s_do = s_dah + 2 * PD;                   // [PD]
-  float* s_w = s_do + PD;                         // [PMAXLOC]
-  float* s_dpi = s_w + PMAXLOC;                   // [PMAXLOC]
-  float* s_ps = s_dpi + PMAXLOC;                  // [4]
-  float* s_red = s_ps + 4;                        // [8]
+  float* s_part2 = smem + DecBwdSmem::PART2;
+  float* s_part4 = smem + DecBwdSmem::PART4;
+  float* s_dc = smem + DecBwdSmem::DC;            // dc carry of the CTA's units
+  float* s_aw = smem + DecBwdSmem::AW;
+  Stager stg{reinterpret_cast<uint64_t*>(smem + DecBwdSmem::BAR), 0u};
+  stg.init();
 
   // ---- stationary weights: rows n = 16 cid + i of the transposed matrices, this rank's K slices
   for (int i = t; i < BNC * 64; i += PT) {
@@ -505,6 +600,7 @@ __global__ void __launch_bounds__(PT, 1) decode_bwd_persist_kernel(const DecBwdA
   GridBar gb{p.bar, 0u, (unsigned)PG};
   const PhaseProf prof{p.prof};
   const float4* sA4 = reinterpret_cast<const float4*>(sA);
+  const int ni = cid < B ? (B - cid + NCL - 1) / NCL : 0;
 
   for (int step = T - 1; step >= 0; --step) {
     prof.mark(step, 0);
@@ -544,8 +640,8 @@ __global__ void __launch_bounds__(PT, 1) decode_bwd_persist_kernel(const DecBwdA
     gb.wait();
     prof.mark(step, 2);
     // ---- S2: datt_res_t[:, 16 cid ..] = da2c_t W_a2c  (K quarter per rank, summed through DSMEM)
-    stage_slice(reinterpret_cast<float4*>(sA), da2c_t + 256 * rank, B, 2 * PD, 64);
-    __syncthreads();
+    stg.load_rows(sA, da2c_t + 256 * rank, B, 256 * 4, (size_t)2 * PD * 4);
+    stg.wait();
     partial_gemm16<2>(sA4, 64, reinterpret_cast<const float4*>(sW2), B, s_part2, false, lane, wid);
     cluster.sync();
     cluster_reduce16(cluster, rank, s_part2, B, dres_t, PD, BNC * cid);
@@ -553,26 +649,26 @@ __global__ void __launch_bounds__(PT, 1) decode_bwd_persist_kernel(const DecBwdA
     gb.arrive();
     // ---- S4a (runs while barrier 2 completes): dh_{t-1} partial over the dsums part of K
     if (step > 0) {
-      stage_slice(reinterpret_cast<float4*>(sA), dcat_t + PD + 640 * rank, B, LC, 160);
-      __syncthreads();
+      __syncthreads();                   // every warp is done with the S2 operand block
+      stg.load_rows(sA, dcat_t + PD + 640 * rank, B, 640 * 4, (size_t)LC * 4);
+      stg.wait();
       partial_gemm16<5>(sA4, 160, reinterpret_cast<const float4*>(sW4a), B, s_part4, false, lane, wid);
     }
     prof.mark(step, 4);
     gb.wait();
     prof.mark(step, 5);
-    // ---- S3: attention backward, one sample per cluster round
-    for (int b = cid; b < B; b += NCL)
-      attention_bwd_item(cluster, rank, b, dres_t + (size_t)b * PD, cat_t + (size_t)b * LC, p.att, p.p_att,
-                         p.pi_all + ((size_t)step * B + b) * A, dcat_t + (size_t)b * LC,
-                         p.de_all + ((size_t)step * B + b) * A, A, s_ah, s_aw, s_dah, s_do, s_w, s_dpi, s_ps, s_red);
+    // ---- S3: attention backward, all samples of this cluster in one batch
+    if (ni > 0)
+      attention_bwd_batch(cluster, rank, cid, NCL, ni, dres_t, cat_t, p.att, p.p_att, p.pi_all + (size_t)step * B * A,
+                          dcat_t, p.de_all + (size_t)step * B * A, A, sA, s_aw);
     prof.mark(step, 6);
     if (step > 0) {
       gb.arrive();
       gb.wait();
       prof.mark(step, 7);
       // ---- S4b: + datt_h part of K, cluster sum -> dh carry
-      stage_slice(reinterpret_cast<float4*>(sA), dcat_t + 128 * rank, B, LC, 32);
-      __syncthreads();
+      stg.load_rows(sA, dcat_t + 128 * rank, B, 128 * 4, (size_t)LC * 4);
+      stg.wait();
       partial_gemm16<1>(sA4, 32, reinterpret_cast<const float4*>(sW4b), B, s_part4, true, lane, wid);
       cluster.sync();
       cluster_reduce16(cluster, rank, s_part4, B, p.dh_carry, PD, BNC * cid);
@@ -582,9 +678,8 @@ __global__ void __launch_bounds__(PT, 1) decode_bwd_persist_kernel(const DecBwdA
   }
 }
 
+size_t dec_fwd_smem() { return (size_t)DecSmem::TOTAL * sizeof(float) + 64; }
 size_t dec_bwd_smem() { return (size_t)DecBwdSmem::TOTAL * sizeof(float) + 64; }
-
-size_t dec_fwd_smem() { return (size_t)(DecSmem::MISC_OFF + PMAXB * 32 + 4 * PD + PMAXLOC + 4 + 8) * sizeof(float) + 64; }
 
 }  // namespace
 
@@ -600,8 +695,9 @@ int decode_persist_cluster(int B, int A, int D, int Dh) {
     cached_dev = dev;
     cached_cs = 0;
     if (sm_count() >= PG && (size_t)max_smem_optin() >= dec_fwd_smem()) {
-      if (max_clusters(decode_fwd_persist_kernel<8>, 8, dec_fwd_smem()) >= PG / 8) cached_cs = 8;
-      else if (max_clusters(decode_fwd_persist_kernel<4>, 4, dec_fwd_smem()) >= PG / 4) cached_cs = 4;
+      // 8-CTA clusters would halve the per-CTA attention slice, but 16 of them (one CTA per SM) do not fit the GPCs of a
+      // B200 (cudaOccupancyMaxActiveClusters < 16 on the pool's parts): 32 clusters of 4
+      if (max_clusters(decode_fwd_persist_kernel<4>, 4, dec_fwd_smem()) >= PG / 4) cached_cs = 4;
     }
   }
   int cs = cached_cs;
@@ -619,7 +715,7 @@ int launch_decode_fwd_persist(int cs, float* cat_all, const float* att, const fl
   DecFwdArgs a{cat_all, att, p_att, w_cat, w_a2c, b_a2c, alpha_w, alpha_b, h_all, c_all, a2c_all, pi_all, res_all, bar,
                T <= 64 ? debug_buffer(0) : nullptr, T, B, A};
   static const bool coop = !env_flag("L2S_DECODE_NOCOOP");
-  if (cs == 8) return launch_persistent(decode_fwd_persist_kernel<8>, 8, dec_fwd_smem(), st, a, coop);
+  L2S_REQUIRE(cs == 4, L2S_ERR_ARG, "att2in2_decode_fwd: unsupported cluster size %d", cs);
   return launch_persistent(decode_fwd_persist_kernel<4>, 4, dec_fwd_smem(), st, a, coop);
 }
 

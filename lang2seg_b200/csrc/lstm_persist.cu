@@ -41,6 +41,8 @@ __global__ void __launch_bounds__(PT, 1) bilstm_fwd_persist_kernel(const LstmFwd
   float* sW = smem;                         // [32][LH]  row = 4 u + gate
   float* sA = sW + 32 * LH;                 // [LMAXB][LH]
   float* s_c = sA + LMAXB * LH;             // [LMAXB][8]
+  Stager stg{reinterpret_cast<uint64_t*>(s_c + LMAXB * 8), 0u};
+  stg.init();
   for (int i = t; i < 32 * LQ; i += PT) {
     const int r = i / LQ, q = i - r * LQ;
     const int u = r >> 2, g = r & 3;
@@ -52,24 +54,25 @@ __global__ void __launch_bounds__(PT, 1) bilstm_fwd_persist_kernel(const LstmFwd
   GridBar gb{p.bar + 32 * dir, 0u, (unsigned)LDIR};
   const float4* sA4 = reinterpret_cast<const float4*>(sA);
   const float4* sW4 = reinterpret_cast<const float4*>(sW);
-  const int unit = 8 * jj + wid;
+  const int uw = wid & 7, rg = wid >> 3;     // warp = (unit of the CTA, row group): rows b = rg + 2 i
+  const int unit = 8 * jj + uw;
 
   for (int s = 0; s < L; ++s) {
     const int tt = dir ? L - 1 - s : s;
     const int tp = dir ? tt + 1 : tt - 1;
     if (s > 0) {
-      stage_rows(reinterpret_cast<float4*>(sA), p.h_all + ((size_t)(tp * 2 + dir) * B) * LH, B, LH);
-      __syncthreads();
+      stg.load_contig(sA, p.h_all + ((size_t)(tp * 2 + dir) * B) * LH, (uint32_t)B * LH * 4u);
+      stg.wait();
     }
-    for (int i0 = 0; i0 < B; i0 += 8) {
+    for (int i0 = 0; rg + 2 * i0 < B; i0 += 8) {
       float tot = 0.f;
       if (s > 0) {
         int arow[8];
 #pragma unroll
-        for (int r = 0; r < 8; ++r) arow[r] = (i0 + r < B) ? i0 + r : 0;
-        tot = gemv_tile<8, 4, 4>(sA4, LQ, arow, sW4, LQ, 4 * wid, lane);
+        for (int r = 0; r < 8; ++r) arow[r] = (rg + 2 * (i0 + r) < B) ? rg + 2 * (i0 + r) : 0;
+        tot = gemv_tile<8, 4, 4>(sA4, LQ, arow, sW4, LQ, 4 * uw, lane);
       }
-      const int b = i0 + (lane >> 2), g = lane & 3;
+      const int b = rg + 2 * (i0 + (lane >> 2)), g = lane & 3;
       float pre = 0.f;
       if (b < B) {
         float* gp = p.G + (((size_t)b * L + tt) * 2 + dir) * 4 * LH + (size_t)g * LH + unit;
@@ -80,7 +83,7 @@ __global__ void __launch_bounds__(PT, 1) bilstm_fwd_persist_kernel(const LstmFwd
       const float pf = __shfl_sync(0xffffffffu, pre, base + 1), pg = __shfl_sync(0xffffffffu, pre, base + 2);
       const float po = __shfl_sync(0xffffffffu, pre, base + 3);
       if (g == 0 && b < B) {
-        const float cp = s > 0 ? s_c[b * 8 + wid] : 0.f;
+        const float cp = s > 0 ? s_c[b * 8 + uw] : 0.f;
         const float hp = s > 0 ? sA[(size_t)b * LH + unit] : 0.f;
         float c = cp, h = hp, o_out = 0.f;
         if (tt < __ldg(p.lens + b)) {
@@ -89,7 +92,7 @@ __global__ void __launch_bounds__(PT, 1) bilstm_fwd_persist_kernel(const LstmFwd
           h = og * tanhf(c);
           o_out = h;
         }
-        s_c[b * 8 + wid] = c;
+        s_c[b * 8 + uw] = c;
         const size_t st = ((size_t)(tt * 2 + dir) * B + b) * LH + unit;
         p.c_all[st] = c;
         p.h_all[st] = h;
@@ -132,6 +135,9 @@ __global__ void __launch_bounds__(PT, 1) bilstm_bwd_persist_kernel(const LstmBwd
   float* s_dh = s_part + LMAXB * 32;        // [LMAXB][8] recurrent gradient of the CTA's units
   float* s_dc = s_dh + LMAXB * 8;           // [LMAXB][8]
   float* s_dhp = s_dc + LMAXB * 8;          // [LMAXB][8] gradient passed through masked steps
+  Stager stg{reinterpret_cast<uint64_t*>(s_dhp + LMAXB * 8), 0u};
+  stg.init();
+  const int cgp = wid & 7, rg = wid >> 3;   // warp = (4-column group, row group): rows b = rg + 2 i
   for (int i = t; i < 32 * LQ; i += PT) {
     const int r = i / LQ, q = i - r * LQ;
     reinterpret_cast<float4*>(sW)[i] = __ldg(
@@ -185,15 +191,15 @@ __global__ void __launch_bounds__(PT, 1) bilstm_bwd_persist_kernel(const LstmBwd
     gb.arrive();
     gb.wait();
     // ---- dh_prev[:, 32 cid ..] = dG_t[:, gate `rank`] . W_hh^T slice, summed over the four gates through DSMEM
-    stage_slice(reinterpret_cast<float4*>(sA), p.dG + ((size_t)tt * 2 + dir) * 4 * LH + (size_t)LH * rank, B, (int)ldg, LQ);
-    __syncthreads();
-    for (int i0 = 0; i0 < B; i0 += 8) {
+    stg.load_rows(sA, p.dG + ((size_t)tt * 2 + dir) * 4 * LH + (size_t)LH * rank, B, LH * 4, ldg * 4);
+    stg.wait();
+    for (int i0 = 0; rg + 2 * i0 < B; i0 += 8) {
       int arow[8];
 #pragma unroll
-      for (int r = 0; r < 8; ++r) arow[r] = (i0 + r < B) ? i0 + r : 0;
-      const float tot = gemv_tile<8, 4, 4>(sA4, LQ, arow, sW4, LQ, 4 * wid, lane);
-      const int b = i0 + (lane >> 2);
-      if (b < B) s_part[b * 32 + 4 * wid + (lane & 3)] = tot;
+      for (int r = 0; r < 8; ++r) arow[r] = (rg + 2 * (i0 + r) < B) ? rg + 2 * (i0 + r) : 0;
+      const float tot = gemv_tile<8, 4, 4>(sA4, LQ, arow, sW4, LQ, 4 * cgp, lane);
+      const int b = rg + 2 * (i0 + (lane >> 2));
+      if (b < B) s_part[b * 32 + 4 * cgp + (lane & 3)] = tot;
     }
     cluster.sync();
     for (int e = t; e < 8 * B; e += PT) {
@@ -206,8 +212,8 @@ __global__ void __launch_bounds__(PT, 1) bilstm_bwd_persist_kernel(const LstmBwd
   }
 }
 
-size_t lstm_fwd_smem() { return (size_t)(32 * LH + LMAXB * LH + LMAXB * 8) * sizeof(float) + 64; }
-size_t lstm_bwd_smem() { return (size_t)(32 * LH + LMAXB * LH + LMAXB * 32 + 3 * LMAXB * 8) * sizeof(float) + 64; }
+size_t lstm_fwd_smem() { return (size_t)(32 * LH + LMAXB * LH + LMAXB * 8 + 4) * sizeof(float) + 64; }
+size_t lstm_bwd_smem() { return (size_t)(32 * LH + LMAXB * LH + LMAXB * 32 + 3 * LMAXB * 8 + 4) * sizeof(float) + 64; }
 
 }  // namespace
 

@@ -12,7 +12,7 @@ namespace {
 
 constexpr int PD = 512;           // rnn_size == att_hid_size
 constexpr int PG = 128;           // CTAs of the persistent grid
-constexpr int PT = 256;           // threads per CTA
+constexpr int PT = 512;           // threads per CTA (16 warps: four per scheduler hide the LDS / FFMA latencies of the tiles)
 constexpr int PMAXB = 64;         // samples
 constexpr int PQ = PD / 4;        // float4 per 512-float row
 constexpr int PMAXLOC = 256;      // attention locations per CTA slice
@@ -47,11 +47,8 @@ struct GridBar {
   unsigned epoch;
   unsigned n;          // CTAs that take part
   __device__ __forceinline__ void arrive() {
-    __syncthreads();                     // every thread's global writes of this phase are ordered before the release
-    if (threadIdx.x == 0) {
-      __threadfence();
-      red_release_gpu(ctr);
-    }
+    __syncthreads();                     // every thread's global writes of this phase happen before thread 0's release
+    if (threadIdx.x == 0) red_release_gpu(ctr);      // release at gpu scope is cumulative over the barrier above
     ++epoch;
   }
   __device__ __forceinline__ void wait() const {
@@ -59,7 +56,6 @@ struct GridBar {
       const unsigned target = epoch * n;
       while (ld_acquire_gpu(ctr) < target) {
       }
-      __threadfence();
     }
     __syncthreads();
   }
@@ -112,21 +108,48 @@ __device__ __forceinline__ float gemv_tile(const float4* __restrict__ sA4, int l
   return transpose_reduce32(acc, lane);
 }
 
-// rows [0,B) x 512 floats from global (produced by other CTAs of this launch: L2 loads, never L1) into shared memory
-__device__ __forceinline__ void stage_rows(float4* __restrict__ sA4, const float* __restrict__ src, int B, int ld) {
-  for (int i = threadIdx.x; i < B * PQ; i += PT) {
-    const int b = i / PQ, q = i - b * PQ;
-    sA4[i] = __ldcg(reinterpret_cast<const float4*>(src + (size_t)b * ld) + q);
+// Operand staging global -> shared through the TMA engine (1-D bulk copies completing on an mbarrier): one elected
+// thread (or warp, for strided rows) issues, everybody waits on the barrier.  Measured against a plain __ldcg loop
+// (12 loads per thread for a 96 KB block = three exposed L2 round trips): 3.0 vs 4.5 us for stage + first tile at
+// B = 48 (profiles/r02e_decode_phases_*).  The data was written by OTHER CTAs of this launch and acquired through the
+// grid barrier; fence.proxy.async orders those generic-proxy observations before the async-proxy reads.  Callers
+// guarantee (CTA barrier) that nobody still reads the destination.
+struct Stager {
+  uint64_t* bar;
+  unsigned phase;
+  __device__ __forceinline__ void init() {
+    if (threadIdx.x == 0) {
+      mbar_init(bar, 1);
+      mbar_fence_init();
+    }
+    phase = 0;
   }
-}
-
-// rows [0,B) x (4 nq) floats starting at src (row stride ld) -> shared memory [B][nq] float4
-__device__ __forceinline__ void stage_slice(float4* __restrict__ sA4, const float* __restrict__ src, int B, int ld, int nq) {
-  for (int i = threadIdx.x; i < B * nq; i += PT) {
-    const int b = i / nq, q = i - b * nq;
-    sA4[i] = __ldcg(reinterpret_cast<const float4*>(src + (size_t)b * ld) + q);
+  // [bytes] contiguous (multiple of 16)
+  __device__ __forceinline__ void load_contig(void* sdst, const void* gsrc, uint32_t bytes) {
+    if (threadIdx.x == 0) {
+      asm volatile("fence.proxy.async;" ::: "memory");
+      mbar_arrive_expect_tx(bar, bytes);
+      for (uint32_t off = 0; off < bytes; off += 32768u)
+        bulk_g2s(reinterpret_cast<char*>(sdst) + off, reinterpret_cast<const char*>(gsrc) + off,
+                 bytes - off < 32768u ? bytes - off : 32768u, bar);
+    }
   }
-}
+  // B rows of row_bytes each (multiple of 16), global row stride gstride bytes, packed in shared memory
+  __device__ __forceinline__ void load_rows(void* sdst, const void* gsrc, int B, uint32_t row_bytes, size_t gstride) {
+    if (threadIdx.x < 32) {
+      asm volatile("fence.proxy.async;" ::: "memory");
+      if (threadIdx.x == 0) mbar_arrive_expect_tx(bar, (uint32_t)B * row_bytes);
+      __syncwarp();
+      for (int b = threadIdx.x; b < B; b += 32)
+        bulk_g2s(reinterpret_cast<char*>(sdst) + (size_t)b * row_bytes, reinterpret_cast<const char*>(gsrc) + (size_t)b * gstride,
+                 row_bytes, bar);
+    }
+  }
+  __device__ __forceinline__ void wait() {
+    mbar_wait(bar, phase & 1u);
+    phase ^= 1u;
+  }
+};
 
 template <class Kern, class Args>
 int launch_persistent(Kern kern, int cs, size_t smem, cudaStream_t st, const Args& args, bool coop) {
