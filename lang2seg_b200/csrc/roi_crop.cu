@@ -969,6 +969,11 @@ roi_sepx_kernel(const float* __restrict__ rois, const int* __restrict__ order, c
 }
 
 constexpr int kRowXMaxStages = 4;
+// ROIs per ring stage.  Finer stages (2 ROIs x up to 8 stages) and a sleep-with-back-off wait instead of the parked
+// try_wait were both measured and changed nothing (cfg-3 2.69 vs 2.64 ms, cfg-5 3.47 vs 3.29 ms): the spinning warps are
+// the ones that are AHEAD; the kernel is bound by the row owners with the most hits per stage, whose per-row chain
+// (record fields -> tile values -> column merge -> read-modify-write) is latency bound.
+constexpr int kRowXGroup = 4;
 
 template <int CC, int S, bool MAXPOOL>
 __global__ void __launch_bounds__((kRowWarps + 1) * 32, 1)
@@ -984,9 +989,9 @@ roi_crop_bwd_rowsx_kernel(const float* __restrict__ dout, const int* __restrict_
   const int WP = W + 4;                                                      // padded row length
   float* map = reinterpret_cast<float*>(smem_raw);                           // [H][WP][LD]
   const int map_floats = (H * WP * LD + 3) & ~3;
-  float* tiles = map + map_floats;                                           // [nstages][kRowGroup][TILE]
-  SepRecX* recs = reinterpret_cast<SepRecX*>(tiles + (size_t)nstages * kRowGroup * TILE);   // [nstages][kRowGroup]
-  uint8_t* atiles = reinterpret_cast<uint8_t*>(recs + (size_t)nstages * kRowGroup);         // [nstages][kRowGroup][ATILE]
+  float* tiles = map + map_floats;                                           // [nstages][kRowXGroup][TILE]
+  SepRecX* recs = reinterpret_cast<SepRecX*>(tiles + (size_t)nstages * kRowXGroup * TILE);   // [nstages][kRowXGroup]
+  uint8_t* atiles = reinterpret_cast<uint8_t*>(recs + (size_t)nstages * kRowXGroup);         // [nstages][kRowXGroup][ATILE]
   __shared__ uint64_t full_bar[kRowXMaxStages], empty_bar[kRowXMaxStages];
 
   const int b = blockIdx.y, c0 = blockIdx.x * CC;
@@ -1004,7 +1009,7 @@ roi_crop_bwd_rowsx_kernel(const float* __restrict__ dout, const int* __restrict_
   __syncthreads();
 
   const int beg = seg[b], end = seg[b + 1];
-  const int nst = (end - beg + kRowGroup - 1) / kRowGroup;
+  const int nst = (end - beg + kRowXGroup - 1) / kRowXGroup;
   const uint32_t tile_bytes = (uint32_t)(cvalid * kPP * sizeof(float));
   const uint32_t arg_bytes = (uint32_t)(cvalid * kPP);
   // winners travel by TMA only when their rows are 16-byte sized / aligned; otherwise they are read in place
@@ -1022,23 +1027,23 @@ roi_crop_bwd_rowsx_kernel(const float* __restrict__ dout, const int* __restrict_
           bulk_prefetch_l2(dout + ((size_t)__ldg(&sep[a].n) * g.C + c0) * kPP, tile_bytes);
       }
       const int cnt = min(32, end - r0);
-      for (int j = 0; j < cnt; j += kRowGroup) {
-        const int gc = min(kRowGroup, cnt - j);               // ROIs in this stage
-        int n[kRowGroup];
+      for (int j = 0; j < cnt; j += kRowXGroup) {
+        const int gc = min(kRowXGroup, cnt - j);               // ROIs in this stage
+        int n[kRowXGroup];
 #pragma unroll
-        for (int q = 0; q < kRowGroup; ++q) n[q] = __shfl_sync(0xffffffffu, nl, (j + q) & 31);
+        for (int q = 0; q < kRowXGroup; ++q) n[q] = __shfl_sync(0xffffffffu, nl, (j + q) & 31);
         if (lane == 0) {
           if (lap > 0) mbar_wait(&empty_bar[sidx], (lap - 1) & 1);
           mbar_arrive_expect_tx(&full_bar[sidx],
                                 (uint32_t)gc * (tile_bytes + (uint32_t)sizeof(SepRecX) + (arg_smem ? arg_bytes : 0u)));
-          bulk_g2s(recs + sidx * kRowGroup, sep + r0 + j, (uint32_t)(gc * sizeof(SepRecX)), &full_bar[sidx]);
+          bulk_g2s(recs + sidx * kRowXGroup, sep + r0 + j, (uint32_t)(gc * sizeof(SepRecX)), &full_bar[sidx]);
 #pragma unroll
-          for (int q = 0; q < kRowGroup; ++q)
+          for (int q = 0; q < kRowXGroup; ++q)
             if (q < gc) {
-              bulk_g2s(tiles + (size_t)(sidx * kRowGroup + q) * TILE, dout + ((size_t)n[q] * g.C + c0) * kPP, tile_bytes,
+              bulk_g2s(tiles + (size_t)(sidx * kRowXGroup + q) * TILE, dout + ((size_t)n[q] * g.C + c0) * kPP, tile_bytes,
                        &full_bar[sidx]);
               if (arg_smem)
-                bulk_g2s(atiles + (size_t)(sidx * kRowGroup + q) * ATILE, argmax + ((size_t)n[q] * g.C + c0) * kPP,
+                bulk_g2s(atiles + (size_t)(sidx * kRowXGroup + q) * ATILE, argmax + ((size_t)n[q] * g.C + c0) * kPP,
                          arg_bytes, &full_bar[sidx]);
             }
         }
@@ -1055,9 +1060,9 @@ roi_crop_bwd_rowsx_kernel(const float* __restrict__ dout, const int* __restrict_
     int sidx = 0, lap = 0;
     for (int k = 0; k < nst; ++k) {
       mbar_wait_parked(&full_bar[sidx], lap & 1);
-      const int gc = min(kRowGroup, end - beg - k * kRowGroup);
+      const int gc = min(kRowXGroup, end - beg - k * kRowXGroup);
       for (int q = 0; q < gc; ++q) {
-        const SepRecX* rec = recs + sidx * kRowGroup + q;
+        const SepRecX* rec = recs + sidx * kRowXGroup + q;
         unsigned hits = rec->wmask[owner];
         if (__ballot_sync(0xffffffffu, hits != 0u) == 0u) continue;        // warp uniform
         // column geometry of the ROI (the same for every lane)
@@ -1069,10 +1074,10 @@ roi_crop_bwd_rowsx_kernel(const float* __restrict__ dout, const int* __restrict_
           wb[j] = rec->lx[j];
           wa[j] = 1.f - wb[j];
         }
-        const float* tcol = tiles + (size_t)(sidx * kRowGroup + q) * TILE + (size_t)cl * kPP;
+        const float* tcol = tiles + (size_t)(sidx * kRowXGroup + q) * TILE + (size_t)cl * kPP;
         const uint8_t* acol = nullptr;
         if (MAXPOOL)
-          acol = arg_smem ? atiles + (size_t)(sidx * kRowGroup + q) * ATILE + (size_t)cl * kPP
+          acol = arg_smem ? atiles + (size_t)(sidx * kRowXGroup + q) * ATILE + (size_t)cl * kPP
                           : argmax + ((size_t)rec->n * g.C + c0 + cl) * kPP;
         while (hits) {
           const int bsel = __ffs(hits) - 1;
@@ -1080,7 +1085,8 @@ roi_crop_bwd_rowsx_kernel(const float* __restrict__ dout, const int* __restrict_
           float v[S];
 #pragma unroll
           for (int j = 0; j < S; ++j) v[j] = 0.f;
-          // every sample row of this ROI that lands in map row yy (adjacent bits of this owner's mask)
+          // every sample row of this ROI that lands in map row yy (adjacent bits of this owner's mask).  (Folding the two
+          // sample rows of a pooled row into one pass -- winner row bit picks the weight -- measured slower: 2.83 vs 2.64 ms.)
           while (hits) {
             const int b2 = __ffs(hits) - 1;
             const int i = b2 >> 1;
@@ -1164,12 +1170,202 @@ roi_crop_bwd_rowsx_kernel(const float* __restrict__ dout, const int* __restrict_
   }
 }
 
+// ------------------------------------------------------------------ forward, row-mirror variant
+// The forward seen the same way as the row-owner backward: lane = channel, the map slice sits in shared memory as
+// [row][col + 2][CC + 1] (conflict-free for channel-wise access, zero guard columns absorb corners outside the map),
+// and the geometry is the SEPARABLE record (14 or 7 column offsets / fractions, as many row offsets / fractions).  A
+// sample row is interpolated as  T[x] = (1 - ly) M[y0][x] + ly M[y0+1][x]  on the distinct map columns it touches (x0_j
+// is non-decreasing in j: a sliding two-column window), then  s_j = (1 - lx_j) T[x0_j] + lx_j T[x0_j + 1]  from
+// registers -- (box width + 1) column loads per sample row instead of four corner loads per sample, no per-lane
+// geometry at all (control flow is warp uniform), and for the 2x2 max variant the two sample rows of a pooled row stay
+// in registers.  The table-driven kernels above spend 16 LDS.128 and ~170 instructions per pooled float4; this one
+// needs ~2.5x fewer shared-memory wavefronts and ~5x fewer instructions (ncu, profiles/).
+// A warp owns whole ROIs; its [CC][49] output tile (and winner tile) leaves by TMA bulk stores.  With CC = 16 the two
+// half-warps take alternate pooled rows of the same ROI (same column geometry => still uniform).
+constexpr int kFwdRowWarps = 8;
+
+template <int CC, int S, bool MAXPOOL>
+__global__ void __launch_bounds__(kFwdRowWarps * 32, 1)
+roi_crop_fwd_rows_kernel(const float* __restrict__ bottom, const int* __restrict__ seg, const SepRecX* __restrict__ sep,
+                         float* __restrict__ out, uint8_t* __restrict__ argmax, CropGeom g) {
+  constexpr int LD = CC + 1;
+  constexpr int SUB = 32 / CC;
+  constexpr int TILE = CC * kPP;
+  constexpr int ATILE = (TILE + 15) & ~15;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int HW = g.H * g.W, W = g.W, H = g.H;
+  const int WP = W + 4;
+  float* map = reinterpret_cast<float*>(smem_raw);                           // [H][WP][LD]
+  const int map_floats = (H * WP * LD + 3) & ~3;
+  float* tiles = map + map_floats;                                           // [kFwdRowWarps][TILE]
+  uint8_t* atiles = reinterpret_cast<uint8_t*>(tiles + kFwdRowWarps * TILE); // [kFwdRowWarps][ATILE]
+
+  const int b = blockIdx.y, c0 = blockIdx.x * CC;
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  const int cvalid = min(CC, g.C - c0);
+  const int beg = seg[b], end = seg[b + 1];
+
+  // ---- stage the map slice: guard columns zero, lanes = consecutive pixels of a row (coalesced), loop over channels
+  for (int i = t; i < map_floats; i += blockDim.x) map[i] = 0.f;
+  __syncthreads();
+  {
+    const float* src = bottom + ((size_t)b * g.C + c0) * HW;
+    const int xblocks = (W + 31) >> 5;
+    for (int it = wid; it < cvalid * H * xblocks; it += kFwdRowWarps) {
+      const int c = it % cvalid, rest = it / cvalid;
+      const int y = rest / xblocks, x = (rest % xblocks) * 32 + lane;
+      if (x < W) map[((size_t)y * WP + x + 2) * LD + c] = __ldg(src + (size_t)c * HW + y * W + x);
+    }
+  }
+  __syncthreads();
+
+  const int ch = lane % CC, sub = lane / CC;
+  const float* mlane = map + 2 * LD + ch;             // (row 0, col 0, my channel)
+  const int row_stride = WP * LD;
+  float* tile = tiles + (size_t)wid * TILE;
+  uint8_t* atile = atiles + (size_t)wid * ATILE;
+  const uint32_t tile_bytes = (uint32_t)(cvalid * kPP * sizeof(float));
+  const bool arg_bulk = MAXPOOL && argmax != nullptr && (g.C % 16 == 0) && (cvalid % 16 == 0);
+
+  struct Rec {
+    int4 xo[2];      // 16 x int16
+    float4 lx[4], ly[4];
+    int4 y0[2];
+    int n;
+  };
+  auto load_rec = [&](int r, Rec& R) {
+    const SepRecX* rp = sep + r;
+    R.xo[0] = __ldg(reinterpret_cast<const int4*>(rp->xoff));
+    R.xo[1] = __ldg(reinterpret_cast<const int4*>(rp->xoff) + 1);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      R.lx[k] = __ldg(reinterpret_cast<const float4*>(rp->lx) + k);
+      R.ly[k] = __ldg(reinterpret_cast<const float4*>(rp->ly) + k);
+    }
+    R.y0[0] = __ldg(reinterpret_cast<const int4*>(rp->y0));
+    R.y0[1] = __ldg(reinterpret_cast<const int4*>(rp->y0) + 1);
+    R.n = __ldg(&rp->n);
+  };
+  auto i16 = [](const int4 (&v)[2], int k) -> int {       // element k of 16 packed int16 (k is a compile-time constant)
+    const int w = k >> 1;
+    const int word = (w == 0) ? v[0].x : (w == 1) ? v[0].y : (w == 2) ? v[0].z : (w == 3) ? v[0].w
+                   : (w == 4) ? v[1].x : (w == 5) ? v[1].y : (w == 6) ? v[1].z : v[1].w;
+    return (k & 1) ? (word >> 16) : (int)(short)(word & 0xffff);
+  };
+  auto f16 = [](const float4 (&v)[4], int k) -> float {
+    const float4 q = v[k >> 2];
+    return (k & 3) == 0 ? q.x : (k & 3) == 1 ? q.y : (k & 3) == 2 ? q.z : q.w;
+  };
+
+  Rec cur, nxt;
+  int r = beg + wid;
+  if (r < end) load_rec(r, cur);
+  for (; r < end; r += kFwdRowWarps) {
+    const bool more = r + kFwdRowWarps < end;
+    if (more) load_rec(r + kFwdRowWarps, nxt);              // in flight during this ROI
+    int xoff[S];
+    float wa[S], wb[S];
+#pragma unroll
+    for (int j = 0; j < S; ++j) {
+      xoff[j] = i16(cur.xo, j);
+      wb[j] = f16(cur.lx, j);
+      wa[j] = 1.f - wb[j];
+    }
+    if (lane == 0) bulk_wait_read<0>();                      // my previous stores have left the tiles
+    __syncwarp();
+    // one sample row: s[j], j < S, for the map rows (y0, y0 + 1) with fraction ly
+    auto sample_row = [&](int y0c, float ly, float (&sv)[S]) {
+      // rows outside the map contribute zero: clamp the index, zero the weight
+      const bool v0 = (unsigned)y0c < (unsigned)H, v1 = (unsigned)(y0c + 1) < (unsigned)H;
+      const float w0 = v0 ? 1.f - ly : 0.f, w1 = v1 ? ly : 0.f;
+      const float* r0 = mlane + (v0 ? y0c : 0) * row_stride;
+      const float* r1 = mlane + (v1 ? y0c + 1 : 0) * row_stride;
+      auto col = [&](int off) { return fmaf(w1, r1[off], w0 * r0[off]); };
+      int cx = xoff[0];
+      float tl = col(cx), tr = col(cx + LD);
+      sv[0] = fmaf(wb[0], tr, wa[0] * tl);
+#pragma unroll
+      for (int j = 1; j < S; ++j) {
+        const int dx = xoff[j] - cx;               // warp uniform
+        if (dx == LD) {
+          tl = tr;
+          tr = col(xoff[j] + LD);
+        } else if (dx != 0) {
+          tl = col(xoff[j]);
+          tr = col(xoff[j] + LD);
+        }
+        cx = xoff[j];
+        sv[j] = fmaf(wb[j], tr, wa[j] * tl);
+      }
+    };
+    constexpr int ROWS = 7;
+    for (int pi = sub; pi < ROWS; pi += SUB) {
+      if (MAXPOOL) {
+        float st[S], sb[S];
+        // 2 pi and 2 pi + 1 are not compile-time constants: fetch the row geometry through a small switch-free select
+        int y0t = 0, y0b = 0;
+        float lyt = 0.f, lyb = 0.f;
+#pragma unroll
+        for (int k = 0; k < ROWS; ++k)
+          if (k == pi) {
+            y0t = i16(cur.y0, 2 * k); y0b = i16(cur.y0, 2 * k + 1);
+            lyt = f16(cur.ly, 2 * k); lyb = f16(cur.ly, 2 * k + 1);
+          }
+        sample_row(y0t, lyt, st);
+        sample_row(y0b, lyb, sb);
+#pragma unroll
+        for (int pj = 0; pj < 7; ++pj) {
+          // first strict maximum in row-major order of the 2x2 block wins (max_pool2d's backward)
+          float m = st[2 * pj];
+          int am = 0;
+          if (st[2 * pj + 1] > m) { m = st[2 * pj + 1]; am = 1; }
+          if (sb[2 * pj] > m) { m = sb[2 * pj]; am = 2; }
+          if (sb[2 * pj + 1] > m) { m = sb[2 * pj + 1]; am = 3; }
+          if (ch < cvalid) {
+            tile[ch * kPP + pi * 7 + pj] = m;
+            atile[ch * kPP + pi * 7 + pj] = (uint8_t)am;
+          }
+        }
+      } else {
+        float sv[S];
+        int y0c = 0;
+        float ly = 0.f;
+#pragma unroll
+        for (int k = 0; k < ROWS; ++k)
+          if (k == pi) { y0c = i16(cur.y0, k); ly = f16(cur.ly, k); }
+        sample_row(y0c, ly, sv);
+#pragma unroll
+        for (int j = 0; j < 7; ++j)
+          if (ch < cvalid) tile[ch * kPP + pi * 7 + j] = sv[j];
+      }
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    const size_t obase = ((size_t)cur.n * g.C + c0) * kPP;
+    if (lane == 0) {
+      bulk_s2g(out + obase, tile, tile_bytes);
+      if (arg_bulk) bulk_s2g(argmax + obase, atile, (uint32_t)(cvalid * kPP));
+      bulk_commit();
+    }
+    if (MAXPOOL && argmax != nullptr && !arg_bulk)
+      for (int i = lane; i < cvalid * kPP; i += 32) argmax[obase + i] = atile[i];
+    if (more) cur = nxt;
+  }
+  if (lane == 0) bulk_wait<0>();
+}
+
+size_t fwd_rows_smem(int H, int W, int cc, bool maxpool) {
+  const size_t map = (((size_t)H * (W + 4) * (cc + 1) + 3) & ~(size_t)3) * 4;
+  const size_t tile = (size_t)cc * kPP;
+  return map + kFwdRowWarps * (tile * 4 + (maxpool ? ((tile + 15) & ~(size_t)15) : 0)) + 128;
+}
+
 // shared memory of the generic row-owner backward for `cc` channels and `nstages` ring stages
 size_t rowsx_smem(int H, int W, int cc, bool maxpool, int nstages) {
   const size_t map = (((size_t)H * (W + 4) * (cc + 1) + 3) & ~(size_t)3) * 4;
   const size_t tile = (size_t)cc * kPP;
   const size_t per_roi = tile * 4 + sizeof(SepRecX) + (maxpool ? ((tile + 15) & ~(size_t)15) : 0);
-  return map + (size_t)nstages * kRowGroup * per_roi + 128;
+  return map + (size_t)nstages * kRowXGroup * per_roi + 128;
 }
 
 // ------------------------------------------------------------------ host side
@@ -1345,13 +1541,45 @@ extern "C" int l2s_roi_crop_fwd(const float* bottom, const float* rois, float* o
   L2S_REQUIRE(make_plan(H * W, g.maxpool, g.rec, &pl), L2S_ERR_SHAPE,
               "roi_crop: feature map %dx%d does not fit the shared-memory staging", H, W);
   Prep pr;
+  roi_invalid_zero_kernel<<<N, 128, 0, st>>>(rois, out, B, C * kPP);
+  L2S_LAUNCH_OK("roi_invalid_zero_kernel");
+  count_launch();
+  // row-mirror kernel (separable records), opt-in: parity green for every variant, but MEASURED SLOWER than the
+  // table-driven kernels on B200 (cfg-3 14x14+max 2.52 vs 1.37 ms, cfg-2 7x7 2.13 vs 0.79 ms): with one output tile per
+  // warp only 8 warps fit next to the map and their dependent LDS -> FMA chains are latency bound
+  {
+    const size_t cap = (size_t)max_smem_optin() - 1024;
+    static const bool rows7 = env_flag("L2S_CROP_FWD_ROWS");        // A/B switch: row-mirror kernel for all variants
+    static const bool table_fwd = env_flag("L2S_CROP_FWD_TABLE");   // diagnostics: force the table-driven kernels
+    int cc = 0;
+    for (int c : {32, 16})
+      if (fwd_rows_smem(H, W, c, g.maxpool) <= cap) { cc = c; break; }
+    if (cc && !table_fwd && rows7) {
+      rc = prepare_order(rois, g, workspace, st, &pr);
+      if (rc) return rc;
+      roi_sepx_kernel<<<g.N, 64, 0, st>>>(rois, pr.order, pr.seg, pr.sepx, g, cc + 1, kRowWarps * (32 / cc));
+      L2S_LAUNCH_OK("roi_sepx_kernel");
+      count_launch();
+      const size_t smem = fwd_rows_smem(H, W, cc, g.maxpool);
+      dim3 grid((g.C + cc - 1) / cc, g.B);
+#define L2S_FROWS(CCV, SV, MPV)                                                                               \
+  do {                                                                                                        \
+    auto kern = roi_crop_fwd_rows_kernel<CCV, SV, MPV>;                                                       \
+    L2S_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
+    kern<<<grid, kFwdRowWarps * 32, smem, st>>>(bottom, pr.seg, pr.sepx, out, argmax, g);                     \
+  } while (0)
+      if (g.maxpool) { if (cc == 32) L2S_FROWS(32, 14, true); else L2S_FROWS(16, 14, true); }
+      else           { if (cc == 32) L2S_FROWS(32, 7, false); else L2S_FROWS(16, 7, false); }
+#undef L2S_FROWS
+      L2S_LAUNCH_OK("roi_crop_fwd_rows_kernel");
+      count_launch();
+      return L2S_OK;
+    }
+  }
   rc = prepare(rois, g, pl.cc / 4, workspace, st, &pr);
   if (rc) return rc;
   const int* seg = pr.seg;
   const unsigned char* table = pr.table;
-  roi_invalid_zero_kernel<<<N, 128, 0, st>>>(rois, out, B, C * kPP);
-  L2S_LAUNCH_OK("roi_invalid_zero_kernel");
-  count_launch();
   // warp-per-ROI kernel: 7x7 crops of maps whose 32-channel slice + one tile per warp fit in shared memory
   const size_t smem_warp = (size_t)(H * W + 1) * 32 * 4 + (size_t)kFwdWarps * 32 * kPP * 4 + 128;
   static const bool force_block = env_flag("L2S_CROP_FWD_BLOCK");     // diagnostics: force the block-synchronous kernel
@@ -1392,7 +1620,8 @@ extern "C" int l2s_roi_crop_bwd(const float* dout, const float* rois, const uint
   // 7x7 row-owner kernel: needs the whole 32-channel accumulator with guard columns + the tile ring in shared memory
   pl.smem_rows = (((size_t)H * (W + 4) * kRowLd + 3) & ~(size_t)3) * 4 +
                  kRowStages * kRowGroup * ((size_t)32 * kPP * 4 + sizeof(SepRec)) + 128;
-  if (!g.maxpool && pl.cc == 32 && pl.smem_rows <= cap && !ranked) {
+  static const bool force_generic = env_flag("L2S_CROP_BWD_ROWSX");   // diagnostics: generic row-owner kernel for 7x7 too
+  if (!g.maxpool && pl.cc == 32 && pl.smem_rows <= cap && !ranked && !force_generic) {
     rc = prepare(rois, g, pl.cc / 4, workspace, st, &pr);
     if (rc) return rc;
     auto kern = roi_crop_bwd_rows_kernel;
