@@ -171,7 +171,7 @@ class HotPathStep:
 
     def __init__(self, wl, device, world):
         from lang2seg_b200.nets.network import HotPathNet
-        from lang2seg_b200.parallel import GradientAllReducer
+        from lang2seg_b200.parallel import FlatGradients
         torch.manual_seed(1234)
         self.wl, self.device = wl, device
         self.parts = wl["parts"]
@@ -179,7 +179,9 @@ class HotPathStep:
         self.net = HotPathNet(dict(seq_length=wl["L"], vocab_size=wl["V"], C4_feat_dim=wl["C"])).to(device).eval()   # eval: dropout off (D8)
         self.params = [p for p in self.net.parameters() if p.requires_grad]
         self.opt = torch.optim.SGD(self.params, lr=1e-5, momentum=0.9, fused=True)
-        self.reducer = GradientAllReducer(self.net.gradient_groups()) if world > 1 else None
+        # N > 1: gradients live in flat per-group buffers (p.grad are views): no pack / unpack around the all-reduce
+        self.flat = FlatGradients(self.net.gradient_groups()) if (world > 1 and not self.fwd_only) else None
+        self._pending = None
         E = wl["I"] * wl["EPI"]
         g = torch.Generator().manual_seed(99)
         # upstream gradients of pool5 (stand in for res5's backward) and, where nothing else consumes the gated map,
@@ -213,20 +215,26 @@ class HotPathStep:
         net._losses.clear()
         return acc
 
-    def fwd_bwd(self, d, meta=None):
-        """forward + backward of the chained hot path; leaves the gradients in p.grad"""
+    def fwd_bwd(self, d, meta=None, split=False):
+        """forward + backward of the chained hot path; leaves the gradients in p.grad.
+        split=True (N > 1): only the backward of the branches that end in the caption model and the heads runs here
+        (their gradient groups are then complete and can be all-reduced while `bwd_rest()` runs the remaining backward:
+        ROI crop -> dynamic filter -> filter generator -> language encoder)."""
         net, parts = self.net, self.parts
         meta = meta if meta is not None else d.get("_meta", {})
         if self.fwd_only:
             return self.forward_only(d, meta)
-        self.opt.zero_grad(set_to_none=True)
+        if self.flat is not None:
+            self.flat.zero()
+        else:
+            self.opt.zero_grad(set_to_none=True)
         X = d["X"].requires_grad_(True)
         gated = net._dynamic_filter(X, d["labels"], expr2img=d["e2i"], resp_target=d.get("resp_tgt"),
                                     lengths=meta.get("lens"))
-        loss = 0
+        loss_a, loss_b = 0, 0
         outs, grads = [], []
         if "resp" in parts:
-            loss = loss + net._losses["loss_response_per_expr"].sum()
+            loss_b = loss_b + net._losses["loss_response_per_expr"].sum()
         if "crop_max" in parts:
             outs.append(net._crop_pool_layer(gated, d["rois"], max_pool=True)); grads.append(self.g_pool_max)
         if "crop7" in parts:
@@ -237,12 +245,32 @@ class HotPathStep:
         if "mask" in parts:
             fc7 = d["fc7"].requires_grad_(True)
             net._mask_prediction(fc7, d["mlab"], d["mtgt"])   # prediction + mask loss as one node (fused backward)
-            loss = loss + net._mask_loss(d["mlab"], d["mtgt"])
+            loss_a = loss_a + net._mask_loss(d["mlab"], d["mtgt"])
         if "caption" in parts:
             att = d["att"].requires_grad_(True)
-            loss = loss + net._cap_loss_weight * net._caption_loss(d["fc"], att, d["cap"], d["msk"],
-                                                                   steps=meta.get("steps"))
-        torch.autograd.backward([loss] + outs, [self.one] + grads)
+            loss_a = loss_a + net._cap_loss_weight * net._caption_loss(d["fc"], att, d["cap"], d["msk"],
+                                                                       steps=meta.get("steps"))
+        roots_a = ([loss_a], [self.one]) if torch.is_tensor(loss_a) else ([], [])
+        roots_b = (([loss_b] if torch.is_tensor(loss_b) else []) + outs, ([self.one] if torch.is_tensor(loss_b) else []) + grads)
+        loss = (loss_a + loss_b).detach()
+        if split:
+            if roots_a[0]:
+                torch.autograd.backward(*roots_a)
+            self._pending = (roots_b, X, fc7, att)
+        else:
+            torch.autograd.backward(roots_a[0] + roots_b[0], roots_a[1] + roots_b[1])
+            self._finish(X, fc7, att)
+        return loss
+
+    def bwd_rest(self):
+        """second half of a split backward (see fwd_bwd)"""
+        roots_b, X, fc7, att = self._pending
+        self._pending = None
+        if roots_b[0]:
+            torch.autograd.backward(*roots_b)
+        self._finish(X, fc7, att)
+
+    def _finish(self, X, fc7, att):
         X.grad = None
         if fc7 is not None:
             fc7.grad = None
@@ -251,16 +279,18 @@ class HotPathStep:
         # drop the references into this step's autograd graph (the reference keeps them in _predictions/_losses for its
         # tensorboard summaries): a graph kept alive across steps pins AccumulateGrad nodes to the stream they were
         # created on, which breaks CUDA-graph capture on another stream
-        net._predictions.clear()
-        net._losses.clear()
-        return loss.detach()
+        self.net._predictions.clear()
+        self.net._losses.clear()
+
+    # gradient groups that are complete after the first half of a split backward
+    EARLY_GROUPS = ("caption", "heads")
 
     def update(self):
         """gradient all-reduce of the three parameter groups (N > 1) and the SGD update"""
         if self.fwd_only:
             return
-        if self.reducer is not None:
-            self.reducer.all_reduce()
+        if self.flat is not None:
+            self.flat.all_reduce()
         self.opt.step()
 
     def __call__(self, d, meta=None):
@@ -548,36 +578,53 @@ def main():
     l0 = _lib.launch_count()
     step(d)
     launches_per_step = _lib.launch_count() - l0          # kernels of libl2s.so per step (counted on an eager step)
-    # The whole step (lang encoder .. SGD update, ~650 launches, shapes static for a given batch geometry) is captured
-    # once in a CUDA graph and replayed: the timed region then measures the kernels, not Python/launch latency.
-    # N = 1: the whole step is one graph.  N > 1: forward+backward is the graph; the NCCL all-reduce and the SGD update
-    # (a handful of launches) stay eager -- NCCL work captured together with its stream/event hand-offs hung here.
-    whole = world == 1
-    body = (lambda: step(d)) if whole else (lambda: step.fwd_bwd(d))
+    # The step (shapes static for a given batch geometry) is captured in CUDA graphs and replayed: the timed region then
+    # measures the kernels, not Python / launch latency.
+    #   N = 1: one graph for the whole step (lang encoder .. SGD update).
+    #   N > 1: three graphs with the NCCL all-reduces launched between them, so that communication overlaps compute:
+    #          A = forward + backward of the caption / head branches  -> all-reduce(caption), all-reduce(heads) start
+    #          B = the rest of the backward (ROI crop, dynamic filter, filter generator, encoder), concurrent with them
+    #              -> all-reduce(filter_generator)
+    #          C = fused SGD update over the flat gradient views.
+    whole = world == 1 or step.fwd_only
     run, graphed = (lambda: step(d)), False
     if not args.no_graph:
         try:
+            def capture(fn, pool=None):
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pool):
+                    out = fn()
+                return g, out
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
-                body()
+                step(d)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                static_loss = body()
-            graph.replay()
-            torch.cuda.synchronize()
-            assert torch.isfinite(static_loss).all()
             if whole:
+                graph, static_loss = capture(lambda: step(d))
                 run = graph.replay
             else:
+                g_a, static_loss = capture(lambda: step.fwd_bwd(d, split=True))
+                g_b, _ = capture(step.bwd_rest, pool=g_a.pool())
+                g_c, _ = capture(step.opt.step, pool=g_a.pool())
+                early = [n for n in step.EARLY_GROUPS]
+                late = [n for n in step.flat.names if n not in early]
+
                 def run():
-                    graph.replay()
-                    step.update()
+                    g_a.replay()
+                    w = step.flat.all_reduce_async(early)
+                    g_b.replay()
+                    w += step.flat.all_reduce_async(late)
+                    step.flat.wait(w)
+                    g_c.replay()
+            run()
+            torch.cuda.synchronize()
+            assert torch.isfinite(static_loss).all()
             graphed = True
         except Exception as exc:      # capture is an optimisation: fall back to eager launches and say so
             print("bench: CUDA graph capture failed (%s); timing eager launches" % str(exc).splitlines()[0], file=sys.stderr)
+            run = lambda: step(d)     # noqa: E731
             torch.cuda.synchronize()
     for _ in range(args.warmup):
         run()
@@ -652,7 +699,9 @@ def main():
                            if "caption" not in wl["parts"] or wl["I"] * wl["EPI"] >= 32 else
                            "inputs + activations per step exceed the 126 MB L2 (att/fc features alone: %d MB)" % (wl["I"] * wl["EPI"] * 196 * 4096 * 4 // 2**20),
                            "includes": includes,
-                           "launch": ("one CUDA graph replay per step" + ("" if world == 1 else " (fwd+bwd) + eager all-reduce/SGD"))
+                           "launch": ("one CUDA graph replay per step" if world == 1 else
+                                      "three CUDA graphs per step (fwd + caption/head backward | rest of the backward | SGD) "
+                                      "with the NCCL all-reduces of the flat gradient groups launched between them")
                            if graphed else "eager launches"},
                 "clocks": clocks, "gpu_launches": launches,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,

@@ -101,3 +101,53 @@ class GradientAllReducer:
     def all_reduce(self):
         self.launch()
         self.wait()
+
+
+class FlatGradients:
+    """Gradients of each parameter group live in ONE pre-allocated flat fp32 buffer and every `p.grad` is a view into
+    it: autograd accumulates in place, the all-reduce runs on the flat buffer directly (no ~200 pack / unpack copy
+    kernels per step) and the fused optimizer reads the views.  Groups can be reduced separately, as soon as their
+    last gradient has been written (bench.py: caption + heads overlap the rest of the backward).
+
+    Use `zero()` instead of `optimizer.zero_grad(set_to_none=True)` (which would drop the views)."""
+
+    def __init__(self, groups, process_group=None):
+        self.pg = process_group
+        self.names = list(groups)
+        self.flat = {}
+        self.params = {}
+        for name, ps in groups.items():
+            ps = [p for p in ps if p.requires_grad]
+            self.params[name] = ps
+            if not ps:
+                continue
+            flat = torch.zeros(sum(p.numel() for p in ps), device=ps[0].device, dtype=torch.float32)
+            off = 0
+            for p in ps:
+                n = p.numel()
+                p.grad = flat[off:off + n].view_as(p)
+                off += n
+            self.flat[name] = flat
+
+    @property
+    def numel(self):
+        return sum(f.numel() for f in self.flat.values())
+
+    def zero(self):
+        for f in self.flat.values():
+            f.zero_()
+
+    def all_reduce_async(self, names=None):
+        """Launch the (sum) all-reduce of the named groups; returns the work handles (empty without a process group)."""
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.pg) == 1:
+            return []
+        return [dist.all_reduce(self.flat[n], op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+                for n in (names or self.names) if n in self.flat]
+
+    @staticmethod
+    def wait(works):
+        for w in works:
+            w.wait()
+
+    def all_reduce(self, names=None):
+        self.wait(self.all_reduce_async(names))

@@ -6,7 +6,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from lang2seg_b200.parallel import GradientAllReducer, shard_images, shard_range
+from lang2seg_b200.parallel import FlatGradients, GradientAllReducer, shard_images, shard_range
 
 
 def test_shard_range_covers_everything():
@@ -36,8 +36,19 @@ def _worker(rank, world, port, out):
     (lin_b(lin_a(full[lo:hi])) ** 2).sum().backward()
     red = GradientAllReducer({"a": list(lin_a.parameters()), "b": list(lin_b.parameters())})
     red.all_reduce()
+    grads = [p.grad.clone() for p in list(lin_a.parameters()) + list(lin_b.parameters())]
+    # the same step through flat gradient buffers (p.grad are views; groups reduced separately, asynchronously)
+    flat = FlatGradients({"a": list(lin_a.parameters()), "b": list(lin_b.parameters())})
+    for _ in range(2):                      # twice: accumulation in place + zero() between steps
+        flat.zero()
+        (lin_b(lin_a(full[lo:hi])) ** 2).sum().backward()
+        wa = flat.all_reduce_async(["b"])
+        wb = flat.all_reduce_async(["a"])
+        flat.wait(wa + wb)
+    flat_grads = [p.grad.clone() for p in list(lin_a.parameters()) + list(lin_b.parameters())]
+    assert all(p.grad.data_ptr() >= flat.flat[n].data_ptr() for n, ps in flat.params.items() for p in ps)
     if rank == 0:
-        torch.save([p.grad for p in list(lin_a.parameters()) + list(lin_b.parameters())], out)
+        torch.save([grads, flat_grads], out)
     dist.destroy_process_group()
 
 
@@ -48,11 +59,13 @@ def test_two_rank_gradient_allreduce_equals_single_process(tmp_path):
     s.close()
     out = str(tmp_path / "g.pt")
     mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
-    got = torch.load(out)
+    got, got_flat = torch.load(out)
     torch.manual_seed(0)
     lin_a, lin_b = torch.nn.Linear(5, 3), torch.nn.Linear(3, 2)
     full = torch.arange(40, dtype=torch.float32).reshape(8, 5) / 10
     (lin_b(lin_a(full)) ** 2).sum().backward()
     ref = [p.grad for p in list(lin_a.parameters()) + list(lin_b.parameters())]
     for a, b in zip(got, ref):
+        assert torch.allclose(a, b, rtol=1e-5, atol=1e-6)
+    for a, b in zip(got_flat, ref):
         assert torch.allclose(a, b, rtol=1e-5, atol=1e-6)
