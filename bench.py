@@ -299,6 +299,89 @@ class HotPathStep:
         return loss
 
 
+class ChainedStep:
+    """The reference-faithful chain WITH res5 in the middle (SURVEY 8d "second number", row a8): dynamic filter ->
+    7x7 crop -> res5 (cuDNN glue, lang2seg_b200/nets/res5_glue.py) -> box head + mask head ; ungated / gated map ->
+    res5 -> caption features -> att2in2 ; all five losses (:449), backward, gradient all-reduce (N > 1), SGD.
+    Host inputs are the image-side tensors only (C4 map, tokens, ROIs, one box + uint8 mask per expression): every
+    target (response, box, mask) is built on the device."""
+
+    KEYS = ("X", "labels", "e2i", "rois", "roi_labels", "gt_boxes", "gt_masks", "cap", "msk")
+
+    def __init__(self, wl, device, world):
+        from lang2seg_b200.nets.network import HotPathNet
+        from lang2seg_b200.nets.res5_glue import Res5Glue
+        from lang2seg_b200.parallel import FlatGradients
+        torch.manual_seed(1234)
+        self.net = HotPathNet(dict(seq_length=wl["L"], vocab_size=wl["V"], C4_feat_dim=wl["C"]),
+                              head_to_tail=Res5Glue(wl["C"], 512, 3)).to(device).eval()
+        self.params = [p for p in self.net.parameters() if p.requires_grad]
+        self.opt = torch.optim.SGD(self.params, lr=1e-6, momentum=0.9, fused=True)
+        self.flat = FlatGradients(self.net.gradient_groups()) if world > 1 else None
+
+    def __call__(self, d, meta):
+        net = self.net
+        if self.flat is not None:
+            self.flat.zero()
+        else:
+            self.opt.zero_grad(set_to_none=True)
+        loss = net.chained_train_step(d["X"], d["labels"], d["e2i"], d["rois"], d["roi_labels"], d["gt_boxes"],
+                                      d["gt_masks"], d["cap"], d["msk"], meta["num_fg"], lengths=meta.get("lens"),
+                                      steps=meta.get("steps"))
+        loss.backward()
+        if self.flat is not None:
+            self.flat.all_reduce()
+        self.opt.step()
+        net._predictions.clear()
+        net._losses.clear()
+        net._proposal_targets = {}
+        return loss.detach()
+
+
+def run_chained(wl, dev, world, rank, dist_on, steps=3, warm=2):
+    """Device-timed and end-to-end (pinned host inputs every step) expressions/s of ChainedStep."""
+    from lang2seg_b200 import synth
+    from lang2seg_b200.pipeline import HostBatchPipeline
+    E = wl["I"] * wl["EPI"]
+    g = torch.Generator().manual_seed(4321 + rank)
+    host = synth.chain_batch(g, wl["I"], wl["EPI"], wl["C"], wl["H"], wl["W"], wl["R"], wl["NFG"], wl["L"], wl["V"])
+    meta = host.pop("_meta")
+    step = ChainedStep(wl, dev, world)
+    d = {k: v.to(dev) for k, v in host.items()}
+    torch.backends.cudnn.benchmark = True       # as the reference does for its fixed-size TRAIN step (:585)
+    for _ in range(warm):
+        loss = step(d, meta)
+    assert torch.isfinite(loss).all(), "chained step produced a non-finite loss"
+    ms = time_region(lambda: step(d, meta), steps, dist_on) / steps
+    pinned = {k: v.pin_memory() for k, v in host.items()}
+    h2d = sum(v.numel() * v.element_size() for v in pinned.values())
+    pipe = HostBatchPipeline(dev, depth=2)
+    out = []
+
+    def e2e_run(n):
+        pipe.submit(pinned)
+        for i in range(n):
+            if i + 1 < n:
+                pipe.submit(pinned)
+            dd = pipe.get()
+            out.append(float(step(dd, meta)))
+            pipe.release()
+
+    ms_e2e = time_region(lambda: e2e_run(steps), 1, dist_on) / steps
+    peak_gb = torch.cuda.max_memory_allocated(dev) / 2**30
+    del step, d
+    torch.cuda.empty_cache()
+    return {"value": E * world / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": steps, "warmup": warm,
+            "e2e": {"value": E * world / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e},
+            "res5": "resnet.layer4 (3 bottlenecks 1024->2048, stride 1, frozen BN folded) on cuDNN fp32, TF32 off -- glue, "
+                    "not one of this repository's kernels (SURVEY 8 row a8)",
+            "res5_rois_per_step": E * wl["R"], "res5_maps_per_step": wl["I"] + E,
+            "launch": "eager (the chain is dominated by the cuDNN convolutions)", "peak_mem_gib": round(peak_gb, 1),
+            "what": "dynfilter -> 7x7 crop -> res5 -> box head + mask head (fg) ; maps -> res5 -> caption features -> "
+                    "att2in2 ; response / cls / box / mask / caption losses, backward, SGD; targets built on the device"}
+
+
 def time_region(fn, steps, dist_on):
     import torch.distributed as dist
     if dist_on:
@@ -350,8 +433,11 @@ def component_rooflines(wl, d, step, pk):
     resp, Y, rl = F.dynamic_filter(d["X"], filt, fuse, d["e2i"], "sigmoid", tgt)
     rk = torch.empty(E, 7, H, W, device=dev)
     lossb = torch.empty(E, device=dev)
+    nbf = _lib.size("l2s_dynfilter_fwd_workspace_bytes", I, E, C, H, W)
+    wsf = torch.empty(nbf, dtype=torch.uint8, device=dev)
     t = ev_time(lambda: call("l2s_dynfilter_fwd", ptr(d["X"]), ptr(filt), ptr(fuse), ptr(d["e2i"]), ptr(resp), ptr(rk),
-                             ptr(Y), ptr(tgt), ptr(lossb if tgt is not None else None), I, E, C, H, W, 0, stream()))
+                             ptr(Y), ptr(tgt), ptr(lossb if tgt is not None else None), I, E, C, H, W, 0, ptr(wsf), nbf,
+                             stream()))
     out.append(dict(kernel="dynfilter_fwd", ms=t, bound="hbm", work=4.0 * C * HW * (I + E)))
     if not step.fwd_only:
         dY = torch.randn_like(Y) * 1e-3
@@ -503,6 +589,35 @@ def cpu_sample(wl, repeats=1, threads=None):
     return E / dt, dt, E
 
 
+def cpu_chain_sample(wl, threads=None):
+    """The res5-chained TRAIN step (oracle.restate.chained_train_losses: the reference's _predict + _add_losses from the
+    dynamic filter on, resnet.layer4 included) on ONE image and its expressions, fwd+bwd on the host cores."""
+    from oracle import restate as R
+    from lang2seg_b200 import synth
+    from lang2seg_b200.nets.network import HotPathNet          # only as the container of default-initialised weights
+    from lang2seg_b200.nets.res5_glue import Res5Glue
+    if threads:
+        torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(4321)
+    d = synth.chain_batch(g, 1, wl["EPI"], wl["C"], wl["H"], wl["W"], wl["R"], wl["NFG"], wl["L"], wl["V"])
+    meta = d.pop("_meta")
+    torch.manual_seed(7)
+    net = HotPathNet(dict(seq_length=wl["L"], vocab_size=wl["V"], C4_feat_dim=wl["C"]), head_to_tail=Res5Glue(wl["C"], 512, 3))
+    p = {(("res5." + k[len("_head."):]) if k.startswith("_head.") else k): v.detach().clone().requires_grad_(v.is_floating_point())
+         for k, v in net.state_dict().items()}
+    enc = {k[len("rnn_encoder."):]: v for k, v in p.items() if k.startswith("rnn_encoder.")}
+    t0 = time.perf_counter()
+    X = d["X"].clone().requires_grad_(True)
+    _, hidden, _ = R.rnn_encoder_packed(d["labels"], enc)
+    _, total = R.chained_train_losses(X, hidden, p, d["e2i"].tolist(), d["rois"], d["roi_labels"], d["gt_boxes"],
+                                      d["gt_masks"].numpy(), d["cap"], d["msk"], meta["num_fg"])
+    total.backward()
+    dt = time.perf_counter() - t0
+    E = wl["EPI"]
+    return {"value": E / dt, "unit": UNIT, "seconds_per_pass": dt,
+            "sample": "1 image x %d expressions x %d ROIs, one fwd+bwd pass of the res5-chained step (no warm-up pass)" % (E, wl["R"])}
+
+
 def run_reference_arm(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -521,13 +636,19 @@ def run_reference_arm(args, wl):
     total = sum(vals)
     value = n_expr / total
     sample = "1 image x %d expressions of the workload per step (reference's native batching), fwd+bwd, torch CPU" % wl["EPI"]
+    chained = None
+    if not args.no_res5 and all(p in wl["parts"] for p in ("resp", "crop7", "mask", "caption")):
+        try:
+            chained = cpu_chain_sample(wl)
+        except Exception as exc:
+            chained = {"unavailable": str(exc).splitlines()[0][:200]}
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
             "config": {"workload": wl["name"], "sample": sample},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "with_res5": chained, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
@@ -542,6 +663,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-components", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of a captured CUDA graph")
+    ap.add_argument("--no-res5", action="store_true",
+                    help="skip the second, res5-chained number (reference-faithful chain with resnet.layer4 as cuDNN glue)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.batch > 0:
@@ -670,6 +793,21 @@ def main():
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": "1 image x %d expressions of the workload (reference's native batching), fwd+bwd, "
                          "oracle torch-CPU port, %.2f s per pass" % (e, dt)}
+        if not args.no_res5 and all(p in wl["parts"] for p in ("resp", "crop7", "mask", "caption")):
+            try:
+                cpu["with_res5"] = cpu_chain_sample(wl)
+            except Exception as exc:
+                cpu["with_res5"] = {"unavailable": str(exc).splitlines()[0][:200]}
+    # ---- the second, labelled number: the same path chained through res5 (cuDNN glue) like the reference's _predict
+    chained = None
+    if not args.no_res5 and all(p in wl["parts"] for p in ("resp", "crop7", "mask", "caption")) and not step.fwd_only:
+        del step, d, host, pipe
+        run = None
+        torch.cuda.empty_cache()
+        try:
+            chained = run_chained(wl, dev, world, rank, dist_on)
+        except Exception as exc:      # the graded line must survive a failure of the glue leg
+            chained = {"unavailable": str(exc).splitlines()[0][:200]}
     if rank == 0:
         roof = None
         if comps:
@@ -707,7 +845,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                         "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
                         "how": "pinned host inputs -> copy stream (double buffered, overlaps the previous step) -> step -> loss.item()"},
-                "roofline": roof, "cpu_baseline": cpu,
+                "roofline": roof, "cpu_baseline": cpu, "with_res5": chained,
                 "components": [{k: (round(v, 5) if isinstance(v, float) else v) for k, v in c.items()} for c in comps]
                 if comps else None}
         print(json.dumps(line), flush=True)

@@ -44,7 +44,14 @@ typedef void* l2s_stream_t; /* cudaStream_t */
 #define L2S_CROP_BWD_RANKED 4 /* backward only: force the sample-per-lane (ranked) kernel where the row-owner kernel
                                * (lane = channel, warp = map rows; 7x7 crops of maps <= ~1300 pixels) is the default */
 
+/* precision of the tensor-core GEMMs (mask head, caption projections, l2s_gemm_bf16x3) */
+#define L2S_PRECISION_FP32 0 /* bf16x3 split products: ~1e-5 from an fp32 GEMM (the default; the 1e-4 parity contract) */
+#define L2S_PRECISION_BF16 1 /* one tensor pass on the bf16-rounded operands: north_star's "bf16 variants within 1e-2" */
+
 int l2s_version(void);
+/* Process-wide precision switch (applies to GEMMs launched after the call); returns L2S_ERR_ARG for an unknown mode. */
+int l2s_set_precision(int mode);
+int l2s_get_precision(void);
 const char* l2s_last_error_string(void);
 /* number of kernels this library launched since load (process wide) */
 uint64_t l2s_launch_count(void);
@@ -66,11 +73,18 @@ int l2s_set_debug_buffer(void* device_buffer, size_t bytes);
  *   rk_saved (E,7,H,W) or NULL: the masked per-filter responses r_k, kept for the backward
  *   Y        (E,C,H,W)   gated features (:570)
  *   resp_target (E,H,W) or NULL ; resp_loss (E) or NULL: per-expression mean BCE-with-logits.
+ *   workspace: l2s_dynfilter_fwd_workspace_bytes() (bf16 planes of the stacked filters + loss partials of the
+ *   tensor-core kernel); with workspace == NULL the call still works and takes the FFMA kernel.
+ *   Kernel: TMA-staged [C x 32 px] feature tiles resident in shared memory, the contraction on tcgen05
+ *   (bf16x3 split, fp32 accumulation in TMEM), masks / fusion / sigmoid / BCE in the TMEM epilogue, gating streamed
+ *   from the resident tile (csrc/dynfilter_tc.cu); shapes outside its range (H*W % 4, C % 32, C > 1024) run the FFMA
+ *   tile kernel of csrc/dynfilter.cu.
  * ------------------------------------------------------------------------------------- */
+size_t l2s_dynfilter_fwd_workspace_bytes(int I, int E, int C, int H, int W);
 int l2s_dynfilter_fwd(const float* X, const float* filt, const float* fuse, const int32_t* expr2img,
                       float* response, float* rk_saved, float* Y, const float* resp_target,
-                      float* resp_loss, int I, int E, int C, int H, int W, int flags,
-                      l2s_stream_t stream);
+                      float* resp_loss, int I, int E, int C, int H, int W, int flags, void* workspace,
+                      size_t workspace_bytes, l2s_stream_t stream);
 
 /* Backward of the above.
  *   rk_saved: what the forward kept, or NULL (then r_k is recomputed into the workspace) ;
@@ -196,6 +210,28 @@ int l2s_mask_bce_fwd(const float* score, const int64_t* labels, const float* tar
                      int ncls, int hw, l2s_stream_t stream);
 int l2s_mask_bce_bwd(const float* score, const int64_t* labels, const float* target, const float* gscale,
                      float* dscore, int n, int ncls, int hw, l2s_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * RPN tail / proposal targets.  Replace the arithmetic of
+ *   proposal_layer        MFR/layer_utils/proposal_layer.py:41-46 (bbox_transform_inv + clip_boxes, MFR/model/bbox_transform.py)
+ *   _sample_rois          MFR/layer_utils/proposal_target_layer.py:137-139 (bbox_overlaps + max), :184-188
+ *                         (_compute_targets + _get_bbox_regression_labels)
+ * fp32 in the reference's operation order without FMA contraction.
+ *   proposal_decode: anchors (N,4), deltas (N,4), scores (N) with element stride score_stride -> boxes5 (N,5)
+ *                    [x1,y1,x2,y2,score] clipped to [0, im_w-1] x [0, im_h-1]: the row layout l2s_nms takes.
+ *   roi_gt_overlaps: rois (N, roi_stride) with the box at column roi_offset, gt_boxes (G, gt_stride) [x1,y1,x2,y2,..] ->
+ *                    max_overlap (N) and gt_assignment (N) int64 = index of the FIRST maximum (+1-pixel IoU convention).
+ *   bbox_targets:    targets, inside_weights (N, 4*num_classes) overwritten: zeros except columns 4*label..4*label+3 of
+ *                    rows with label > 0 ; labels (N) fp32 ; means/stds/inside weights are HOST arrays of 4 floats.
+ * ------------------------------------------------------------------------------------- */
+int l2s_proposal_decode(const float* anchors, const float* deltas, const float* scores, int64_t score_stride,
+                        float* boxes5, int N, float im_h, float im_w, l2s_stream_t stream);
+int l2s_roi_gt_overlaps(const float* rois, int roi_stride, int roi_offset, const float* gt_boxes, int gt_stride,
+                        float* max_overlap, int64_t* gt_assignment, int N, int G, l2s_stream_t stream);
+int l2s_bbox_targets(const float* rois, int roi_stride, int roi_offset, const float* gt_boxes, int gt_stride,
+                     const int64_t* gt_assignment, const float* labels, float* targets, float* inside_weights,
+                     int N, int num_classes, const float* means4_host, const float* stds4_host,
+                     const float* inside4_host, l2s_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * Box head glue.  Replaces the pieces of Network._region_classification

@@ -18,7 +18,10 @@ SIGNATURES = {
     "l2s_last_error_string": (ctypes.c_char_p, []),
     "l2s_launch_count": (ctypes.c_uint64, []),
     "l2s_set_debug_buffer": (_i, [_vp, _sz]),
-    "l2s_dynfilter_fwd": (_i, [_vp] * 9 + [_i] * 6 + [_vp]),
+    "l2s_set_precision": (_i, [_i]),
+    "l2s_get_precision": (_i, []),
+    "l2s_dynfilter_fwd_workspace_bytes": (_sz, [_i] * 5),
+    "l2s_dynfilter_fwd": (_i, [_vp] * 9 + [_i] * 6 + [_vp, _sz, _vp]),
     "l2s_dynfilter_bwd_workspace_bytes": (_sz, [_i] * 5),
     "l2s_dynfilter_bwd": (_i, [_vp] * 13 + [_i] * 6 + [_vp, _sz, _vp]),
     "l2s_roi_crop_workspace_bytes": (_sz, [_i, _i, _i]),
@@ -35,6 +38,9 @@ SIGNATURES = {
     "l2s_mask_head_fwd_stages": (_i, [_vp] * 8 + [_i] * 4 + [_vp, _sz, _i, _vp]),
     "l2s_mask_head_bwd": (_i, [_vp] * 9 + [_i] * 4 + [_vp, _sz, _vp]),
     "l2s_mask_head_bce_bwd": (_i, [_vp] * 12 + [_i] * 4 + [_vp, _sz, _vp]),
+    "l2s_proposal_decode": (_i, [_vp, _vp, _vp, _i64, _vp, _i, _f, _f, _vp]),
+    "l2s_roi_gt_overlaps": (_i, [_vp, _i, _i, _vp, _i, _vp, _vp, _i, _i, _vp]),
+    "l2s_bbox_targets": (_i, [_vp, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "l2s_spatial_mean_fwd": (_i, [_vp, _vp, _i64, _i, _vp]),
     "l2s_spatial_mean_bwd": (_i, [_vp, _vp, _i64, _i, _vp]),
     "l2s_softmax_argmax": (_i, [_vp, _i64, _vp, _vp, _i, _i, _vp]),

@@ -73,6 +73,12 @@ int launch_decode_bwd_persist(const float* dh_all, const float* cat_all, const f
                               float* dres_all, float* de_all, float* dh_carry, int T, int B, int A, unsigned* bar,
                               cudaStream_t st);
 
+// tensor-core dynamic filter forward (dynfilter_tc.cu): 0 = ran, 1 = shape outside its range, < 0 = error
+size_t dynfilter_tc_workspace_bytes(int E, int C, int HW);
+int launch_dynfilter_tc_fwd(const float* X, const float* filt, const float* fuse, const int* e2i, float* response,
+                            float* rk_saved, float* Y, const float* target, float* loss, int I, int E, int C, int H,
+                            int W, int flags, void* workspace, size_t ws_bytes, cudaStream_t st);
+
 // persistent bi-LSTM kernels (lstm_persist.cu)
 bool bilstm_persist_ok(int L, int B, int H);
 int launch_bilstm_fwd_persist(float* G, const float* w_hh, const int* lens, float* c_all, float* h_all, float* out,

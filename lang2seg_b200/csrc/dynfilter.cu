@@ -583,10 +583,15 @@ int check(const void* X, const void* f, const void* w, const void* e2i, int I, i
 
 using namespace l2s;
 
+extern "C" size_t l2s_dynfilter_fwd_workspace_bytes(int I, int E, int C, int H, int W) {
+  (void)I;
+  return dynfilter_tc_workspace_bytes(E > 0 ? E : 0, C > 0 ? C : 0, (H > 0 && W > 0) ? H * W : 0);
+}
+
 extern "C" int l2s_dynfilter_fwd(const float* X, const float* filt, const float* fuse, const int32_t* expr2img,
                                  float* response, float* rk_saved, float* Y, const float* resp_target,
-                                 float* resp_loss, int I, int E, int C, int H, int W, int flags,
-                                 l2s_stream_t stream) {
+                                 float* resp_loss, int I, int E, int C, int H, int W, int flags, void* workspace,
+                                 size_t workspace_bytes, l2s_stream_t stream) {
   int rc = check(X, filt, fuse, expr2img, I, E, C, H, W, flags);
   if (rc) return rc;
   L2S_REQUIRE(response && Y, L2S_ERR_ARG, "dynfilter_fwd: null output");
@@ -594,6 +599,10 @@ extern "C" int l2s_dynfilter_fwd(const float* X, const float* filt, const float*
   cudaStream_t st = (cudaStream_t)stream;
   const DfGeom g = make_geom(I, E, C, H, W, flags);
   if (resp_loss) L2S_CUDA_OK(cudaMemsetAsync(resp_loss, 0, sizeof(float) * E, st));
+  // tensor-core kernel (dynfilter_tc.cu) where the shape allows it: 0 = ran, 1 = not applicable, < 0 = error
+  rc = launch_dynfilter_tc_fwd(X, filt, fuse, expr2img, response, rk_saved, Y, resp_target, resp_loss, I, E, C, H, W, flags,
+                               workspace, workspace_bytes, st);
+  if (rc <= 0) return rc;
   const bool vec = (g.HW % 4 == 0) && aligned16(X) && aligned16(Y);
   const size_t cap = (size_t)max_smem_optin();
   if (fwd_smem(C, 16) <= cap && vec)

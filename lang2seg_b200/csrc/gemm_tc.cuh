@@ -4,6 +4,8 @@
 //     acc += A_hi*B_hi + A_hi*B_lo + A_lo*B_hi          (fp32 accumulation in TMEM)
 // The dropped terms are O(2^-16) relative, so results sit ~1e-5 from an fp32 GEMM -- inside the
 // 1e-4 parity budget that rules out single-pass TF32/bf16 (hard parts).
+// With l2s_set_precision(L2S_PRECISION_BF16) the same kernel issues the A_hi*B_hi pass only and its producer leaves
+// the lo planes alone: the bf16 variant (1e-2 tolerance).
 //
 // Persistent, warp-specialised CTA (64 + 128*MH*EW threads), CTA tile = (128*MH) x BN:
 //   warp 0      TMA producer: ring of {A_hi, A_lo, B_hi, B_lo} tiles, one mbarrier per stage
@@ -118,7 +120,8 @@ struct Maps {
 
 template <int BN, int MH, int EW, bool A_MN, bool B_MN, class Epi>
 __global__ void __launch_bounds__(64 + 128 * MH * EW, 1)
-gemm_bf16x3_kernel(const __grid_constant__ Maps maps, int M, int N, int K, int nsplit, int kb_per_split, Epi epi) {
+gemm_bf16x3_kernel(const __grid_constant__ Maps maps, int M, int N, int K, int nsplit, int kb_per_split, int passes,
+                   Epi epi) {
   using P = SmemPlan<BN, MH, EW>;
   constexpr int STAGES = P::STAGES;
   constexpr int NACC = P::NACC;
@@ -170,27 +173,28 @@ gemm_bf16x3_kernel(const __grid_constant__ Maps maps, int M, int N, int K, int n
           const int s = it % STAGES;
           if (it >= STAGES) mbar_wait(&empty[s], ((it / STAGES) - 1) & 1);
           uint8_t* st = tiles + s * P::STAGE;
-          mbar_arrive_expect_tx(&full[s], P::STAGE);
+          const bool lo = passes == 3;        // the single-pass bf16 variant never touches the lo planes
+          mbar_arrive_expect_tx(&full[s], lo ? P::STAGE : P::STAGE / 2);
           const int k0 = kb * BK, m0 = tm * TM, n0 = tn * BN;
           if (!A_MN) {
             tma_load_2d(st, &maps.a_hi, k0, m0, &full[s]);
-            tma_load_2d(st + P::A_BYTES, &maps.a_lo, k0, m0, &full[s]);
+            if (lo) tma_load_2d(st + P::A_BYTES, &maps.a_lo, k0, m0, &full[s]);
           } else {
 #pragma unroll
             for (int j = 0; j < TM / 64; ++j) {
               tma_load_2d(st + j * (BK * 128), &maps.a_hi, m0 + 64 * j, k0, &full[s]);
-              tma_load_2d(st + P::A_BYTES + j * (BK * 128), &maps.a_lo, m0 + 64 * j, k0, &full[s]);
+              if (lo) tma_load_2d(st + P::A_BYTES + j * (BK * 128), &maps.a_lo, m0 + 64 * j, k0, &full[s]);
             }
           }
           uint8_t* sb = st + 2 * P::A_BYTES;
           if (!B_MN) {
             tma_load_2d(sb, &maps.b_hi, k0, n0, &full[s]);
-            tma_load_2d(sb + P::B_BYTES, &maps.b_lo, k0, n0, &full[s]);
+            if (lo) tma_load_2d(sb + P::B_BYTES, &maps.b_lo, k0, n0, &full[s]);
           } else {
 #pragma unroll
             for (int j = 0; j < BN / 64; ++j) {
               tma_load_2d(sb + j * (BK * 128), &maps.b_hi, n0 + 64 * j, k0, &full[s]);
-              tma_load_2d(sb + P::B_BYTES + j * (BK * 128), &maps.b_lo, n0 + 64 * j, k0, &full[s]);
+              if (lo) tma_load_2d(sb + P::B_BYTES + j * (BK * 128), &maps.b_lo, n0 + 64 * j, k0, &full[s]);
             }
           }
         }
@@ -236,9 +240,14 @@ gemm_bf16x3_kernel(const __grid_constant__ Maps maps, int M, int N, int K, int n
                 alo = make_desc(sh + P::A_BYTES + kk * 2048, BK * 128, 1024, kLayoutSW128);
               }
               const uint32_t d_half = d_tmem + h * BN;
-              umma_f16(d_half, alo, bhi, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
-              umma_f16(d_half, ahi, blo, idesc, 1u);
-              umma_f16(d_half, ahi, bhi, idesc, 1u);
+              const uint32_t acc0 = (kb > kb0 || kk > 0) ? 1u : 0u;
+              if (passes == 3) {
+                umma_f16(d_half, alo, bhi, idesc, acc0);
+                umma_f16(d_half, ahi, blo, idesc, 1u);
+                umma_f16(d_half, ahi, bhi, idesc, 1u);
+              } else {
+                umma_f16(d_half, ahi, bhi, idesc, acc0);
+              }
             }
           }
           umma_commit(&empty[s]);                 // smem stage free once these MMAs retire
@@ -289,6 +298,10 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn encode_fn();
 
+// tensor passes per product: 3 = bf16x3 split (fp32 accurate, the default), 1 = hi planes only (the bf16 variant of
+// north_star's tolerance clause: 1e-2).  Process-wide switch, l2s_set_precision() in include/l2s.h.
+int gemm_passes();
+
 // bf16 operand plane.  K-major: memory [rows][K] (ld elements per row).  MN-major: memory [K][rows].
 int make_operand_map(CUtensorMap* out, const void* ptr, int64_t rows, int64_t K, int64_t ld, bool mn_major,
                      int box_rows);
@@ -319,7 +332,7 @@ int launch_gemm_mh(const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda, cons
   const size_t smem = P::TOTAL;
   L2S_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  kern<<<grid, P::THREADS, smem, st>>>(maps, M, N, K, nsplit, kb_per, epi);
+  kern<<<grid, P::THREADS, smem, st>>>(maps, M, N, K, nsplit, kb_per, gemm_passes(), epi);
   L2S_LAUNCH_OK("gemm_bf16x3_kernel");
   count_launch();
   return L2S_OK;

@@ -80,6 +80,9 @@ int auto_split(int tiles, int kblocks, int epi_kb) {
   return best;
 }
 
+static int g_precision = L2S_PRECISION_FP32;     // set through l2s_set_precision()
+int gemm_passes() { return g_precision == L2S_PRECISION_BF16 ? 1 : 3; }
+
 int forced_shape() {   // read on every call so that the parity tests can pin every CTA shape on any GEMM
   const char* e = getenv("L2S_GEMM_SHAPE");
   return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : -1;
@@ -675,6 +678,14 @@ int check_head(int n, int Cin, int Cmid, int ncls) {
 }  // namespace l2s
 
 using namespace l2s;
+
+extern "C" int l2s_set_precision(int mode) {
+  L2S_REQUIRE(mode == L2S_PRECISION_FP32 || mode == L2S_PRECISION_BF16, L2S_ERR_ARG, "set_precision: unknown mode %d", mode);
+  tc::g_precision = mode;
+  return L2S_OK;
+}
+
+extern "C" int l2s_get_precision(void) { return tc::g_precision; }
 
 extern "C" int l2s_split_bf16(const float* src, uint16_t* hi, uint16_t* lo, int64_t rows, int64_t cols, int64_t ld_src,
                               int64_t ld_dst, l2s_stream_t stream) {

@@ -36,8 +36,10 @@ class _DynamicFilter(torch.autograd.Function):
         Y = torch.empty(E, C, H, W, device=X.device, dtype=torch.float32)
         tgt = f32c(resp_target) if resp_target is not None else None
         loss = torch.empty(E, device=X.device, dtype=torch.float32) if tgt is not None else None
+        nbytes = _lib.size("l2s_dynfilter_fwd_workspace_bytes", I, E, C, H, W)
+        ws = _ws(nbytes, X.device)
         call("l2s_dynfilter_fwd", ptr(X), ptr(filt), ptr(fuse), ptr(e2i), ptr(response), ptr(rk), ptr(Y),
-             ptr(tgt), ptr(loss), I, E, C, H, W, gate, stream())
+             ptr(tgt), ptr(loss), I, E, C, H, W, gate, ptr(ws), nbytes, stream())
         ctx.save_for_backward(X, filt, fuse, e2i, response, rk, tgt)
         ctx.gate = gate
         ctx.set_materialize_grads(False)       # unused outputs arrive as None in backward (handled there)
@@ -755,6 +757,41 @@ class _CaptionFeats(torch.autograd.Function):
 def caption_features(feats_before, feats_after, att_size=14):
     """network_cycle_response.py:428-438 -> fc (B,2C), att (B,S,S,2C)."""
     return _CaptionFeats.apply(feats_before, feats_after, att_size)
+
+
+# ------------------------------------------------------------------------------------------------
+# precision of the tensor-core GEMMs (mask head, caption projections)
+# ------------------------------------------------------------------------------------------------
+_PRECISIONS = {"fp32": 0, "bf16": 1}
+
+
+def set_precision(mode):
+    """'fp32' (default): bf16x3 split products, ~1e-5 from an fp32 GEMM (the 1e-4 parity contract).
+    'bf16': one tensor pass on the bf16-rounded operands -- north_star's bf16 variants (1e-2).  Process wide;
+    a CUDA graph keeps the mode it was captured with."""
+    if mode not in _PRECISIONS:
+        raise ValueError("precision must be one of %s" % sorted(_PRECISIONS))
+    call("l2s_set_precision", _PRECISIONS[mode])
+
+
+def get_precision():
+    return {v: k for k, v in _PRECISIONS.items()}[int(_lib.load().l2s_get_precision())]
+
+
+class precision:
+    """with precision('bf16'): ...  -- scoped set_precision()."""
+
+    def __init__(self, mode):
+        self.mode = mode
+
+    def __enter__(self):
+        self.prev = get_precision()
+        set_precision(self.mode)
+        return self
+
+    def __exit__(self, *exc):
+        set_precision(self.prev)
+        return False
 
 
 # ------------------------------------------------------------------------------------------------

@@ -155,9 +155,10 @@ class Network(nn.Module):
             total = total + L["loss_response"]
         if cap_labels is not None:
             if att_feats is None:
-                before = self._head_to_tail(P["net_conv_before"] if P["net_conv_before"].shape[0] == P["net_conv"].shape[0]
-                                            else P["net_conv_before"][self._expr2img])
                 after = self._head_to_tail(P["net_conv"])
+                before = self._head_to_tail(P["net_conv_before"])       # once per IMAGE, then shared by its expressions
+                if before.shape[0] != after.shape[0]:
+                    before = before[self._expr2img]
                 fc_feats, att_feats = L2F.caption_features(before, after, 14)
             # LanguageModelCriterion normalises by the number of caption tokens of the batch: for E > 1 the sum of the
             # per-expression losses is not a multiple of the batched mean, so the batched mean is used as is
@@ -215,6 +216,34 @@ class HotPathNet(Network):
             raise RuntimeError("res5 / fc6-7 is outside this repository's scope: pass head_to_tail=<module>")
         return self._head(pool5)
 
+    def chained_train_step(self, X, labels, expr2img, rois, roi_labels, gt_boxes, gt_masks, cap_labels, cap_masks,
+                           num_fg, lengths=None, steps=None):
+        """The reference-faithful TRAIN chain of `_predict` (:576-600) + `_add_losses` (:375-453) from the dynamic
+        filter on, WITH res5 (`head_to_tail`) in the middle -- the "second number" of SURVEY 8d:
+
+            dynamic filter (+ response target resized on the device, :418) -> 7x7 crop of the gated map -> res5 ->
+            box head on every ROI (cross entropy + smooth L1) and mask head on the foreground ROIs (:592-596) ;
+            ungated / gated map -> res5 -> caption features (:424-438) -> att2in2 + LM criterion ; weighted sum (:449).
+
+        Batched layout: rois (N,5) [expression index,x1,y1,x2,y2] with the `num_fg` foreground ROIs of ALL expressions
+        first (the reference keeps fg first, proposal_target_layer.py:177); roi_labels (N,) float (0 = background);
+        gt_boxes (E,5) / gt_masks (E,imH,imW) uint8: one referred object per expression, so a ROI's assigned ground
+        truth is its expression.  All targets (response, box, mask) are built on the device from these."""
+        from ..layer_utils.proposal_target_layer import CFG as PT_CFG, bbox_regression_targets
+        E, (H, W) = labels.shape[0], X.shape[2:]
+        resp_tgt = L2F.resize_masks_nearest(gt_masks, H, W)
+        gated = self._dynamic_filter(X, labels, expr2img=expr2img, resp_target=resp_tgt, lengths=lengths)
+        pool5 = self._crop_pool_layer(gated, rois, max_pool=False)
+        spatial_fc7 = self._head_to_tail(pool5)
+        self._region_classification(spatial_fc7)
+        assign = rois[:, 0].long()
+        bt, biw = bbox_regression_targets(rois, gt_boxes, assign, roi_labels, self._num_classes, PT_CFG)
+        mt = L2F.mask_targets(gt_masks, rois[:num_fg], assign[:num_fg], MASK_SIZE)
+        self._proposal_targets = {"labels": roi_labels.long(), "bbox_targets": bt, "bbox_inside_weights": biw,
+                                  "bbox_outside_weights": (biw > 0).float(), "mask_targets": mt}
+        self._mask_prediction(spatial_fc7[:num_fg], roi_labels[:num_fg].long(), mt)
+        return self._add_hot_path_losses(cap_labels, cap_masks, steps=steps, num_expressions=E)
+
     def gradient_groups(self):
         """The three parameter groups whose gradients are all-reduced (north_star)."""
         fg = list(self.rnn_encoder.parameters()) + list(self.response_fc.parameters())
@@ -222,4 +251,7 @@ class HotPathNet(Network):
             fg += list(getattr(self, "dynamic_fc_%d" % k).parameters())
         heads = [p for m in (self.cls_score_net, self.bbox_pred_net, self.mask_up_sampling, self.mask_pred_net)
                  for p in m.parameters()]
-        return {"filter_generator": fg, "caption": list(self.caption_model.parameters()), "heads": heads}
+        groups = {"filter_generator": fg, "caption": list(self.caption_model.parameters()), "heads": heads}
+        if isinstance(self._head, nn.Module):      # trainable res5 glue (14.9 M more parameters)
+            groups["res5"] = [p for p in self._head.parameters() if p.requires_grad]
+        return groups

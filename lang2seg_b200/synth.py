@@ -31,3 +31,36 @@ def caption_targets(labels, lens, L):
     cap[:, 1:L + 1] = labels
     msk = (torch.arange(L + 2)[None] < (lens[:, None] + 2)).float()
     return cap, msk
+
+
+def chain_batch(gen, I, EPI, C, H, W, R, NFG, L, vocab, num_classes=81):
+    """Host inputs of the res5-chained TRAIN step (HotPathNet.chained_train_step): one referred object per expression
+    (box + uint8 mask in image pixels, 16 px per C4 cell), R ROIs per expression of which the first NFG are jittered
+    copies of the object's box (foreground); the foreground ROIs of ALL expressions come first in `rois`."""
+    E = I * EPI
+    im_h, im_w = H * 16, W * 16
+    labels, lens = synth_labels(gen, E, L, vocab)
+    cap, msk = caption_targets(labels, lens, L)
+    x1 = torch.rand(E, generator=gen) * 0.5 * im_w
+    y1 = torch.rand(E, generator=gen) * 0.5 * im_h
+    bw = 0.2 * im_w + torch.rand(E, generator=gen) * 0.3 * im_w
+    bh = 0.2 * im_h + torch.rand(E, generator=gen) * 0.3 * im_h
+    cls = torch.randint(1, num_classes, (E,), generator=gen).float()
+    gt = torch.stack([x1, y1, (x1 + bw).clamp(max=im_w - 1), (y1 + bh).clamp(max=im_h - 1), cls], 1).floor()
+    yy, xx = torch.arange(im_h)[None, :, None], torch.arange(im_w)[None, None, :]
+    inside = (xx >= gt[:, 0, None, None]) & (xx <= gt[:, 2, None, None]) & (yy >= gt[:, 1, None, None]) & (yy <= gt[:, 3, None, None])
+    masks = (inside & (torch.rand(E, im_h, im_w, generator=gen) < 0.8)).to(torch.uint8)
+    fg, bg = [], []
+    for e in range(E):
+        jit = (torch.rand(NFG, 4, generator=gen) - 0.5) * 0.16 * torch.stack([bw[e], bh[e], bw[e], bh[e]])
+        b = gt[e, :4][None] + jit
+        b[:, 0::2] = b[:, 0::2].clamp(0, im_w - 1)
+        b[:, 1::2] = b[:, 1::2].clamp(0, im_h - 1)
+        fg.append(torch.cat([torch.full((NFG, 1), float(e)), b], 1))
+        bg.append(synth_rois(gen, R - NFG, im_h, im_w, e))
+    rois = torch.cat(fg + bg).float()
+    roi_labels = torch.cat([cls.repeat_interleave(NFG), torch.zeros(E * (R - NFG))])
+    return {"X": torch.relu(torch.randn(I, C, H, W, generator=gen)), "labels": labels,
+            "e2i": torch.arange(I).repeat_interleave(EPI).int(), "rois": rois, "roi_labels": roi_labels,
+            "gt_boxes": gt.float(), "gt_masks": masks, "cap": cap, "msk": msk,
+            "_meta": {"lens": lens.clone(), "steps": int(lens.max()) + 1, "num_fg": E * NFG}}

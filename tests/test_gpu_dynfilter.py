@@ -38,7 +38,13 @@ def test_golden(golden, tag):
 @pytest.mark.parametrize("cfg", [dict(I=3, C=96, H=32, W=32, e2i=[0, 0, 1, 1, 1, 2, 2]),
                                  dict(I=2, C=512, H=37, W=62, e2i=[0, 1, 1]),
                                  dict(I=4, C=1024, H=8, W=12, e2i=[0, 2, 2, 3]),      # image 1 has no expression
-                                 dict(I=1, C=20, H=9, W=13, e2i=[0])])
+                                 dict(I=1, C=20, H=9, W=13, e2i=[0]),
+                                 # tensor-core kernel (H*W % 4 == 0, C % 32 == 0): the cfg-2 shape, 20 expressions on one
+                                 # image (two chunks of the 128 MMA rows), a ragged last pixel tile, a single expression
+                                 dict(I=2, C=1024, H=32, W=32, e2i=[0, 0, 0, 1, 1, 1]),
+                                 dict(I=2, C=64, H=16, W=16, e2i=[0] * 20 + [1]),
+                                 dict(I=2, C=256, H=36, W=35, e2i=[0, 1, 1]),
+                                 dict(I=1, C=512, H=32, W=32, e2i=[0])])
 @pytest.mark.parametrize("gate", ["sigmoid", "linear"])
 def test_vs_oracle(cfg, gate):
     import lang2seg_b200.functional as F
@@ -73,8 +79,7 @@ def test_vs_oracle(cfg, gate):
 def test_partition_bounds_contract():
     """Integer partition boundaries: with X = 1 and one-hot filters r_k is exactly C * M_k."""
     import lang2seg_b200.functional as F
-    for H, W in [(38, 63), (37, 62), (9, 13), (32, 32)]:
-        C = 8
+    for H, W, C in [(38, 63, 8), (37, 62, 8), (9, 13, 8), (32, 32, 8), (32, 32, 32), (36, 35, 64)]:   # FFMA and tcgen05 paths
         X = torch.ones(1, C, H, W, device="cuda")
         masks = R.partition_masks(H, W)
         for k in range(7):
@@ -83,7 +88,7 @@ def test_partition_bounds_contract():
             fuse = torch.zeros(1, 7, device="cuda")
             fuse[0, k] = 1.0
             r, _, _ = F.dynamic_filter(X, filt, fuse)
-            assert torch.equal(r[0, 0].cpu(), masks[k] * C), (H, W, k)
+            assert torch.equal(r[0, 0].cpu(), masks[k] * C), (H, W, C, k)
 
 
 @pytest.mark.parametrize("E,C,Dh", [(48, 1024, 1024), (3, 512, 1024), (70, 64, 32)])

@@ -176,3 +176,80 @@ def test_linear_tc_vs_fp64(gemm_shape):
     assert relerr(gx, Gd @ wd) < 3e-5
     assert relerr(gw, Gd.t() @ xd) < 3e-5
     assert relerr(gb, Gd.sum(0)) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------
+# bf16 variants (north_star: "bf16 variants within 1e-2"): one tensor pass on the bf16-rounded operands
+# ------------------------------------------------------------------------------------------------
+BF16_TOL = 1e-2
+
+
+@pytest.mark.parametrize("layout", ["kk", "mm", "mk", "km"])
+def test_gemm_bf16_single_pass(layout):
+    import lang2seg_b200.functional as F
+    M, N, K = 1000, 1024, 136
+    g = torch.Generator().manual_seed(11)
+    A, B = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g)
+    ref = A.double() @ B.double().t()
+    a_mn, b_mn = layout[0] == "m", layout[1] == "m"
+    a_hi, a_lo = F.split_bf16((A.t().contiguous() if a_mn else A).cuda())
+    b_hi, b_lo = F.split_bf16((B.t().contiguous() if b_mn else B).cuda())
+    with F.precision("bf16"):
+        assert F.get_precision() == "bf16"
+        D = F.gemm_bf16x3(a_hi, a_lo, b_hi, b_lo, M, N, K, a_mn, b_mn)
+        Ds = F.gemm_bf16x3(a_hi, a_lo, b_hi, b_lo, M, N, K, a_mn, b_mn, split_k=0) if layout == "mm" else D
+    assert F.get_precision() == "fp32"
+    # exactly the product of the bf16-rounded operands (fp32 accumulation), and within 1e-2 of the fp32 product
+    exact = a_hi.float().cpu().double() @ b_hi.float().cpu().double().t() if layout == "kk" else None
+    if exact is not None:
+        assert relerr(D, exact) < 1e-5
+    e = relerr(D, ref)
+    assert 1e-4 < e < BF16_TOL, "single pass must really be single pass (error %g)" % e
+    assert relerr(Ds, ref) < BF16_TOL
+    D3 = F.gemm_bf16x3(a_hi, a_lo, b_hi, b_lo, M, N, K, a_mn, b_mn)
+    assert relerr(D3, ref) < 3e-5, "the switch must not leak out of the context"
+
+
+@pytest.mark.parametrize("n", [1, 8])
+def test_mask_head_bf16_variant_vs_oracle(n):
+    import lang2seg_b200.functional as F
+    g = torch.Generator().manual_seed(40 + n)
+    x = torch.relu(torch.randn(n, 2048, 7, 7, generator=g))
+    up_w, up_b = torch.randn(2048, 256, 2, 2, generator=g) * 0.01, torch.randn(256, generator=g) * 0.01
+    pw, pb = torch.randn(81, 256, 1, 1, generator=g) * 0.01, torch.randn(81, generator=g) * 0.01
+    labels = torch.randint(1, 81, (n,), generator=g)
+    tgt = (torch.rand(n, 14, 14, generator=g) < 0.5).float()
+
+    def run(dev):
+        ts = [t.to(dev).clone().requires_grad_(True) for t in (x, up_w, up_b, pw, pb)]
+        if dev == "cpu":
+            s, p = R.mask_head(*ts)
+            loss = R.mask_loss(s, labels, tgt)
+        else:
+            with F.precision("bf16"):
+                s, p, loss = F.mask_head_with_loss(*ts, labels.to(dev), tgt.to(dev))
+                return [s, p, loss] + list(torch.autograd.grad(loss, ts))
+        return [s, p, loss] + list(torch.autograd.grad(loss, ts))
+
+    ref, out = run("cpu"), run("cuda")
+    for name, a, b in zip(["score", "prob", "loss", "dx", "d_up_w", "d_up_b", "d_pred_w", "d_pred_b"], out, ref):
+        assert relerr(a, b) < BF16_TOL, name
+
+
+def test_linear_bf16_variant():
+    import lang2seg_b200.functional as F
+    g = torch.Generator().manual_seed(5)
+    M, K, N = 1960, 2048, 512
+    x = torch.relu(torch.randn(M, K, generator=g))
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g)
+    G = torch.randn(M, N, generator=g)
+    xs, ws, bs = (t.cuda().requires_grad_(True) for t in (x, w, b))
+    with F.precision("bf16"):
+        y = F.linear(xs, ws, bs)
+        gx, gw, gb = torch.autograd.grad((y * G.cuda()).sum(), [xs, ws, bs])
+    xd, wd, bd, Gd = x.double(), w.double(), b.double(), G.double()
+    assert relerr(y, xd @ wd.t() + bd) < BF16_TOL
+    assert relerr(gx, Gd @ wd) < BF16_TOL
+    assert relerr(gw, Gd.t() @ xd) < BF16_TOL
+    assert relerr(gb, Gd.sum(0)) < 1e-5

@@ -70,3 +70,44 @@ def test_hot_path_step_vs_oracle():
     assert relerr(net.dynamic_fc_3.weight.grad, dyn_w[3].grad) < TOL
     assert relerr(net.mask_up_sampling.weight.grad, upw.grad) < TOL
     assert relerr(net.caption_model.logit.weight.grad, capp["logit.weight"].grad) < TOL
+
+
+def test_chained_step_with_res5_vs_oracle():
+    """the reference-faithful TRAIN chain with res5 (`head_to_tail`, cuDNN glue) between the ROI crop
+    and the heads and between the maps and the caption features -- HotPathNet.chained_train_step against
+    oracle.restate.chained_train_losses with the same parameters (loss terms, input and parameter gradients)."""
+    from lang2seg_b200 import synth
+    from lang2seg_b200.nets.network import HotPathNet
+    from lang2seg_b200.nets.res5_glue import Res5Glue
+    torch.manual_seed(3)
+    C, mid = 64, 32
+    opt = dict(C4_feat_dim=C, fc_feat_size=8 * mid, att_feat_size=8 * mid, vocab_size=300)
+    net = HotPathNet(opt, fc7_dim=4 * mid, mask_mid=32, head_to_tail=Res5Glue(C, mid, 3)).cuda().eval()
+    g = torch.Generator().manual_seed(11)
+    d = synth.chain_batch(g, 2, 2, C, 16, 16, 10, 3, 10, 300)
+    meta = d.pop("_meta")
+    dc = {k: v.cuda() for k, v in d.items()}
+    Xc = dc["X"].requires_grad_(True)
+    total = net.chained_train_step(Xc, dc["labels"], dc["e2i"], dc["rois"], dc["roi_labels"], dc["gt_boxes"], dc["gt_masks"],
+                                   dc["cap"], dc["msk"], meta["num_fg"], lengths=meta["lens"], steps=meta["steps"])
+    total.backward()
+    losses = {k: float(v) for k, v in net._losses.items() if torch.is_tensor(v) and v.numel() == 1}
+
+    p = {(("res5." + k[len("_head."):]) if k.startswith("_head.") else k): v.detach().cpu().clone().requires_grad_(v.is_floating_point())
+         for k, v in net.state_dict().items()}
+    enc = {k[len("rnn_encoder."):]: v for k, v in p.items() if k.startswith("rnn_encoder.")}
+    Xo = d["X"].clone().requires_grad_(True)
+    _, hidden, _ = R.rnn_encoder(d["labels"], enc)
+    Lo, to = R.chained_train_losses(Xo, hidden, p, d["e2i"].tolist(), d["rois"], d["roi_labels"], d["gt_boxes"],
+                                    d["gt_masks"].numpy(), d["cap"], d["msk"], meta["num_fg"])
+    to.backward()
+    for k in ("cross_entropy", "loss_box", "loss_mask", "loss_response", "loss_caption"):
+        assert relerr(losses[k], Lo[k]) < TOL, k
+    assert relerr(total, to) < TOL
+    assert relerr(Xc.grad, Xo.grad) < TOL
+    for name in ("dynamic_fc_3.weight", "_head.layer4.0.conv2.weight", "_head.layer4.2.conv3.weight", "cls_score_net.weight",
+                 "bbox_pred_net.weight", "mask_up_sampling.weight", "caption_model.logit.weight", "rnn_encoder.embedding.weight"):
+        gk = dict(net.named_parameters())[name].grad
+        go = p[("res5." + name[len("_head."):]) if name.startswith("_head.") else name].grad
+        assert gk is not None and go is not None, name
+        assert relerr(gk, go) < TOL, name
