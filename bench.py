@@ -471,6 +471,22 @@ def component_rooflines(wl, d, step, pk):
             out.append(dict(kernel=tag + "_bwd", ms=t, bound="hbm", work=work))
             del dYb
         del pool, arg
+    # --- Caffe-style RoI max-pool (POOLING_MODE != 'crop'; not part of the step, timed for its roofline only):
+    # fwd reads <= the map once per expression + writes pool and argmax, bwd reads both and writes the map
+    if "crop7" in parts and wl is WORKLOADS["cfg2"]:
+        pool = torch.empty(N, C, 7, 7, device=dev)
+        arg = torch.empty(N, C, 7, 7, device=dev, dtype=torch.int32)
+        work = 8.0 * C * 49 * Rn * E + 4.0 * C * HW * E
+        t = ev_time(lambda: call("l2s_roi_maxpool_fwd", 7, 7, 1.0 / 16, ptr(Y), ptr(d["rois"]), ptr(pool), ptr(arg), E, C, H, W, N,
+                                 stream()))
+        out.append(dict(kernel="roi_maxpool_fwd (not in the step)", ms=t, bound="hbm", work=work))
+        if not step.fwd_only:
+            dYb = torch.empty_like(Y)
+            t = ev_time(lambda: call("l2s_roi_maxpool_bwd", 7, 7, 1.0 / 16, ptr(step.g_pool), ptr(d["rois"]), ptr(dYb), ptr(arg),
+                                     E, C, H, W, N, stream()))
+            out.append(dict(kernel="roi_maxpool_bwd (not in the step)", ms=t, bound="hbm", work=work))
+            del dYb
+        del pool, arg
     # --- mask head (tensor bound): fwd 2*n*49*2048*1024 + 2*n*196*256*81 ; bwd = 2x
     if "mask" in parts:
         n = E * NFG
@@ -812,7 +828,8 @@ def main():
         roof = None
         if comps:
             gemms = [c for c in comps if c["kernel"].startswith("gemm_")]
-            dom = max((c for c in comps if not c["kernel"].startswith("gemm_")), key=lambda c: c["ms"])
+            dom = max((c for c in comps if not c["kernel"].startswith("gemm_") and "not in the step" not in c["kernel"]),
+                      key=lambda c: c["ms"])
             if dom["bound"] == "tensor" and gemms:
                 dom = gemms[0]
             roof = {"kernel": dom["kernel"], "bound": dom["bound"], "achieved": dom["achieved"], "peak": dom["peak"],

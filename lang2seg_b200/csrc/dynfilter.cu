@@ -598,11 +598,11 @@ extern "C" int l2s_dynfilter_fwd(const float* X, const float* filt, const float*
   if (E == 0) return L2S_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const DfGeom g = make_geom(I, E, C, H, W, flags);
-  if (resp_loss) L2S_CUDA_OK(cudaMemsetAsync(resp_loss, 0, sizeof(float) * E, st));
   // tensor-core kernel (dynfilter_tc.cu) where the shape allows it: 0 = ran, 1 = not applicable, < 0 = error
   rc = launch_dynfilter_tc_fwd(X, filt, fuse, expr2img, response, rk_saved, Y, resp_target, resp_loss, I, E, C, H, W, flags,
                                workspace, workspace_bytes, st);
   if (rc <= 0) return rc;
+  if (resp_loss) L2S_CUDA_OK(cudaMemsetAsync(resp_loss, 0, sizeof(float) * E, st));   // the FFMA kernel accumulates into it
   const bool vec = (g.HW % 4 == 0) && aligned16(X) && aligned16(Y);
   const size_t cap = (size_t)max_smem_optin();
   if (fwd_smem(C, 16) <= cap && vec)

@@ -212,6 +212,11 @@ def test_gemm_bf16_single_pass(layout):
 
 @pytest.mark.parametrize("n", [1, 8])
 def test_mask_head_bf16_variant_vs_oracle(n):
+    """One tensor pass on bf16-rounded operands.  Forward: within 1e-2 of the fp32 oracle.  Backward: the head is
+    piecewise linear, and rounding the operands moves ~0.25 % of the ReLU pre-activations across zero, which changes
+    single gradient entries by O(1) of their size whatever the arithmetic behind it -- so the gradients are compared
+    (1e-2) with the oracle evaluated on the same bf16-rounded inputs and weights (identical ReLU pattern), i.e. the
+    reference computation in bf16 storage, and the forward additionally with the unrounded fp32 oracle."""
     import lang2seg_b200.functional as F
     g = torch.Generator().manual_seed(40 + n)
     x = torch.relu(torch.randn(n, 2048, 7, 7, generator=g))
@@ -219,21 +224,25 @@ def test_mask_head_bf16_variant_vs_oracle(n):
     pw, pb = torch.randn(81, 256, 1, 1, generator=g) * 0.01, torch.randn(81, generator=g) * 0.01
     labels = torch.randint(1, 81, (n,), generator=g)
     tgt = (torch.rand(n, 14, 14, generator=g) < 0.5).float()
+    rb = lambda t: t.bfloat16().float()        # noqa: E731
 
-    def run(dev):
-        ts = [t.to(dev).clone().requires_grad_(True) for t in (x, up_w, up_b, pw, pb)]
-        if dev == "cpu":
-            s, p = R.mask_head(*ts)
-            loss = R.mask_loss(s, labels, tgt)
-        else:
-            with F.precision("bf16"):
-                s, p, loss = F.mask_head_with_loss(*ts, labels.to(dev), tgt.to(dev))
-                return [s, p, loss] + list(torch.autograd.grad(loss, ts))
+    def oracle(xx, uw, pww):
+        ts = [t.clone().requires_grad_(True) for t in (xx, uw, up_b, pww, pb)]
+        s, p = R.mask_head(*ts)
+        loss = R.mask_loss(s, labels, tgt)
         return [s, p, loss] + list(torch.autograd.grad(loss, ts))
 
-    ref, out = run("cpu"), run("cuda")
-    for name, a, b in zip(["score", "prob", "loss", "dx", "d_up_w", "d_up_b", "d_pred_w", "d_pred_b"], out, ref):
+    ts = [t.cuda().clone().requires_grad_(True) for t in (x, up_w, up_b, pw, pb)]
+    with F.precision("bf16"):
+        s, p, loss = F.mask_head_with_loss(*ts, labels.cuda(), tgt.cuda())
+        out = [s, p, loss] + list(torch.autograd.grad(loss, ts))
+    names = ["score", "prob", "loss", "dx", "d_up_w", "d_up_b", "d_pred_w", "d_pred_b"]
+    ref32 = oracle(x, up_w, pw)
+    for name, a, b in list(zip(names, out, ref32))[:3]:
         assert relerr(a, b) < BF16_TOL, name
+    refbf = oracle(rb(x), rb(up_w), rb(pw))
+    for name, a, b in zip(names, out, refbf):
+        assert relerr(a, b) < BF16_TOL, name + " (oracle on bf16-rounded operands)"
 
 
 def test_linear_bf16_variant():
