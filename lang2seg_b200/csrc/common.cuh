@@ -79,6 +79,13 @@ int launch_dynfilter_tc_fwd(const float* X, const float* filt, const float* fuse
                             float* rk_saved, float* Y, const float* target, float* loss, int I, int E, int C, int H,
                             int W, int flags, void* workspace, size_t ws_bytes, cudaStream_t st);
 
+// TMA-streamed dynamic filter backward (dynfilter_bwd_tma.cu): 0 = ran, 1 = shape outside its range, < 0 = error
+size_t dynfilter_bwd_tma_workspace_bytes(int I);
+int launch_dynfilter_bwd_tma(const float* X, const float* filt, const float* fuse, const int* e2i, const float* response,
+                             const float* dY, const float* dresp, const float* target, const float* gscale, float* dX,
+                             float* drbuf, int I, int E, int C, int H, int W, int flags, void* seg_ws, size_t seg_bytes,
+                             cudaStream_t st);
+
 // persistent bi-LSTM kernels (lstm_persist.cu)
 bool bilstm_persist_ok(int L, int B, int H);
 int launch_bilstm_fwd_persist(float* G, const float* w_hh, const int* lens, float* c_all, float* h_all, float* out,

@@ -486,6 +486,92 @@ dynfilter_dfilt_kernel(const float* __restrict__ X, const float* __restrict__ fu
   }
 }
 
+// Vectorised variant of the above for float4-aligned maps (H*W % 4 == 0): warp = channel row, every lane issues its
+// eight 16-byte loads of X up front (the first version walked the row with one dependent 4-byte load per iteration and
+// took as long as the whole forward), the 7 partition masks of a pixel come from a one-byte bit table in shared memory
+// (built once per CTA: the only place with a division) and are shared by the expressions of the chunk.
+constexpr int EBV = 3;
+__global__ void __launch_bounds__(256)
+dynfilter_dfilt_vec_kernel(const float* __restrict__ X, const float* __restrict__ fuse, const int* __restrict__ e2i,
+                           const float* __restrict__ drbuf, float* __restrict__ dfilt, DfGeom g) {
+  extern __shared__ __align__(16) float smem[];   // [EBV][HW] dr, then [HW] mask bits (u8)
+  uint8_t* mbits = reinterpret_cast<uint8_t*>(smem + (size_t)EBV * g.HW);
+  const int i = blockIdx.y, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int c = blockIdx.x * 8 + wid;
+  int e0, e1;
+  expr_range(e2i, g.E, i, &e0, &e1);
+  if (e0 == e1) return;
+  for (int p = threadIdx.x; p < g.HW; p += blockDim.x) {
+    unsigned b = 0;
+#pragma unroll
+    for (int k = 0; k < NF; ++k) b |= (mask_k(g, k, p) != 0.f ? 1u : 0u) << k;
+    mbits[p] = (uint8_t)b;
+  }
+  const float4* Xc = reinterpret_cast<const float4*>(X + ((size_t)i * g.C + min(c, g.C - 1)) * g.HW);
+  const int nq = g.HW >> 2;                       // float4 per row
+  for (int eb = e0; eb < e1; eb += EBV) {
+    const int ne = min(EBV, e1 - eb);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < ne * nq; idx += blockDim.x)
+      reinterpret_cast<float4*>(smem)[idx] = __ldg(reinterpret_cast<const float4*>(drbuf + (size_t)eb * g.HW) + idx);
+    __syncthreads();
+    float acc[EBV][NF];
+#pragma unroll
+    for (int a = 0; a < EBV; ++a)
+#pragma unroll
+      for (int k = 0; k < NF; ++k) acc[a][k] = 0.f;
+    for (int q0 = 0; q0 < nq; q0 += 32 * 8) {
+      float4 x[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int q = q0 + u * 32 + lane;
+        x[u] = q < nq ? __ldg(Xc + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int q = q0 + u * 32 + lane;
+        if (q < nq) {
+          const unsigned bits = reinterpret_cast<const unsigned*>(mbits)[q];
+          const float xv[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
+          // the masks of the four pixels as 0/1 floats, once for all expressions of the chunk (k = 0 is all ones)
+          float mf[4][NF - 1];
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int k = 1; k < NF; ++k) mf[j][k - 1] = ((bits >> (8 * j + k)) & 1u) ? 1.f : 0.f;
+#pragma unroll
+          for (int a = 0; a < EBV; ++a) {
+            if (a < ne) {
+              const float4 d = reinterpret_cast<const float4*>(smem + (size_t)a * g.HW)[q];
+              const float dv[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float v = dv[j] * xv[j];
+                acc[a][0] += v;
+#pragma unroll
+                for (int k = 1; k < NF; ++k) acc[a][k] = fmaf(mf[j][k - 1], v, acc[a][k]);
+              }
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < EBV; ++a)
+#pragma unroll
+      for (int k = 0; k < NF; ++k) acc[a][k] = warp_sum(acc[a][k]);
+    if (lane == 0 && c < g.C) {
+#pragma unroll
+      for (int a = 0; a < EBV; ++a)
+        if (a < ne) {
+#pragma unroll
+          for (int k = 0; k < NF; ++k)
+            dfilt[((size_t)(eb + a) * NF + k) * g.C + c] = __ldg(fuse + (eb + a) * NF + k) * acc[a][k];
+        }
+    }
+  }
+}
+
 // dw[e,k] = sum_p dr[e,p] * r_k[e,p]
 __global__ void dynfilter_dfuse_kernel(const float* __restrict__ drbuf, const float* __restrict__ rk,
                                        float* __restrict__ dfuse, int HW) {
@@ -615,8 +701,9 @@ extern "C" int l2s_dynfilter_fwd(const float* X, const float* filt, const float*
 }
 
 extern "C" size_t l2s_dynfilter_bwd_workspace_bytes(int I, int E, int C, int H, int W) {
-  (void)I; (void)C;
-  return (size_t)E * H * W * sizeof(float) * (1 + NF) + 256;   // dr + recomputed r_k
+  (void)C;
+  // dr + recomputed r_k + the per-image expression ranges of the TMA-streamed kernel
+  return (size_t)E * H * W * sizeof(float) * (1 + NF) + 256 + dynfilter_bwd_tma_workspace_bytes(I > 0 ? I : 0);
 }
 
 extern "C" int l2s_dynfilter_bwd(const float* X, const float* filt, const float* fuse, const int32_t* expr2img,
@@ -640,7 +727,15 @@ extern "C" int l2s_dynfilter_bwd(const float* X, const float* filt, const float*
   float* rk_ws = drbuf + (size_t)E * g.HW;
   const bool vec = (g.HW % 4 == 0) && aligned16(X) && aligned16(dY) && aligned16(dX);
   const size_t cap = (size_t)max_smem_optin();
-  if (vec && C <= kRegCh * (kThreads / 4) && bwd_reg_smem(C, 16) <= cap) {
+  // TMA-streamed kernel (dynfilter_bwd_tma.cu) where the shape allows it: 0 = ran, 1 = not applicable, < 0 = error
+  void* seg_ws = reinterpret_cast<char*>(workspace) + (((size_t)E * g.HW * sizeof(float) * (1 + NF) + 255) & ~(size_t)255);
+  rc = launch_dynfilter_bwd_tma(X, filt, fuse, expr2img, response, dY, dresponse, resp_target, resp_gscale, dX, drbuf, I, E, C,
+                                H, W, flags, seg_ws, dynfilter_bwd_tma_workspace_bytes(I), st);
+  if (rc < 0) return rc;
+  if (rc == 0) {
+    // ran
+  } else if (vec && C <= kRegCh * (kThreads / 4) && bwd_reg_smem(C, 16) <= cap) {
+    rc = 0;
     auto kern = dynfilter_bwd_reg_kernel<16>;
     const size_t smem = bwd_reg_smem(C, 16);
     L2S_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -659,12 +754,20 @@ extern "C" int l2s_dynfilter_bwd(const float* X, const float* filt, const float*
     return fail(L2S_ERR_SHAPE, "dynfilter_bwd: C=%d too large for the shared-memory tile", C);
   if (rc) return rc;
   {
-    const size_t smem = (size_t)EB * g.HW * sizeof(float);
-    L2S_REQUIRE(smem <= cap, L2S_ERR_SHAPE, "dynfilter_bwd: H*W=%d too large", g.HW);
-    L2S_CUDA_OK(cudaFuncSetAttribute(dynfilter_dfilt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem_v = ((size_t)EBV * g.HW * sizeof(float) + g.HW + 15) & ~(size_t)15;
     dim3 grid((C + 7) / 8, I);
-    dynfilter_dfilt_kernel<<<grid, 256, smem, st>>>(X, fuse, expr2img, drbuf, dfilt, g);
-    L2S_LAUNCH_OK("dynfilter_dfilt_kernel");
+    static const bool scalar_dfilt = env_flag("L2S_DFILT_SCALAR");
+    if (vec && aligned16(drbuf) && smem_v <= cap && !scalar_dfilt) {
+      L2S_CUDA_OK(cudaFuncSetAttribute(dynfilter_dfilt_vec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v));
+      dynfilter_dfilt_vec_kernel<<<grid, 256, smem_v, st>>>(X, fuse, expr2img, drbuf, dfilt, g);
+      L2S_LAUNCH_OK("dynfilter_dfilt_vec_kernel");
+    } else {
+      const size_t smem = (size_t)EB * g.HW * sizeof(float);
+      L2S_REQUIRE(smem <= cap, L2S_ERR_SHAPE, "dynfilter_bwd: H*W=%d too large", g.HW);
+      L2S_CUDA_OK(cudaFuncSetAttribute(dynfilter_dfilt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      dynfilter_dfilt_kernel<<<grid, 256, smem, st>>>(X, fuse, expr2img, drbuf, dfilt, g);
+      L2S_LAUNCH_OK("dynfilter_dfilt_kernel");
+    }
   }
   {
     const float* rk = rk_saved;

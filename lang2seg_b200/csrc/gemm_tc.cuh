@@ -118,10 +118,29 @@ struct Maps {
   CUtensorMap a_hi, a_lo, b_hi, b_lo;
 };
 
+// Work item -> (tm, tn, split).  raster 0: the K splits of one output tile are adjacent (the co-resident CTAs then work on
+// ~16 output tiles x all splits).  raster 1 (split-K launches): split-major -- the co-resident CTAs work on ALL output
+// tiles of a few K ranges, so every A panel is shared by tiles_n CTAs and every B panel by tiles_m CTAs while it is hot
+// in L2 (the weight-gradient GEMM read its operands 1.96x from DRAM with raster 0, profiles/r01).
+__device__ __forceinline__ void decode_tile(int tile, int tiles_m, int tiles_n, int nsplit, int raster, int* tm, int* tn,
+                                            int* split) {
+  if (raster == 0) {
+    *split = tile % nsplit;
+    *tn = (tile / nsplit) % tiles_n;
+    *tm = tile / (nsplit * tiles_n);
+  } else {
+    const int mn = tiles_m * tiles_n;
+    *split = tile / mn;
+    const int r = tile - *split * mn;
+    *tn = r % tiles_n;
+    *tm = r / tiles_n;
+  }
+}
+
 template <int BN, int MH, int EW, bool A_MN, bool B_MN, class Epi>
 __global__ void __launch_bounds__(64 + 128 * MH * EW, 1)
 gemm_bf16x3_kernel(const __grid_constant__ Maps maps, int M, int N, int K, int nsplit, int kb_per_split, int passes,
-                   Epi epi) {
+                   int raster, Epi epi) {
   using P = SmemPlan<BN, MH, EW>;
   constexpr int STAGES = P::STAGES;
   constexpr int NACC = P::NACC;
@@ -165,9 +184,8 @@ gemm_bf16x3_kernel(const __grid_constant__ Maps maps, int M, int N, int K, int n
       prefetch_tmap(&maps.a_hi); prefetch_tmap(&maps.a_lo); prefetch_tmap(&maps.b_hi); prefetch_tmap(&maps.b_lo);
       uint32_t it = 0;
       for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-        const int split = tile % nsplit;
-        const int tn = (tile / nsplit) % tiles_n;
-        const int tm = tile / (nsplit * tiles_n);
+        int split, tn, tm;
+        decode_tile(tile, tiles_m, tiles_n, nsplit, raster, &tm, &tn, &split);
         const int kb0 = split * kb_per_split, kb1 = min(kblocks, kb0 + kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % STAGES;
@@ -205,7 +223,8 @@ gemm_bf16x3_kernel(const __grid_constant__ Maps maps, int M, int N, int K, int n
     constexpr uint32_t idesc = make_idesc(BN, A_MN, B_MN);
     uint32_t it = 0, tcount = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++tcount) {
-      const int split = tile % nsplit;
+      int split, tn_unused, tm_unused;
+      decode_tile(tile, tiles_m, tiles_n, nsplit, raster, &tm_unused, &tn_unused, &split);
       const int kb0 = split * kb_per_split, kb1 = min(kblocks, kb0 + kb_per_split);
       const int acc = tcount % NACC;
       if (tcount >= NACC) mbar_wait(&tempty[acc], ((tcount / NACC) - 1) & 1);
@@ -264,9 +283,8 @@ gemm_bf16x3_kernel(const __grid_constant__ Maps maps, int M, int N, int K, int n
     float* scratch = scratch_all + (size_t)(warp - 2) * (P::SCRATCH / 4);
     uint32_t tcount = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++tcount) {
-      const int split = tile % nsplit;
-      const int tn = (tile / nsplit) % tiles_n;
-      const int tm = tile / (nsplit * tiles_n);
+      int split, tn, tm;
+      decode_tile(tile, tiles_m, tiles_n, nsplit, raster, &tm, &tn, &split);
       const int acc = tcount % NACC;
       mbar_wait(&tfull[acc], (tcount / NACC) & 1);
       fence_after_sync();
@@ -301,6 +319,8 @@ EncodeTiledFn encode_fn();
 // tensor passes per product: 3 = bf16x3 split (fp32 accurate, the default), 1 = hi planes only (the bf16 variant of
 // north_star's tolerance clause: 1e-2).  Process-wide switch, l2s_set_precision() in include/l2s.h.
 int gemm_passes();
+// split-K work-item order: true = split-major (default), L2S_GEMM_RASTER=0 restores tile-major (A/B diagnostics)
+bool split_raster();
 
 // bf16 operand plane.  K-major: memory [rows][K] (ld elements per row).  MN-major: memory [K][rows].
 int make_operand_map(CUtensorMap* out, const void* ptr, int64_t rows, int64_t K, int64_t ld, bool mn_major,
@@ -332,7 +352,7 @@ int launch_gemm_mh(const uint16_t* a_hi, const uint16_t* a_lo, int64_t lda, cons
   const size_t smem = P::TOTAL;
   L2S_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  kern<<<grid, P::THREADS, smem, st>>>(maps, M, N, K, nsplit, kb_per, gemm_passes(), epi);
+  kern<<<grid, P::THREADS, smem, st>>>(maps, M, N, K, nsplit, kb_per, gemm_passes(), (nsplit > 1 && split_raster()) ? 1 : 0, epi);
   L2S_LAUNCH_OK("gemm_bf16x3_kernel");
   count_launch();
   return L2S_OK;

@@ -83,6 +83,11 @@ int auto_split(int tiles, int kblocks, int epi_kb) {
 static int g_precision = L2S_PRECISION_FP32;     // set through l2s_set_precision()
 int gemm_passes() { return g_precision == L2S_PRECISION_BF16 ? 1 : 3; }
 
+bool split_raster() {
+  static const bool on = [] { const char* e = getenv("L2S_GEMM_RASTER"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
 int forced_shape() {   // read on every call so that the parity tests can pin every CTA shape on any GEMM
   const char* e = getenv("L2S_GEMM_SHAPE");
   return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : -1;

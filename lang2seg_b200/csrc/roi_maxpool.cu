@@ -5,7 +5,8 @@
 //                      first strict maximum in row-major order, argmax = flat (c*H+h)*W+w, empty
 //                      bin -> 0 / -1.  Integer contract: bins and argmax are bit-exact.
 //   backward:104-179 -- the reference gathers over all ROIs per input element (O(R) each); the
-//                      same sums are produced here by scattering top_diff to argmax.
+//                      same sums are produced here by an owner-computes scatter in shared memory
+//                      (deterministic; roi_maxpool_bwd_owner_kernel), atomics only for huge maps.
 // Unlike the reference (batch must be 1, roi_pooling_cuda.c:27-30) any batch size is accepted.
 #include "common.cuh"
 
@@ -67,6 +68,87 @@ __global__ void roi_maxpool_bwd_kernel(const float* __restrict__ top, const floa
   }
 }
 
+// Deterministic owner-computes backward.  CTA = (image, chunk of CC channels) keeps the gradient of its map slice in shared
+// memory ([pixel][CC+1]: lane = channel, odd stride), walks the ROIs of its image in ascending order (compacted 256 at a
+// time, order preserving), stages each ROI's (top_grad, argmax) tiles with coalesced loads and lets warp w apply exactly the
+// bins whose arg-max pixel lies in ITS contiguous pixel band -- so every accumulator has one owner and is updated in a
+// fixed (ROI, bin) order: bit-reproducible, no atomics (the scatter kernel above sums in arrival order).  The map slice
+// is written once at the end; no memset of the output is needed.
+template <int CC>
+__global__ void __launch_bounds__(256)
+roi_maxpool_bwd_owner_kernel(const float* __restrict__ top, const float* __restrict__ rois, const int* __restrict__ argmax,
+                             float* __restrict__ bottom, int B, int C, int H, int W, int N, int PP) {
+  constexpr int LD = CC + 1;
+  extern __shared__ __align__(16) float smem[];
+  const int HW = H * W;
+  float* acc = smem;                                       // [HW][LD]
+  float* s_top = acc + (size_t)HW * LD;                    // [CC][PP]
+  int* s_arg = reinterpret_cast<int*>(s_top + CC * PP);    // [CC][PP]
+  int* s_list = s_arg + CC * PP;                           // [256] ROI ids of this image in the current block of 256
+  __shared__ int s_wcnt[8];
+  const int b = blockIdx.y, c0 = blockIdx.x * CC;
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  const int cvalid = min(CC, C - c0);
+  for (int i = t; i < HW * LD; i += 256) acc[i] = 0.f;
+  // owner = (warp, lane group): lane = channel, and with CC < 32 the 32 / CC lane groups of a warp own separate pixel
+  // bands (never the same accumulator from two lanes of one instruction)
+  constexpr int SUB = 32 / CC;
+  const int ch = lane % CC, band = wid * SUB + lane / CC;
+  const int lo = (int)(((long long)HW * band) / (8 * SUB)), hi = (int)(((long long)HW * (band + 1)) / (8 * SUB));
+  const int coff = (c0 + ch) * HW;
+  for (int base = 0; base < N; base += 256) {
+    // ---- order-preserving compaction of the ROIs of image b among base .. base + 255
+    const int n = base + t;
+    const bool mine = n < N && (int)__ldg(rois + 5 * (size_t)n) == b;
+    const unsigned bal = __ballot_sync(0xffffffffu, mine);
+    if (lane == 0) s_wcnt[wid] = __popc(bal);
+    __syncthreads();
+    int pre = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      if (w < wid) pre += s_wcnt[w];
+      tot += s_wcnt[w];
+    }
+    if (mine) s_list[pre + __popc(bal & ((1u << lane) - 1u))] = n;
+    __syncthreads();
+    for (int q = 0; q < tot; ++q) {
+      const int r = s_list[q];
+      const size_t src = ((size_t)r * C + c0) * PP;
+      for (int i = t; i < cvalid * PP; i += 256) {
+        s_top[i] = __ldg(top + src + i);
+        s_arg[i] = __ldg(argmax + src + i);
+      }
+      __syncthreads();
+      if (ch < cvalid)
+        for (int bin = 0; bin < PP; ++bin) {
+          const int px = s_arg[ch * PP + bin] - coff;      // empty bins (-1) fall below every band
+          if (px >= lo && px < hi) acc[(size_t)px * LD + ch] += s_top[ch * PP + bin];
+        }
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  float* dst = bottom + ((size_t)b * C + c0) * HW;
+  for (int i = t; i < cvalid * HW; i += 256) {
+    const int c = i / HW, px = i - c * HW;
+    dst[i] = acc[(size_t)px * LD + c];
+  }
+}
+
+template <int CC>
+size_t owner_smem(int HW, int PP) { return ((size_t)HW * (CC + 1) + 2 * (size_t)CC * PP + 256) * 4; }
+
+template <int CC>
+int launch_owner(const float* top, const float* rois, const int* argmax, float* bottom, int B, int C, int H, int W, int N,
+                 int PP, cudaStream_t st) {
+  const size_t smem = owner_smem<CC>(H * W, PP);
+  L2S_CUDA_OK(cudaFuncSetAttribute(roi_maxpool_bwd_owner_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  roi_maxpool_bwd_owner_kernel<CC><<<dim3((C + CC - 1) / CC, B), 256, smem, st>>>(top, rois, argmax, bottom, B, C, H, W, N, PP);
+  L2S_LAUNCH_OK("roi_maxpool_bwd_owner_kernel");
+  count_launch();
+  return L2S_OK;
+}
+
 }  // namespace
 }  // namespace l2s
 
@@ -98,6 +180,16 @@ extern "C" int l2s_roi_maxpool_bwd(int ph, int pw, float scale, const float* top
   L2S_REQUIRE(ph > 0 && pw > 0 && B > 0 && C > 0 && H > 0 && W > 0 && N >= 0, L2S_ERR_SHAPE,
               "roi_maxpool_bwd: bad shape");
   cudaStream_t st = (cudaStream_t)stream;
+  // owner-computes kernel (deterministic) with the widest channel chunk whose map slice fits in shared memory; the atomic
+  // scatter kernel only for maps beyond that (L2S_ROIPOOL_BWD_ATOMIC=1 forces it: A/B diagnostics)
+  static const bool atomic_only = env_flag("L2S_ROIPOOL_BWD_ATOMIC");
+  if (N > 0 && !atomic_only) {
+    const size_t cap = (size_t)max_smem_optin();
+    const int HW = H * W, PP = ph * pw;
+    if (owner_smem<32>(HW, PP) <= cap) return launch_owner<32>(top_grad, rois, argmax, bottom_grad, B, C, H, W, N, PP, st);
+    if (owner_smem<16>(HW, PP) <= cap) return launch_owner<16>(top_grad, rois, argmax, bottom_grad, B, C, H, W, N, PP, st);
+    if (owner_smem<8>(HW, PP) <= cap) return launch_owner<8>(top_grad, rois, argmax, bottom_grad, B, C, H, W, N, PP, st);
+  }
   L2S_CUDA_OK(cudaMemsetAsync(bottom_grad, 0, (size_t)B * C * H * W * sizeof(float), st));
   if (N == 0) return L2S_OK;
   const size_t total = (size_t)N * C * ph * pw;

@@ -143,8 +143,10 @@ def test_roi_maxpool_bit_exact(shape):
     assert torch.equal(out.cpu(), ref)               # integer bins + fp32 max: bit exact
     assert torch.equal(arg.cpu(), refarg)
     top = torch.randn(ref.shape, generator=g)
-    (gb,) = torch.autograd.grad((out * top.cuda()).sum(), fc)
+    (gb,) = torch.autograd.grad((out * top.cuda()).sum(), fc, retain_graph=True)
     assert relerr(gb, R.roi_max_pool_backward(top, rois, refarg, f.shape)) < 1e-6
+    (gb2,) = torch.autograd.grad((out * top.cuda()).sum(), fc)
+    assert torch.equal(gb, gb2), "owner-computes backward: fixed summation order, bit-identical re-run"
 
 
 def test_roi_maxpool_vs_reference_cuda_kernel():
