@@ -19,7 +19,7 @@ LIB = os.path.join(HERE, "libl2s.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 SOURCES = ["core.cu", "roi_crop.cu", "roi_maxpool.cu", "dynfilter.cu", "dynfilter_tc.cu", "dynfilter_bwd_tma.cu", "att.cu", "decode.cu", "decode_persist.cu", "lstm.cu", "lstm_persist.cu", "mask_head.cu", "targets.cu", "nms.cu", "heads.cu", "proposals.cu"]
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-         "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+         "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"] + os.environ.get("L2S_NVCC_FLAGS", "").split()   # A/B experiments: -DNAME=value
 
 
 def _deps():

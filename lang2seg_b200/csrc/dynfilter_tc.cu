@@ -323,7 +323,13 @@ dynfilter_tc_fwd_kernel(const __grid_constant__ DtMaps maps, const float* __rest
             if (j < ne) {
               float4 y;
               y.x = x.x * gq[j].x; y.y = x.y * gq[j].y; y.z = x.z * gq[j].z; y.w = x.w * gq[j].w;
+#if defined(L2S_DT_STORE) && L2S_DT_STORE == 1
+              *reinterpret_cast<float4*>(Y + ((size_t)(ec + j) * g.C + c) * g.HW + p) = y;      // A/B: default write-back store
+#elif defined(L2S_DT_STORE) && L2S_DT_STORE == 2
+              __stwt(reinterpret_cast<float4*>(Y + ((size_t)(ec + j) * g.C + c) * g.HW + p), y);
+#else
               __stcs(reinterpret_cast<float4*>(Y + ((size_t)(ec + j) * g.C + c) * g.HW + p), y);
+#endif
             }
         }
       }

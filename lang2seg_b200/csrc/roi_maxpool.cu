@@ -68,63 +68,104 @@ __global__ void roi_maxpool_bwd_kernel(const float* __restrict__ top, const floa
   }
 }
 
-// Deterministic owner-computes backward.  CTA = (image, chunk of CC channels) keeps the gradient of its map slice in shared
-// memory ([pixel][CC+1]: lane = channel, odd stride), walks the ROIs of its image in ascending order (compacted 256 at a
-// time, order preserving), stages each ROI's (top_grad, argmax) tiles with coalesced loads and lets warp w apply exactly the
-// bins whose arg-max pixel lies in ITS contiguous pixel band -- so every accumulator has one owner and is updated in a
-// fixed (ROI, bin) order: bit-reproducible, no atomics (the scatter kernel above sums in arrival order).  The map slice
-// is written once at the end; no memset of the output is needed.
+// ---------------------------------------------------------------------------------------------------------------------
+// Deterministic backward: CTA = (image, chunk of CC channels) with the gradient of the map slice resident in shared
+// memory as [pixel][CC+1] (lane = channel, odd stride).  The ROIs of the image are found by an order-preserving
+// compaction of the batch-index column, 256 at a time.
+// (Forward: two shared-memory-resident variants of this layout -- warp = bin with block barriers per ROI, 12.5 ms, and
+// warp = ROI with bulk stores, 14.3 ms at cfg-2 sizes -- lost against the thread-per-output kernel above, 8.2 ms: with
+// the 135 KB slice resident only 6-8 warps fit per SM and the bin scans are latency bound; the gather kernel hides
+// the same latency behind 64 warps per SM out of L2.  Removed; numbers in profiles/r02_ab.md.)
+// ---------------------------------------------------------------------------------------------------------------------
+// ROIs of image b among base .. base + 255 -> s_list (ascending), returns their number.  All 256 threads call it.
+__device__ __forceinline__ int compact_rois(const float* __restrict__ rois, int N, int base, int b, int* s_list, int* s_wcnt) {
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  const int n = base + t;
+  const bool mine = n < N && (int)__ldg(rois + 5 * (size_t)n) == b;
+  const unsigned bal = __ballot_sync(0xffffffffu, mine);
+  __syncthreads();                       // the previous block's list and counts are no longer in use
+  if (lane == 0) s_wcnt[wid] = __popc(bal);
+  __syncthreads();
+  int pre = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) {
+    if (w < wid) pre += s_wcnt[w];
+    tot += s_wcnt[w];
+  }
+  if (mine) s_list[pre + __popc(bal & ((1u << lane) - 1u))] = n;
+  __syncthreads();
+  return tot;
+}
+
+// Deterministic owner-computes backward.  The gradient of the map slice accumulates in shared memory; the CTA walks the
+// ROIs of its image in ascending order, the (top_grad, argmax) tiles of the next ROIs arrive by 1-D bulk copies (TMA engine,
+// three in flight) while the current one is applied, and warp w (lane group) applies exactly the bins whose arg-max pixel
+// lies in ITS contiguous pixel band -- every accumulator has one owner and is updated in a fixed (ROI, bin) order:
+// bit-reproducible, no atomics (the scatter kernel above sums in arrival order).  The slice is written once at the end;
+// no memset of the output is needed.
+constexpr int kOwnStages = 3;
 template <int CC>
 __global__ void __launch_bounds__(256)
 roi_maxpool_bwd_owner_kernel(const float* __restrict__ top, const float* __restrict__ rois, const int* __restrict__ argmax,
-                             float* __restrict__ bottom, int B, int C, int H, int W, int N, int PP) {
+                             float* __restrict__ bottom, int B, int C, int H, int W, int N, int PP, int bulk) {
   constexpr int LD = CC + 1;
   extern __shared__ __align__(16) float smem[];
   const int HW = H * W;
+  const int TILE = (CC * PP + 3) & ~3;                     // floats per staged tile (16-byte multiple)
   float* acc = smem;                                       // [HW][LD]
-  float* s_top = acc + (size_t)HW * LD;                    // [CC][PP]
-  int* s_arg = reinterpret_cast<int*>(s_top + CC * PP);    // [CC][PP]
-  int* s_list = s_arg + CC * PP;                           // [256] ROI ids of this image in the current block of 256
+  float* s_top = acc + (((size_t)HW * LD + 3) & ~(size_t)3);   // [kOwnStages][TILE]
+  int* s_arg = reinterpret_cast<int*>(s_top + kOwnStages * TILE);   // [kOwnStages][TILE]
+  int* s_list = s_arg + kOwnStages * TILE;                 // [256] ROI ids of this image in the current block of 256
   __shared__ int s_wcnt[8];
+  __shared__ uint64_t full[kOwnStages];
   const int b = blockIdx.y, c0 = blockIdx.x * CC;
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
   const int cvalid = min(CC, C - c0);
   for (int i = t; i < HW * LD; i += 256) acc[i] = 0.f;
+  if (t == 0) {
+    for (int s = 0; s < kOwnStages; ++s) mbar_init(&full[s], 1);
+    mbar_fence_init();
+  }
   // owner = (warp, lane group): lane = channel, and with CC < 32 the 32 / CC lane groups of a warp own separate pixel
   // bands (never the same accumulator from two lanes of one instruction)
   constexpr int SUB = 32 / CC;
   const int ch = lane % CC, band = wid * SUB + lane / CC;
   const int lo = (int)(((long long)HW * band) / (8 * SUB)), hi = (int)(((long long)HW * (band + 1)) / (8 * SUB));
   const int coff = (c0 + ch) * HW;
+  const uint32_t tile_bytes = (uint32_t)(cvalid * PP * 4);
+  int it = 0;                                              // tiles consumed so far (ring position / parity)
   for (int base = 0; base < N; base += 256) {
-    // ---- order-preserving compaction of the ROIs of image b among base .. base + 255
-    const int n = base + t;
-    const bool mine = n < N && (int)__ldg(rois + 5 * (size_t)n) == b;
-    const unsigned bal = __ballot_sync(0xffffffffu, mine);
-    if (lane == 0) s_wcnt[wid] = __popc(bal);
-    __syncthreads();
-    int pre = 0, tot = 0;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) {
-      if (w < wid) pre += s_wcnt[w];
-      tot += s_wcnt[w];
-    }
-    if (mine) s_list[pre + __popc(bal & ((1u << lane) - 1u))] = n;
-    __syncthreads();
-    for (int q = 0; q < tot; ++q) {
-      const int r = s_list[q];
-      const size_t src = ((size_t)r * C + c0) * PP;
-      for (int i = t; i < cvalid * PP; i += 256) {
-        s_top[i] = __ldg(top + src + i);
-        s_arg[i] = __ldg(argmax + src + i);
-      }
-      __syncthreads();
-      if (ch < cvalid)
-        for (int bin = 0; bin < PP; ++bin) {
-          const int px = s_arg[ch * PP + bin] - coff;      // empty bins (-1) fall below every band
-          if (px >= lo && px < hi) acc[(size_t)px * LD + ch] += s_top[ch * PP + bin];
+    const int tot = compact_rois(rois, N, base, b, s_list, s_wcnt);
+    auto issue = [&](int q, int slot) {                    // thread 0: both tiles of ROI s_list[q] into `slot`
+      const size_t src = ((size_t)s_list[q] * C + c0) * PP;
+      mbar_arrive_expect_tx(&full[slot], 2 * tile_bytes);
+      bulk_g2s(s_top + slot * TILE, top + src, tile_bytes, &full[slot]);
+      bulk_g2s(s_arg + slot * TILE, argmax + src, tile_bytes, &full[slot]);
+    };
+    if (bulk && t == 0)
+      for (int q = 0; q < min(tot, kOwnStages); ++q) issue(q, (it + q) % kOwnStages);
+    for (int q = 0; q < tot; ++q, ++it) {
+      const int slot = it % kOwnStages;
+      if (bulk) {
+        mbar_wait(&full[slot], (it / kOwnStages) & 1);
+      } else {
+        const size_t src = ((size_t)s_list[q] * C + c0) * PP;
+        for (int i = t; i < cvalid * PP; i += 256) {
+          s_top[slot * TILE + i] = __ldg(top + src + i);
+          s_arg[slot * TILE + i] = __ldg(argmax + src + i);
         }
-      __syncthreads();
+        __syncthreads();
+      }
+      if (ch < cvalid) {
+        const float* tt = s_top + slot * TILE + ch * PP;
+        const int* aa = s_arg + slot * TILE + ch * PP;
+        for (int bin = 0; bin < PP; ++bin) {
+          const int px = aa[bin] - coff;                   // empty bins (-1) fall below every band
+          if (px >= lo && px < hi) acc[(size_t)px * LD + ch] += tt[bin];
+        }
+      }
+      __syncthreads();                                     // the slot has been read by everyone
+      if (bulk && t == 0 && q + kOwnStages < tot) issue(q + kOwnStages, slot);
     }
   }
   __syncthreads();
@@ -136,14 +177,19 @@ roi_maxpool_bwd_owner_kernel(const float* __restrict__ top, const float* __restr
 }
 
 template <int CC>
-size_t owner_smem(int HW, int PP) { return ((size_t)HW * (CC + 1) + 2 * (size_t)CC * PP + 256) * 4; }
-
+size_t owner_smem(int HW, int PP) {
+  return (((size_t)HW * (CC + 1) + 3) / 4 * 4 + 2 * (size_t)kOwnStages * ((CC * PP + 3) / 4 * 4) + 256) * 4;
+}
 template <int CC>
 int launch_owner(const float* top, const float* rois, const int* argmax, float* bottom, int B, int C, int H, int W, int N,
                  int PP, cudaStream_t st) {
   const size_t smem = owner_smem<CC>(H * W, PP);
+  // bulk copies need 16-byte aligned, 16-byte multiple tiles: true for whole chunks of CC channels (C % CC == 0)
+  const int bulk = (C % CC == 0) && ((CC * PP * 4) % 16 == 0) && aligned16(top) && aligned16(argmax) &&
+                   (((size_t)C * PP * 4) % 16 == 0);
   L2S_CUDA_OK(cudaFuncSetAttribute(roi_maxpool_bwd_owner_kernel<CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  roi_maxpool_bwd_owner_kernel<CC><<<dim3((C + CC - 1) / CC, B), 256, smem, st>>>(top, rois, argmax, bottom, B, C, H, W, N, PP);
+  roi_maxpool_bwd_owner_kernel<CC><<<dim3((C + CC - 1) / CC, B), 256, smem, st>>>(top, rois, argmax, bottom, B, C, H, W, N, PP,
+                                                                                 bulk);
   L2S_LAUNCH_OK("roi_maxpool_bwd_owner_kernel");
   count_launch();
   return L2S_OK;
@@ -180,10 +226,10 @@ extern "C" int l2s_roi_maxpool_bwd(int ph, int pw, float scale, const float* top
   L2S_REQUIRE(ph > 0 && pw > 0 && B > 0 && C > 0 && H > 0 && W > 0 && N >= 0, L2S_ERR_SHAPE,
               "roi_maxpool_bwd: bad shape");
   cudaStream_t st = (cudaStream_t)stream;
-  // owner-computes kernel (deterministic) with the widest channel chunk whose map slice fits in shared memory; the atomic
-  // scatter kernel only for maps beyond that (L2S_ROIPOOL_BWD_ATOMIC=1 forces it: A/B diagnostics)
-  static const bool atomic_only = env_flag("L2S_ROIPOOL_BWD_ATOMIC");
-  if (N > 0 && !atomic_only) {
+  // L2S_ROIPOOL_BWD_DETERMINISTIC=1: the owner-computes kernel (bit-reproducible, 8.8 ms at cfg-2 sizes) instead of the
+  // atomic scatter (2.6 ms, sums in arrival order: equal within 1e-6 relative run to run)
+  const bool owner = env_flag("L2S_ROIPOOL_BWD_DETERMINISTIC");   // read per call: the tests toggle it
+  if (N > 0 && owner) {
     const size_t cap = (size_t)max_smem_optin();
     const int HW = H * W, PP = ph * pw;
     if (owner_smem<32>(HW, PP) <= cap) return launch_owner<32>(top_grad, rois, argmax, bottom_grad, B, C, H, W, N, PP, st);
