@@ -179,7 +179,7 @@ class HotPathStep:
         self.net = HotPathNet(dict(seq_length=wl["L"], vocab_size=wl["V"], C4_feat_dim=wl["C"])).to(device).eval()   # eval: dropout off (D8)
         self.params = [p for p in self.net.parameters() if p.requires_grad]
         self.opt = torch.optim.SGD(self.params, lr=1e-5, momentum=0.9, fused=True)
-        # N > 1: gradients live in flat per-group buffers (p.grad are views): no pack / unpack around the all-reduce
+        # N > 1: gradients are packed into flat per-group buffers by one fused copy per group (p.grad become views)
         self.flat = FlatGradients(self.net.gradient_groups()) if (world > 1 and not self.fwd_only) else None
         self._pending = None
         E = wl["I"] * wl["EPI"]
@@ -224,10 +224,7 @@ class HotPathStep:
         meta = meta if meta is not None else d.get("_meta", {})
         if self.fwd_only:
             return self.forward_only(d, meta)
-        if self.flat is not None:
-            self.flat.zero()
-        else:
-            self.opt.zero_grad(set_to_none=True)
+        self.opt.zero_grad(set_to_none=True)      # N > 1: the fresh gradients are packed into the flat buffers below
         X = d["X"].requires_grad_(True)
         gated = net._dynamic_filter(X, d["labels"], expr2img=d["e2i"], resp_target=d.get("resp_tgt"),
                                     lengths=meta.get("lens"))
@@ -256,9 +253,12 @@ class HotPathStep:
         if split:
             if roots_a[0]:
                 torch.autograd.backward(*roots_a)
+            self.flat.pack(self.EARLY_GROUPS)
             self._pending = (roots_b, X, fc7, att)
         else:
             torch.autograd.backward(roots_a[0] + roots_b[0], roots_a[1] + roots_b[1])
+            if self.flat is not None:
+                self.flat.pack()
             self._finish(X, fc7, att)
         return loss
 
@@ -268,6 +268,7 @@ class HotPathStep:
         self._pending = None
         if roots_b[0]:
             torch.autograd.backward(*roots_b)
+        self.flat.pack([n for n in self.flat.names if n not in self.EARLY_GROUPS])
         self._finish(X, fc7, att)
 
     def _finish(self, X, fc7, att):
@@ -321,15 +322,13 @@ class ChainedStep:
 
     def __call__(self, d, meta):
         net = self.net
-        if self.flat is not None:
-            self.flat.zero()
-        else:
-            self.opt.zero_grad(set_to_none=True)
+        self.opt.zero_grad(set_to_none=True)
         loss = net.chained_train_step(d["X"], d["labels"], d["e2i"], d["rois"], d["roi_labels"], d["gt_boxes"],
                                       d["gt_masks"], d["cap"], d["msk"], meta["num_fg"], lengths=meta.get("lens"),
                                       steps=meta.get("steps"))
         loss.backward()
         if self.flat is not None:
+            self.flat.pack()
             self.flat.all_reduce()
         self.opt.step()
         net._predictions.clear()
@@ -750,11 +749,13 @@ def main():
                 early = [n for n in step.EARLY_GROUPS]
                 late = [n for n in step.flat.names if n not in early]
 
+                nocomm = os.environ.get("L2S_BENCH_NOCOMM") == "1"    # diagnostics: the three graphs without the collectives
+
                 def run():
                     g_a.replay()
-                    w = step.flat.all_reduce_async(early)
+                    w = [] if nocomm else step.flat.all_reduce_async(early)
                     g_b.replay()
-                    w += step.flat.all_reduce_async(late)
+                    w += [] if nocomm else step.flat.all_reduce_async(late)
                     step.flat.wait(w)
                     g_c.replay()
             run()

@@ -77,6 +77,13 @@ def dynamic_filter(X, filt, fuse, expr2img=None, gate="sigmoid", resp_target=Non
     if expr2img is None:
         assert X.shape[0] == E, "expr2img is required when #images != #expressions"
         expr2img = torch.arange(E, device=X.device, dtype=torch.int32)
+    elif not (torch.is_tensor(expr2img) and expr2img.is_cuda):
+        # a host-side map is validated here for free (the kernels find an image's expressions by its sorted ranges: an
+        # unsorted or out-of-range map would silently skip expressions); a device tensor is the caller's contract
+        e = torch.as_tensor(expr2img).reshape(-1).long()
+        if e.numel() != E or (e.numel() and (int(e.min()) < 0 or int(e.max()) >= X.shape[0] or bool((e[1:] < e[:-1]).any()))):
+            raise _lib.L2SError("dynamic_filter: expr2img must hold %d non-decreasing image indices in [0, %d)" % (E, X.shape[0]))
+        expr2img = e
     g = GATE_SIGMOID if gate == "sigmoid" else GATE_LINEAR
     return _DynamicFilter.apply(X, filt, fuse, expr2img, g, resp_target)
 

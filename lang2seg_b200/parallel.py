@@ -104,18 +104,23 @@ class GradientAllReducer:
 
 
 class FlatGradients:
-    """Gradients of each parameter group live in ONE pre-allocated flat fp32 buffer and every `p.grad` is a view into
-    it: autograd accumulates in place, the all-reduce runs on the flat buffer directly (no ~200 pack / unpack copy
-    kernels per step) and the fused optimizer reads the views.  Groups can be reduced separately, as soon as their
-    last gradient has been written (bench.py: caption + heads overlap the rest of the backward).
+    """Gradients of each parameter group live in ONE pre-allocated flat fp32 buffer and `p.grad` are views into it, so
+    the all-reduce runs on the flat buffer directly and the fused optimizer reads the views.  Groups can be reduced
+    separately, as soon as their last gradient has been written (bench.py: caption + heads overlap the rest of the
+    backward).  Two ways to fill the buffers:
 
-    Use `zero()` instead of `optimizer.zero_grad(set_to_none=True)` (which would drop the views)."""
+      * `zero()` + backward: autograd accumulates into the views in place -- one `add_` kernel per parameter
+        (~100 launches, measured 0.23 ms per cfg-2 step);
+      * `optimizer.zero_grad(set_to_none=True)` + backward + `pack(names)`: autograd hands over freshly written gradient
+        tensors (no accumulate kernels) and ONE fused multi-tensor copy per group moves them into the flat buffer and
+        re-points `p.grad` at the views (what bench.py does)."""
 
     def __init__(self, groups, process_group=None):
         self.pg = process_group
         self.names = list(groups)
         self.flat = {}
         self.params = {}
+        self.views = {}
         for name, ps in groups.items():
             ps = [p for p in ps if p.requires_grad]
             self.params[name] = ps
@@ -123,11 +128,14 @@ class FlatGradients:
                 continue
             flat = torch.zeros(sum(p.numel() for p in ps), device=ps[0].device, dtype=torch.float32)
             off = 0
+            views = []
             for p in ps:
                 n = p.numel()
-                p.grad = flat[off:off + n].view_as(p)
+                views.append(flat[off:off + n].view_as(p))
+                p.grad = views[-1]
                 off += n
             self.flat[name] = flat
+            self.views[name] = views
 
     @property
     def numel(self):
@@ -136,6 +144,22 @@ class FlatGradients:
     def zero(self):
         for f in self.flat.values():
             f.zero_()
+
+    def pack(self, names=None):
+        """Move the gradients autograd just produced (separate tensors, after zero_grad(set_to_none=True)) into the flat
+        buffers with one fused multi-tensor copy per group and make `p.grad` the views again.  A parameter without a
+        gradient keeps `grad = None`; its slice of the buffer stays zero."""
+        for n in (names or self.names):
+            if n not in self.flat:
+                continue
+            src, dst, ps = [], [], []
+            for p, v in zip(self.params[n], self.views[n]):
+                if p.grad is not None and p.grad.data_ptr() != v.data_ptr():
+                    src.append(p.grad); dst.append(v); ps.append(p)
+            if src:
+                torch._foreach_copy_(dst, src)
+                for p, v in zip(ps, dst):
+                    p.grad = v
 
     def all_reduce_async(self, names=None):
         """Launch the (sum) all-reduce of the named groups; returns the work handles (empty without a process group)."""

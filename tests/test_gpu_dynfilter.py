@@ -112,3 +112,16 @@ def test_filter_generator_fused_vs_oracle(E, C, Dh):
     assert relerr(h.grad, ho.grad) < TOL
     for k, v in mod.named_parameters():
         assert relerr(v.grad, p[k].grad) < TOL, k
+
+
+def test_expr2img_is_validated_on_the_host():
+    """an unsorted / out-of-range host-side expr2img raises instead of silently skipping expressions."""
+    import lang2seg_b200.functional as F
+    from lang2seg_b200._lib import L2SError
+    X = torch.randn(2, 64, 8, 8, device="cuda")
+    filt, fuse = torch.randn(3, 7, 64, device="cuda"), torch.randn(3, 7, device="cuda")
+    for bad in ([1, 0, 1], [0, 1, 2], [0, 0], [-1, 0, 1]):
+        with pytest.raises(L2SError):
+            F.dynamic_filter(X, filt, fuse, bad)
+    r, Y, _ = F.dynamic_filter(X, filt, fuse, [0, 1, 1])
+    assert r.shape == (3, 1, 8, 8) and Y.shape == (3, 64, 8, 8)

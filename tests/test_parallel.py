@@ -47,6 +47,18 @@ def _worker(rank, world, port, out):
         flat.wait(wa + wb)
     flat_grads = [p.grad.clone() for p in list(lin_a.parameters()) + list(lin_b.parameters())]
     assert all(p.grad.data_ptr() >= flat.flat[n].data_ptr() for n, ps in flat.params.items() for p in ps)
+    # the pack() protocol: fresh gradients (set_to_none) -> one fused copy per group -> views again
+    for _ in range(2):
+        for p in list(lin_a.parameters()) + list(lin_b.parameters()):
+            p.grad = None
+        (lin_b(lin_a(full[lo:hi])) ** 2).sum().backward()
+        flat.pack(["b"])
+        wb = flat.all_reduce_async(["b"])
+        flat.pack(["a"])
+        flat.wait(wb + flat.all_reduce_async(["a"]))
+    assert all(p.grad.data_ptr() == v.data_ptr() for n in flat.names for p, v in zip(flat.params[n], flat.views[n]))
+    packed_grads = [p.grad.clone() for p in list(lin_a.parameters()) + list(lin_b.parameters())]
+    assert all(torch.equal(a, b) for a, b in zip(flat_grads, packed_grads))
     if rank == 0:
         torch.save([grads, flat_grads], out)
     dist.destroy_process_group()
