@@ -574,22 +574,25 @@ mask_bce_du_kernel(const float* __restrict__ score, const int64_t* __restrict__ 
 __global__ void __launch_bounds__(256)
 gemm_f32_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D, int M, int N, int K,
                 int64_t sam, int64_t sak, int64_t sbn, int64_t sbk, int64_t ldd, int accumulate) {
-  __shared__ float As[16][65], Bs[16][65];
+  __shared__ __align__(16) float As[16][68], Bs[16][68];      // rows of 272 bytes: the 4-wide fragments are one LDS.128
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
   float acc[4][4] = {};
   for (int k0 = 0; k0 < K; k0 += 16) {
+    // consecutive threads walk the CONTIGUOUS index of each operand (k for row-major operands, the row index for
+    // transposed ones: the weight-gradient products dY^T X read both operands with unit row stride)
     for (int i = threadIdx.x; i < 64 * 16; i += 256) {
-      const int r = i >> 4, k = i & 15;
-      As[k][r] = (m0 + r < M && k0 + k < K) ? __ldg(A + (int64_t)(m0 + r) * sam + (int64_t)(k0 + k) * sak) : 0.f;
-      Bs[k][r] = (n0 + r < N && k0 + k < K) ? __ldg(B + (int64_t)(n0 + r) * sbn + (int64_t)(k0 + k) * sbk) : 0.f;
+      const int ra = sam == 1 ? (i & 63) : (i >> 4), ka = sam == 1 ? (i >> 6) : (i & 15);
+      const int rb = sbn == 1 ? (i & 63) : (i >> 4), kb = sbn == 1 ? (i >> 6) : (i & 15);
+      As[ka][ra] = (m0 + ra < M && k0 + ka < K) ? __ldg(A + (int64_t)(m0 + ra) * sam + (int64_t)(k0 + ka) * sak) : 0.f;
+      Bs[kb][rb] = (n0 + rb < N && k0 + kb < K) ? __ldg(B + (int64_t)(n0 + rb) * sbn + (int64_t)(k0 + kb) * sbk) : 0.f;
     }
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-      float a[4], b[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) { a[i] = As[k][ty * 4 + i]; b[i] = Bs[k][tx * 4 + i]; }
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -606,6 +609,67 @@ gemm_f32_kernel(const float* __restrict__ A, const float* __restrict__ B, float*
         float* d = D + (int64_t)m * ldd + n;
         *d = accumulate ? *d + acc[i][j] : acc[i][j];
       }
+    }
+}
+
+// ---- weight-gradient GEMM  D[M][N] = sum_k A[k][m] * B[k][n]  (dW = dY^T X for a few hundred rows) ------------------
+// Both operands are read in place, K outermost with contiguous rows (no transposes).  128 x 64 tile, 256 threads,
+// 8 x 4 outputs per thread (three LDS.128 per 32 FMA), k-step 8, shared memory double buffered with the next k-tile
+// prefetched into registers while the current one is multiplied: one barrier per k-step.  Exact fp32 FFMA, fixed
+// summation order (deterministic).  Requires M % 4 == 0, N % 4 == 0 and 16-byte aligned rows (lda, ldb % 4 == 0).
+__global__ void __launch_bounds__(256)
+wgrad_f32_kernel(const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ D, int M, int N, int K,
+                 int64_t lda, int64_t ldb, int64_t ldd) {
+  __shared__ __align__(16) float As[2][8][128], Bs[2][8][64];
+  const int t = threadIdx.x;
+  const int tx = t & 15, ty = t >> 4;                    // outputs: rows ty*8 .. +7, cols tx*4 .. +3
+  const int m0 = blockIdx.y * 128, n0 = blockIdx.x * 64;
+  // loaders: A tile 8 x 128 = 256 float4 (one per thread), B tile 8 x 64 = 128 float4 (threads 0..127)
+  const int ak = t >> 5, am = (t & 31) * 4;
+  const int bk = (t & 127) >> 4, bn = (t & 15) * 4;
+  const bool bload = t < 128;
+  auto ldA = [&](int k0) {
+    const int k = k0 + ak, m = m0 + am;
+    return (k < K && m < M) ? __ldg(reinterpret_cast<const float4*>(A + (int64_t)k * lda + m)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  auto ldB = [&](int k0) {
+    const int k = k0 + bk, n = n0 + bn;
+    return (bload && k < K && n < N) ? __ldg(reinterpret_cast<const float4*>(B + (int64_t)k * ldb + n))
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  float acc[8][4] = {};
+  float4 ra = ldA(0), rb = ldB(0);
+  *reinterpret_cast<float4*>(&As[0][ak][am]) = ra;
+  if (bload) *reinterpret_cast<float4*>(&Bs[0][bk][bn]) = rb;
+  __syncthreads();
+  int buf = 0;
+  for (int k0 = 0; k0 < K; k0 += 8) {
+    const bool more = k0 + 8 < K;
+    if (more) { ra = ldA(k0 + 8); rb = ldB(k0 + 8); }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 8 + 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (more) {
+      *reinterpret_cast<float4*>(&As[buf ^ 1][ak][am]) = ra;
+      if (bload) *reinterpret_cast<float4*>(&Bs[buf ^ 1][bk][bn]) = rb;
+      __syncthreads();
+      buf ^= 1;
+    }
+  }
+  const int n = n0 + tx * 4;
+  if (n < N)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int m = m0 + ty * 8 + i;
+      if (m < M) *reinterpret_cast<float4*>(D + (int64_t)m * ldd + n) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
     }
 }
 
@@ -731,6 +795,14 @@ extern "C" int l2s_gemm_f32(const float* A, const float* B, float* D, int M, int
                             int64_t sbn, int64_t sbk, int64_t ldd, int accumulate, l2s_stream_t stream) {
   L2S_REQUIRE(A && B && D, L2S_ERR_ARG, "gemm_f32: null pointer");
   L2S_REQUIRE(M > 0 && N > 0 && K > 0, L2S_ERR_SHAPE, "gemm_f32: bad shape");
+  // dW = dY^T X shape: both operands K-outermost with contiguous, 16-byte aligned rows -> the register-blocked kernel
+  if (sam == 1 && sbn == 1 && !accumulate && M % 4 == 0 && N % 4 == 0 && sak % 4 == 0 && sbk % 4 == 0 && ldd % 4 == 0 &&
+      aligned16(A) && aligned16(B) && aligned16(D)) {
+    wgrad_f32_kernel<<<dim3((N + 63) / 64, (M + 127) / 128), 256, 0, (cudaStream_t)stream>>>(A, B, D, M, N, K, sak, sbk, ldd);
+    L2S_LAUNCH_OK("wgrad_f32_kernel");
+    count_launch();
+    return L2S_OK;
+  }
   gemm_f32_kernel<<<dim3((N + 63) / 64, (M + 63) / 64), 256, 0, (cudaStream_t)stream>>>(A, B, D, M, N, K, sam, sak, sbn,
                                                                                           sbk, ldd, accumulate);
   L2S_LAUNCH_OK("gemm_f32_kernel");

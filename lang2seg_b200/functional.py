@@ -571,8 +571,8 @@ class _Att2in2Decode(torch.autograd.Function):
              ptr(aw), ptr(c_all), ptr(a2c_all), ptr(pi_all), ptr(dcat_all), ptr(da2c_all), ptr(dres_all), ptr(de_all),
              ptr(dp_att), ptr(datt), ptr(dalpha), T, B, A, D, Dh, ptr(ws), nbytes, stream())
         # weight gradients: one GEMM each over the stacked rows (h_{-1} = 0 contributes nothing)
-        dw_cat = dcat_all[1:].reshape(-1, LC).t() @ h_all[:-1].reshape(-1, D)
-        dw_a2c = da2c_all.reshape(-1, 2 * D).t() @ res_all.reshape(-1, D)
+        dw_cat = wgrad_f32(dcat_all[1:].reshape(-1, LC), h_all[:-1].reshape(-1, D))
+        dw_a2c = wgrad_f32(da2c_all.reshape(-1, 2 * D), res_all.reshape(-1, D))
         return (dcat_all[:, :, Dh:], datt, dp_att, dw_cat[:Dh], colsum(dcat_all.view(T * B, LC)[:, :Dh]), dw_cat[Dh:], dw_a2c,
                 colsum(da2c_all), dalpha.view(aw_shape), de_all.sum().reshape(ab_shape))
 
@@ -613,7 +613,7 @@ class _LinearSmallFn(torch.autograd.Function):
                 dx = torch.empty(M, K, device=dy.device, dtype=torch.float32)
                 call("l2s_gemm_f32", ptr(dy), ptr(w), ptr(dx), M, K, N, N, 1, 1, K, K, 0, stream())
         if ctx.needs_input_grad[1]:
-            dw = dy.t() @ x
+            dw = wgrad_f32(dy, x)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = colsum(dy)
         return dx, dw, db
@@ -682,8 +682,8 @@ class _BiLSTM(torch.autograd.Function):
         zero = h_all.new_zeros(1, B, H)
         hp_f = torch.cat([zero, h_all[:-1, 0]], 0)           # state before time t, forward direction
         hp_b = torch.cat([h_all[1:, 1], zero], 0)            # ... backward direction (previous = time t+1)
-        dw_f = dG5[:, :, 0].transpose(0, 1).reshape(L * B, 4 * H).t() @ hp_f.reshape(L * B, H)
-        dw_b = dG5[:, :, 1].transpose(0, 1).reshape(L * B, 4 * H).t() @ hp_b.reshape(L * B, H)
+        dw_f = wgrad_f32(dG5[:, :, 0].transpose(0, 1).reshape(L * B, 4 * H), hp_f.reshape(L * B, H))
+        dw_b = wgrad_f32(dG5[:, :, 1].transpose(0, 1).reshape(L * B, 4 * H), hp_b.reshape(L * B, H))
         return dG, dw_f, dw_b, None
 
 
@@ -876,6 +876,17 @@ def dense(x, weight, bias=None):
     else:
         y = linear_small_fn(x2, weight, bias)
     return y.view(*lead, N)
+
+
+def wgrad_f32(dy, x):
+    """dW = dy^T @ x for a small number of rows (dy (R,N), x (R,K) -> (N,K)), exact fp32 on the library's FFMA GEMM:
+    both operands are read in place with unit row stride (no transposes, no cuBLAS SIMT launch)."""
+    dy, x = f32c(dy), f32c(x)
+    R, N = dy.shape
+    K = x.shape[1]
+    D = torch.empty(N, K, device=dy.device, dtype=torch.float32)
+    call("l2s_gemm_f32", ptr(dy), ptr(x), ptr(D), N, K, R, 1, N, 1, K, K, 0, stream())
+    return D
 
 
 def gemm_f32(A, B, accumulate=False, out=None):

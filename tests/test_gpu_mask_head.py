@@ -262,3 +262,16 @@ def test_linear_bf16_variant():
     assert relerr(gx, Gd @ wd) < BF16_TOL
     assert relerr(gw, Gd.t() @ xd) < BF16_TOL
     assert relerr(gb, Gd.sum(0)) < 1e-5
+
+
+@pytest.mark.parametrize("R,N,K", [(48, 7176, 1024), (480, 2048, 512), (336, 3072, 512), (7, 128, 64), (50, 70, 130)])
+def test_wgrad_f32(R, N, K):
+    """dW = dY^T X of the skinny linears / recurrences on the library's FFMA GEMM (register-blocked kernel for 4-aligned
+    shapes, the generic one otherwise), bit-identical re-run."""
+    import lang2seg_b200.functional as F
+    g = torch.Generator().manual_seed(R + N + K)
+    dy, x = torch.randn(R, N, generator=g), torch.randn(R, K, generator=g)
+    D = F.wgrad_f32(dy.cuda(), x.cuda())
+    assert D.shape == (N, K)
+    assert relerr(D, dy.double().t() @ x.double()) < 2e-6
+    assert torch.equal(D, F.wgrad_f32(dy.cuda(), x.cuda()))
