@@ -633,6 +633,16 @@ def cpu_chain_sample(wl, threads=None):
             "sample": "1 image x %d expressions x %d ROIs, one fwd+bwd pass of the res5-chained step (no warm-up pass)" % (E, wl["R"])}
 
 
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.lower().startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def run_reference_arm(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -661,7 +671,7 @@ def run_reference_arm(args, wl):
             "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
             "config": {"workload": wl["name"], "sample": sample},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "cpu": cpu_model(), "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "with_res5": chained, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -807,7 +817,7 @@ def main():
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
         v, dt, e = cpu_sample(wl, repeats=max(1, int(12.0 / max(1.0, 0.7 * wl["EPI"]))))
-        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "cpu": cpu_model(), "kind": "port",
                "sample": "1 image x %d expressions of the workload (reference's native batching), fwd+bwd, "
                          "oracle torch-CPU port, %.2f s per pass" % (e, dt)}
         if not args.no_res5 and all(p in wl["parts"] for p in ("resp", "crop7", "mask", "caption")):
