@@ -605,6 +605,17 @@ def cpu_sample(wl, repeats=1, threads=None):
 
 
 def cpu_chain_sample(wl, threads=None):
+    """The res5-chained step on the host cores: the reference's own modules when they are installed (kind "reference"),
+    else the oracle port below."""
+    if reference_modules_available():
+        v, dt, e = cpu_sample_reference(wl, with_res5=True, threads=threads)
+        return {"value": v, "unit": UNIT, "seconds_per_pass": dt, "kind": "reference",
+                "sample": "1 image x %d expressions x %d ROIs, one fwd+bwd pass of the reference's own _predict chain with "
+                          "resnet.layer4 (no warm-up pass)" % (e, wl["R"])}
+    return _cpu_chain_sample_port(wl, threads)
+
+
+def _cpu_chain_sample_port(wl, threads=None):
     """The res5-chained TRAIN step (oracle.restate.chained_train_losses: the reference's _predict + _add_losses from the
     dynamic filter on, resnet.layer4 included) on ONE image and its expressions, fwd+bwd on the host cores."""
     from oracle import restate as R
@@ -629,8 +640,131 @@ def cpu_chain_sample(wl, threads=None):
     total.backward()
     dt = time.perf_counter() - t0
     E = wl["EPI"]
-    return {"value": E / dt, "unit": UNIT, "seconds_per_pass": dt,
+    return {"value": E / dt, "unit": UNIT, "seconds_per_pass": dt, "kind": "port",
             "sample": "1 image x %d expressions x %d ROIs, one fwd+bwd pass of the res5-chained step (no warm-up pass)" % (E, wl["R"])}
+
+
+def reference_modules_available():
+    """True when the reference's own python modules can be imported under oracle/shim.py: /root/reference in the
+    development container, or the copy that oracle/install_reference.py leaves under baseline/_ref (travels to the box)."""
+    try:
+        from oracle import shim
+        return shim.available()
+    except Exception:
+        return False
+
+
+_REF_NET = {}
+
+
+def cpu_sample_reference(wl, with_res5=False, threads=None, warm=False):
+    """kind "reference": ONE image and its expressions through the reference's OWN unmodified modules (oracle/shim.py,
+    BASELINE.md section 2 D1-D8), fwd+bwd, one expression at a time as the reference does:
+    `RNNEncoder` + `Network._predict` of nets.resnet_v1_cycle_response.resnetv1 (dynamic filter, `_crop_pool_layer`,
+    `_region_classification`, `_mask_prediction`; backbone and RPN stubbed: D6/D7) + `caption_models` att2in2 +
+    `LanguageModelCriterion`; the loss terms are the reference's own expressions (network_cycle_response.py:404-422).
+    Without res5 `_head_to_tail` is replaced by the synthetic features of the workload (as on the B200 arm) and the
+    upstream gradient of pool5 stands in for res5's backward; with res5 the reference's `resnet.layer4` runs in the chain
+    (crop -> layer4 -> heads ; maps -> layer4 -> caption features, :424-438)."""
+    import torch.nn.functional as F
+    from oracle import shim
+    from lang2seg_b200 import synth
+    if threads:
+        torch.set_num_threads(threads)
+    parts, fwd_only = wl["parts"], bool(wl.get("fwd_only"))
+    import contextlib
+    key = (wl["L"], wl["V"], wl["C"])
+    if key not in _REF_NET:
+        with contextlib.redirect_stdout(sys.stderr), shim.cpu_only():   # the reference prints while it builds: stdout is the ONE JSON line
+            _REF_NET[key] = shim.build_reference_net(dict(seq_length=wl["L"], vocab_size=wl["V"], C4_feat_dim=wl["C"]), seed=7)
+    net = _REF_NET[key]
+    import misc.utils as ref_utils                    # the reference's lib/misc/utils.py (on sys.path after shim.install())
+    crit = ref_utils.LanguageModelCriterion()
+    w1 = dict(wl, I=1)
+    E, Rn, NFG, H, W = w1["EPI"], w1["R"], w1["NFG"], w1["H"], w1["W"]
+    if with_res5:
+        g = torch.Generator().manual_seed(4321)
+        d = synth.chain_batch(g, 1, E, w1["C"], H, W, Rn, NFG, w1["L"], w1["V"])
+        meta = d.pop("_meta")
+    else:
+        d = make_inputs(w1, 4321, "cpu")
+    g_pool = torch.randn(Rn, w1["C"], 7, 7) * 1e-4
+    g_Y = torch.randn(1, w1["C"], H, W) * 1e-4
+    orig_head = type(net)._head_to_tail
+
+    def one():
+        net.zero_grad()
+        with torch.set_grad_enabled(not fwd_only):
+            total = torch.zeros(())
+            for e in range(E):                          # the reference runs one (image, expression) pair per step
+                X = d["X"][:1].clone().requires_grad_(not fwd_only)
+                labels = d["labels"][e:e + 1]
+                labels = labels[:, :max(1, int((labels != 0).sum()))]     # as Network.forward does (:634-636)
+                if with_res5:
+                    nfg = NFG
+                    rois_e = torch.cat([d["rois"][e * NFG:(e + 1) * NFG], d["rois"][E * NFG + e * (Rn - NFG):E * NFG + (e + 1) * (Rn - NFG)]]).clone()
+                    rois_e[:, 0] = 0
+                    net._head_to_tail = lambda pool5: orig_head(net, pool5)
+                    stash = {}
+                else:
+                    nfg = NFG if "mask" in parts else 0
+                    rois_e = d["rois"][e * Rn:(e + 1) * Rn].clone() if Rn else torch.zeros(1, 5)
+                    rois_e[:, 0] = 0
+                    fc7 = d["fc7"][e * NFG:(e + 1) * NFG].clone().requires_grad_(not fwd_only) if "mask" in parts else None
+                    stash = {}
+
+                    def head(pool5, fc7=fc7, stash=stash):
+                        stash["pool5"] = pool5
+                        out = pool5.new_zeros(pool5.shape[0], 2048, 7, 7)
+                        if fc7 is not None:
+                            out = torch.cat([fc7, out[fc7.shape[0]:]], 0)
+                        return out
+                    net._head_to_tail = head
+                gated, _, _, _, _ = shim.run_predict(net, X, labels, rois_e, mode="TRAIN", num_fg=max(nfg, 1) if not with_res5 and nfg == 0 else nfg)
+                loss = torch.zeros(())
+                if "resp" in parts or with_res5:
+                    resp = net._predictions["response"].squeeze(1).squeeze(0)
+                    tgt = d["resp_tgt"][e] if not with_res5 else torch.from_numpy(
+                        __import__("scipy.misc", fromlist=["imresize"]).imresize(d["gt_masks"][e].numpy(), (H, W), interp="nearest").astype("float32"))
+                    loss = loss + F.binary_cross_entropy_with_logits(resp, tgt)                      # :415-422
+                if with_res5 or "mask" in parts:
+                    ms = net._predictions["mask_score"]
+                    lab = (d["roi_labels"][e * NFG:(e + 1) * NFG].long() if with_res5 else d["mlab"][e * NFG:(e + 1) * NFG])
+                    idx = lab.view(-1, 1, 1, 1).expand(lab.numel(), 1, 14, 14)
+                    mt = (torch.zeros(lab.numel(), 14, 14) if with_res5 else d["mtgt"][e * NFG:(e + 1) * NFG])
+                    loss = loss + F.binary_cross_entropy_with_logits(torch.gather(ms, 1, idx).squeeze(1), mt)   # :404-413
+                if with_res5:
+                    cls = net._predictions["cls_score"]
+                    rl = torch.cat([d["roi_labels"][e * NFG:(e + 1) * NFG], torch.zeros(Rn - NFG)]).long()
+                    loss = loss + F.cross_entropy(cls.view(-1, cls.shape[-1]), rl)                    # :390-394
+                    fb = orig_head(net, net._predictions["net_conv_before"])
+                    fa = orig_head(net, gated)
+                    fcf = torch.cat((fb.mean(3).mean(2), fa.mean(3).mean(2)), 1)
+                    attf = torch.cat((F.adaptive_avg_pool2d(fb, [14, 14]).permute(0, 2, 3, 1).contiguous(),
+                                      F.adaptive_avg_pool2d(fa, [14, 14]).permute(0, 2, 3, 1).contiguous()), 3)   # :424-438
+                    cap, msk = d["cap"][e:e + 1], d["msk"][e:e + 1]
+                    loss = loss + crit(net.caption_model(fcf, attf, cap), cap[:, 1:], msk[:, 1:])
+                else:
+                    if "crop7" in parts or "crop_max" in parts:
+                        loss = loss + (stash["pool5"] * g_pool).sum()
+                    if "dY" in parts:
+                        loss = loss + (gated * g_Y).sum()
+                    if "caption" in parts:
+                        att = d["att"][e:e + 1].clone().requires_grad_(not fwd_only)
+                        cap, msk = d["cap"][e:e + 1], d["msk"][e:e + 1]
+                        loss = loss + crit(net.caption_model(d["fc"][e:e + 1], att, cap), cap[:, 1:], msk[:, 1:])
+                total = total + loss
+            if not fwd_only:
+                total.backward()
+        net._head_to_tail = lambda pool5: orig_head(net, pool5)
+
+    with contextlib.redirect_stdout(sys.stderr), shim.cpu_only():      # the reference's .cuda() calls stay on the host
+        if warm:
+            one()
+        t0 = time.perf_counter()
+        one()
+        dt = time.perf_counter() - t0
+    return E / dt, dt, E
 
 
 def cpu_model():
@@ -649,18 +783,29 @@ def run_reference_arm(args, wl):
         return
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    use_ref = reference_modules_available()
+    sample_fn = cpu_sample_reference if use_ref else (lambda w: cpu_sample(w, 1))
+    kind = "reference" if use_ref else "port"
     vals = []
+    if use_ref:
+        try:
+            cpu_sample_reference(wl, warm=True)            # build the net + one untimed pass even with --warmup 0
+        except Exception as exc:                           # fall back to the oracle port rather than print nothing
+            print("bench: reference modules failed (%s); timing the oracle port" % str(exc).splitlines()[0], file=sys.stderr)
+            use_ref = False
+            sample_fn, kind = (lambda w: cpu_sample(w, 1)), "port"
     for _ in range(args.warmup):
-        cpu_sample(wl, 1)
-    t0 = time.perf_counter()
+        sample_fn(wl)
     n_expr = 0
     for _ in range(args.steps):
-        v, dt, e = cpu_sample(wl, 1)
+        v, dt, e = sample_fn(wl)
         n_expr += e
         vals.append(dt)
     total = sum(vals)
     value = n_expr / total
-    sample = "1 image x %d expressions of the workload per step (reference's native batching), fwd+bwd, torch CPU" % wl["EPI"]
+    sample = ("1 image x %d expressions of the workload per step (reference's native batching), fwd+bwd, torch CPU; " % wl["EPI"]) + \
+             ("the reference's own unmodified modules under oracle/shim.py (baseline/_ref)" if use_ref else
+              "oracle torch-CPU port (the reference modules are not installed under baseline/_ref)")
     chained = None
     if not args.no_res5 and all(p in wl["parts"] for p in ("resp", "crop7", "mask", "caption")):
         try:
@@ -671,7 +816,7 @@ def run_reference_arm(args, wl):
             "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
             "config": {"workload": wl["name"], "sample": sample},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "cpu": cpu_model(), "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "cpu": cpu_model(), "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "with_res5": chained, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -816,10 +961,26 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:      # the CPU leg is timed at N = 1 only
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
-        v, dt, e = cpu_sample(wl, repeats=max(1, int(12.0 / max(1.0, 0.7 * wl["EPI"]))))
-        cpu = {"value": v, "unit": UNIT, "cores": cores, "cpu": cpu_model(), "kind": "port",
+        ref_ok = reference_modules_available()
+        if ref_ok:
+            try:
+                reps = max(1, int(12.0 / max(1.0, 0.7 * wl["EPI"])))
+                cpu_sample_reference(wl, warm=True)            # builds the reference net, warms up
+                t0 = time.perf_counter()
+                for _ in range(reps):
+                    v, dt, e = cpu_sample_reference(wl)
+                dt = (time.perf_counter() - t0) / reps
+                v = e / dt
+                kind, how = "reference", "the reference's own unmodified modules under oracle/shim.py (baseline/_ref)"
+            except Exception as exc:      # the B200 line must survive a failure of the baseline leg: fall back to the port
+                print("bench: reference modules failed (%s); timing the oracle port" % str(exc).splitlines()[0], file=sys.stderr)
+                ref_ok = False
+        if not ref_ok:
+            v, dt, e = cpu_sample(wl, repeats=max(1, int(12.0 / max(1.0, 0.7 * wl["EPI"]))))
+            kind, how = "port", "oracle torch-CPU port"
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "cpu": cpu_model(), "kind": kind,
                "sample": "1 image x %d expressions of the workload (reference's native batching), fwd+bwd, "
-                         "oracle torch-CPU port, %.2f s per pass" % (e, dt)}
+                         "%s, %.2f s per pass" % (e, how, dt)}
         if not args.no_res5 and all(p in wl["parts"] for p in ("resp", "crop7", "mask", "caption")):
             try:
                 cpu["with_res5"] = cpu_chain_sample(wl)

@@ -29,7 +29,15 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-REF_ROOT = os.environ.get("L2S_REFERENCE_ROOT", "/root/reference")
+def _default_root():
+    """/root/reference where it is mounted (development container); else the copy that oracle/install_reference.py left
+    under baseline/_ref (git-ignored, travels to the GPU box)."""
+    if os.path.isdir("/root/reference/lib"):
+        return "/root/reference"
+    return os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+
+
+REF_ROOT = os.environ.get("L2S_REFERENCE_ROOT") or _default_root()
 _MFR = os.path.join(REF_ROOT, "pyutils", "mask-faster-rcnn", "lib")
 _LIB = os.path.join(REF_ROOT, "lib")
 
@@ -81,6 +89,23 @@ def _imresize(arr, size, interp="bilinear", mode=None):
         h, w = int(size[0]), int(size[1])
     flt = {"nearest": Image.NEAREST, "bilinear": Image.BILINEAR, "bicubic": Image.BICUBIC}[interp]
     return np.asarray(Image.fromarray(arr).resize((w, h), flt))
+
+
+import contextlib
+
+
+@contextlib.contextmanager
+def cpu_only():
+    """D5, scoped: `Tensor.cuda()` / `Module.cuda()` are the identity while the reference modules run as the CPU baseline
+    on a box that HAS a GPU (install() only patches them for good where CUDA is absent); restored on exit so that the
+    caller's own GPU code is untouched."""
+    t, m = torch.Tensor.cuda, torch.nn.Module.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    torch.nn.Module.cuda = lambda self, *a, **k: self
+    try:
+        yield
+    finally:
+        torch.Tensor.cuda, torch.nn.Module.cuda = t, m
 
 
 def install():
