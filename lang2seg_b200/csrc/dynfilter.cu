@@ -49,6 +49,10 @@ __device__ __forceinline__ float mask_k(const DfGeom& g, int k, int p) {
   return m ? 1.f : 0.f;
 }
 
+// floats of the [7][C] filter block in shared memory, rounded so that the arrays carved out behind it stay 16-byte aligned
+// for any C (they are read as float4 on the vector paths)
+__host__ __device__ __forceinline__ size_t fs_floats(int C) { return ((size_t)NF * C + 3) & ~(size_t)3; }
+
 // expressions of image i: expr2img is non-decreasing
 __device__ __forceinline__ void expr_range(const int* __restrict__ e2i, int E, int i, int* e0, int* e1) {
   int lo = 0, hi = E;
@@ -63,6 +67,37 @@ __device__ __forceinline__ float bce_logits(float x, float t) {
   return fmaxf(x, 0.f) - x * t + log1pf(expf(-fabsf(x)));
 }
 
+// Four consecutive pixels of a map row at an 8-byte aligned address.  H*W only has to be EVEN for the vector paths (600 x
+// 1000 inputs give 38x63 / 37x62 maps: H*W % 4 == 2, so a row starts 16- or 8-byte aligned alternately): one 16-byte
+// access where the address allows it, two 8-byte accesses otherwise; `n` = pixels of the quad inside the row (4, 2 or <= 0).
+template <bool STREAM>
+__device__ __forceinline__ float4 ld_quad(const float* p, int n) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (n >= 4 && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+    v = STREAM ? __ldcs(reinterpret_cast<const float4*>(p)) : __ldg(reinterpret_cast<const float4*>(p));
+  } else if (n >= 2) {
+    const float2 a = STREAM ? __ldcs(reinterpret_cast<const float2*>(p)) : __ldg(reinterpret_cast<const float2*>(p));
+    v.x = a.x; v.y = a.y;
+    if (n >= 4) {
+      const float2 b = STREAM ? __ldcs(reinterpret_cast<const float2*>(p) + 1) : __ldg(reinterpret_cast<const float2*>(p) + 1);
+      v.z = b.x; v.w = b.y;
+    }
+  }
+  return v;
+}
+template <bool STREAM>
+__device__ __forceinline__ void st_quad(float* p, float4 v, int n) {
+  if (n >= 4 && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+    if (STREAM) __stcs(reinterpret_cast<float4*>(p), v); else *reinterpret_cast<float4*>(p) = v;
+  } else if (n >= 2) {
+    if (STREAM) __stcs(reinterpret_cast<float2*>(p), make_float2(v.x, v.y)); else *reinterpret_cast<float2*>(p) = make_float2(v.x, v.y);
+    if (n >= 4) {
+      if (STREAM) __stcs(reinterpret_cast<float2*>(p) + 1, make_float2(v.z, v.w));
+      else *(reinterpret_cast<float2*>(p) + 1) = make_float2(v.z, v.w);
+    }
+  }
+}
+
 // load a [C x TP] tile of a (C,HW) map into smem (row stride TP), zero padded
 template <int TP, bool VEC>
 __device__ __forceinline__ void load_tile(float* __restrict__ xs, const float* __restrict__ src, int C, int HW,
@@ -74,9 +109,7 @@ __device__ __forceinline__ void load_tile(float* __restrict__ xs, const float* _
     constexpr int CSTEP = kThreads / Q;
     const int p = p0 + 4 * pq;
     for (int c = cs; c < C; c += CSTEP) {
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (p < HW) v = __ldg(reinterpret_cast<const float4*>(src + (size_t)c * HW + p));
-      reinterpret_cast<float4*>(xs)[c * Q + pq] = v;
+      reinterpret_cast<float4*>(xs)[c * Q + pq] = ld_quad<false>(src + (size_t)c * HW + p, HW - p);
     }
   } else {
     const int pp = t % TP, cs = t / TP;
@@ -129,7 +162,7 @@ dynfilter_fwd_kernel(const float* __restrict__ X, const float* __restrict__ filt
   extern __shared__ __align__(16) float smem[];
   float* xs = smem;                        // [C][TP]
   float* fs = xs + (size_t)g.C * TP;       // [7][C]
-  float* red = fs + (size_t)NF * g.C;      // [8][7][TP]
+  float* red = fs + fs_floats(g.C);      // [8][7][TP]
   float* dk = red + 8 * NF * TP;           // [7][TP]
   float* gate = dk + NF * TP;              // [TP]
 
@@ -190,7 +223,7 @@ dynfilter_fwd_kernel(const float* __restrict__ X, const float* __restrict__ filt
         for (int c = cs; c < g.C; c += CSTEP) {
           float4 x = reinterpret_cast<const float4*>(xs)[c * Q + pq];
           x.x *= gq.x; x.y *= gq.y; x.z *= gq.z; x.w *= gq.w;
-          __stcs(reinterpret_cast<float4*>(Ye + (size_t)c * g.HW + p), x);
+          st_quad<true>(Ye + (size_t)c * g.HW + p, x, g.HW - p);
         }
     } else {
       const int pp = t % TP, c1 = t / TP;
@@ -216,7 +249,7 @@ dynfilter_bwd_kernel(const float* __restrict__ X, const float* __restrict__ filt
   float* xs = smem;                         // [C][TP]
   float* dxs = xs + (size_t)g.C * TP;       // [C][TP]
   float* fs = dxs + (size_t)g.C * TP;       // [7][C]
-  float* red = fs + (size_t)NF * g.C;       // [8][1][TP]
+  float* red = fs + fs_floats(g.C);       // [8][1][TP]
   float* ds = red + 8 * TP;                 // [TP]
   float* gate = ds + TP;                    // [TP]
   float* mwdr = gate + TP;                  // [7][TP]  w_k * M_k[p] * dr[p]
@@ -246,7 +279,7 @@ dynfilter_bwd_kernel(const float* __restrict__ X, const float* __restrict__ filt
       const int p = p0 + 4 * pq;
       if (p < g.HW)
         for (int c = cs; c < g.C; c += CSTEP) {
-          const float4 v = __ldcs(reinterpret_cast<const float4*>(dYe + (size_t)c * g.HW + p));
+          const float4 v = ld_quad<true>(dYe + (size_t)c * g.HW + p, g.HW - p);
           const float4 x = reinterpret_cast<const float4*>(xs)[c * Q + pq];
           acc[0][0] = fmaf(v.x, x.x, acc[0][0]);
           acc[0][1] = fmaf(v.y, x.y, acc[0][1]);
@@ -305,7 +338,7 @@ dynfilter_bwd_kernel(const float* __restrict__ X, const float* __restrict__ filt
     const int p = p0 + 4 * pq;
     if (p < g.HW)
       for (int c = cs; c < g.C; c += CSTEP)
-        *reinterpret_cast<float4*>(dXi + (size_t)c * g.HW + p) = reinterpret_cast<const float4*>(dxs)[c * Q + pq];
+        st_quad<false>(dXi + (size_t)c * g.HW + p, reinterpret_cast<const float4*>(dxs)[c * Q + pq], g.HW - p);
   } else {
     const int pp = t % TP, c1 = t / TP;
     const int p = p0 + pp;
@@ -332,7 +365,7 @@ dynfilter_bwd_reg_kernel(const float* __restrict__ X, const float* __restrict__ 
   extern __shared__ __align__(16) float smem[];
   float* xs = smem;                         // [C][TP]
   float* fs = xs + (size_t)g.C * TP;        // [7][C]
-  float* red = fs + (size_t)NF * g.C;       // [8][1][TP]
+  float* red = fs + fs_floats(g.C);       // [8][1][TP]
   float* ds = red + 8 * TP;                 // [TP]
   float* gate = ds + TP;                    // [TP]
   float* mwdr = gate + TP;                  // [7][TP]  w_k * M_k[p] * dr[p]
@@ -369,8 +402,7 @@ dynfilter_bwd_reg_kernel(const float* __restrict__ X, const float* __restrict__ 
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int c = cs + (h + j) * CSTEP;
-          v[j] = (c < g.C) ? __ldcs(reinterpret_cast<const float4*>(dYe + (size_t)c * g.HW + p))
-                           : make_float4(0.f, 0.f, 0.f, 0.f);
+          v[j] = (c < g.C) ? ld_quad<true>(dYe + (size_t)c * g.HW + p, g.HW - p) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -428,7 +460,7 @@ dynfilter_bwd_reg_kernel(const float* __restrict__ X, const float* __restrict__ 
 #pragma unroll
     for (int j = 0; j < kRegCh; ++j) {
       const int c = cs + j * CSTEP;
-      if (c < g.C) *reinterpret_cast<float4*>(dXi + (size_t)c * g.HW + p) = dacc[j];
+      if (c < g.C) st_quad<false>(dXi + (size_t)c * g.HW + p, dacc[j], g.HW - p);
     }
   }
 }
@@ -486,11 +518,23 @@ dynfilter_dfilt_kernel(const float* __restrict__ X, const float* __restrict__ fu
   }
 }
 
-// Vectorised variant of the above for float4-aligned maps (H*W % 4 == 0): warp = channel row, every lane issues its
-// eight 16-byte loads of X up front (the first version walked the row with one dependent 4-byte load per iteration and
-// took as long as the whole forward), the 7 partition masks of a pixel come from a one-byte bit table in shared memory
-// (built once per CTA: the only place with a division) and are shared by the expressions of the chunk.
+// Vectorised variant of the above: warp = channel row, every lane issues its eight 16-byte loads of X up front (the
+// first version walked the row with one dependent 4-byte load per iteration and took as long as the whole forward), the
+// 7 partition masks of a pixel come from a one-byte bit table in shared memory (built once per CTA: the only place with
+// a division) and are shared by the expressions of the chunk.  A16 = rows are 16-byte aligned (H*W % 4 == 0).  Otherwise
+// H*W is even (600 x 1000 inputs: 38x63 and 37x62 maps) and a row starts 16- or only 8-byte aligned depending on the
+// parity of its index: the float4 body then starts at pixel `head` (0 or 2) of the row, the two pixels left over at the
+// other end are taken by two lanes, and the dr rows / mask bits -- whose alignment relative to the body differs from
+// warp to warp -- are read in 8-byte / 2-byte halves.
 constexpr int EBV = 3;
+
+__device__ __forceinline__ void dfilt_accum(float (&acc)[NF], float v, unsigned bits) {
+  acc[0] += v;
+#pragma unroll
+  for (int k = 1; k < NF; ++k) acc[k] = fmaf(((bits >> k) & 1u) ? 1.f : 0.f, v, acc[k]);
+}
+
+template <bool A16>
 __global__ void __launch_bounds__(256)
 dynfilter_dfilt_vec_kernel(const float* __restrict__ X, const float* __restrict__ fuse, const int* __restrict__ e2i,
                            const float* __restrict__ drbuf, float* __restrict__ dfilt, DfGeom g) {
@@ -498,6 +542,22 @@ dynfilter_dfilt_vec_kernel(const float* __restrict__ X, const float* __restrict_
   uint8_t* mbits = reinterpret_cast<uint8_t*>(smem + (size_t)EBV * g.HW);
   const int i = blockIdx.y, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int c = blockIdx.x * 8 + wid;
+  const size_t rowoff = ((size_t)i * g.C + min(c, g.C - 1)) * g.HW;
+  const int head = A16 ? 0 : (int)((4 - (rowoff & 3)) & 3);            // 0 or 2: pixels before the 16-byte aligned body
+  const float* Xrow = X + rowoff;
+  const float4* Xc = reinterpret_cast<const float4*>(Xrow + head);
+  const int nq = (g.HW - head) >> 2;                                    // float4 of the body
+  const int rest = head ? 0 : nq * 4;                                   // first of the (HW - 4 nq) left-over pixels
+  const int nrest = g.HW - 4 * nq;                                      // 0 (A16) or 2
+  // The first eight float4 of the row are requested before anything else: the expression-range search, the mask table
+  // and the staging of dr (three dependent L2 round trips on a CTA that lives for a few microseconds) then overlap the
+  // DRAM latency of X instead of preceding it.  X does not depend on the expression chunk, so the batch is reused.
+  float4 xpre[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int q = u * 32 + lane;
+    xpre[u] = q < nq ? __ldg(Xc + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   int e0, e1;
   expr_range(e2i, g.E, i, &e0, &e1);
   if (e0 == e1) return;
@@ -507,31 +567,46 @@ dynfilter_dfilt_vec_kernel(const float* __restrict__ X, const float* __restrict_
     for (int k = 0; k < NF; ++k) b |= (mask_k(g, k, p) != 0.f ? 1u : 0u) << k;
     mbits[p] = (uint8_t)b;
   }
-  const float4* Xc = reinterpret_cast<const float4*>(X + ((size_t)i * g.C + min(c, g.C - 1)) * g.HW);
-  const int nq = g.HW >> 2;                       // float4 per row
   for (int eb = e0; eb < e1; eb += EBV) {
     const int ne = min(EBV, e1 - eb);
     __syncthreads();
-    for (int idx = threadIdx.x; idx < ne * nq; idx += blockDim.x)
-      reinterpret_cast<float4*>(smem)[idx] = __ldg(reinterpret_cast<const float4*>(drbuf + (size_t)eb * g.HW) + idx);
+    if (A16) {
+      for (int idx = threadIdx.x; idx < ne * (g.HW >> 2); idx += blockDim.x)
+        reinterpret_cast<float4*>(smem)[idx] = __ldg(reinterpret_cast<const float4*>(drbuf + (size_t)eb * g.HW) + idx);
+    } else {
+      for (int idx = threadIdx.x; idx < ne * (g.HW >> 1); idx += blockDim.x)
+        reinterpret_cast<float2*>(smem)[idx] = __ldg(reinterpret_cast<const float2*>(drbuf + (size_t)eb * g.HW) + idx);
+    }
     __syncthreads();
     float acc[EBV][NF];
 #pragma unroll
     for (int a = 0; a < EBV; ++a)
 #pragma unroll
       for (int k = 0; k < NF; ++k) acc[a][k] = 0.f;
+    if (!A16 && lane < nrest) {                                         // the two pixels outside the aligned body
+      const int p = rest + lane;
+      const float x = __ldg(Xrow + p);
+      const unsigned bits = mbits[p];
+#pragma unroll
+      for (int a = 0; a < EBV; ++a)
+        if (a < ne) dfilt_accum(acc[a], smem[(size_t)a * g.HW + p] * x, bits);
+    }
     for (int q0 = 0; q0 < nq; q0 += 32 * 8) {
       float4 x[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const int q = q0 + u * 32 + lane;
-        x[u] = q < nq ? __ldg(Xc + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        x[u] = q0 == 0 ? xpre[u] : (q < nq ? __ldg(Xc + q) : make_float4(0.f, 0.f, 0.f, 0.f));
       }
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
         const int q = q0 + u * 32 + lane;
         if (q < nq) {
-          const unsigned bits = reinterpret_cast<const unsigned*>(mbits)[q];
+          const int p = head + 4 * q;
+          unsigned bits;
+          if (A16) bits = reinterpret_cast<const unsigned*>(mbits)[q];
+          else bits = (unsigned)*reinterpret_cast<const uint16_t*>(mbits + p) |
+                      ((unsigned)*reinterpret_cast<const uint16_t*>(mbits + p + 2) << 16);
           const float xv[4] = {x[u].x, x[u].y, x[u].z, x[u].w};
           // the masks of the four pixels as 0/1 floats, once for all expressions of the chunk (k = 0 is all ones)
           float mf[4][NF - 1];
@@ -542,7 +617,14 @@ dynfilter_dfilt_vec_kernel(const float* __restrict__ X, const float* __restrict_
 #pragma unroll
           for (int a = 0; a < EBV; ++a) {
             if (a < ne) {
-              const float4 d = reinterpret_cast<const float4*>(smem + (size_t)a * g.HW)[q];
+              float4 d;
+              if (A16) {
+                d = reinterpret_cast<const float4*>(smem + (size_t)a * g.HW)[q];
+              } else {
+                const float2 d0 = *reinterpret_cast<const float2*>(smem + (size_t)a * g.HW + p);
+                const float2 d1 = *reinterpret_cast<const float2*>(smem + (size_t)a * g.HW + p + 2);
+                d = make_float4(d0.x, d0.y, d1.x, d1.y);
+              }
               const float dv[4] = {d.x, d.y, d.z, d.w};
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
@@ -626,9 +708,9 @@ DfGeom make_geom(int I, int E, int C, int H, int W, int flags) {
   return g;
 }
 
-size_t fwd_smem(int C, int TP) { return ((size_t)C * TP + (size_t)NF * C + 8 * NF * TP + NF * TP + TP) * 4; }
-size_t bwd_reg_smem(int C, int TP) { return ((size_t)C * TP + (size_t)NF * C + 8 * TP + 2 * TP + NF * TP) * 4; }
-size_t bwd_smem(int C, int TP) { return ((size_t)2 * C * TP + (size_t)NF * C + 8 * TP + 2 * TP + NF * TP) * 4; }
+size_t fwd_smem(int C, int TP) { return ((size_t)C * TP + fs_floats(C) + 8 * NF * TP + NF * TP + TP) * 4; }
+size_t bwd_reg_smem(int C, int TP) { return ((size_t)C * TP + fs_floats(C) + 8 * TP + 2 * TP + NF * TP) * 4; }
+size_t bwd_smem(int C, int TP) { return ((size_t)2 * C * TP + fs_floats(C) + 8 * TP + 2 * TP + NF * TP) * 4; }
 
 template <int TP, bool VEC>
 int launch_fwd(const float* X, const float* filt, const float* fuse, const int* e2i, float* response, float* rk,
@@ -689,7 +771,7 @@ extern "C" int l2s_dynfilter_fwd(const float* X, const float* filt, const float*
                                workspace, workspace_bytes, st);
   if (rc <= 0) return rc;
   if (resp_loss) L2S_CUDA_OK(cudaMemsetAsync(resp_loss, 0, sizeof(float) * E, st));   // the FFMA kernel accumulates into it
-  const bool vec = (g.HW % 4 == 0) && aligned16(X) && aligned16(Y);
+  const bool vec = (g.HW % 2 == 0) && aligned16(X) && aligned16(Y);      // rows 8-byte aligned at least (ld_quad / st_quad)
   const size_t cap = (size_t)max_smem_optin();
   if (fwd_smem(C, 16) <= cap && vec)
     return launch_fwd<16, true>(X, filt, fuse, expr2img, response, rk_saved, Y, resp_target, resp_loss, g, st);
@@ -725,7 +807,7 @@ extern "C" int l2s_dynfilter_bwd(const float* X, const float* filt, const float*
   }
   float* drbuf = reinterpret_cast<float*>(workspace);
   float* rk_ws = drbuf + (size_t)E * g.HW;
-  const bool vec = (g.HW % 4 == 0) && aligned16(X) && aligned16(dY) && aligned16(dX);
+  const bool vec = (g.HW % 2 == 0) && aligned16(X) && aligned16(dY) && aligned16(dX);
   const size_t cap = (size_t)max_smem_optin();
   // TMA-streamed kernel (dynfilter_bwd_tma.cu) where the shape allows it: 0 = ran, 1 = not applicable, < 0 = error
   void* seg_ws = reinterpret_cast<char*>(workspace) + (((size_t)E * g.HW * sizeof(float) * (1 + NF) + 255) & ~(size_t)255);
@@ -758,8 +840,9 @@ extern "C" int l2s_dynfilter_bwd(const float* X, const float* filt, const float*
     dim3 grid((C + 7) / 8, I);
     static const bool scalar_dfilt = env_flag("L2S_DFILT_SCALAR");
     if (vec && aligned16(drbuf) && smem_v <= cap && !scalar_dfilt) {
-      L2S_CUDA_OK(cudaFuncSetAttribute(dynfilter_dfilt_vec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v));
-      dynfilter_dfilt_vec_kernel<<<grid, 256, smem_v, st>>>(X, fuse, expr2img, drbuf, dfilt, g);
+      auto kern = (g.HW % 4 == 0) ? dynfilter_dfilt_vec_kernel<true> : dynfilter_dfilt_vec_kernel<false>;
+      L2S_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_v));
+      kern<<<grid, 256, smem_v, st>>>(X, fuse, expr2img, drbuf, dfilt, g);
       L2S_LAUNCH_OK("dynfilter_dfilt_vec_kernel");
     } else {
       const size_t smem = (size_t)EB * g.HW * sizeof(float);

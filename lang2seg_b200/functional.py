@@ -848,7 +848,10 @@ class _LinearTC(torch.autograd.Function):
         dyh, dyl = split_bf16(dy)
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = gemm_bf16x3(dyh, dyl, wh, wl, M, K, N, a_mn=False, b_mn=True)           # dY [M,N] . W [N,K]
+            # dY [M,N] . W [N,K]; with a few hundred rows (i2h, logit: T*B = 528) there are only 8-10 output tiles for
+            # 148 SMs and each walks the whole N: let the library split the contraction (as for dW)
+            few_tiles = ((M + 127) // 128) * ((K + 255) // 256) * 2 <= 148 and N >= 1024
+            dx = gemm_bf16x3(dyh, dyl, wh, wl, M, K, N, a_mn=False, b_mn=True, split_k=0 if few_tiles else 1)
         if ctx.needs_input_grad[1]:
             dw = gemm_bf16x3(dyh, dyl, xh, xl, N, K, M, a_mn=True, b_mn=True, split_k=0)  # dY^T [N,M] . X [M,K]; split chosen by the library
         if ctx.has_bias and ctx.needs_input_grad[2]:

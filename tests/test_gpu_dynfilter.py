@@ -44,7 +44,12 @@ def test_golden(golden, tag):
                                  dict(I=2, C=1024, H=32, W=32, e2i=[0, 0, 0, 1, 1, 1]),
                                  dict(I=2, C=64, H=16, W=16, e2i=[0] * 20 + [1]),
                                  dict(I=2, C=256, H=36, W=35, e2i=[0, 1, 1]),
-                                 dict(I=1, C=512, H=32, W=32, e2i=[0])])
+                                 dict(I=1, C=512, H=32, W=32, e2i=[0]),
+                                 # H*W % 4 == 2 (600 x 1000 inputs: 38x63 / 37x62 maps): rows alternate between 16- and 8-byte
+                                 # alignment; four expressions on one image = two dfilt chunks; odd C shifts whole images
+                                 dict(I=2, C=40, H=38, W=63, e2i=[0, 0, 0, 0, 1]),
+                                 dict(I=3, C=33, H=6, W=7, e2i=[0, 1, 1, 2]),
+                                 dict(I=2, C=33, H=8, W=8, e2i=[0, 1])])                 # odd C on the float4 path
 @pytest.mark.parametrize("gate", ["sigmoid", "linear"])
 def test_vs_oracle(cfg, gate):
     import lang2seg_b200.functional as F
