@@ -732,6 +732,9 @@ roi_crop_bwd_kernel(const float* __restrict__ dout, const int* __restrict__ seg,
 //     geometry does not depend on i) and written with ONE set of 14 read-modify-writes;
 //   * mode: whether the 14 corner columns are pairwise distinct (one batch of 14 independent loads / FMAs / stores),
 //     or x0 is strictly increasing (two batches: left corners, right corners), or neither (serial chain).
+//     (Merging shared columns in registers -- one RMW per distinct column, pattern shipped in the record -- was built and
+//     measured: 1.35 -> 1.63 ms.  A warp sees less than one map row per ROI on average, so the instructions that decode
+//     the pattern per (ROI, row) cost more issue slots than the saved wavefronts return; profiles/r02_ab.md.)
 // Bit-reproducible (fixed order, no atomics).
 constexpr int kRowStages = 3;
 constexpr int kRowGroup = 4;        // ROIs per stage
