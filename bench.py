@@ -465,8 +465,9 @@ def component_rooflines(wl, d, step, pk):
         if not step.fwd_only:
             gp = step.g_pool_max if flags else step.g_pool
             dYb = torch.empty_like(Y)
+            # as in the step: the backward reuses the ROI binning / geometry records the forward left in ws2
             t = ev_time(lambda: call("l2s_roi_crop_bwd", ptr(gp), ptr(d["rois"]), ptr(arg), ptr(dYb), E, C, H, W, N, 7,
-                                     flags, 0.0, 0.0, ptr(ws2), nb2, stream()))
+                                     flags | F.CROP_WS_PREPARED, 0.0, 0.0, ptr(ws2), nb2, stream()))
             out.append(dict(kernel=tag + "_bwd", ms=t, bound="hbm", work=work))
             del dYb
         del pool, arg

@@ -43,6 +43,9 @@ typedef void* l2s_stream_t; /* cudaStream_t */
 #define L2S_CROP_ALIGN 2    /* _crop_pool_layer_align (network_cycle_response.py:151-182)  */
 #define L2S_CROP_BWD_RANKED 4 /* backward only: force the sample-per-lane (ranked) kernel where the row-owner kernel
                                * (lane = channel, warp = map rows; 7x7 crops of maps <= ~1300 pixels) is the default */
+#define L2S_CROP_WS_PREPARED 8 /* backward only: `workspace` is the very buffer l2s_roi_crop_fwd filled for the same rois,
+                                * sizes and flags (untouched since): the ROI binning and geometry records in it are
+                                * reused instead of recomputed (3 small launches, ~64 us at 12288 ROIs) */
 
 /* precision of the tensor-core GEMMs (mask head, caption projections, l2s_gemm_bf16x3) */
 #define L2S_PRECISION_FP32 0 /* bf16x3 split products: ~1e-5 from an fp32 GEMM (the default; the 1e-4 parity contract) */

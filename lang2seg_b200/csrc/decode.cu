@@ -341,9 +341,21 @@ __global__ void colsum_kernel(const float* __restrict__ in, float* __restrict__ 
   pdl_launch_dependents();
   pdl_wait();
   if (c >= C) return;
-  float s = 0.f;
-  for (int r = 0; r < R; ++r) s += in[(size_t)r * C + c];
-  out[c] = s;
+  // eight loads in flight per thread (the chain of dependent 4-byte loads made this a latency-bound 4-8 us kernel);
+  // the summation order is still fixed: bit-reproducible
+  float s[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) s[u] = 0.f;
+  int r = 0;
+  for (; r + 8 <= R; r += 8) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = in[(size_t)(r + u) * C + c];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s[u] += v[u];
+  }
+  for (; r < R; ++r) s[0] += in[(size_t)r * C + c];
+  out[c] = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
 }
 
 // partial[chunk][c] = sum of rows [chunk*RPC, (chunk+1)*RPC) of in (R x C, row stride ld): thread = column, coalesced rows
@@ -353,16 +365,24 @@ colsum_partial_kernel(const float* __restrict__ in, int64_t ld, float* __restric
   const int c = blockIdx.x * 128 + threadIdx.x;
   const int r0 = blockIdx.y * kColsumRows, r1 = min(R, r0 + kColsumRows);
   if (c >= C) return;
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  // sixteen loads in flight per thread: 8 round trips per 128-row chunk instead of 32
+  float s[16];
+#pragma unroll
+  for (int u = 0; u < 16; ++u) s[u] = 0.f;
   int r = r0;
-  for (; r + 4 <= r1; r += 4) {
-    s0 += __ldg(in + (size_t)r * ld + c);
-    s1 += __ldg(in + (size_t)(r + 1) * ld + c);
-    s2 += __ldg(in + (size_t)(r + 2) * ld + c);
-    s3 += __ldg(in + (size_t)(r + 3) * ld + c);
+  for (; r + 16 <= r1; r += 16) {
+    float v[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) v[u] = __ldg(in + (size_t)(r + u) * ld + c);
+#pragma unroll
+    for (int u = 0; u < 16; ++u) s[u] += v[u];
   }
-  for (; r < r1; ++r) s0 += __ldg(in + (size_t)r * ld + c);
-  partial[(size_t)blockIdx.y * C + c] = (s0 + s1) + (s2 + s3);
+  for (; r < r1; ++r) s[0] += __ldg(in + (size_t)r * ld + c);
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1)
+#pragma unroll
+    for (int u = 0; u < o; ++u) s[u] += s[u + o];
+  partial[(size_t)blockIdx.y * C + c] = s[0];
 }
 
 struct DecodeWs {

@@ -1408,7 +1408,7 @@ int check_common(const void* a, const void* rois, const void* o, int B, int C, i
   L2S_REQUIRE(pool == 7, L2S_ERR_SHAPE, "roi_crop: pool must be 7 (cfg.POOLING_SIZE), got %d", pool);
   L2S_REQUIRE(C % 4 == 0, L2S_ERR_SHAPE, "roi_crop: C must be a multiple of 4, got %d", C);
   L2S_REQUIRE(aligned16(a) && aligned16(o), L2S_ERR_ALIGN, "roi_crop: map / pooled pointers must be 16-byte aligned");
-  L2S_REQUIRE((flags & ~(L2S_CROP_MAX_POOL | L2S_CROP_ALIGN | L2S_CROP_BWD_RANKED)) == 0, L2S_ERR_ARG,
+  L2S_REQUIRE((flags & ~(L2S_CROP_MAX_POOL | L2S_CROP_ALIGN | L2S_CROP_BWD_RANKED | L2S_CROP_WS_PREPARED)) == 0, L2S_ERR_ARG,
               "roi_crop: unknown flags %d", flags);
   if (flags & L2S_CROP_ALIGN)
     L2S_REQUIRE(im_h > 1.f && im_w > 1.f, L2S_ERR_ARG, "roi_crop: align mode needs the image size");
@@ -1453,14 +1453,21 @@ struct Prep {
   SepRecX* sepx;
 };
 
-// bins the ROIs by batch index (2 small launches)
-int prepare_order(const float* rois, const CropGeom& g, void* ws, cudaStream_t st, Prep* p) {
+// where the binning and the records live inside the caller's workspace
+void prep_pointers(const CropGeom& g, void* ws, Prep* p) {
   int* counts = reinterpret_cast<int*>(ws);
   p->seg = counts + g.B;
   p->order = counts + 2 * g.B + 1;
   p->table = reinterpret_cast<unsigned char*>(ws) + table_offset(g.B, g.N);
   p->sep = reinterpret_cast<SepRec*>(p->table + (size_t)g.N * g.rec);
   p->sepx = reinterpret_cast<SepRecX*>(p->table + (size_t)g.N * g.rec + (g.S == 7 ? (size_t)g.N * sizeof(SepRec) : 0));
+}
+
+// bins the ROIs by batch index (2 small launches); `reuse`: the forward call already did (L2S_CROP_WS_PREPARED)
+int prepare_order(const float* rois, const CropGeom& g, void* ws, cudaStream_t st, Prep* p, bool reuse = false) {
+  prep_pointers(g, ws, p);
+  if (reuse) return L2S_OK;
+  int* counts = reinterpret_cast<int*>(ws);
   roi_count_kernel<<<g.B, 256, 0, st>>>(rois, g.N, counts);
   L2S_LAUNCH_OK("roi_count_kernel");
   roi_order_kernel<<<g.B, 256, 0, st>>>(rois, g.N, counts, p->seg, p->order);
@@ -1470,13 +1477,24 @@ int prepare_order(const float* rois, const CropGeom& g, void* ws, cudaStream_t s
 }
 
 // ... and writes the per-sample geometry records (forward, ranked backward, 7x7 row-owner backward)
-int prepare(const float* rois, const CropGeom& g, int cgn, void* ws, cudaStream_t st, Prep* p) {
-  int rc = prepare_order(rois, g, ws, st, p);
-  if (rc) return rc;
+int prepare(const float* rois, const CropGeom& g, int cgn, void* ws, cudaStream_t st, Prep* p, bool reuse = false) {
+  int rc = prepare_order(rois, g, ws, st, p, reuse);
+  if (rc || reuse) return rc;
   roi_geom_kernel<<<g.N, g.S == 7 ? 64 : 256, 0, st>>>(rois, p->order, p->seg, p->table, g.S == 7 ? p->sep : nullptr, g, cgn);
   L2S_LAUNCH_OK("roi_geom_kernel");
   count_launch();
   return L2S_OK;
+}
+
+// whether l2s_roi_crop_fwd takes the opt-in row-mirror kernel for this shape (it then writes the ROI binning and its own
+// separable records, but not the geometry table / 7x7 records the default forward leaves in the workspace)
+bool fwd_uses_row_mirror(int H, int W, bool maxpool) {
+  static const bool rows7 = env_flag("L2S_CROP_FWD_ROWS"), table_fwd = env_flag("L2S_CROP_FWD_TABLE");
+  if (!rows7 || table_fwd) return false;
+  const size_t cap = (size_t)max_smem_optin() - 1024;
+  for (int c : {32, 16})
+    if (fwd_rows_smem(H, W, c, maxpool) <= cap) return true;
+  return false;
 }
 
 template <int CC, bool MP>
@@ -1557,7 +1575,7 @@ extern "C" int l2s_roi_crop_fwd(const float* bottom, const float* rois, float* o
     int cc = 0;
     for (int c : {32, 16})
       if (fwd_rows_smem(H, W, c, g.maxpool) <= cap) { cc = c; break; }
-    if (cc && !table_fwd && rows7) {
+    if (cc && !table_fwd && rows7) {   // == fwd_uses_row_mirror(H, W, g.maxpool)
       rc = prepare_order(rois, g, workspace, st, &pr);
       if (rc) return rc;
       roi_sepx_kernel<<<g.N, 64, 0, st>>>(rois, pr.order, pr.seg, pr.sepx, g, cc + 1, kRowWarps * (32 / cc));
@@ -1619,13 +1637,17 @@ extern "C" int l2s_roi_crop_bwd(const float* dout, const float* rois, const uint
               "roi_crop: feature map %dx%d does not fit the shared-memory staging", H, W);
   const size_t cap = (size_t)max_smem_optin() - 1024;
   const bool ranked = (flags & L2S_CROP_BWD_RANKED) != 0;
+  // L2S_CROP_WS_PREPARED: the workspace is the one the forward call with the same arguments filled -- the ROI binning
+  // (always) and the geometry table / 7x7 separable records (default forward kernels) are reused instead of recomputed
+  const bool ws_order = (flags & L2S_CROP_WS_PREPARED) != 0;
+  const bool ws_table = ws_order && !fwd_uses_row_mirror(H, W, g.maxpool != 0);
   Prep pr;
   // 7x7 row-owner kernel: needs the whole 32-channel accumulator with guard columns + the tile ring in shared memory
   pl.smem_rows = (((size_t)H * (W + 4) * kRowLd + 3) & ~(size_t)3) * 4 +
                  kRowStages * kRowGroup * ((size_t)32 * kPP * 4 + sizeof(SepRec)) + 128;
   static const bool force_generic = env_flag("L2S_CROP_BWD_ROWSX");   // diagnostics: generic row-owner kernel for 7x7 too
   if (!g.maxpool && pl.cc == 32 && pl.smem_rows <= cap && !ranked && !force_generic) {
-    rc = prepare(rois, g, pl.cc / 4, workspace, st, &pr);
+    rc = ws_table ? prepare(rois, g, pl.cc / 4, workspace, st, &pr, true) : prepare(rois, g, pl.cc / 4, workspace, st, &pr);
     if (rc) return rc;
     auto kern = roi_crop_bwd_rows_kernel;
     L2S_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem_rows));
@@ -1642,7 +1664,7 @@ extern "C" int l2s_roi_crop_bwd(const float* dout, const float* rois, const uint
       if (rowsx_smem(H, W, c, g.maxpool, 2) <= cap) { cc = c; break; }
     if (cc) {
       for (nst = 2; nst < kRowXMaxStages && rowsx_smem(H, W, cc, g.maxpool, nst + 1) <= cap; ++nst) {}
-      rc = prepare_order(rois, g, workspace, st, &pr);
+      rc = prepare_order(rois, g, workspace, st, &pr, ws_order);
       if (rc) return rc;
       roi_sepx_kernel<<<g.N, 64, 0, st>>>(rois, pr.order, pr.seg, pr.sepx, g, cc + 1, kRowWarps * (32 / cc));
       L2S_LAUNCH_OK("roi_sepx_kernel");
@@ -1663,7 +1685,7 @@ extern "C" int l2s_roi_crop_bwd(const float* dout, const float* rois, const uint
       return L2S_OK;
     }
   }
-  rc = prepare(rois, g, pl.cc / 4, workspace, st, &pr);
+  rc = prepare(rois, g, pl.cc / 4, workspace, st, &pr, ws_table);
   if (rc) return rc;
   const int* seg = pr.seg;
   const unsigned char* table = pr.table;

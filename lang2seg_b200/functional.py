@@ -6,6 +6,8 @@ raises.  Shapes are the reference's logical NCHW shapes.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib
@@ -13,7 +15,7 @@ from ._lib import call, f32c, ptr, stream
 
 NUM_FILTERS = 7
 GATE_SIGMOID, GATE_LINEAR = 0, 1
-CROP_MAX_POOL, CROP_ALIGN, CROP_BWD_RANKED = 1, 2, 4
+CROP_MAX_POOL, CROP_ALIGN, CROP_BWD_RANKED, CROP_WS_PREPARED = 1, 2, 4, 8
 
 
 def _ws(nbytes, device):
@@ -105,20 +107,18 @@ class _RoICrop(torch.autograd.Function):
         ws = _ws(nbytes, bottom.device)
         call("l2s_roi_crop_fwd", ptr(bottom), ptr(rois), ptr(out), ptr(arg), B, C, H, W, N, pool, flags,
              float(im_h), float(im_w), ptr(ws), nbytes, stream())
-        ctx.save_for_backward(rois, arg)
+        ctx.save_for_backward(rois, arg, ws)      # the workspace keeps the ROI binning + geometry records for the backward
         ctx.meta = (B, C, H, W, N, pool, flags, float(im_h), float(im_w))
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        rois, arg = ctx.saved_tensors
+        rois, arg, ws = ctx.saved_tensors
         B, C, H, W, N, pool, flags, im_h, im_w = ctx.meta
         dout = f32c(dout)
         dbottom = torch.empty(B, C, H, W, device=dout.device, dtype=torch.float32)
-        nbytes = _lib.size("l2s_roi_crop_workspace_bytes", B, N, flags)
-        ws = _ws(nbytes, dout.device)
-        call("l2s_roi_crop_bwd", ptr(dout), ptr(rois), ptr(arg), ptr(dbottom), B, C, H, W, N, pool, flags,
-             im_h, im_w, ptr(ws), nbytes, stream())
+        call("l2s_roi_crop_bwd", ptr(dout), ptr(rois), ptr(arg), ptr(dbottom), B, C, H, W, N, pool,
+             flags | CROP_WS_PREPARED, im_h, im_w, ptr(ws), ws.numel(), stream())
         return dbottom, None, None, None, None, None
 
 
@@ -571,8 +571,8 @@ class _Att2in2Decode(torch.autograd.Function):
              ptr(aw), ptr(c_all), ptr(a2c_all), ptr(pi_all), ptr(dcat_all), ptr(da2c_all), ptr(dres_all), ptr(de_all),
              ptr(dp_att), ptr(datt), ptr(dalpha), T, B, A, D, Dh, ptr(ws), nbytes, stream())
         # weight gradients: one GEMM each over the stacked rows (h_{-1} = 0 contributes nothing)
-        dw_cat = wgrad_f32(dcat_all[1:].reshape(-1, LC), h_all[:-1].reshape(-1, D))
-        dw_a2c = wgrad_f32(da2c_all.reshape(-1, 2 * D), res_all.reshape(-1, D))
+        dw_cat = wgrad(dcat_all[1:].reshape(-1, LC), h_all[:-1].reshape(-1, D))
+        dw_a2c = wgrad(da2c_all.reshape(-1, 2 * D), res_all.reshape(-1, D))
         return (dcat_all[:, :, Dh:], datt, dp_att, dw_cat[:Dh], colsum(dcat_all.view(T * B, LC)[:, :Dh]), dw_cat[Dh:], dw_a2c,
                 colsum(da2c_all), dalpha.view(aw_shape), de_all.sum().reshape(ab_shape))
 
@@ -682,8 +682,8 @@ class _BiLSTM(torch.autograd.Function):
         zero = h_all.new_zeros(1, B, H)
         hp_f = torch.cat([zero, h_all[:-1, 0]], 0)           # state before time t, forward direction
         hp_b = torch.cat([h_all[1:, 1], zero], 0)            # ... backward direction (previous = time t+1)
-        dw_f = wgrad_f32(dG5[:, :, 0].transpose(0, 1).reshape(L * B, 4 * H), hp_f.reshape(L * B, H))
-        dw_b = wgrad_f32(dG5[:, :, 1].transpose(0, 1).reshape(L * B, 4 * H), hp_b.reshape(L * B, H))
+        dw_f = wgrad(dG5[:, :, 0].transpose(0, 1).reshape(L * B, 4 * H), hp_f.reshape(L * B, H))
+        dw_b = wgrad(dG5[:, :, 1].transpose(0, 1).reshape(L * B, 4 * H), hp_b.reshape(L * B, H))
         return dG, dw_f, dw_b, None
 
 
@@ -890,6 +890,24 @@ def wgrad_f32(dy, x):
     D = torch.empty(N, K, device=dy.device, dtype=torch.float32)
     call("l2s_gemm_f32", ptr(dy), ptr(x), ptr(D), N, K, R, 1, N, 1, K, K, 0, stream())
     return D
+
+
+def wgrad(dy, x):
+    """dW = dy^T @ x (dy (R,N), x (R,K) -> (N,K)) for the recurrences' weights.  With a few hundred stacked rows (T*B of
+    the decode loop, L*B of the bi-LSTM) the FFMA GEMM above runs for ~55 us per call at a quarter of the fp32 peak; the
+    tcgen05 bf16x3 GEMM reads the same operands in place through MN-major descriptors (no transposes) and needs no
+    split-K here (16-48 output tiles, 8-9 k-blocks each), so the result stays bit-reproducible.  L2S_WGRAD_FFMA=1 keeps
+    the FFMA kernel (A/B)."""
+    R, N = dy.shape
+    K = x.shape[1]
+    if R >= 256 and N % 8 == 0 and K % 8 == 0 and not _WGRAD_FFMA:
+        dyh, dyl = split_bf16(dy)
+        xh, xl = split_bf16(x)
+        return gemm_bf16x3(dyh, dyl, xh, xl, N, K, R, a_mn=True, b_mn=True, split_k=1)
+    return wgrad_f32(dy, x)
+
+
+_WGRAD_FFMA = os.environ.get("L2S_WGRAD_FFMA", "0") == "1"
 
 
 def gemm_f32(A, B, accumulate=False, out=None):

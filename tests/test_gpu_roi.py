@@ -258,3 +258,37 @@ def test_crop_bench_scale_properties(max_pool):
             got = gY[e:e + 1]
         (gref,) = torch.autograd.grad((ref * Ge).sum(), ye)
         assert relerr(got, gref) < TOL
+
+
+@pytest.mark.parametrize("max_pool", [False, True, "ranked"])
+def test_crop_bwd_workspace_reuse_is_bit_identical(max_pool):
+    """The autograd path hands the forward's workspace (ROI binning + geometry records) to the backward
+    (L2S_CROP_WS_PREPARED); a stand-alone l2s_roi_crop_bwd call with a fresh workspace must give the same bits."""
+    F = _f()
+    from lang2seg_b200 import _lib
+    from lang2seg_b200._lib import call, ptr, stream
+    ranked = max_pool == "ranked"
+    mp = max_pool is True
+    B, C, H, W, N = 3, 64, 32, 32, 40
+    g = torch.Generator().manual_seed(77)
+    bottom = torch.randn(B, C, H, W, generator=g).cuda().requires_grad_(True)
+    rois = torch.cat([R.synth_rois(g, N, H * 16, W * 16, b) for b in range(B)])
+    rois = rois[torch.randperm(rois.shape[0], generator=g)].cuda()
+    out = F.roi_crop(bottom, rois, max_pool=mp, bwd_ranked=ranked)
+    G = torch.randn(out.shape, generator=g).cuda()
+    (gb,) = torch.autograd.grad((out * G).sum(), bottom)
+    flags = (F.CROP_MAX_POOL if mp else 0) | (F.CROP_BWD_RANKED if ranked else 0)
+    arg = None
+    nb = _lib.size("l2s_roi_crop_workspace_bytes", B, rois.shape[0], flags)
+    ws = torch.empty(nb, dtype=torch.uint8, device="cuda")
+    if mp:      # the stand-alone call needs the winners: rerun the forward through the C ABI
+        arg = torch.empty(out.shape, dtype=torch.uint8, device="cuda")
+        out2 = torch.empty_like(out)
+        call("l2s_roi_crop_fwd", ptr(bottom.detach()), ptr(rois), ptr(out2), ptr(arg), B, C, H, W, rois.shape[0], 7, flags,
+             0.0, 0.0, ptr(ws), nb, stream())
+        assert torch.equal(out2, out)
+        ws = torch.empty(nb, dtype=torch.uint8, device="cuda")
+    gb2 = torch.empty_like(gb)
+    call("l2s_roi_crop_bwd", ptr(G), ptr(rois), ptr(arg), ptr(gb2), B, C, H, W, rois.shape[0], 7, flags, 0.0, 0.0, ptr(ws), nb,
+         stream())
+    assert torch.equal(gb, gb2)
