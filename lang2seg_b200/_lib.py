@@ -61,6 +61,7 @@ SIGNATURES = {
     "l2s_bilstm_workspace_bytes": (_sz, [_i] * 3),
     "l2s_bilstm_fwd": (_i, [_vp] * 7 + [_i] * 3 + [_vp, _sz, _vp]),
     "l2s_bilstm_bwd": (_i, [_vp] * 7 + [_i] * 3 + [_vp, _sz, _vp]),
+    "l2s_embedding_bwd": (_i, [_vp] * 3 + [_i] * 3 + [_vp]),
     "l2s_linear_small_workspace_bytes": (_sz, [_i] * 3),
     "l2s_linear_small": (_i, [_vp] * 4 + [_i] * 7 + [_vp, _sz, _vp]),
     "l2s_logsoftmax_nll_fwd": (_i, [_vp] * 5 + [_i] * 2 + [_vp]),

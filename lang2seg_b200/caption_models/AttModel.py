@@ -72,7 +72,7 @@ class AttModel(nn.Module):
         self.att_feat_size = opt["att_feat_size"]
         self.att_hid_size = opt["att_hid_size"]
         self.ss_prob = 0.0
-        self.embed = nn.Sequential(nn.Embedding(self.vocab_size + 1, self.input_encoding_size), nn.ReLU(),
+        self.embed = nn.Sequential(L2F.Embedding(self.vocab_size + 1, self.input_encoding_size), nn.ReLU(),
                                    nn.Dropout(self.drop_prob_lm))
         self.fc_embed = nn.Sequential(nn.Linear(self.fc_feat_size, self.rnn_size), nn.ReLU(),
                                       nn.Dropout(self.drop_prob_lm))

@@ -175,6 +175,33 @@ __global__ void split_kernel(const float* __restrict__ src, uint16_t* __restrict
   }
 }
 
+// Contiguous case (cols == ld_src == ld_dst, 8 | rows * cols, 16-byte aligned): thread = 8 consecutive elements, two
+// 16-byte loads and one 16-byte store per plane, packed cvt.rn.bf16x2 -- same rounding as split2.  The element-wise
+// kernel above pays a 64-bit division and two 2-byte stores per element (the 19 M elements of the att_feats operand took
+// longer than the GEMM they feed).
+__device__ __forceinline__ void split_pair2(float a, float b, uint32_t* hi, uint32_t* lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  const uint32_t hu = *reinterpret_cast<const uint32_t*>(&h);
+  const float ra = a - __uint_as_float(hu << 16), rb = b - __uint_as_float(hu & 0xffff0000u);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(ra, rb);
+  *hi = hu;
+  *lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+__global__ void __launch_bounds__(256)
+split_vec_kernel(const float4* __restrict__ src, uint4* __restrict__ hi, uint4* __restrict__ lo, int64_t n8) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+    const float4 a = __ldcs(src + 2 * i), b = __ldcs(src + 2 * i + 1);
+    uint4 h, l;
+    split_pair2(a.x, a.y, &h.x, &l.x);
+    split_pair2(a.z, a.w, &h.y, &l.y);
+    split_pair2(b.x, b.y, &h.z, &l.z);
+    split_pair2(b.z, b.w, &h.w, &l.w);
+    hi[i] = h;
+    lo[i] = l;
+  }
+}
+
 // ---- generic epilogue ------------------------------------------------------------------------
 struct EpiGeneric {
   float* D;
@@ -761,7 +788,17 @@ extern "C" int l2s_split_bf16(const float* src, uint16_t* hi, uint16_t* lo, int6
   L2S_REQUIRE(src && hi && lo, L2S_ERR_ARG, "split_bf16: null pointer");
   L2S_REQUIRE(rows >= 0 && cols >= 0 && ld_dst >= cols && ld_src >= cols, L2S_ERR_SHAPE, "split_bf16: bad shape");
   if (rows * ld_dst == 0) return L2S_OK;
-  const int blocks = (int)std::min<int64_t>((rows * ld_dst + 255) / 256, (int64_t)sm_count() * 16);
+  const int64_t total = rows * ld_dst;
+  if (cols == ld_src && cols == ld_dst && total % 8 == 0 && aligned16(src) && aligned16(hi) && aligned16(lo)) {
+    const int64_t n8 = total / 8;
+    const int blocks = (int)std::min<int64_t>((n8 + 255) / 256, (int64_t)sm_count() * 16);
+    split_vec_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(src), reinterpret_cast<uint4*>(hi),
+                                                               reinterpret_cast<uint4*>(lo), n8);
+    L2S_LAUNCH_OK("split_vec_kernel");
+    count_launch();
+    return L2S_OK;
+  }
+  const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 16);
   split_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, hi, lo, rows, cols, ld_src, ld_dst);
   L2S_LAUNCH_OK("split_kernel");
   count_launch();

@@ -874,7 +874,10 @@ def dense(x, weight, bias=None):
     x2 = x.reshape(-1, x.shape[-1])
     M, K = x2.shape
     N = weight.shape[0]
-    if M >= 256 and K % 8 == 0 and N % 8 == 0:
+    # few rows but a large weight (filter generator: 48 expressions x (7C + 8) x 1024): the skinny FFMA kernels then
+    # spend 46 (fwd) + 79 (dX incl. the transposed copy of W) + 55 (dW) us per step on work the tensor pipe does in ~10 us
+    # each -- the mostly empty 128-row tiles do not matter, the weight traffic does
+    if (M >= 256 or (M >= 8 and N * K >= (1 << 21) and not _DENSE_SMALL_FFMA)) and K % 8 == 0 and N % 8 == 0:
         y = linear(x2, weight, bias)
     else:
         y = linear_small_fn(x2, weight, bias)
@@ -890,6 +893,44 @@ def wgrad_f32(dy, x):
     D = torch.empty(N, K, device=dy.device, dtype=torch.float32)
     call("l2s_gemm_f32", ptr(dy), ptr(x), ptr(D), N, K, R, 1, N, 1, K, K, 0, stream())
     return D
+
+
+class _Embedding(torch.autograd.Function):
+    """nn.Embedding lookup whose weight gradient is the library's fixed-order row sum (l2s_embedding_bwd) instead of
+    torch's sort + segmented reduce (24-30 us per call for the ~500 tokens of a step)."""
+
+    @staticmethod
+    def forward(ctx, idx, weight):
+        ctx.save_for_backward(idx)
+        ctx.vd = weight.shape
+        return weight.index_select(0, idx.reshape(-1)).view(*idx.shape, weight.shape[1])
+
+    @staticmethod
+    def backward(ctx, dy):
+        (idx,) = ctx.saved_tensors
+        V, D = ctx.vd
+        dy = f32c(dy).view(-1, D)
+        dW = torch.empty(V, D, device=dy.device, dtype=torch.float32)
+        call("l2s_embedding_bwd", ptr(idx.reshape(-1).contiguous()), ptr(dy), ptr(dW), dy.shape[0], V, D, stream())
+        return None, dW
+
+
+def embedding(idx, weight):
+    """weight[idx] (idx int64 of any shape, weight (V,D) fp32 with D % 4 == 0)."""
+    return _Embedding.apply(idx, weight)
+
+
+class Embedding(torch.nn.Embedding):
+    """nn.Embedding with the same parameter name / shape (checkpoints load unchanged); CUDA training lookups go through
+    `embedding` above, everything else (CPU tensors, padding_idx / max_norm / sparse options) through torch."""
+
+    def forward(self, input):
+        if (input.is_cuda and self.weight.is_cuda and input.dtype == torch.int64 and self.padding_idx is None
+                and self.max_norm is None and not self.sparse and not self.scale_grad_by_freq
+                and self.weight.dtype == torch.float32 and self.weight.shape[1] % 4 == 0
+                and torch.is_grad_enabled() and self.weight.requires_grad):
+            return embedding(input, self.weight)
+        return super().forward(input)
 
 
 def wgrad(dy, x):
@@ -908,6 +949,7 @@ def wgrad(dy, x):
 
 
 _WGRAD_FFMA = os.environ.get("L2S_WGRAD_FFMA", "0") == "1"
+_DENSE_SMALL_FFMA = os.environ.get("L2S_DENSE_SMALL_FFMA", "0") == "1"      # A/B: skinny FFMA kernels for few-row linears
 
 
 def gemm_f32(A, B, accumulate=False, out=None):

@@ -19,7 +19,7 @@ class RNNEncoder(nn.Module):
                  input_dropout_p=0, dropout_p=0, n_layers=1, rnn_type="lstm", variable_lengths=True):
         super().__init__()
         self.variable_lengths = variable_lengths
-        self.embedding = nn.Embedding(vocab_size, word_embedding_size)
+        self.embedding = L2F.Embedding(vocab_size, word_embedding_size)
         self.input_dropout = nn.Dropout(input_dropout_p)
         self.mlp = nn.Sequential(nn.Linear(word_embedding_size, word_vec_size), nn.ReLU())
         self.rnn_type = rnn_type

@@ -266,3 +266,28 @@ def test_colsum_vs_fp64(R, C):
     assert relerr(F.colsum(x[:, :C]), ref[:, :C].sum(0)) < 1e-6          # row-strided view, no copy
     assert relerr(F.colsum(x.reshape(R, 1, C + 5)), ref.sum(0)) < 1e-6   # any leading dimensions
     assert torch.equal(F.colsum(x[:, :C]), F.colsum(x[:, :C]))           # fixed order
+
+
+@pytest.mark.parametrize("shape,V,D", [((11, 48), 2000, 512), ((48, 10), 1999, 512), ((3,), 7, 4), ((2, 1500), 50, 2052)])
+def test_embedding_vs_torch(shape, V, D):
+    """L2F.Embedding: same lookup, weight gradient = fixed-order sum of the matching rows (duplicates, unused rows = 0,
+    more rows than one index chunk, rows wider than one column block)."""
+    import lang2seg_b200.functional as F
+    g = torch.Generator().manual_seed(V + D)
+    idx = torch.randint(0, V, shape, generator=g).cuda()
+    ref = torch.nn.Embedding(V, D).cuda()
+    mod = F.Embedding(V, D).cuda()
+    mod.load_state_dict(ref.state_dict())
+    G = torch.randn(*shape, D, generator=g).cuda()
+    out = mod(idx)
+    assert torch.equal(out, ref(idx))
+    (out * G).sum().backward()
+    (ref(idx) * G).sum().backward()
+    want = torch.zeros(V, D, dtype=torch.float64).index_add_(0, idx.reshape(-1).cpu(), G.reshape(-1, D).double().cpu())
+    assert relerr(mod.weight.grad, want) < 1e-6 and relerr(ref.weight.grad, want) < 1e-6
+    g1 = mod.weight.grad.clone()
+    mod.weight.grad = None
+    (mod(idx) * G).sum().backward()
+    assert torch.equal(g1, mod.weight.grad)                                # bit-reproducible
+    with torch.no_grad():
+        assert torch.equal(mod(idx), out)                                  # no-grad lookups take torch's path
