@@ -375,7 +375,7 @@ size_t l2s_colsum_workspace_bytes(int R, int C);
 int l2s_colsum(const float* in, int64_t ld, float* out, int R, int C, void* workspace, size_t workspace_bytes,
                l2s_stream_t stream);
 /* Weight gradient of nn.Embedding (AttModel.py:41 `embed`, lang_encoder.py:22 `embedding`): dW[v,:] = sum of dy[r,:] over
- * the rows r with idx[r] == v, in ascending r (fixed order: bit-reproducible); rows of dW without a match are zero
+ * the rows r with idx[r] == v, in a fixed order (bit-reproducible); rows of dW without a match are zero
  * filled, so the caller does not clear dW.  idx values outside [0,V) are ignored.  D % 4 == 0, 16-byte aligned. */
 int l2s_embedding_bwd(const int64_t* idx, const float* dy, float* dW, int R, int V, int D, l2s_stream_t stream);
 size_t l2s_linear_small_workspace_bytes(int M, int N, int K);

@@ -341,21 +341,39 @@ __global__ void colsum_kernel(const float* __restrict__ in, float* __restrict__ 
   pdl_launch_dependents();
   pdl_wait();
   if (c >= C) return;
-  // eight loads in flight per thread (the chain of dependent 4-byte loads made this a latency-bound 4-8 us kernel);
-  // the summation order is still fixed: bit-reproducible
-  float s[8];
-#pragma unroll
-  for (int u = 0; u < 8; ++u) s[u] = 0.f;
+  float s = 0.f;
   int r = 0;
-  for (; r + 8 <= R; r += 8) {
-    float v[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) v[u] = in[(size_t)(r + u) * C + c];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) s[u] += v[u];
+  for (; r < R; ++r) s += in[(size_t)r * C + c];
+  out[c] = s;
+}
+
+// One-stage variant for up to ~1000 rows (the T*B = 528 rows of the decode chain, the 672 dalpha partials): CTA = 32
+// columns x 32 warps, warp w adds rows w, w + 32, ... (lane = column: one 128-byte line per row), the 32 partial sums are
+// added in warp order.  The two-stage pair below costs 32 dependent round trips + a second launch (10-14 us) for these
+// sizes; ptxas keeps only a couple of a thread's loads in flight, so the parallelism has to come from warps.
+constexpr int kColsumSmallWarps = 32;
+__global__ void __launch_bounds__(kColsumSmallWarps * 32)
+colsum_small_kernel(const float* __restrict__ in, int64_t ld, float* __restrict__ out, int R, int C) {
+  __shared__ float s[kColsumSmallWarps][33];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  float a0 = 0.f, a1 = 0.f;
+  if (c < C) {
+    int r = wid;
+    for (; r + kColsumSmallWarps < R; r += 2 * kColsumSmallWarps) {
+      a0 += __ldg(in + (size_t)r * ld + c);
+      a1 += __ldg(in + (size_t)(r + kColsumSmallWarps) * ld + c);
+    }
+    if (r < R) a0 += __ldg(in + (size_t)r * ld + c);
   }
-  for (; r < R; ++r) s[0] += in[(size_t)r * C + c];
-  out[c] = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
+  s[wid][lane] = a0 + a1;
+  __syncthreads();
+  if (wid == 0 && c < C) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < kColsumSmallWarps; ++w) t += s[w][lane];
+    out[c] = t;
+  }
 }
 
 // partial[chunk][c] = sum of rows [chunk*RPC, (chunk+1)*RPC) of in (R x C, row stride ld): thread = column, coalesced rows
@@ -365,24 +383,16 @@ colsum_partial_kernel(const float* __restrict__ in, int64_t ld, float* __restric
   const int c = blockIdx.x * 128 + threadIdx.x;
   const int r0 = blockIdx.y * kColsumRows, r1 = min(R, r0 + kColsumRows);
   if (c >= C) return;
-  // sixteen loads in flight per thread: 8 round trips per 128-row chunk instead of 32
-  float s[16];
-#pragma unroll
-  for (int u = 0; u < 16; ++u) s[u] = 0.f;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
   int r = r0;
-  for (; r + 16 <= r1; r += 16) {
-    float v[16];
-#pragma unroll
-    for (int u = 0; u < 16; ++u) v[u] = __ldg(in + (size_t)(r + u) * ld + c);
-#pragma unroll
-    for (int u = 0; u < 16; ++u) s[u] += v[u];
+  for (; r + 4 <= r1; r += 4) {
+    s0 += __ldg(in + (size_t)r * ld + c);
+    s1 += __ldg(in + (size_t)(r + 1) * ld + c);
+    s2 += __ldg(in + (size_t)(r + 2) * ld + c);
+    s3 += __ldg(in + (size_t)(r + 3) * ld + c);
   }
-  for (; r < r1; ++r) s[0] += __ldg(in + (size_t)r * ld + c);
-#pragma unroll
-  for (int o = 8; o > 0; o >>= 1)
-#pragma unroll
-    for (int u = 0; u < o; ++u) s[u] += s[u + o];
-  partial[(size_t)blockIdx.y * C + c] = s[0];
+  for (; r < r1; ++r) s0 += __ldg(in + (size_t)r * ld + c);
+  partial[(size_t)blockIdx.y * C + c] = (s0 + s1) + (s2 + s3);
 }
 
 struct DecodeWs {
@@ -438,43 +448,64 @@ extern "C" int l2s_linear_small(const float* A, const float* W, const float* bia
   return launch_linear_small(A, lda, W, ldw, bias, D, ldd, M, N, K, accumulate, workspace, workspace_bytes, st);
 }
 
-// dW[v,:] = sum_{r: idx[r] == v} dy[r,:], r ascending.  CTA = vocabulary row v: the R indices are scanned from shared
-// memory in chunks (block-uniform branch), the matching rows are added as float4 by thread = 4 columns.  torch's
-// embedding_dense_backward (sort + segmented reduce) takes 24-30 us for the 500 rows of a step; this is one launch of a
-// few microseconds with the zero fill of the untouched rows included.
-constexpr int kEmbChunk = 1024;
-__global__ void __launch_bounds__(128)
+// dW[v,:] = sum_{r: idx[r] == v} dy[r,:] in a FIXED order (bit-reproducible).  CTA = vocabulary row v, 16 warps.  Warp w
+// takes the 32-row blocks w, w + 16, ... of the index list (lane = index, one ballot per block) and adds the matching
+// rows, four float4 columns per lane; the warps' partial sums are then added in warp order by warp 0.
+// Zero-padded captions make token 0 match half of the ~500 rows of a step, and ptxas keeps only two of a lane's loads in
+// flight however the loop is written -- versions with 4 warps that walked the matches of that one CTA took 25-75 us per
+// launch (torch's sort + segmented reduce: 24-30 us); with 16 warps the matches of the hot row are spread over 16
+// independent load streams.  The zero fill of unmatched rows is part of the store.
+constexpr int kEmbWarps = 16;
+__global__ void __launch_bounds__(kEmbWarps * 32)
 embedding_bwd_kernel(const int64_t* __restrict__ idx, const float* __restrict__ dy, float* __restrict__ dW, int R, int D) {
-  __shared__ int s_idx[kEmbChunk];
-  const int v = blockIdx.x, t = threadIdx.x;
+  __shared__ float4 s_acc[kEmbWarps - 1][128];
+  __shared__ int s_any;
+  const int v = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int nq = D >> 2;
-  // up to 4 float4 per thread (D <= 2048); wider rows loop over column blocks
-  for (int q0 = 0; q0 < nq; q0 += 4 * 128) {
+  for (int q0 = 0; q0 < nq; q0 += 128) {                 // column block of 128 float4: lane owns q0 + lane + 32 c
+    __syncthreads();                                      // s_acc / s_any of the previous column block read out
+    if (threadIdx.x == 0) s_any = 0;
+    __syncthreads();
     float4 acc[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int r0 = 0; r0 < R; r0 += kEmbChunk) {
-      const int nr = min(kEmbChunk, R - r0);
-      __syncthreads();
-      for (int i = t; i < nr; i += 128) s_idx[i] = (int)__ldg(idx + r0 + i);
-      __syncthreads();
-      for (int i = 0; i < nr; ++i) {
-        if (s_idx[i] != v) continue;
-        const float4* row = reinterpret_cast<const float4*>(dy + (size_t)(r0 + i) * D);
+    for (int c = 0; c < 4; ++c) acc[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool any = false;
+    for (int r0 = 32 * wid; r0 < R; r0 += 32 * kEmbWarps) {
+      const int r = r0 + lane;
+      const int my = r < R ? (int)__ldg(idx + r) : -1;
+      unsigned m = __ballot_sync(0xffffffffu, my == v);
+      any |= m != 0;
+      while (m) {
+        const float4* row = reinterpret_cast<const float4*>(dy + (size_t)(r0 + __ffs(m) - 1) * D);
+        m &= m - 1;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int q = q0 + u * 128 + t;
+        for (int c = 0; c < 4; ++c) {
+          const int q = q0 + lane + 32 * c;
           if (q < nq) {
             const float4 x = __ldg(row + q);
-            acc[u].x += x.x; acc[u].y += x.y; acc[u].z += x.z; acc[u].w += x.w;
+            acc[c].x += x.x; acc[c].y += x.y; acc[c].z += x.z; acc[c].w += x.w;
           }
         }
       }
     }
+    if (any && lane == 0) s_any = 1;                      // benign race: every writer stores 1
+    if (wid > 0) {
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int q = q0 + u * 128 + t;
-      if (q < nq) reinterpret_cast<float4*>(dW + (size_t)v * D)[q] = acc[u];
+      for (int c = 0; c < 4; ++c) s_acc[wid - 1][lane + 32 * c] = acc[c];
+    }
+    __syncthreads();
+    if (wid == 0) {
+      const bool some = s_any != 0;                       // rows nobody matched (most of the vocabulary): plain zero fill
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int q = q0 + lane + 32 * c;
+        if (some)
+          for (int w = 0; w < kEmbWarps - 1; ++w) {
+            const float4 p = s_acc[w][lane + 32 * c];
+            acc[c].x += p.x; acc[c].y += p.y; acc[c].z += p.z; acc[c].w += p.w;
+          }
+        if (q < nq) reinterpret_cast<float4*>(dW + (size_t)v * D)[q] = acc[c];
+      }
     }
   }
 }
@@ -483,7 +514,7 @@ extern "C" int l2s_embedding_bwd(const int64_t* idx, const float* dy, float* dW,
   L2S_REQUIRE(R >= 0 && V > 0 && D > 0 && D % 4 == 0, L2S_ERR_SHAPE, "embedding_bwd: bad shape R=%d V=%d D=%d", R, V, D);
   L2S_REQUIRE(dW && (R == 0 || (idx && dy)), L2S_ERR_ARG, "embedding_bwd: null pointer");
   L2S_REQUIRE(aligned16(dW) && (R == 0 || aligned16(dy)), L2S_ERR_ARG, "embedding_bwd: dy / dW must be 16-byte aligned");
-  embedding_bwd_kernel<<<V, 128, 0, (cudaStream_t)stream>>>(idx, dy, dW, R, D);
+  embedding_bwd_kernel<<<V, kEmbWarps * 32, 0, (cudaStream_t)stream>>>(idx, dy, dW, R, D);
   L2S_LAUNCH_OK("embedding_bwd_kernel");
   count_launch();
   return L2S_OK;
@@ -505,6 +536,12 @@ extern "C" int l2s_colsum(const float* in, int64_t ld, float* out, int R, int C,
   }
   L2S_REQUIRE(in, L2S_ERR_ARG, "colsum: null input");
   L2S_REQUIRE(workspace && workspace_bytes >= l2s_colsum_workspace_bytes(R, C), L2S_ERR_WORKSPACE, "colsum: workspace too small");
+  if (R <= 1024) {
+    colsum_small_kernel<<<(C + 31) / 32, kColsumSmallWarps * 32, 0, st>>>(in, ld, out, R, C);
+    L2S_LAUNCH_OK("colsum_small_kernel");
+    count_launch();
+    return L2S_OK;
+  }
   const int chunks = (R + kColsumRows - 1) / kColsumRows;
   float* partial = reinterpret_cast<float*>(workspace);
   colsum_partial_kernel<<<dim3((C + 127) / 128, chunks), 128, 0, st>>>(in, ld, partial, R, C);
@@ -621,8 +658,14 @@ extern "C" int l2s_att2in2_decode_bwd(const float* dh_all, const float* cat_all,
   L2S_CUDA_OK(cudaFuncSetAttribute(att_accum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   L2S_CUDA_OK(launch_chain(att_accum_kernel, dim3(nchunk, B), dim3(kAccThreads), smem, st, p_att, cat_all, LC, dres_all,
                            de_all, pi_all, alpha_w, dp_att, datt_feats, w.dalpha_part, T, B, A, D, Dh));
-  L2S_CUDA_OK(launch_chain(colsum_kernel, dim3((Dh + 127) / 128), dim3(128), 0, st, (const float*)w.dalpha_part, dalpha_w,
-                           nchunk * B, Dh));
+  if (nchunk * B <= 4096) {     // 672 partial rows at cfg-2: warps in parallel over the rows (the one-thread-per-column chain took 19 us)
+    colsum_small_kernel<<<(Dh + 31) / 32, kColsumSmallWarps * 32, 0, st>>>((const float*)w.dalpha_part, (int64_t)Dh, dalpha_w,
+                                                                         nchunk * B, Dh);
+    L2S_LAUNCH_OK("colsum_small_kernel");
+  } else {
+    L2S_CUDA_OK(launch_chain(colsum_kernel, dim3((Dh + 127) / 128), dim3(128), 0, st, (const float*)w.dalpha_part, dalpha_w,
+                             nchunk * B, Dh));
+  }
   count_launch(2);
   return L2S_OK;
 }

@@ -574,7 +574,7 @@ class _Att2in2Decode(torch.autograd.Function):
         dw_cat = wgrad(dcat_all[1:].reshape(-1, LC), h_all[:-1].reshape(-1, D))
         dw_a2c = wgrad(da2c_all.reshape(-1, 2 * D), res_all.reshape(-1, D))
         return (dcat_all[:, :, Dh:], datt, dp_att, dw_cat[:Dh], colsum(dcat_all.view(T * B, LC)[:, :Dh]), dw_cat[Dh:], dw_a2c,
-                colsum(da2c_all), dalpha.view(aw_shape), de_all.sum().reshape(ab_shape))
+                colsum(da2c_all), dalpha.view(aw_shape), colsum(de_all.view(T * B, -1)).sum().reshape(ab_shape))
 
 
 def att2in2_decode(i2h_all, att_feats, p_att, w_h2att, b_h2att, w_h2h, w_a2c, b_a2c, alpha_w, alpha_b):

@@ -20,6 +20,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", default="cfg2")
     ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--trace", default="", help="comma-separated kernel-name substrings (or 'all'): per-launch timeline of the last step")
     a = ap.parse_args()
     wl = WORKLOADS[a.workload]
     dev = torch.device("cuda:0")
@@ -50,6 +51,22 @@ def main():
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:70]:
         print("%-110s %8.1f %12.1f %6.2f%%" % (k, v[0] / a.steps, v[1] / a.steps, 100 * v[1] / tot))
 
+
+    # launch-by-launch timeline of the LAST step for the kernels matching --trace (name substring): start offset, duration
+    if a.trace:
+        evs = [ev for ev in prof.events() if ev.device_type == torch.autograd.DeviceType.CUDA]
+        evs.sort(key=lambda ev: ev.time_range.start)
+        per = len(evs) // a.steps
+        last = evs[-per:]
+        t0 = last[0].time_range.start
+        print("\n# timeline of the last step (%d device events), kernels matching %r" % (per, a.trace))
+        prev_end = t0
+        for ev in last:
+            dur = ev.device_time if hasattr(ev, "device_time") else ev.cuda_time
+            gap = ev.time_range.start - prev_end
+            prev_end = max(prev_end, ev.time_range.end)
+            if a.trace == "all" or any(p in ev.name for p in a.trace.split(",")):
+                print("%10.1f us  +%7.1f us  gap %6.1f  %s" % (ev.time_range.start - t0, dur, gap, ev.name[:120]))
 
     # framework-side operators by (inclusive) device time, with their input shapes
     print("\n# aten operators by device time (per step, inclusive of children)")
