@@ -195,6 +195,16 @@ class HotPathStep:
             if "dY" in self.parts:
                 self.g_Y = (torch.randn(E, wl["C"], wl["H"], wl["W"], generator=g) * 1e-4).to(device)
         self.one = torch.ones((), device=device)
+        # Independent branches of the step on their own streams (forward and -- through autograd's stream semantics --
+        # backward), so that the captured CUDA graph has parallel branches: the att2in2 branch is latency bound
+        # (persistent recurrences on 128 CTAs with 64 KB of shared memory each) and shares the SMs with bandwidth-bound
+        # kernels of the other branches; the mask head overlaps the encoder / filter-generator chain and the crops' tails.
+        # Measured on one box (profiles/r02_ab.md): cfg2 9.30 -> 9.05 ms/step, cfg3 8.28 -> 7.86, cfg4 2.29 -> 2.01.
+        # Only under graph capture: eager launches (the e2e leg) pay more for the stream switches than they gain.
+        # L2S_BENCH_STREAMS=0 keeps everything on one stream.
+        nstreams = int(os.environ.get("L2S_BENCH_STREAMS", "2"))
+        self.side = torch.cuda.Stream(device) if (nstreams >= 1 and "caption" in self.parts and not self.fwd_only) else None
+        self.side2 = torch.cuda.Stream(device) if (nstreams >= 2 and "mask" in self.parts and not self.fwd_only) else None
 
     def forward_only(self, d, meta):
         """cfg-1: the inference-side forward (network_cycle_response.py:576-596 without res5) -> a scalar checksum"""
@@ -217,17 +227,33 @@ class HotPathStep:
 
     def fwd_bwd(self, d, meta=None, split=False):
         """forward + backward of the chained hot path; leaves the gradients in p.grad.
-        split=True (N > 1): only the backward of the branches that end in the caption model and the heads runs here
-        (their gradient groups are then complete and can be all-reduced while `bwd_rest()` runs the remaining backward:
-        ROI crop -> dynamic filter -> filter generator -> language encoder)."""
+        split=True (N > 1): the backward runs down to the generated filters here (the caption / head gradient groups are
+        then complete and are all-reduced while `bwd_rest()` runs the remaining backward: filter generator -> language
+        encoder)."""
         net, parts = self.net, self.parts
         meta = meta if meta is not None else d.get("_meta", {})
         if self.fwd_only:
             return self.forward_only(d, meta)
         self.opt.zero_grad(set_to_none=True)      # N > 1: the fresh gradients are packed into the flat buffers below
         X = d["X"].requires_grad_(True)
+        cap_loss = att = None
+        branch = torch.cuda.is_current_stream_capturing()
+        if self.side is not None and branch:
+            cur = torch.cuda.current_stream()
+            self.side.wait_stream(cur)
+            with torch.cuda.stream(self.side):
+                att = d["att"].requires_grad_(True)
+                cap_loss = net._cap_loss_weight * net._caption_loss(d["fc"], att, d["cap"], d["msk"], steps=meta.get("steps"))
+        mask_loss = fc7 = None
+        if self.side2 is not None and branch:
+            cur = torch.cuda.current_stream()
+            self.side2.wait_stream(cur)
+            with torch.cuda.stream(self.side2):
+                fc7 = d["fc7"].requires_grad_(True)
+                net._mask_prediction(fc7, d["mlab"], d["mtgt"])
+                mask_loss = net._mask_loss(d["mlab"], d["mtgt"])
         gated = net._dynamic_filter(X, d["labels"], expr2img=d["e2i"], resp_target=d.get("resp_tgt"),
-                                    lengths=meta.get("lens"))
+                                    lengths=meta.get("lens"), cut_filters=split)
         loss_a, loss_b = 0, 0
         outs, grads = [], []
         if "resp" in parts:
@@ -238,23 +264,33 @@ class HotPathStep:
             outs.append(net._crop_pool_layer(gated, d["rois"], max_pool=False)); grads.append(self.g_pool)
         if "dY" in parts:
             outs.append(gated); grads.append(self.g_Y)
-        fc7 = att = None
-        if "mask" in parts:
+        if mask_loss is not None:
+            torch.cuda.current_stream().wait_stream(self.side2)
+            mask_loss.record_stream(torch.cuda.current_stream())
+            loss_a = loss_a + mask_loss
+        elif "mask" in parts:
             fc7 = d["fc7"].requires_grad_(True)
             net._mask_prediction(fc7, d["mlab"], d["mtgt"])   # prediction + mask loss as one node (fused backward)
             loss_a = loss_a + net._mask_loss(d["mlab"], d["mtgt"])
-        if "caption" in parts:
+        if "caption" in parts and cap_loss is None:
             att = d["att"].requires_grad_(True)
             loss_a = loss_a + net._cap_loss_weight * net._caption_loss(d["fc"], att, d["cap"], d["msk"],
                                                                        steps=meta.get("steps"))
+        elif cap_loss is not None:
+            torch.cuda.current_stream().wait_stream(self.side)
+            cap_loss.record_stream(torch.cuda.current_stream())
+            loss_a = loss_a + cap_loss
         roots_a = ([loss_a], [self.one]) if torch.is_tensor(loss_a) else ([], [])
         roots_b = (([loss_b] if torch.is_tensor(loss_b) else []) + outs, ([self.one] if torch.is_tensor(loss_b) else []) + grads)
         loss = (loss_a + loss_b).detach()
         if split:
-            if roots_a[0]:
-                torch.autograd.backward(*roots_a)
+            # everything except the filter generator + language encoder: the backward stops at the generated filters
+            # (their gradients are kept), so that the branches still overlap inside this graph and the all-reduce of
+            # the caption / head groups overlaps the rest
+            torch.autograd.backward(roots_a[0] + roots_b[0], roots_a[1] + roots_b[1])
+            stops = net._predictions.get("dynamic_filters")        # ((filt, fuse), their detached leaves) or None
             self.flat.pack(self.EARLY_GROUPS)
-            self._pending = (roots_b, X, fc7, att)
+            self._pending = (stops, X, fc7, att)
         else:
             torch.autograd.backward(roots_a[0] + roots_b[0], roots_a[1] + roots_b[1])
             if self.flat is not None:
@@ -264,10 +300,10 @@ class HotPathStep:
 
     def bwd_rest(self):
         """second half of a split backward (see fwd_bwd)"""
-        roots_b, X, fc7, att = self._pending
+        stops, X, fc7, att = self._pending
         self._pending = None
-        if roots_b[0]:
-            torch.autograd.backward(*roots_b)
+        if stops:
+            torch.autograd.backward(list(stops[0]), [t.grad for t in stops[1]])
         self.flat.pack([n for n in self.flat.names if n not in self.EARLY_GROUPS])
         self._finish(X, fc7, att)
 
@@ -864,7 +900,8 @@ def main():
     pk = peaks()
     E = wl["I"] * wl["EPI"]
 
-    step = HotPathStep(wl, dev, world)
+    force_split = os.environ.get("L2S_BENCH_FORCE_SPLIT") == "1"      # diagnostics: the N > 1 graph structure on one GPU
+    step = HotPathStep(wl, dev, 2 if (force_split and world == 1) else world)
     d = make_inputs(wl, 1234 + rank, dev)
     for _ in range(args.warmup):
         step(d)
@@ -880,7 +917,7 @@ def main():
     #          B = the rest of the backward (ROI crop, dynamic filter, filter generator, encoder), concurrent with them
     #              -> all-reduce(filter_generator)
     #          C = fused SGD update over the flat gradient views.
-    whole = world == 1 or step.fwd_only
+    whole = (world == 1 and not force_split) or step.fwd_only
     run, graphed = (lambda: step(d)), False
     if not args.no_graph:
         try:
@@ -918,6 +955,9 @@ def main():
             torch.cuda.synchronize()
             assert torch.isfinite(static_loss).all()
             graphed = True
+            if rank == 0:
+                print("bench: loss of the graphed step %.9g (streams: %d)" % (
+                    float(static_loss), 1 + (step.side is not None) + (step.side2 is not None)), file=sys.stderr)
         except Exception as exc:      # capture is an optimisation: fall back to eager launches and say so
             print("bench: CUDA graph capture failed (%s); timing eager launches" % str(exc).splitlines()[0], file=sys.stderr)
             run = lambda: step(d)     # noqa: E731
@@ -1030,7 +1070,8 @@ def main():
                            "launch": ("one CUDA graph replay per step" if world == 1 else
                                       "three CUDA graphs per step (fwd + caption/head backward | rest of the backward | SGD) "
                                       "with the NCCL all-reduces of the flat gradient groups launched between them")
-                           if graphed else "eager launches"},
+                           if graphed else "eager launches",
+                           "streams": (1 + (step.side is not None) + (step.side2 is not None)) if graphed else 1},
                 "clocks": clocks, "gpu_launches": launches,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                         "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,

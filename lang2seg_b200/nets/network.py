@@ -79,14 +79,22 @@ class Network(nn.Module):
         return mask_prob
 
     # ---- dynamic filter ------------------------------------------------------------------------
-    def _dynamic_filter(self, net_conv, labels=None, hidden=None, expr2img=None, resp_target=None, lengths=None):
+    def _dynamic_filter(self, net_conv, labels=None, hidden=None, expr2img=None, resp_target=None, lengths=None,
+                        cut_filters=False):
         """net_conv (I,C,H,W) ; labels (E,L) tokens or precomputed hidden (E,Dh).
 
-        Stores _predictions['net_conv_before'] / ['response'] like :504,:568 and returns the gated map."""
+        Stores _predictions['net_conv_before'] / ['response'] like :504,:568 and returns the gated map.
+        cut_filters: the autograd graph is cut at the generated filters (the response layer sees detached leaves); the
+        caller finishes the backward with `torch.autograd.backward(filters, [leaf.grad ...])` -- bench.py (N > 1) runs
+        that last part (filter generator, language encoder) while the other gradient groups are being all-reduced."""
         self._predictions["net_conv_before"] = net_conv
         if hidden is None:
             _, hidden, _ = self.rnn_encoder(labels, lengths)
         filt, fuse = generate_filters(hidden, [getattr(self, "dynamic_fc_%d" % k) for k in range(7)], self.response_fc)
+        if cut_filters and torch.is_grad_enabled() and filt.requires_grad:
+            leaves = (filt.detach().requires_grad_(True), fuse.detach().requires_grad_(True))
+            self._predictions["dynamic_filters"] = ((filt, fuse), leaves)
+            filt, fuse = leaves
         response, gated, resp_loss = L2F.dynamic_filter(net_conv, filt, fuse, expr2img, self._gate, resp_target)
         self._predictions["response"] = response
         self._predictions["net_conv"] = gated
