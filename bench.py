@@ -962,6 +962,7 @@ def main():
             print("bench: CUDA graph capture failed (%s); timing eager launches" % str(exc).splitlines()[0], file=sys.stderr)
             run = lambda: step(d)     # noqa: E731
             torch.cuda.synchronize()
+    streams_used = (1 + (step.side is not None) + (step.side2 is not None)) if graphed else 1    # parallel branches of the graph
     for _ in range(args.warmup):
         run()
     sampler = ClockSampler(local) if rank == 0 else None
@@ -1071,7 +1072,7 @@ def main():
                                       "three CUDA graphs per step (fwd + caption/head backward | rest of the backward | SGD) "
                                       "with the NCCL all-reduces of the flat gradient groups launched between them")
                            if graphed else "eager launches",
-                           "streams": (1 + (step.side is not None) + (step.side2 is not None)) if graphed else 1},
+                           "streams": streams_used},
                 "clocks": clocks, "gpu_launches": launches,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                         "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
