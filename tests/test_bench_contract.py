@@ -55,3 +55,58 @@ def test_reference_arm_prints_one_json_line():
     assert d["value"] > 0 and d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.gpu
+@pytest.mark.timeout(600)
+def test_branch_streams_and_split_backward_leave_the_step_unchanged(monkeypatch):
+    """bench.HotPathStep under CUDA-graph capture: (a) the three branch streams, (b) the N > 1 structure (backward cut at
+    the generated filters, two graphs) must give the loss and the parameter gradients of the one-stream, one-graph step."""
+    import torch
+    sys.path.insert(0, ROOT)
+    import bench
+
+    wl = bench.WORKLOADS["tiny"]
+    dev = torch.device("cuda:0")
+
+    def run(streams, split):
+        monkeypatch.setenv("L2S_BENCH_STREAMS", str(streams))
+        step = bench.HotPathStep(wl, dev, 2 if split else 1)
+        d = bench.make_inputs(wl, 1234, dev)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                      # warm-up outside capture (lazy initialisations)
+            if split:
+                step.fwd_bwd(d, split=True); step.bwd_rest()
+            else:
+                step.fwd_bwd(d)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g1 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g1):
+            loss = step.fwd_bwd(d, split=split)
+        graphs = [g1]
+        if split:
+            g2 = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g2, pool=g1.pool()):
+                step.bwd_rest()
+            graphs.append(g2)
+        for g in graphs:
+            g.replay()
+        torch.cuda.synchronize()
+        grads = {n: p.grad.detach().clone() for n, p in step.net.named_parameters() if p.grad is not None}
+        return float(loss), grads, (step.side is not None) + (step.side2 is not None)
+
+    l0, g0, n0 = run(0, False)
+    l1, g1_, n1 = run(2, False)
+    l2, g2_, n2 = run(2, True)
+    assert n0 == 0 and n1 == 2 and n2 == 2
+    assert l0 == l1 == l2
+    assert set(g0) == set(g1_) == set(g2_) and len(g0) > 20
+    for k in g0:
+        den = float(g0[k].abs().max()) + 1e-30
+        assert float((g0[k] - g1_[k]).abs().max()) / den < 1e-5, k      # split-K atomics: not bit-identical run to run
+        assert float((g0[k] - g2_[k]).abs().max()) / den < 1e-5, k
