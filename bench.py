@@ -5,7 +5,7 @@
 A "step" is one forward+backward pass of the chained hot path over one batch of synthetic input
 (SURVEY.md section 8d): lang encoder -> filter generator -> dynamic filter (+response BCE) ->
 ROI crop (consumes the gated map) -> mask head (+mask BCE, synthetic res5 features) -> att2in2
-(+LM loss, synthetic fc/att features), gradient all-reduce of the three parameter groups (N>1)
+(+LM loss, synthetic fc/att features), gradient all-reduce of the parameter groups (N>1)
 and the SGD update.  res5 is cuDNN glue outside the graded step.
 
 N>1 is launched by torchrun (one rank per GPU); every rank processes its own shard of images /
@@ -284,11 +284,11 @@ class HotPathStep:
         roots_b = (([loss_b] if torch.is_tensor(loss_b) else []) + outs, ([self.one] if torch.is_tensor(loss_b) else []) + grads)
         loss = (loss_a + loss_b).detach()
         if split:
-            # everything except the filter generator + language encoder: the backward stops at the generated filters
-            # (their gradients are kept), so that the branches still overlap inside this graph and the all-reduce of
-            # the caption / head groups overlaps the rest
+            # everything except the language encoder: the backward stops at the expression embedding (its gradient is
+            # kept), so that the branches still overlap inside this graph and the all-reduce of the caption / head /
+            # filter-generator groups overlaps the rest
             torch.autograd.backward(roots_a[0] + roots_b[0], roots_a[1] + roots_b[1])
-            stops = net._predictions.get("dynamic_filters")        # ((filt, fuse), their detached leaves) or None
+            stops = net._predictions.get("graph_cut")              # ((hidden,), (its detached leaf,)) or None
             self.flat.pack(self.EARLY_GROUPS)
             self._pending = (stops, X, fc7, att)
         else:
@@ -320,10 +320,10 @@ class HotPathStep:
         self.net._losses.clear()
 
     # gradient groups that are complete after the first half of a split backward
-    EARLY_GROUPS = ("caption", "heads")
+    EARLY_GROUPS = ("caption", "heads", "filter_generator")
 
     def update(self):
-        """gradient all-reduce of the three parameter groups (N > 1) and the SGD update"""
+        """gradient all-reduce of the parameter groups (N > 1) and the SGD update"""
         if self.fwd_only:
             return
         if self.flat is not None:
@@ -913,9 +913,9 @@ def main():
     # measures the kernels, not Python / launch latency.
     #   N = 1: one graph for the whole step (lang encoder .. SGD update).
     #   N > 1: three graphs with the NCCL all-reduces launched between them, so that communication overlaps compute:
-    #          A = forward + backward of the caption / head branches  -> all-reduce(caption), all-reduce(heads) start
-    #          B = the rest of the backward (ROI crop, dynamic filter, filter generator, encoder), concurrent with them
-    #              -> all-reduce(filter_generator)
+    #          A = forward + the backward of all three branches down to the expression embedding
+    #              -> all-reduce(caption), all-reduce(heads), all-reduce(filter_generator) start
+    #          B = the rest of the backward (language encoder), concurrent with them -> all-reduce(encoder)
     #          C = fused SGD update over the flat gradient views.
     whole = (world == 1 and not force_split) or step.fwd_only
     run, graphed = (lambda: step(d)), False
@@ -1069,7 +1069,7 @@ def main():
                            "inputs + activations per step exceed the 126 MB L2 (att/fc features alone: %d MB)" % (wl["I"] * wl["EPI"] * 196 * 4096 * 4 // 2**20),
                            "includes": includes,
                            "launch": ("one CUDA graph replay per step" if world == 1 else
-                                      "three CUDA graphs per step (fwd + caption/head backward | rest of the backward | SGD) "
+                                      "three CUDA graphs per step (fwd + backward down to the expression embedding | encoder backward | SGD) "
                                       "with the NCCL all-reduces of the flat gradient groups launched between them")
                            if graphed else "eager launches",
                            "streams": streams_used},

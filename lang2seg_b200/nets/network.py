@@ -84,17 +84,18 @@ class Network(nn.Module):
         """net_conv (I,C,H,W) ; labels (E,L) tokens or precomputed hidden (E,Dh).
 
         Stores _predictions['net_conv_before'] / ['response'] like :504,:568 and returns the gated map.
-        cut_filters: the autograd graph is cut at the generated filters (the response layer sees detached leaves); the
-        caller finishes the backward with `torch.autograd.backward(filters, [leaf.grad ...])` -- bench.py (N > 1) runs
-        that last part (filter generator, language encoder) while the other gradient groups are being all-reduced."""
+        cut_filters: the autograd graph is cut at the expression embedding (the filter generator sees a detached leaf;
+        `_predictions["graph_cut"]` = ((hidden,), (leaf,))); the caller finishes the backward with
+        `torch.autograd.backward([hidden], [leaf.grad])` -- bench.py (N > 1) runs that last part (the language encoder)
+        while the gradient groups that are already complete are being all-reduced."""
         self._predictions["net_conv_before"] = net_conv
         if hidden is None:
             _, hidden, _ = self.rnn_encoder(labels, lengths)
+        if cut_filters and torch.is_grad_enabled() and hidden.requires_grad:
+            leaf = hidden.detach().requires_grad_(True)
+            self._predictions["graph_cut"] = ((hidden,), (leaf,))
+            hidden = leaf
         filt, fuse = generate_filters(hidden, [getattr(self, "dynamic_fc_%d" % k) for k in range(7)], self.response_fc)
-        if cut_filters and torch.is_grad_enabled() and filt.requires_grad:
-            leaves = (filt.detach().requires_grad_(True), fuse.detach().requires_grad_(True))
-            self._predictions["dynamic_filters"] = ((filt, fuse), leaves)
-            filt, fuse = leaves
         response, gated, resp_loss = L2F.dynamic_filter(net_conv, filt, fuse, expr2img, self._gate, resp_target)
         self._predictions["response"] = response
         self._predictions["net_conv"] = gated
@@ -253,13 +254,17 @@ class HotPathNet(Network):
         return self._add_hot_path_losses(cap_labels, cap_masks, steps=steps, num_expressions=E)
 
     def gradient_groups(self):
-        """The three parameter groups whose gradients are all-reduced (north_star)."""
-        fg = list(self.rnn_encoder.parameters()) + list(self.response_fc.parameters())
+        """The parameter groups whose gradients are all-reduced (north_star)."""
+        fg = list(self.response_fc.parameters())
         for k in range(7):
             fg += list(getattr(self, "dynamic_fc_%d" % k).parameters())
         heads = [p for m in (self.cls_score_net, self.bbox_pred_net, self.mask_up_sampling, self.mask_pred_net)
                  for p in m.parameters()]
-        groups = {"filter_generator": fg, "caption": list(self.caption_model.parameters()), "heads": heads}
+        # the filter generator of north_star / SURVEY 8e as two buckets: its projections (7,353,375 parameters, complete
+        # as soon as the dynamic filter's backward has run) and the language encoder (5,489,640, the last gradients of
+        # the step) -- so that only the encoder's 22 MB are all-reduced after the backward has finished
+        groups = {"filter_generator": fg, "encoder": list(self.rnn_encoder.parameters()),
+                  "caption": list(self.caption_model.parameters()), "heads": heads}
         if isinstance(self._head, nn.Module):      # trainable res5 glue (SURVEY 8e: 14.9 M more parameters)
             groups["res5"] = [p for p in self._head.parameters() if p.requires_grad]
         return groups
