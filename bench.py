@@ -920,12 +920,13 @@ def main():
     whole = (world == 1 and not force_split) or step.fwd_only
     run, graphed = (lambda: step(d)), False
     if not args.no_graph:
-        try:
-            def capture(fn, pool=None):
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, pool=pool):
-                    out = fn()
-                return g, out
+        def capture(fn, pool=None):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=pool):
+                out = fn()
+            return g, out
+
+        def build_graphs():
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
@@ -934,34 +935,58 @@ def main():
             torch.cuda.synchronize()
             if whole:
                 graph, static_loss = capture(lambda: step(d))
-                run = graph.replay
-            else:
-                g_a, static_loss = capture(lambda: step.fwd_bwd(d, split=True))
-                g_b, _ = capture(step.bwd_rest, pool=g_a.pool())
-                g_c, _ = capture(step.opt.step, pool=g_a.pool())
-                early = [n for n in step.EARLY_GROUPS]
-                late = [n for n in step.flat.names if n not in early]
+                return graph.replay, static_loss
+            g_a, static_loss = capture(lambda: step.fwd_bwd(d, split=True))
+            g_b, _ = capture(step.bwd_rest, pool=g_a.pool())
+            g_c, _ = capture(step.opt.step, pool=g_a.pool())
+            early = [n for n in step.EARLY_GROUPS]
+            late = [n for n in step.flat.names if n not in early]
+            nocomm = os.environ.get("L2S_BENCH_NOCOMM") == "1"    # diagnostics: the three graphs without the collectives
 
-                nocomm = os.environ.get("L2S_BENCH_NOCOMM") == "1"    # diagnostics: the three graphs without the collectives
+            def run_split():
+                g_a.replay()
+                w = [] if nocomm else step.flat.all_reduce_async(early)
+                g_b.replay()
+                w += [] if nocomm else step.flat.all_reduce_async(late)
+                step.flat.wait(w)
+                g_c.replay()
+            return run_split, static_loss
 
-                def run():
-                    g_a.replay()
-                    w = [] if nocomm else step.flat.all_reduce_async(early)
-                    g_b.replay()
-                    w += [] if nocomm else step.flat.all_reduce_async(late)
-                    step.flat.wait(w)
-                    g_c.replay()
-            run()
+        def all_ranks_ok(ok):
+            """a capture failure on one rank must take every rank down the same path (the collectives have to match)"""
+            if not dist_on:
+                return ok
+            flag = torch.tensor([0 if ok else 1], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+            return int(flag) == 0
+
+        # 1st attempt: branch streams; 2nd: one stream; otherwise eager launches (capture is an optimisation, said so below)
+        for attempt in range(2):
+            err = None
+            try:
+                if attempt == 0 and os.environ.get("L2S_BENCH_TEST_CAPTURE_FAIL") == "1":    # diagnostics: exercise the retry
+                    raise RuntimeError("injected capture failure")
+                run_g, static_loss = build_graphs()
+                run_g()
+                torch.cuda.synchronize()
+                assert torch.isfinite(static_loss).all()
+            except Exception as exc:
+                err = str(exc).splitlines()[0] if str(exc) else repr(exc)
+            if all_ranks_ok(err is None):
+                run, graphed = run_g, True
+                if rank == 0:
+                    print("bench: loss of the graphed step %.9g (streams: %d)" % (
+                        float(static_loss), 1 + (step.side is not None) + (step.side2 is not None)), file=sys.stderr)
+                break
             torch.cuda.synchronize()
-            assert torch.isfinite(static_loss).all()
-            graphed = True
-            if rank == 0:
-                print("bench: loss of the graphed step %.9g (streams: %d)" % (
-                    float(static_loss), 1 + (step.side is not None) + (step.side2 is not None)), file=sys.stderr)
-        except Exception as exc:      # capture is an optimisation: fall back to eager launches and say so
-            print("bench: CUDA graph capture failed (%s); timing eager launches" % str(exc).splitlines()[0], file=sys.stderr)
+            step._pending = None
+            if attempt == 0 and (step.side is not None or step.side2 is not None):
+                print("bench: CUDA graph capture with branch streams failed (%s); retrying on one stream" % err, file=sys.stderr)
+                step.side = step.side2 = None
+                continue
+            print("bench: CUDA graph capture failed (%s); timing eager launches" % err, file=sys.stderr)
             run = lambda: step(d)     # noqa: E731
-            torch.cuda.synchronize()
+            break
     streams_used = (1 + (step.side is not None) + (step.side2 is not None)) if graphed else 1    # parallel branches of the graph
     for _ in range(args.warmup):
         run()
