@@ -203,6 +203,7 @@ class HotPathStep:
         # Only under graph capture: eager launches (the e2e leg) pay more for the stream switches than they gain.
         # L2S_BENCH_STREAMS=0 keeps everything on one stream.
         nstreams = int(os.environ.get("L2S_BENCH_STREAMS", "2"))
+        # (stream priorities for the branches were measured and changed nothing: profiles/r02_ab.md)
         self.side = torch.cuda.Stream(device) if (nstreams >= 1 and "caption" in self.parts and not self.fwd_only) else None
         self.side2 = torch.cuda.Stream(device) if (nstreams >= 2 and "mask" in self.parts and not self.fwd_only) else None
 
