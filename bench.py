@@ -1,6 +1,6 @@
 """bench.py -- expressions/sec of the lang2seg hot path (fwd+bwd) on B200, next to its CPU baseline.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload cfg2|cfg4|tiny]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload cfg1|cfg2|cfg3|cfg4|cfg5|tiny]
 
 A "step" is one forward+backward pass of the chained hot path over one batch of synthetic input
 (SURVEY.md section 8d): lang encoder -> filter generator -> dynamic filter (+response BCE) ->
@@ -8,11 +8,17 @@ ROI crop (consumes the gated map) -> mask head (+mask BCE, synthetic res5 featur
 (+LM loss, synthetic fc/att features), gradient all-reduce of the parameter groups (N>1)
 and the SGD update.  res5 is cuDNN glue outside the graded step.
 
+The step is captured in CUDA graphs; its three data-independent branches (encoder -> dynamic filter -> crop | mask
+head | att2in2) are issued on separate streams during capture, so they overlap forward and backward (HotPathStep).
+
 N>1 is launched by torchrun (one rank per GPU); every rank processes its own shard of images /
 expressions (weak scaling) and only parameter gradients cross NVLink.
 
-Prints ONE JSON line (rank 0).  `--impl reference` times the oracle's torch-CPU port of the
-reference modules on the host cores instead (rank 0 only).
+Prints ONE JSON line (rank 0).  `--impl reference` times the reference's own modules (baseline/_ref, under the
+compatibility shim; else the oracle's torch-CPU port) on the host cores instead (rank 0 only).
+
+Diagnostics (environment): L2S_BENCH_STREAMS=0|1|2 (branch streams, default 2), L2S_BENCH_FORCE_SPLIT=1 (the N > 1
+graph structure on one GPU), L2S_BENCH_NOCOMM=1 (N > 1 without the collectives).
 """
 from __future__ import annotations
 
