@@ -305,6 +305,63 @@ class HotPathStep:
             self._finish(X, fc7, att)
         return loss
 
+    # ---- N > 1, concurrent-graph structure: every branch is its own CUDA graph (forward + backward + gradient pack),
+    # replayed on its own stream; the all-reduce of a branch's gradient group is launched behind that branch alone
+    def _zero(self, names):
+        for n in names:
+            for p in self.flat.params.get(n, []):
+                p.grad = None
+
+    def branch_caption(self, d, meta=None):
+        meta = meta if meta is not None else d.get("_meta", {})
+        net = self.net
+        self._zero(["caption"])
+        att = d["att"].requires_grad_(True)
+        loss = net._cap_loss_weight * net._caption_loss(d["fc"], att, d["cap"], d["msk"], steps=meta.get("steps"))
+        torch.autograd.backward([loss], [self.one])
+        self.flat.pack(["caption"])
+        att.grad = None
+        return loss.detach()
+
+    def branch_mask(self, d):
+        net = self.net
+        self._zero(["heads"])
+        fc7 = d["fc7"].requires_grad_(True)
+        net._mask_prediction(fc7, d["mlab"], d["mtgt"])
+        loss = net._mask_loss(d["mlab"], d["mtgt"])
+        torch.autograd.backward([loss], [self.one])
+        self.flat.pack(["heads"])
+        fc7.grad = None
+        for k in ("mask_score", "mask_prob"):
+            net._predictions.pop(k, None)
+        net._losses.pop("mask_loss", None)
+        return loss.detach()
+
+    def branch_main(self, d, meta=None):
+        """language encoder -> filter generator -> dynamic filter -> ROI crops, backward down to the expression
+        embedding (bwd_rest() finishes the encoder)"""
+        meta = meta if meta is not None else d.get("_meta", {})
+        net, parts = self.net, self.parts
+        self._zero(["filter_generator", "encoder"])
+        X = d["X"].requires_grad_(True)
+        gated = net._dynamic_filter(X, d["labels"], expr2img=d["e2i"], resp_target=d.get("resp_tgt"),
+                                    lengths=meta.get("lens"), cut_filters=True)
+        roots, grads = [], []
+        loss = torch.zeros((), device=self.device)
+        if "resp" in parts:
+            loss = net._losses["loss_response_per_expr"].sum()
+            roots.append(loss); grads.append(self.one)
+        if "crop_max" in parts:
+            roots.append(net._crop_pool_layer(gated, d["rois"], max_pool=True)); grads.append(self.g_pool_max)
+        if "crop7" in parts:
+            roots.append(net._crop_pool_layer(gated, d["rois"], max_pool=False)); grads.append(self.g_pool)
+        if "dY" in parts:
+            roots.append(gated); grads.append(self.g_Y)
+        torch.autograd.backward(roots, grads)
+        self.flat.pack(["filter_generator"])
+        self._pending = (net._predictions.get("graph_cut"), X, None, None)
+        return loss.detach()
+
     def bwd_rest(self):
         """second half of a split backward (see fwd_bwd)"""
         stops, X, fc7, att = self._pending
@@ -378,6 +435,60 @@ class ChainedStep:
         net._losses.clear()
         net._proposal_targets = {}
         return loss.detach()
+
+
+def build_branch_graphs(step, d, nocomm=False):
+    """N > 1: one CUDA graph per branch (caption | mask head | encoder..crops), replayed concurrently on their own
+    streams, + the encoder's backward + the SGD update.  Each gradient group's all-reduce is launched (outside the
+    graphs, on NCCL's stream) behind ITS branch only, so it overlaps the other branches.  Returns (run, losses)."""
+    def capture(fn, pool=None):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, pool=pool):
+            out = fn()
+        return g, out
+
+    parts = step.parts
+    flat = step.flat
+    losses = []
+    g_cap = g_mask = None
+    if "caption" in parts:
+        g_cap, l = capture(lambda: step.branch_caption(d))
+        losses.append(l)
+    if "mask" in parts:
+        g_mask, l = capture(lambda: step.branch_mask(d))
+        losses.append(l)
+    g_main, l = capture(lambda: step.branch_main(d))
+    losses.append(l)
+    g_enc, _ = capture(step.bwd_rest, pool=g_main.pool())
+    g_sgd, _ = capture(step.opt.step, pool=g_main.pool())
+    s_cap = step.side if step.side is not None else torch.cuda.Stream(step.device)
+    s_mask = step.side2 if step.side2 is not None else torch.cuda.Stream(step.device)
+    ar = (lambda names: []) if nocomm else flat.all_reduce_async
+
+    def run():
+        cur = torch.cuda.current_stream()
+        works = []
+        if g_cap is not None:
+            s_cap.wait_stream(cur)
+            with torch.cuda.stream(s_cap):
+                g_cap.replay()
+                works += ar(["caption"])
+        if g_mask is not None:
+            s_mask.wait_stream(cur)
+            with torch.cuda.stream(s_mask):
+                g_mask.replay()
+                works += ar(["heads"])
+        g_main.replay()
+        works += ar(["filter_generator"])
+        g_enc.replay()
+        works += ar(["encoder"])
+        if g_cap is not None:
+            cur.wait_stream(s_cap)
+        if g_mask is not None:
+            cur.wait_stream(s_mask)
+        flat.wait(works)
+        g_sgd.replay()
+    return run, losses
 
 
 def run_chained(wl, dev, world, rank, dist_on, steps=3, warm=2):
@@ -925,7 +1036,7 @@ def main():
     #          B = the rest of the backward (language encoder), concurrent with them -> all-reduce(encoder)
     #          C = fused SGD update over the flat gradient views.
     whole = (world == 1 and not force_split) or step.fwd_only
-    run, graphed = (lambda: step(d)), False
+    run, graphed, launch_desc = (lambda: step(d)), False, "eager launches"
     if not args.no_graph:
         def capture(fn, pool=None):
             g = torch.cuda.CUDAGraph()
@@ -967,33 +1078,61 @@ def main():
             dist.all_reduce(flag, op=dist.ReduceOp.MAX)
             return int(flag) == 0
 
-        # 1st attempt: branch streams; 2nd: one stream; otherwise eager launches (capture is an optimisation, said so below)
-        for attempt in range(2):
+        def build_branch():
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                step(d)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            run_b, losses = build_branch_graphs(step, d, nocomm=os.environ.get("L2S_BENCH_NOCOMM") == "1")
+            run_b()
+            return run_b, torch.stack([l.float() for l in losses]).sum()
+
+        def one_stream():
+            step.side = step.side2 = None
+
+        # capture is an optimisation: structures are tried in this order, then eager launches (said so in the line)
+        if whole:
+            plans = [("one CUDA graph replay per step", None, build_graphs),
+                     ("one CUDA graph replay per step", one_stream, build_graphs)]
+        else:
+            three = ("three CUDA graphs per step (fwd + backward down to the expression embedding | encoder backward | SGD) "
+                     "with the NCCL all-reduces of the flat gradient groups launched between them")
+            plans = [("one CUDA graph per branch (att2in2 | mask head | encoder..crops + encoder backward), replayed "
+                      "concurrently on three streams, each gradient group all-reduced (NCCL) behind its own branch; SGD graph",
+                      None, build_branch),
+                     (three, None, build_graphs), (three, one_stream, build_graphs)]
+            if os.environ.get("L2S_BENCH_BRANCH_GRAPHS") == "0":
+                plans = plans[1:]
+        for attempt, (desc, prep, builder) in enumerate(plans):
             err = None
             try:
+                if prep is not None:
+                    prep()
                 if attempt == 0 and os.environ.get("L2S_BENCH_TEST_CAPTURE_FAIL") == "1":    # diagnostics: exercise the retry
                     raise RuntimeError("injected capture failure")
-                run_g, static_loss = build_graphs()
+                run_g, static_loss = builder()
                 run_g()
                 torch.cuda.synchronize()
                 assert torch.isfinite(static_loss).all()
             except Exception as exc:
                 err = str(exc).splitlines()[0] if str(exc) else repr(exc)
             if all_ranks_ok(err is None):
-                run, graphed = run_g, True
+                run, graphed, launch_desc = run_g, True, desc
                 if rank == 0:
-                    print("bench: loss of the graphed step %.9g (streams: %d)" % (
-                        float(static_loss), 1 + (step.side is not None) + (step.side2 is not None)), file=sys.stderr)
+                    print("bench: loss of the graphed step %.9g (streams: %d; %s)" % (
+                        float(static_loss), 1 + (step.side is not None) + (step.side2 is not None), desc[:40]), file=sys.stderr)
                 break
             torch.cuda.synchronize()
             step._pending = None
-            if attempt == 0 and (step.side is not None or step.side2 is not None):
-                print("bench: CUDA graph capture with branch streams failed (%s); retrying on one stream" % err, file=sys.stderr)
-                step.side = step.side2 = None
-                continue
-            print("bench: CUDA graph capture failed (%s); timing eager launches" % err, file=sys.stderr)
-            run = lambda: step(d)     # noqa: E731
-            break
+            step.net._predictions.clear()
+            step.net._losses.clear()
+            more = attempt + 1 < len(plans)
+            print("bench: CUDA graph capture failed (%s); %s" % (err, "trying the next structure" if more else
+                                                                 "timing eager launches"), file=sys.stderr)
+            if not more:
+                run = lambda: step(d)     # noqa: E731
     streams_used = (1 + (step.side is not None) + (step.side2 is not None)) if graphed else 1    # parallel branches of the graph
     for _ in range(args.warmup):
         run()
@@ -1100,10 +1239,7 @@ def main():
                            if "caption" not in wl["parts"] or wl["I"] * wl["EPI"] >= 32 else
                            "inputs + activations per step exceed the 126 MB L2 (att/fc features alone: %d MB)" % (wl["I"] * wl["EPI"] * 196 * 4096 * 4 // 2**20),
                            "includes": includes,
-                           "launch": ("one CUDA graph replay per step" if world == 1 else
-                                      "three CUDA graphs per step (fwd + backward down to the expression embedding | encoder backward | SGD) "
-                                      "with the NCCL all-reduces of the flat gradient groups launched between them")
-                           if graphed else "eager launches",
+                           "launch": launch_desc,
                            "streams": streams_used},
                 "clocks": clocks, "gpu_launches": launches,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,

@@ -100,13 +100,39 @@ def test_branch_streams_and_split_backward_leave_the_step_unchanged(monkeypatch)
         grads = {n: p.grad.detach().clone() for n, p in step.net.named_parameters() if p.grad is not None}
         return float(loss), grads, (step.side is not None) + (step.side2 is not None)
 
+    def run_branch_graphs():
+        """the N > 1 structure of bench.py: one graph per branch, replayed concurrently on three streams"""
+        monkeypatch.setenv("L2S_BENCH_STREAMS", "2")
+        step = bench.HotPathStep(wl, dev, 2)
+        d = bench.make_inputs(wl, 1234, dev)
+        p0 = {n: p.detach().clone() for n, p in step.net.named_parameters()}
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            step.fwd_bwd(d, split=True); step.bwd_rest(); step.update()     # the optimizer's momentum state exists before capture
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        with torch.no_grad():                                               # ... and the parameters are those of the other runs
+            for n, p in step.net.named_parameters():
+                p.copy_(p0[n])
+        run_b, losses = bench.build_branch_graphs(step, d)
+        run_b()
+        torch.cuda.synchronize()
+        grads = {n: p.grad.detach().clone() for n, p in step.net.named_parameters() if p.grad is not None}
+        moved = [n for n, p in step.net.named_parameters() if p.grad is not None and not torch.equal(p.detach(), p0[n])]
+        return float(torch.stack([l.float() for l in losses]).sum()), grads, moved
+
     l0, g0, n0 = run(0, False)
     l1, g1_, n1 = run(2, False)
     l2, g2_, n2 = run(2, True)
+    l3, g3_, moved = run_branch_graphs()
     assert n0 == 0 and n1 == 2 and n2 == 2
     assert l0 == l1 == l2
-    assert set(g0) == set(g1_) == set(g2_) and len(g0) > 20
+    assert abs(l3 - l0) <= 1e-6 * abs(l0)                                 # the three losses are added in another order
+    assert set(g0) == set(g1_) == set(g2_) == set(g3_) and len(g0) > 20
+    assert len(moved) > 20                                                # the SGD graph ran on the packed gradients
     for k in g0:
         den = float(g0[k].abs().max()) + 1e-30
         assert float((g0[k] - g1_[k]).abs().max()) / den < 1e-5, k      # split-K atomics: not bit-identical run to run
         assert float((g0[k] - g2_[k]).abs().max()) / den < 1e-5, k
+        assert float((g0[k] - g3_[k]).abs().max()) / den < 1e-5, k
