@@ -96,10 +96,10 @@ def test_partition_bounds_contract():
             assert torch.equal(r[0, 0].cpu(), masks[k] * C), (H, W, C, k)
 
 
-@pytest.mark.parametrize("E,C,Dh", [(48, 1024, 1024), (3, 512, 1024), (70, 64, 32)])
+@pytest.mark.parametrize("E,C,Dh", [(48, 1024, 1024), (16, 1024, 1024), (8, 512, 1024), (3, 512, 1024), (70, 64, 32)])
 def test_filter_generator_fused_vs_oracle(E, C, Dh):
     """generate_filters: the seven dynamic_fc projections + response_fc as ONE GEMM (fwd, dX, dW) vs 8 torch Linears: on the
-    tcgen05 GEMM from 8 expressions on when the stacked weight is large (48 rows in mostly empty 128-row tiles),
+    tcgen05 GEMM from 8 expressions on when the stacked weight is large (48 / 16 / 8 rows in mostly empty 128-row tiles),
     the skinny exact-fp32 kernels otherwise."""
     from lang2seg_b200.layers.dynamic_filter import DynamicFilterResponse, generate_filters
     torch.manual_seed(E + C)
