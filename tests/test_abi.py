@@ -63,6 +63,37 @@ def test_cpu_tensors_are_rejected():
         F.roi_max_pool(torch.zeros(1, 4, 8, 8), torch.zeros(1, 5))
 
 
+def test_new_entry_points_validate_on_the_host():
+    """l2s_embedding_bwd / the L2S_CROP_WS_PREPARED flag: argument checks run before any CUDA call."""
+    from lang2seg_b200 import _lib
+    lib = _lib.load()
+    p16 = ctypes.c_void_p(16)
+    assert lib.l2s_embedding_bwd(p16, p16, p16, 4, 10, 6, None) != 0 and b"bad shape" in lib.l2s_last_error_string()      # D % 4
+    assert lib.l2s_embedding_bwd(p16, p16, None, 4, 10, 8, None) != 0 and b"null" in lib.l2s_last_error_string()
+    assert lib.l2s_embedding_bwd(p16, ctypes.c_void_p(20), p16, 4, 10, 8, None) != 0 and b"aligned" in lib.l2s_last_error_string()
+    # unknown crop flag bits are rejected, the workspace-reuse bit (8) is accepted as a flag (the null pointers then fail)
+    rc = lib.l2s_roi_crop_bwd(None, None, None, None, 1, 8, 16, 16, 1, 7, 16, 0.0, 0.0, None, 0, None)
+    assert rc != 0
+    rc = lib.l2s_roi_crop_bwd(p16, p16, None, p16, 1, 8, 16, 16, 1, 7, 16, 0.0, 0.0, p16, 1 << 20, None)
+    assert rc != 0 and b"unknown flags" in lib.l2s_last_error_string()
+
+
+def test_embedding_module_keeps_the_reference_interface():
+    """L2F.Embedding is nn.Embedding for checkpoints and for CPU tensors (only CUDA training lookups use the library)."""
+    import torch
+    import lang2seg_b200.functional as F
+    ref = torch.nn.Embedding(11, 8)
+    mod = F.Embedding(11, 8)
+    assert list(mod.state_dict()) == list(ref.state_dict()) == ["weight"]
+    mod.load_state_dict(ref.state_dict(), strict=True)
+    idx = torch.tensor([[1, 2, 2], [0, 10, 3]])
+    out = mod(idx)
+    assert torch.equal(out, ref(idx))
+    out.sum().backward()
+    ref(idx).sum().backward()
+    assert torch.equal(mod.weight.grad, ref.weight.grad)
+
+
 def test_header_is_plain_c99(tmp_path):
     """include/l2s.h is the C ABI: it must compile as C (no C++ or torch types in any signature)."""
     import shutil
