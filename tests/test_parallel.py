@@ -59,6 +59,21 @@ def _worker(rank, world, port, out):
     assert all(p.grad.data_ptr() == v.data_ptr() for n in flat.names for p, v in zip(flat.params[n], flat.views[n]))
     packed_grads = [p.grad.clone() for p in list(lin_a.parameters()) + list(lin_b.parameters())]
     assert all(torch.equal(a, b) for a, b in zip(flat_grads, packed_grads))
+    # the cut protocol of the N > 1 step (bench.py: Network._dynamic_filter(cut_filters=True) + bwd_rest()): the graph is
+    # cut at an intermediate tensor, the downstream group is packed and on the wire while the upstream backward runs
+    for _ in range(2):
+        for p in list(lin_a.parameters()) + list(lin_b.parameters()):
+            p.grad = None
+        hidden = lin_a(full[lo:hi])
+        leaf = hidden.detach().requires_grad_(True)
+        (lin_b(leaf) ** 2).sum().backward()                  # stops at the leaf; lin_b's gradients are complete
+        flat.pack(["b"])
+        wb = flat.all_reduce_async(["b"])
+        torch.autograd.backward([hidden], [leaf.grad])        # the rest of the backward
+        flat.pack(["a"])
+        flat.wait(wb + flat.all_reduce_async(["a"]))
+    cut_grads = [p.grad.clone() for p in list(lin_a.parameters()) + list(lin_b.parameters())]
+    assert all(torch.allclose(a, b, rtol=1e-6, atol=1e-7) for a, b in zip(flat_grads, cut_grads))
     if rank == 0:
         torch.save([grads, flat_grads], out)
     dist.destroy_process_group()
