@@ -57,6 +57,30 @@ def test_reference_arm_prints_one_json_line():
     assert d["gpu_launches"] == 0
 
 
+def test_recorded_bench_line_has_every_contract_key():
+    """The line the B200 arm printed at HEAD (profiles/r02s3_bench_cfg2.json) carries the keys of the benchmark contract."""
+    path = os.path.join(ROOT, "profiles", "r02s3_bench_cfg2.json")
+    d = json.loads(open(path).read().strip().splitlines()[-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert k in d, k
+    assert d["n_gpus"] == 1 and d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None
+    assert d["config"]["workload"].startswith("cfg2") and "model" not in d["config"]
+    assert abs(d["value"] - 48 * 1e3 / d["ms_per_step"]) / d["value"] < 1e-6            # 48 expressions per step
+    for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"):
+        assert k in d["e2e"], k
+    assert d["e2e"]["h2d_bytes_per_step"] > 1e9 and d["e2e"]["value"] < d["value"]
+    r = d["roofline"]
+    for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert k in r, k
+    assert r["bound"] == "tensor" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    c = d["cpu_baseline"]
+    for k in ("value", "unit", "cores", "kind", "sample"):
+        assert k in c, k
+    assert c["kind"] in ("reference", "port") and d["gpu_launches"] > 0
+    assert d["clocks"]["sm_mhz"] > 0 and not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+
+
 import pytest  # noqa: E402
 
 
